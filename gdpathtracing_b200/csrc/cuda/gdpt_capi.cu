@@ -1,0 +1,770 @@
+// gdpt_capi.cu -- implementation of the C-ABI declared in include/gdpt.h:
+// device / shader / RID bookkeeping that stands in for the gdcs ComputeShader +
+// RenderingDevice pair, the binding-table validation, construction of the
+// derived traversal layout, and the frame drivers that launch the kernels of
+// pt_kernels.cu.  No CPU rendering path exists here: every entry point either
+// drives the GPU or fails.
+#include "gdpt.h"
+#include "pt_kernels.cuh"
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+using namespace gdpt;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+enum ResourceKind { RES_BUFFER, RES_IMAGE, RES_LAYERED };
+
+struct Resource {
+    ResourceKind kind = RES_BUFFER;
+    void *dptr = nullptr;
+    uint64_t size = 0;
+    int width = 0, height = 0, layers = 1;
+    gdpt_data_format format = GDPT_FORMAT_R8G8B8A8_UNORM;
+    std::vector<uint8_t> shadow; // host copy of storage buffers (used to derive layouts)
+};
+
+enum ShaderKind { SHADER_MAIN, SHADER_PROGRESSIVE };
+
+} // namespace
+
+struct gdpt_device {
+    int ordinal = 0;
+    cudaStream_t stream = nullptr;
+    std::string last_error;
+    std::map<gdpt_rid, Resource> resources;
+    gdpt_rid next_rid = 1;
+    void *pinned_staging = nullptr; // small H2D staging (camera, params)
+    cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
+};
+
+struct gdpt_shader {
+    gdpt_device *dev = nullptr;
+    ShaderKind kind = SHADER_MAIN;
+    std::map<std::pair<int, int>, gdpt_rid> bindings; // (set, binding) -> rid
+    std::vector<gdpt_rid> owned;
+    bool initialized = false, uniforms_ready = false;
+    // "#define" options
+    int max_depth = 5;
+    bool debug_steps = false;
+    int trace_segments = 0;
+    uint32_t visits_per_ray = 0;
+    int variant = 0;
+    // main-shader state built by finish_create_uniforms
+    FrameArgs args;
+    std::vector<void *> derived; // device allocations owned by this shader
+    int shard_part = 0, shard_parts = 1, shard_band = 4;
+    gdpt_frame_stats stats;
+    bool stats_valid = false;
+};
+
+namespace {
+
+int fail(gdpt_device *d, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (d) d->last_error = buf; else g_create_error = buf;
+    return code;
+}
+
+#define GDPT_CUDA(dev, call)                                                                                        \
+    do {                                                                                                             \
+        cudaError_t e__ = (call);                                                                                    \
+        if (e__ != cudaSuccess)                                                                                      \
+            return fail((dev), GDPT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+Resource *find(gdpt_device *d, gdpt_rid rid)
+{
+    auto it = d->resources.find(rid);
+    return it == d->resources.end() ? nullptr : &it->second;
+}
+
+uint64_t texel_bytes(gdpt_data_format f)
+{
+    switch (f) {
+    case GDPT_FORMAT_R8G8B8A8_UNORM: return 4;
+    case GDPT_FORMAT_R32_SFLOAT: return 4;
+    case GDPT_FORMAT_R32G32B32A32_SFLOAT: return 16;
+    }
+    return 0;
+}
+
+std::string basename_of(const char *path)
+{
+    std::string s(path ? path : "");
+    size_t p = s.find_last_of("/\\");
+    return p == std::string::npos ? s : s.substr(p + 1);
+}
+
+// "#define NAME [value]" -> (NAME, value)
+bool parse_define(const char *line, std::string *name, long *value, bool *has_value)
+{
+    char n[128];
+    long v = 0;
+    int got = sscanf(line, " # define %127s %ld", n, &v);
+    if (got < 1) got = sscanf(line, " #define %127s %ld", n, &v);
+    if (got < 1) return false;
+    *name = n; *value = v; *has_value = (got >= 2);
+    return true;
+}
+
+Resource *bound(gdpt_shader *s, int set, int binding)
+{
+    auto it = s->bindings.find({ set, binding });
+    if (it == s->bindings.end()) return nullptr;
+    return find(s->dev, it->second);
+}
+
+template <typename T> int dev_alloc(gdpt_shader *s, T **out, size_t count)
+{
+    void *p = nullptr;
+    GDPT_CUDA(s->dev, cudaMalloc(&p, count * sizeof(T) > 0 ? count * sizeof(T) : 16));
+    s->derived.push_back(p);
+    *out = static_cast<T *>(p);
+    return GDPT_OK;
+}
+
+template <typename T> int dev_upload(gdpt_shader *s, const T **out, const std::vector<T> &v)
+{
+    T *p = nullptr;
+    int rc = dev_alloc(s, &p, v.size());
+    if (rc) return rc;
+    if (!v.empty()) GDPT_CUDA(s->dev, cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s->dev->stream));
+    *out = p;
+    return GDPT_OK;
+}
+
+// Build WideNode / LeafRec / InstRec tables from the uploaded reference arrays.
+int build_derived_layout(gdpt_shader *s, const Resource &bvh_r, const Resource &blas_r, const Resource &tlas_r)
+{
+    gdpt_device *d = s->dev;
+    const gdpt_bvh_node *bvh = reinterpret_cast<const gdpt_bvh_node *>(bvh_r.shadow.data());
+    const gdpt_blas_instance *blas = reinterpret_cast<const gdpt_blas_instance *>(blas_r.shadow.data());
+    const gdpt_tlas_node *tlas = reinterpret_cast<const gdpt_tlas_node *>(tlas_r.shadow.data());
+    const uint32_t n_nodes = (uint32_t)(bvh_r.size / sizeof(gdpt_bvh_node));
+    const uint32_t n_blas = (uint32_t)(blas_r.size / sizeof(gdpt_blas_instance));
+    const uint32_t n_tlas = (uint32_t)(tlas_r.size / sizeof(gdpt_tlas_node));
+    if (n_tlas == 0 || n_blas == 0) return fail(d, GDPT_ERR_BAD_BINDING, "empty TLAS / instance buffer");
+    if (n_nodes >= LINK_INDEX_MASK) return fail(d, GDPT_ERR_UNSUPPORTED, "too many BVH nodes");
+
+    // BLAS: internal nodes and leaves get their own dense numbering
+    std::vector<uint32_t> link(n_nodes);
+    uint32_t n_internal = 0, n_leaf = 0;
+    for (uint32_t i = 0; i < n_nodes; i++) link[i] = bvh[i].tri_count > 0 ? (LINK_LEAF | n_leaf++) : n_internal++;
+    std::vector<WideNode> wide(n_internal);
+    std::vector<LeafRec> leaves(n_leaf);
+    for (uint32_t i = 0; i < n_nodes; i++) {
+        const gdpt_bvh_node &n = bvh[i];
+        if (n.tri_count > 0) {
+            LeafRec &l = leaves[link[i] & LINK_INDEX_MASK];
+            l.first_tri = n.first_tri_index; l.tri_count = n.tri_count; l.orig = i; l.pad = 0;
+        } else {
+            if (n.left_child >= n_nodes || n.right_child >= n_nodes)
+                return fail(d, GDPT_ERR_BAD_BINDING, "BVH node %u has a child index out of range", i);
+            WideNode &w = wide[link[i]];
+            const gdpt_bvh_node &L = bvh[n.left_child], &R = bvh[n.right_child];
+            for (int k = 0; k < 3; k++) { w.lmin[k] = L.aabb_min[k]; w.lmax[k] = L.aabb_max[k]; w.rmin[k] = R.aabb_min[k]; w.rmax[k] = R.aabb_max[k]; }
+            w.left = link[n.left_child]; w.right = link[n.right_child]; w.orig = i; w.pad = 0;
+        }
+    }
+    // TLAS: same split; leaves index the instance table directly
+    std::vector<uint32_t> tlink(n_tlas);
+    uint32_t nt_internal = 0;
+    for (uint32_t i = 0; i < n_tlas; i++) {
+        if (tlas[i].left_right == 0) {
+            if (tlas[i].blas >= n_blas) return fail(d, GDPT_ERR_BAD_BINDING, "TLAS leaf %u names instance %u of %u", i, tlas[i].blas, n_blas);
+            tlink[i] = LINK_TLAS | LINK_LEAF | tlas[i].blas;
+        } else tlink[i] = LINK_TLAS | nt_internal++;
+    }
+    std::vector<WideNode> wtlas(nt_internal);
+    std::vector<InstRec> inst(n_blas);
+    for (uint32_t b = 0; b < n_blas; b++) {
+        if (blas[b].root >= n_nodes) return fail(d, GDPT_ERR_BAD_BINDING, "instance %u root out of range", b);
+        memcpy(inst[b].inv, blas[b].inverse_transform, sizeof(inst[b].inv));
+        inst[b].root_link = link[blas[b].root];
+        inst[b].root_orig = blas[b].root;
+        inst[b].tlas_orig = 0; inst[b].pad = 0;
+    }
+    for (uint32_t i = 0; i < n_tlas; i++) {
+        const gdpt_tlas_node &n = tlas[i];
+        if (n.left_right == 0) {
+            if (i > 0) inst[n.blas].tlas_orig = i; // leaves sit at 1..I in instance order (bvh.cpp:278-287)
+            continue;
+        }
+        const uint32_t l = n.left_right & 0xFFFFu, r = n.left_right >> 16;
+        if (l >= n_tlas || r >= n_tlas) return fail(d, GDPT_ERR_BAD_BINDING, "TLAS node %u has a child out of range", i);
+        WideNode &w = wtlas[tlink[i] & LINK_INDEX_MASK];
+        for (int k = 0; k < 3; k++) { w.lmin[k] = tlas[l].aabb_min[k]; w.lmax[k] = tlas[l].aabb_max[k]; w.rmin[k] = tlas[r].aabb_min[k]; w.rmax[k] = tlas[r].aabb_max[k]; }
+        w.left = tlink[l]; w.right = tlink[r]; w.orig = i; w.pad = 0;
+    }
+    // node 0 is a copy of the final root (bvh.cpp:316); with a single instance that root is
+    // itself the leaf, and the traversal pops it as node 0
+    if (tlas[0].left_right == 0) inst[tlas[0].blas].tlas_orig = 0;
+
+    int rc;
+    if ((rc = dev_upload(s, &s->args.sc.wide_nodes, wide))) return rc;
+    if ((rc = dev_upload(s, &s->args.sc.leaf_recs, leaves))) return rc;
+    if ((rc = dev_upload(s, &s->args.sc.wide_tlas, wtlas))) return rc;
+    if ((rc = dev_upload(s, &s->args.sc.inst_recs, inst))) return rc;
+    s->args.sc.tlas_root_link = tlink[0];
+    GDPT_CUDA(d, cudaStreamSynchronize(d->stream)); // host vectors die at return
+    return GDPT_OK;
+}
+
+void compute_shard(gdpt_shader *s)
+{
+    FrameArgs &a = s->args;
+    a.shard_part = s->shard_part; a.shard_parts = s->shard_parts; a.shard_band = s->shard_band;
+    int rows = 0;
+    if (a.shard_parts <= 1) rows = a.height;
+    else
+        for (int y = 0; y < a.height; y++)
+            if ((y / a.shard_band) % a.shard_parts == a.shard_part) rows++;
+    a.local_rows = rows;
+    const uint32_t tiles_x = ((uint32_t)a.width + 7u) / 8u, tiles_y = ((uint32_t)rows + 3u) / 4u;
+    a.n_work = tiles_x * tiles_y * 32u;
+}
+
+int finish_main(gdpt_shader *s)
+{
+    gdpt_device *d = s->dev;
+    Resource *out = bound(s, 0, 0), *depth = bound(s, 0, 1), *params = bound(s, 0, 2), *camera = bound(s, 0, 3);
+    Resource *tg = bound(s, 1, 0), *td = bound(s, 1, 1), *mat = bound(s, 1, 2), *bvh = bound(s, 1, 3), *blas = bound(s, 1, 4),
+             *tlas = bound(s, 1, 5), *tex = bound(s, 2, 0);
+    if (!out || !depth || !params || !camera || !tg || !td || !mat || !bvh || !blas || !tlas || !tex)
+        return fail(d, GDPT_ERR_BAD_BINDING, "main.glsl needs set0 b0-3, set1 b0-5 and set2 b0 (main.glsl:98-155)");
+    if (out->kind != RES_IMAGE || out->format != GDPT_FORMAT_R8G8B8A8_UNORM) return fail(d, GDPT_ERR_BAD_BINDING, "set0 b0 must be an rgba8 image");
+    if (depth->kind != RES_IMAGE || depth->format != GDPT_FORMAT_R32_SFLOAT) return fail(d, GDPT_ERR_BAD_BINDING, "set0 b1 must be an r32f image");
+    if (params->kind != RES_BUFFER || params->size < sizeof(gdpt_render_params)) return fail(d, GDPT_ERR_BAD_BINDING, "set0 b2 must hold the 36 B Params block");
+    if (camera->kind != RES_BUFFER || camera->size < 156) return fail(d, GDPT_ERR_BAD_BINDING, "set0 b3 must hold the Camera block");
+    if (tex->kind != RES_LAYERED || tex->format != GDPT_FORMAT_R8G8B8A8_UNORM) return fail(d, GDPT_ERR_BAD_BINDING, "set2 b0 must be an rgba8 texture array");
+    if (tg->size % sizeof(gdpt_triangle_geometry) || td->size % sizeof(gdpt_triangle_data) || mat->size % sizeof(gdpt_material) ||
+        bvh->size % sizeof(gdpt_bvh_node) || blas->size % sizeof(gdpt_blas_instance) || tlas->size % sizeof(gdpt_tlas_node))
+        return fail(d, GDPT_ERR_BAD_BINDING, "a scene buffer is not a whole number of records");
+    if (tg->size / sizeof(gdpt_triangle_geometry) != td->size / sizeof(gdpt_triangle_data))
+        return fail(d, GDPT_ERR_BAD_BINDING, "triangle geometry/data arrays differ in length");
+
+    gdpt_render_params rp;
+    memcpy(&rp, params->shadow.data(), sizeof(rp));
+    if (rp.width <= 0 || rp.height <= 0 || rp.width != out->width || rp.height != out->height || depth->width != out->width ||
+        depth->height != out->height)
+        return fail(d, GDPT_ERR_BAD_BINDING, "Params width/height (%d x %d) must match the bound images", rp.width, rp.height);
+
+    for (void *p : s->derived) cudaFree(p);
+    s->derived.clear();
+    FrameArgs &a = s->args;
+    memset(&a, 0, sizeof(a));
+    a.sc.tri_geom = static_cast<const gdpt_triangle_geometry *>(tg->dptr);
+    a.sc.tri_data = static_cast<const gdpt_triangle_data *>(td->dptr);
+    a.sc.materials = static_cast<const gdpt_material *>(mat->dptr);
+    a.sc.bvh = static_cast<const gdpt_bvh_node *>(bvh->dptr);
+    a.sc.blas = static_cast<const gdpt_blas_instance *>(blas->dptr);
+    a.sc.tlas = static_cast<const gdpt_tlas_node *>(tlas->dptr);
+    a.sc.textures = static_cast<const uint8_t *>(tex->dptr);
+    a.sc.tex_w = tex->width; a.sc.tex_h = tex->height; a.sc.tex_layers = tex->layers;
+    a.sc.n_tris = (uint32_t)(tg->size / sizeof(gdpt_triangle_geometry));
+    a.sc.n_nodes = (uint32_t)(bvh->size / sizeof(gdpt_bvh_node));
+    a.sc.n_blas = (uint32_t)(blas->size / sizeof(gdpt_blas_instance));
+    a.sc.n_tlas = (uint32_t)(tlas->size / sizeof(gdpt_tlas_node));
+    a.sc.n_materials = (uint32_t)(mat->size / sizeof(gdpt_material));
+    int rc = build_derived_layout(s, *bvh, *blas, *tlas);
+    if (rc) return rc;
+
+    a.camera = static_cast<const gdpt_camera *>(camera->dptr);
+    a.width = rp.width; a.height = rp.height; a.max_depth = s->max_depth;
+    a.out_rgba8 = static_cast<uint32_t *>(out->dptr);
+    a.out_depth = static_cast<float *>(depth->dptr);
+    a.queue_cap = (uint32_t)((size_t)rp.width * rp.height);
+    if ((rc = dev_alloc(s, &a.queue[0], (size_t)a.queue_cap * 5))) return rc;
+    if ((rc = dev_alloc(s, &a.queue[1], (size_t)a.queue_cap * 5))) return rc;
+    if ((rc = dev_alloc(s, &a.hit_list, (size_t)a.queue_cap))) return rc;
+    if ((rc = dev_alloc(s, &a.counters, 1))) return rc;
+    a.refill_below = 20; a.burst = 4;
+    if (const char *e = getenv("GDPT_REFILL_BELOW")) a.refill_below = atoi(e);
+    if (const char *e = getenv("GDPT_BURST")) a.burst = atoi(e);
+    if (a.refill_below < 1) a.refill_below = 1;
+    if (a.refill_below > 32) a.refill_below = 32;
+    if (a.burst < 1) a.burst = 1;
+    a.debug_steps = s->debug_steps ? 1 : 0;
+    a.trace_segments = s->trace_segments;
+    a.visits_per_ray = s->visits_per_ray;
+    if (s->trace_segments > 0) {
+        const size_t n = (size_t)s->trace_segments * rp.width * rp.height;
+        if ((rc = dev_alloc(s, &a.trace, n))) return rc;
+        if (s->visits_per_ray > 0 && (rc = dev_alloc(s, &a.visits, (size_t)rp.width * rp.height * s->visits_per_ray))) return rc;
+    }
+    compute_shard(s);
+    init_launch_shapes(d->ordinal);
+    return GDPT_OK;
+}
+
+int finish_progressive(gdpt_shader *s)
+{
+    gdpt_device *d = s->dev;
+    Resource *params = bound(s, 0, 0), *screen = bound(s, 0, 1), *accum = bound(s, 0, 2);
+    if (!params || !screen || !accum) return fail(d, GDPT_ERR_BAD_BINDING, "progressive_rendering.glsl needs set0 b0-2 (progressive_rendering.glsl:5-16)");
+    if (params->kind != RES_BUFFER || params->size < sizeof(gdpt_progressive_params)) return fail(d, GDPT_ERR_BAD_BINDING, "set0 b0 must hold the 12 B Params block");
+    if (screen->kind != RES_IMAGE || screen->format != GDPT_FORMAT_R8G8B8A8_UNORM) return fail(d, GDPT_ERR_BAD_BINDING, "set0 b1 must be the rgba8 screen image");
+    if (accum->kind != RES_IMAGE || accum->format != GDPT_FORMAT_R32G32B32A32_SFLOAT) return fail(d, GDPT_ERR_BAD_BINDING, "set0 b2 must be an rgba32f image");
+    if (screen->width != accum->width || screen->height != accum->height) return fail(d, GDPT_ERR_BAD_BINDING, "screen and accumulation images differ in size");
+    init_launch_shapes(d->ordinal);
+    return GDPT_OK;
+}
+
+// Enqueue one K1 dispatch on the device stream.
+int enqueue_k1(gdpt_shader *s)
+{
+    gdpt_device *d = s->dev;
+    FrameArgs &a = s->args;
+    const bool trace = s->trace_segments > 0 || s->debug_steps;
+    GDPT_CUDA(d, cudaMemsetAsync(a.counters, 0, sizeof(FrameCounters), d->stream));
+    if (trace && a.trace) GDPT_CUDA(d, cudaMemsetAsync(a.trace, 0xFF, (size_t)a.trace_segments * a.width * a.height * sizeof(gdpt_trace_record), d->stream));
+    if (trace && a.visits) GDPT_CUDA(d, cudaMemsetAsync(a.visits, 0xFF, (size_t)a.width * a.height * a.visits_per_ray * sizeof(uint32_t), d->stream));
+    launch_primary(a, trace, d->stream);
+    if (!s->debug_steps) {
+        for (int i = 0; i < a.max_depth; i++) {
+            launch_shade(a, i, d->stream);
+            if (i + 1 < a.max_depth) launch_trace(a, i + 1, trace, d->stream);
+        }
+    }
+    GDPT_CUDA(d, cudaGetLastError());
+    s->stats_valid = false;
+    s->stats.kernel_launches = (uint32_t)k1_launch_count(a.max_depth, s->debug_steps);
+    return GDPT_OK;
+}
+
+int enqueue_k2(gdpt_shader *p, int part, int parts, int band)
+{
+    gdpt_device *d = p->dev;
+    Resource *params = bound(p, 0, 0), *screen = bound(p, 0, 1), *accum = bound(p, 0, 2);
+    if (parts > 1 && (screen->width & 3)) return fail(d, GDPT_ERR_UNSUPPORTED, "sharded accumulation needs a width that is a multiple of 4");
+    launch_progressive(static_cast<uint32_t *>(screen->dptr), static_cast<float4 *>(accum->dptr),
+                       static_cast<const gdpt_progressive_params *>(params->dptr), screen->width, screen->height, part, parts, band,
+                       d->stream);
+    GDPT_CUDA(d, cudaGetLastError());
+    return GDPT_OK;
+}
+
+int collect_stats(gdpt_shader *s)
+{
+    gdpt_device *d = s->dev;
+    FrameCounters c;
+    GDPT_CUDA(d, cudaMemcpyAsync(&c, s->args.counters, sizeof(c), cudaMemcpyDeviceToHost, d->stream));
+    GDPT_CUDA(d, cudaStreamSynchronize(d->stream));
+    gdpt_frame_stats &st = s->stats;
+    uint64_t rays = (uint64_t)s->args.width * s->args.local_rows;
+    if (!s->debug_steps)
+        for (int i = 1; i < s->args.max_depth; i++) rays += c.qcount[i];
+    st.rays = rays;
+    st.primary_hits = c.primary_hits;
+    st.node_pops = c.node_pops; st.box_tests = c.box_tests; st.tri_tests = c.tri_tests; st.tlas_leaves = c.tlas_leaves;
+    st.max_stack = c.max_stack;
+    if (c.overflow) return fail(d, GDPT_ERR_UNSUPPORTED, "a ray exceeded the reference's 64+64 traversal stack entries");
+    s->stats_valid = true;
+    return GDPT_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+uint32_t gdpt_abi_version(void) { return 1u; }
+
+const char *gdpt_last_error(const gdpt_device *device) { return device ? device->last_error.c_str() : g_create_error.c_str(); }
+
+int gdpt_device_create(int cuda_ordinal, gdpt_device **out_device)
+{
+    if (!out_device) return fail(nullptr, GDPT_ERR_INVALID_ARG, "out_device is NULL");
+    *out_device = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, GDPT_ERR_NO_DEVICE, "no CUDA device available (%s); this backend has no CPU path", cudaGetErrorString(e));
+    if (cuda_ordinal < 0 || cuda_ordinal >= count) return fail(nullptr, GDPT_ERR_NO_DEVICE, "CUDA ordinal %d out of range (0..%d)", cuda_ordinal, count - 1);
+    gdpt_device *d = new gdpt_device();
+    d->ordinal = cuda_ordinal;
+    if (cudaSetDevice(cuda_ordinal) != cudaSuccess || cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaHostAlloc(&d->pinned_staging, 4096, cudaHostAllocDefault) != cudaSuccess) {
+        fail(nullptr, GDPT_ERR_CUDA, "device %d: stream/staging setup failed: %s", cuda_ordinal, cudaGetErrorString(cudaGetLastError()));
+        delete d;
+        return GDPT_ERR_CUDA;
+    }
+    for (int i = 0; i < 4; i++) cudaEventCreate(&d->ev[i]);
+    init_launch_shapes(cuda_ordinal);
+    *out_device = d;
+    return GDPT_OK;
+}
+
+void gdpt_device_destroy(gdpt_device *d)
+{
+    if (!d) return;
+    cudaSetDevice(d->ordinal);
+    cudaStreamSynchronize(d->stream);
+    for (auto &kv : d->resources) cudaFree(kv.second.dptr);
+    for (int i = 0; i < 4; i++) if (d->ev[i]) cudaEventDestroy(d->ev[i]);
+    if (d->pinned_staging) cudaFreeHost(d->pinned_staging);
+    cudaStreamDestroy(d->stream);
+    delete d;
+}
+
+int gdpt_device_synchronize(gdpt_device *d)
+{
+    if (!d) return GDPT_ERR_INVALID_ARG;
+    GDPT_CUDA(d, cudaStreamSynchronize(d->stream));
+    return GDPT_OK;
+}
+
+uint64_t gdpt_device_stream(gdpt_device *d) { return d ? (uint64_t)(uintptr_t)d->stream : 0; }
+
+void *gdpt_host_alloc(uint64_t size)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, size, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+void gdpt_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+int gdpt_shader_create(gdpt_device *d, const char *shader_path, const char *const *args, int n_args, gdpt_shader **out)
+{
+    if (!d || !out) return fail(d, GDPT_ERR_INVALID_ARG, "device/out_shader is NULL");
+    *out = nullptr;
+    const std::string base = basename_of(shader_path);
+    gdpt_shader *s = new gdpt_shader();
+    s->dev = d;
+    if (base == "main.glsl") s->kind = SHADER_MAIN;
+    else if (base == "progressive_rendering.glsl") s->kind = SHADER_PROGRESSIVE;
+    else {
+        delete s;
+        return fail(d, GDPT_ERR_UNKNOWN_SHADER, "no CUDA kernel set for shader '%s'", shader_path ? shader_path : "(null)");
+    }
+    for (int i = 0; i < n_args; i++) {
+        std::string name; long value = 0; bool has_value = false;
+        if (!args[i] || !parse_define(args[i], &name, &value, &has_value)) continue;
+        if (name == "DEBUG_STEPS") s->debug_steps = true;
+        else if (name == "MAX_DEPTH" && has_value) s->max_depth = (int)value;
+        else if (name == "GDPT_TRACE") s->trace_segments = has_value ? (int)value : 1;
+        else if (name == "GDPT_TRACE_VISITS" && has_value) s->visits_per_ray = (uint32_t)value;
+        else if (name == "GDPT_VARIANT" && has_value) s->variant = (int)value;
+    }
+    if (s->max_depth < 1 || s->max_depth > kMaxDepth) {
+        delete s;
+        return fail(d, GDPT_ERR_INVALID_ARG, "MAX_DEPTH must be in 1..%d", (int)kMaxDepth);
+    }
+    if (s->trace_segments > s->max_depth) s->trace_segments = s->max_depth;
+    memset(&s->args, 0, sizeof(s->args));
+    memset(&s->stats, 0, sizeof(s->stats));
+    s->initialized = true;
+    *out = s;
+    return GDPT_OK;
+}
+
+void gdpt_shader_destroy(gdpt_shader *s)
+{
+    if (!s) return;
+    gdpt_device *d = s->dev;
+    cudaSetDevice(d->ordinal);
+    cudaStreamSynchronize(d->stream);
+    for (void *p : s->derived) cudaFree(p);
+    for (gdpt_rid rid : s->owned) {
+        Resource *r = find(d, rid);
+        if (r) { cudaFree(r->dptr); d->resources.erase(rid); }
+    }
+    delete s;
+}
+
+static gdpt_rid new_resource(gdpt_shader *s, Resource &&r, int binding, int set)
+{
+    gdpt_device *d = s->dev;
+    const gdpt_rid rid = d->next_rid++;
+    d->resources[rid] = std::move(r);
+    s->owned.push_back(rid);
+    s->bindings[{ set, binding }] = rid;
+    s->uniforms_ready = false;
+    return rid;
+}
+
+gdpt_rid gdpt_shader_create_storage_buffer_uniform(gdpt_shader *s, const void *data, uint64_t size, int binding, int set)
+{
+    if (!s || !s->initialized || (size && !data)) { if (s) fail(s->dev, GDPT_ERR_INVALID_ARG, "create_storage_buffer_uniform: bad arguments"); return 0; }
+    gdpt_device *d = s->dev;
+    cudaSetDevice(d->ordinal);
+    Resource r;
+    r.kind = RES_BUFFER; r.size = size;
+    if (cudaMalloc(&r.dptr, size ? size : 16) != cudaSuccess) { fail(d, GDPT_ERR_CUDA, "cudaMalloc(%llu) failed: %s", (unsigned long long)size, cudaGetErrorString(cudaGetLastError())); return 0; }
+    r.shadow.assign(static_cast<const uint8_t *>(data), static_cast<const uint8_t *>(data) + size);
+    if (size && cudaMemcpyAsync(r.dptr, r.shadow.data(), size, cudaMemcpyHostToDevice, d->stream) != cudaSuccess) {
+        fail(d, GDPT_ERR_CUDA, "upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+        cudaFree(r.dptr);
+        return 0;
+    }
+    cudaStreamSynchronize(d->stream);
+    return new_resource(s, std::move(r), binding, set);
+}
+
+int gdpt_shader_update_storage_buffer_uniform(gdpt_shader *s, gdpt_rid rid, const void *data, uint64_t size)
+{
+    if (!s || !data) return GDPT_ERR_INVALID_ARG;
+    gdpt_device *d = s->dev;
+    Resource *r = find(d, rid);
+    if (!r || r->kind != RES_BUFFER) return fail(d, GDPT_ERR_INVALID_ARG, "update_storage_buffer_uniform: unknown buffer RID");
+    if (size > r->size) return fail(d, GDPT_ERR_INVALID_ARG, "update of %llu B exceeds the %llu B buffer", (unsigned long long)size, (unsigned long long)r->size);
+    cudaSetDevice(d->ordinal);
+    memcpy(r->shadow.data(), data, size);
+    GDPT_CUDA(d, cudaMemcpyAsync(r->dptr, r->shadow.data(), size, cudaMemcpyHostToDevice, d->stream));
+    GDPT_CUDA(d, cudaStreamSynchronize(d->stream));
+    return GDPT_OK;
+}
+
+int gdpt_shader_get_storage_buffer_uniform(gdpt_shader *s, gdpt_rid rid, void *out, uint64_t capacity)
+{
+    if (!s || !out) return GDPT_ERR_INVALID_ARG;
+    gdpt_device *d = s->dev;
+    Resource *r = find(d, rid);
+    if (!r || r->kind != RES_BUFFER) return fail(d, GDPT_ERR_INVALID_ARG, "get_storage_buffer_uniform: unknown buffer RID");
+    if (capacity < r->size) return fail(d, GDPT_ERR_INVALID_ARG, "output capacity too small");
+    cudaSetDevice(d->ordinal);
+    GDPT_CUDA(d, cudaMemcpyAsync(out, r->dptr, r->size, cudaMemcpyDeviceToHost, d->stream));
+    GDPT_CUDA(d, cudaStreamSynchronize(d->stream));
+    return GDPT_OK;
+}
+
+gdpt_rid gdpt_shader_create_image_uniform(gdpt_shader *s, const void *pixels, int width, int height, gdpt_data_format format,
+                                          int binding, int set)
+{
+    if (!s || !s->initialized || width <= 0 || height <= 0 || texel_bytes(format) == 0) { if (s) fail(s->dev, GDPT_ERR_INVALID_ARG, "create_image_uniform: bad arguments"); return 0; }
+    gdpt_device *d = s->dev;
+    cudaSetDevice(d->ordinal);
+    Resource r;
+    r.kind = RES_IMAGE; r.width = width; r.height = height; r.format = format; r.layers = 1;
+    r.size = (uint64_t)width * height * texel_bytes(format);
+    if (cudaMalloc(&r.dptr, r.size) != cudaSuccess) { fail(d, GDPT_ERR_CUDA, "cudaMalloc(%llu) failed: %s", (unsigned long long)r.size, cudaGetErrorString(cudaGetLastError())); return 0; }
+    cudaError_t e = pixels ? cudaMemcpyAsync(r.dptr, pixels, r.size, cudaMemcpyHostToDevice, d->stream) : cudaMemsetAsync(r.dptr, 0, r.size, d->stream);
+    if (e != cudaSuccess) { fail(d, GDPT_ERR_CUDA, "image upload failed: %s", cudaGetErrorString(e)); cudaFree(r.dptr); return 0; }
+    cudaStreamSynchronize(d->stream);
+    return new_resource(s, std::move(r), binding, set);
+}
+
+gdpt_rid gdpt_shader_create_layered_image_uniform(gdpt_shader *s, const void *const *layers, int n_layers, int width, int height,
+                                                  gdpt_data_format format, int binding, int set)
+{
+    if (!s || !s->initialized || !layers || n_layers <= 0 || width <= 0 || height <= 0 || format != GDPT_FORMAT_R8G8B8A8_UNORM) {
+        if (s) fail(s->dev, GDPT_ERR_INVALID_ARG, "create_layered_image_uniform: bad arguments");
+        return 0;
+    }
+    gdpt_device *d = s->dev;
+    cudaSetDevice(d->ordinal);
+    Resource r;
+    r.kind = RES_LAYERED; r.width = width; r.height = height; r.format = format; r.layers = n_layers;
+    const uint64_t layer_bytes = (uint64_t)width * height * 4;
+    r.size = layer_bytes * n_layers;
+    if (cudaMalloc(&r.dptr, r.size) != cudaSuccess) { fail(d, GDPT_ERR_CUDA, "cudaMalloc(%llu) failed: %s", (unsigned long long)r.size, cudaGetErrorString(cudaGetLastError())); return 0; }
+    for (int l = 0; l < n_layers; l++) {
+        cudaError_t e = layers[l] ? cudaMemcpyAsync(static_cast<uint8_t *>(r.dptr) + l * layer_bytes, layers[l], layer_bytes, cudaMemcpyHostToDevice, d->stream)
+                                  : cudaMemsetAsync(static_cast<uint8_t *>(r.dptr) + l * layer_bytes, 0, layer_bytes, d->stream);
+        if (e != cudaSuccess) { fail(d, GDPT_ERR_CUDA, "layer upload failed: %s", cudaGetErrorString(e)); cudaFree(r.dptr); return 0; }
+    }
+    cudaStreamSynchronize(d->stream);
+    return new_resource(s, std::move(r), binding, set);
+}
+
+int gdpt_shader_get_image_uniform_buffer(gdpt_shader *s, gdpt_rid rid, int layer, void *out, uint64_t capacity)
+{
+    if (!s || !out) return GDPT_ERR_INVALID_ARG;
+    gdpt_device *d = s->dev;
+    Resource *r = find(d, rid);
+    if (!r || r->kind == RES_BUFFER) return fail(d, GDPT_ERR_INVALID_ARG, "get_image_uniform_buffer: unknown image RID");
+    if (layer < 0 || layer >= r->layers) return fail(d, GDPT_ERR_INVALID_ARG, "layer %d out of range", layer);
+    const uint64_t layer_bytes = r->size / (uint64_t)r->layers;
+    if (capacity < layer_bytes) return fail(d, GDPT_ERR_INVALID_ARG, "output capacity too small");
+    cudaSetDevice(d->ordinal);
+    GDPT_CUDA(d, cudaMemcpyAsync(out, static_cast<uint8_t *>(r->dptr) + layer * layer_bytes, layer_bytes, cudaMemcpyDeviceToHost, d->stream));
+    GDPT_CUDA(d, cudaStreamSynchronize(d->stream));
+    return GDPT_OK;
+}
+
+int gdpt_shader_add_existing_buffer(gdpt_shader *s, gdpt_rid rid, gdpt_uniform_type uniform_type, int binding, int set)
+{
+    if (!s) return GDPT_ERR_INVALID_ARG;
+    gdpt_device *d = s->dev;
+    Resource *r = find(d, rid);
+    if (!r) return fail(d, GDPT_ERR_INVALID_ARG, "add_existing_buffer: RID does not belong to this device");
+    if ((uniform_type == GDPT_UNIFORM_TYPE_IMAGE) != (r->kind == RES_IMAGE)) return fail(d, GDPT_ERR_INVALID_ARG, "add_existing_buffer: uniform type does not match the resource");
+    s->bindings[{ set, binding }] = rid;
+    s->uniforms_ready = false;
+    return GDPT_OK;
+}
+
+int gdpt_shader_finish_create_uniforms(gdpt_shader *s)
+{
+    if (!s || !s->initialized) return GDPT_ERR_INVALID_ARG;
+    cudaSetDevice(s->dev->ordinal);
+    const int rc = (s->kind == SHADER_MAIN) ? finish_main(s) : finish_progressive(s);
+    s->uniforms_ready = (rc == GDPT_OK);
+    return rc;
+}
+
+int gdpt_shader_check_ready(const gdpt_shader *s) { return (s && s->initialized && s->uniforms_ready) ? 1 : 0; }
+
+int gdpt_shader_set_shard(gdpt_shader *s, int part, int n_parts, int band_rows)
+{
+    if (!s || s->kind != SHADER_MAIN) return GDPT_ERR_INVALID_ARG;
+    if (n_parts < 1 || part < 0 || part >= n_parts || band_rows < 4 || (band_rows & 3))
+        return fail(s->dev, GDPT_ERR_INVALID_ARG, "set_shard: need 0 <= part < n_parts and band_rows a positive multiple of 4");
+    s->shard_part = part; s->shard_parts = n_parts; s->shard_band = band_rows;
+    if (s->uniforms_ready) compute_shard(s);
+    return GDPT_OK;
+}
+
+int gdpt_shader_compute(gdpt_shader *s, int gx, int gy, int gz)
+{
+    if (!s) return GDPT_ERR_INVALID_ARG;
+    gdpt_device *d = s->dev;
+    if (!gdpt_shader_check_ready(s)) return fail(d, GDPT_ERR_NOT_READY, "compute() before finish_create_uniforms()"); // gdcs.cpp:239-240
+    cudaSetDevice(d->ordinal);
+    int w, h;
+    if (s->kind == SHADER_MAIN) { w = s->args.width; h = s->args.height; }
+    else { Resource *screen = bound(s, 0, 1); w = screen->width; h = screen->height; }
+    if (gx != (w + 31) / 32 || gy != (h + 31) / 32 || gz != 1)
+        return fail(d, GDPT_ERR_INVALID_ARG, "compute(%d,%d,%d): expected ceil(W/32) x ceil(H/32) x 1 = (%d,%d,1)", gx, gy, gz, (w + 31) / 32, (h + 31) / 32);
+    int rc;
+    if (s->kind == SHADER_MAIN) {
+        GDPT_CUDA(d, cudaEventRecord(d->ev[0], d->stream));
+        if ((rc = enqueue_k1(s))) return rc;
+        GDPT_CUDA(d, cudaEventRecord(d->ev[1], d->stream));
+        if ((rc = collect_stats(s))) return rc;
+        GDPT_CUDA(d, cudaEventElapsedTime(&s->stats.k1_ms, d->ev[0], d->ev[1]));
+    } else {
+        GDPT_CUDA(d, cudaEventRecord(d->ev[2], d->stream));
+        if ((rc = enqueue_k2(s, 0, 1, 4))) return rc;
+        GDPT_CUDA(d, cudaEventRecord(d->ev[3], d->stream));
+        GDPT_CUDA(d, cudaStreamSynchronize(d->stream));
+        GDPT_CUDA(d, cudaEventElapsedTime(&s->stats.k2_ms, d->ev[2], d->ev[3]));
+    }
+    return GDPT_OK;
+}
+
+static int enqueue_frame(gdpt_shader *m, gdpt_shader *p, const gdpt_camera *camera, gdpt_denoising mode, uint32_t frame_count)
+{
+    if (!m || m->kind != SHADER_MAIN || !camera) return GDPT_ERR_INVALID_ARG;
+    gdpt_device *d = m->dev;
+    if (!gdpt_shader_check_ready(m)) return fail(d, GDPT_ERR_NOT_READY, "main shader is not ready");
+    if (mode == GDPT_DENOISE_TEMPORAL_REPROJECTION) return fail(d, GDPT_ERR_UNSUPPORTED, "temporal reprojection is not implemented yet");
+    if (mode == GDPT_DENOISE_PROGRESSIVE_RENDERING) {
+        if (!p || p->kind != SHADER_PROGRESSIVE || p->dev != d || !gdpt_shader_check_ready(p)) return fail(d, GDPT_ERR_NOT_READY, "progressive shader missing or not ready");
+        if (bound(p, 0, 1) != bound(m, 0, 0)) return fail(d, GDPT_ERR_BAD_BINDING, "progressive shader must share the main shader's output image (add_existing_buffer)");
+    }
+    cudaSetDevice(d->ordinal);
+    // the previous frame's staging must have been consumed before we overwrite it
+    GDPT_CUDA(d, cudaStreamSynchronize(d->stream));
+    uint8_t *stage = static_cast<uint8_t *>(d->pinned_staging);
+    memcpy(stage, camera, sizeof(gdpt_camera));
+    Resource *cam_r = bound(m, 0, 3);
+    memcpy(cam_r->shadow.data(), camera, cam_r->size < sizeof(gdpt_camera) ? cam_r->size : sizeof(gdpt_camera));
+    GDPT_CUDA(d, cudaMemcpyAsync(cam_r->dptr, stage, cam_r->size < sizeof(gdpt_camera) ? cam_r->size : sizeof(gdpt_camera), cudaMemcpyHostToDevice, d->stream));
+    int rc;
+    GDPT_CUDA(d, cudaEventRecord(d->ev[0], d->stream));
+    if ((rc = enqueue_k1(m))) return rc;
+    GDPT_CUDA(d, cudaEventRecord(d->ev[1], d->stream));
+    if (mode == GDPT_DENOISE_PROGRESSIVE_RENDERING) {
+        Resource *pp = bound(p, 0, 0);
+        gdpt_progressive_params host_pp = { m->args.width, m->args.height, frame_count };
+        memcpy(stage + 256, &host_pp, sizeof(host_pp));
+        memcpy(pp->shadow.data(), &host_pp, sizeof(host_pp));
+        GDPT_CUDA(d, cudaMemcpyAsync(pp->dptr, stage + 256, sizeof(host_pp), cudaMemcpyHostToDevice, d->stream));
+        GDPT_CUDA(d, cudaEventRecord(d->ev[2], d->stream));
+        if ((rc = enqueue_k2(p, m->shard_part, m->shard_parts, m->shard_band))) return rc;
+        GDPT_CUDA(d, cudaEventRecord(d->ev[3], d->stream));
+    }
+    return GDPT_OK;
+}
+
+int gdpt_render_frame_async(gdpt_shader *m, gdpt_shader *p, const gdpt_camera *camera, gdpt_denoising mode, uint32_t frame_count)
+{
+    return enqueue_frame(m, p, camera, mode, frame_count);
+}
+
+int gdpt_render_frame(gdpt_shader *m, gdpt_shader *p, const gdpt_camera *camera, gdpt_denoising mode, uint32_t frame_count,
+                      void *out_rgba8, float *out_depth)
+{
+    int rc = enqueue_frame(m, p, camera, mode, frame_count);
+    if (rc) return rc;
+    gdpt_device *d = m->dev;
+    const size_t n = (size_t)m->args.width * m->args.height;
+    if (out_rgba8) GDPT_CUDA(d, cudaMemcpyAsync(out_rgba8, m->args.out_rgba8, n * 4, cudaMemcpyDeviceToHost, d->stream));
+    if (out_depth) GDPT_CUDA(d, cudaMemcpyAsync(out_depth, m->args.out_depth, n * 4, cudaMemcpyDeviceToHost, d->stream));
+    GDPT_CUDA(d, cudaStreamSynchronize(d->stream));
+    return GDPT_OK;
+}
+
+int gdpt_rid_device_pointer(gdpt_device *d, gdpt_rid rid, uint64_t *out_ptr, uint64_t *out_size)
+{
+    if (!d) return GDPT_ERR_INVALID_ARG;
+    Resource *r = find(d, rid);
+    if (!r) return fail(d, GDPT_ERR_INVALID_ARG, "unknown RID");
+    if (out_ptr) *out_ptr = (uint64_t)(uintptr_t)r->dptr;
+    if (out_size) *out_size = r->size;
+    return GDPT_OK;
+}
+
+int gdpt_shader_get_stats(gdpt_shader *s, gdpt_frame_stats *out)
+{
+    if (!s || !out || s->kind != SHADER_MAIN) return GDPT_ERR_INVALID_ARG;
+    gdpt_device *d = s->dev;
+    if (!gdpt_shader_check_ready(s)) return fail(d, GDPT_ERR_NOT_READY, "shader not ready");
+    cudaSetDevice(d->ordinal);
+    if (!s->stats_valid) {
+        int rc = collect_stats(s);
+        if (rc) return rc;
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, d->ev[0], d->ev[1]) == cudaSuccess) s->stats.k1_ms = ms;
+        if (cudaEventElapsedTime(&ms, d->ev[2], d->ev[3]) == cudaSuccess) s->stats.k2_ms = ms;
+        cudaGetLastError(); // events never recorded -> not an error for the caller
+    }
+    *out = s->stats;
+    return GDPT_OK;
+}
+
+int gdpt_shader_read_trace(gdpt_shader *s, int segment, gdpt_trace_record *out, uint64_t capacity)
+{
+    if (!s || !out || s->kind != SHADER_MAIN) return GDPT_ERR_INVALID_ARG;
+    gdpt_device *d = s->dev;
+    if (!gdpt_shader_check_ready(s) || !s->args.trace) return fail(d, GDPT_ERR_NOT_READY, "shader was not created with \"#define GDPT_TRACE\"");
+    if (segment < 0 || segment >= s->args.trace_segments) return fail(d, GDPT_ERR_INVALID_ARG, "segment %d not recorded (GDPT_TRACE %d)", segment, s->args.trace_segments);
+    const size_t n = (size_t)s->args.width * s->args.height;
+    if (capacity < n) return fail(d, GDPT_ERR_INVALID_ARG, "trace capacity too small");
+    cudaSetDevice(d->ordinal);
+    GDPT_CUDA(d, cudaMemcpyAsync(out, s->args.trace + (size_t)segment * n, n * sizeof(gdpt_trace_record), cudaMemcpyDeviceToHost, d->stream));
+    GDPT_CUDA(d, cudaStreamSynchronize(d->stream));
+    return GDPT_OK;
+}
+
+int gdpt_shader_read_visits(gdpt_shader *s, uint32_t *out, uint32_t max_per_ray, uint64_t capacity)
+{
+    if (!s || !out || s->kind != SHADER_MAIN) return GDPT_ERR_INVALID_ARG;
+    gdpt_device *d = s->dev;
+    if (!gdpt_shader_check_ready(s) || !s->args.visits) return fail(d, GDPT_ERR_NOT_READY, "shader was not created with \"#define GDPT_TRACE_VISITS n\"");
+    if (max_per_ray != s->args.visits_per_ray) return fail(d, GDPT_ERR_INVALID_ARG, "max_per_ray must equal GDPT_TRACE_VISITS (%u)", s->args.visits_per_ray);
+    const size_t n = (size_t)s->args.width * s->args.height * max_per_ray;
+    if (capacity < n) return fail(d, GDPT_ERR_INVALID_ARG, "visits capacity too small");
+    cudaSetDevice(d->ordinal);
+    GDPT_CUDA(d, cudaMemcpyAsync(out, s->args.visits, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, d->stream));
+    GDPT_CUDA(d, cudaStreamSynchronize(d->stream));
+    return GDPT_OK;
+}
+
+} // extern "C"

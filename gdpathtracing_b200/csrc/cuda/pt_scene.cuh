@@ -1,0 +1,80 @@
+// pt_scene.cuh -- device-side scene view and the derived ("wide") traversal
+// layout the backend builds from the uploaded reference arrays when the binding
+// table is finalised.
+//
+// Why a derived layout: the reference reads, per internal-node pop, its own
+// 48 B record plus BOTH children's 48 B records to get their boxes
+// (main.glsl:277,285-289), and re-reads a child when it is popped.  For
+// incoherent rays every such read is its own L1 wavefront, which bounds
+// traversal long before issue slots do.  We keep node identity and visiting
+// order exactly as in the reference, but store, per INTERNAL node, both child
+// boxes and both child links in one 64 B record (4 x 128-bit loads from one
+// 128 B line), and per LEAF a 16 B descriptor.  Child links are pre-encoded so
+// a popped entry says which table it indexes without another load.
+//
+//   link bits: [31] TLAS level   [30] leaf   [29:0] index into the table
+//     BLAS internal -> wide_nodes[]     BLAS leaf -> leaf_recs[]
+//     TLAS internal -> wide_tlas[]      TLAS leaf -> inst_recs[]
+//
+// `orig` fields carry the reference node index for the parity trace.
+#ifndef GDPT_PT_SCENE_CUH
+#define GDPT_PT_SCENE_CUH
+
+#include "gdpt_wire.h"
+#include <stdint.h>
+
+namespace gdpt {
+
+enum : uint32_t {
+    LINK_TLAS = 0x80000000u,
+    LINK_LEAF = 0x40000000u,
+    LINK_INDEX_MASK = 0x3FFFFFFFu,
+    LINK_NONE = 0xFFFFFFFFu
+};
+
+// 64 B, 64 B-aligned.  Boxes of the left (L) and right (R) child:
+//   q0 = Lmin.x Lmin.y Lmin.z Lmax.x   q1 = Lmax.y Lmax.z Rmin.x Rmin.y
+//   q2 = Rmin.z Rmax.x Rmax.y Rmax.z   q3 = left_link right_link orig_id 0
+struct __attribute__((aligned(64))) WideNode {
+    float lmin[3]; float lmax[3];
+    float rmin[3]; float rmax[3];
+    uint32_t left, right, orig, pad;
+};
+static_assert(sizeof(WideNode) == 64, "WideNode is one half cache line");
+
+struct __attribute__((aligned(16))) LeafRec {
+    uint32_t first_tri, tri_count, orig, pad;
+};
+static_assert(sizeof(LeafRec) == 16, "LeafRec is one 128-bit load");
+
+// Per instance: what a TLAS-leaf visit needs (main.glsl:316-323).
+struct __attribute__((aligned(16))) InstRec {
+    float inv[16];          // BLASInstance.inverse_transform, column-major
+    uint32_t root_link;     // pre-encoded link of BLASInstance.root
+    uint32_t tlas_orig;     // reference TLAS node index of this leaf
+    uint32_t root_orig;     // reference BVH node index of the root
+    uint32_t pad;
+};
+static_assert(sizeof(InstRec) == 80, "InstRec is five 128-bit loads");
+
+struct SceneView {
+    // uploaded reference buffers (set 1 bindings 0..5, set 2 binding 0)
+    const gdpt_triangle_geometry *tri_geom;
+    const gdpt_triangle_data *tri_data;
+    const gdpt_material *materials;
+    const gdpt_bvh_node *bvh;
+    const gdpt_blas_instance *blas;
+    const gdpt_tlas_node *tlas;
+    const uint8_t *textures;
+    int32_t tex_w, tex_h, tex_layers;
+    uint32_t n_tris, n_nodes, n_blas, n_tlas, n_materials;
+    // derived
+    const WideNode *wide_nodes;
+    const LeafRec *leaf_recs;
+    const WideNode *wide_tlas;
+    const InstRec *inst_recs;
+    uint32_t tlas_root_link;
+};
+
+} // namespace gdpt
+#endif

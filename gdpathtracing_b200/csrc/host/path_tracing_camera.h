@@ -1,0 +1,116 @@
+// path_tracing_camera.h -- Godot-free twins of the reference's PathTracingCamera
+// node (src/path_tracing/path_tracing_camera.{h,cpp}), its Camera uniform block
+// (src/path_tracing/render_parameters.h:14-38) and the ProgressiveRendering post
+// process driver (src/path_tracing/post_processing/progressive_rendering.{h,cpp}).
+// Same properties, same init()/render() call sequence against ComputeShader;
+// the engine services a Node gets from Godot (window size, global transform,
+// the TextureRect that shows the frame) are explicit setters/getters here.
+#ifndef GDPT_PATH_TRACING_CAMERA_H
+#define GDPT_PATH_TRACING_CAMERA_H
+
+#include "compute_shader.h"
+#include "geometry_group3d.h"
+#include "xform_math.h"
+
+#include <cstdint>
+#include <vector>
+
+namespace gdpt {
+
+// Camera::set_camera_transform (render_parameters.h:23-38)
+struct CameraBlock : gdpt_camera {
+    CameraBlock();
+    void set_camera_transform(const Xform3 &model, const Mat4 &projection);
+};
+
+class ProgressiveRendering {
+public:
+    ProgressiveRendering() {}
+    ~ProgressiveRendering();
+    void init(gdpt_device *rd, gdpt_rid original_screen_texture_rid, int width, int height);
+    // frame_count policy of progressive_rendering.cpp:53-60; returns the value dispatched with
+    uint32_t advance(const Xform3 &camera_transform);
+    void render(const Xform3 &camera_transform);
+    ComputeShader *shader() const { return cs_; }
+    uint32_t frame_count() const { return params_.frame_count; }
+    gdpt_rid frame_buffer_rid() const { return frame_buffer_rid_; }
+
+private:
+    ComputeShader *cs_ = nullptr;
+    gdpt_progressive_params params_ = { 0, 0, 1 };
+    Xform3 previous_transform_; // identity, like a default-constructed Transform3D
+    gdpt_rid params_rid_ = 0, screen_rid_ = 0, frame_buffer_rid_ = 0;
+};
+
+class PathTracingCamera {
+public:
+    enum Denoising { PROGRESSIVE_RENDERING = 0, TEMPORAL_REPROJECTION = 1, NONE = 2 };
+
+    PathTracingCamera() {}
+    ~PathTracingCamera();
+
+    // --- reference properties (path_tracing_camera.cpp:3-31) ---
+    float get_fov() const { return fov_; }
+    void set_fov(float v) { fov_ = v; }
+    GeometryGroup3D *get_geometry_group() const { return geometry_group_; }
+    void set_geometry_group(GeometryGroup3D *g) { geometry_group_ = g; }
+    Denoising get_denoising_mode() const { return denoising_mode_; }
+    void set_denoising_mode(Denoising m) { denoising_mode_ = m; }
+    // output_texture: the frame lands in get_output_image() instead of a TextureRect
+    const uint8_t *get_output_image() const { return output_image_; }
+
+    // --- what Godot supplies to a node ---
+    void set_window_size(int w, int h) { window_w_ = w; window_h_ = h; }   // DisplayServer::window_get_size()
+    void set_global_transform(const Xform3 &t) { global_transform_ = t; }   // Node3D::get_global_transform()
+
+    // --- backend parameters (no upstream counterpart) ---
+    void set_max_depth(int d) { max_depth_ = d; }          // the disabled num_bounces property (:9-11); 5 = main.glsl:377
+    void set_cuda_device(int ordinal) { cuda_ordinal_ = ordinal; }
+    void set_frame_index(uint32_t f) { camera_.frame_index = f; } // upstream leaves it uninitialised (render_parameters.h:19)
+    void set_shard(int part, int parts, int band_rows) { shard_part_ = part; shard_parts_ = parts; shard_band_ = band_rows; }
+    void set_trace(int segments, uint32_t visits_per_ray) { trace_segments_ = segments; visits_per_ray_ = visits_per_ray; }
+    void set_debug_steps(bool on) { debug_steps_ = on; }
+    // true: one gdpt_render_frame call per frame; false: the reference's dispatch-by-dispatch sequence
+    void set_fused_frame(bool on) { fused_frame_ = on; }
+
+    // NOTIFICATION_READY / NOTIFICATION_INTERNAL_PROCESS bodies (path_tracing_camera.cpp:111-232)
+    bool init();
+    void render();
+    // render without the device->host read-back (frame stays in the output RID)
+    void render_device_only();
+
+    ComputeShader *compute_shader() const { return cs_; }
+    ProgressiveRendering *progressive() const { return progressive_renderer_; }
+    gdpt_rid output_texture_rid() const { return output_texture_rid_; }
+    gdpt_rid depth_texture_rid() const { return depth_texture_rid_; }
+    int width() const { return render_parameters_.width; }
+    int height() const { return render_parameters_.height; }
+    const gdpt_camera &camera_block() const { return camera_; }
+    uint32_t last_frame_count() const { return last_frame_count_; }
+
+private:
+    void ensure_progressive();
+    float fov_ = 90.0f;
+    ComputeShader *cs_ = nullptr;
+    ProgressiveRendering *progressive_renderer_ = nullptr;
+    GeometryGroup3D *geometry_group_ = nullptr;
+    uint8_t *output_image_ = nullptr; // pinned, W*H*4
+    gdpt_render_params render_parameters_ = {};
+    CameraBlock camera_;
+    Mat4 projection_matrix_;
+    Xform3 global_transform_;
+    int window_w_ = 0, window_h_ = 0;
+    gdpt_rid output_texture_rid_ = 0, depth_texture_rid_ = 0, render_parameters_rid_ = 0, camera_rid_ = 0;
+    gdpt_rid triangles_geometry_rid_ = 0, triangles_data_rid_ = 0, materials_rid_ = 0, bvh_tree_rid_ = 0, blas_rid_ = 0, tlas_rid_ = 0,
+             texture_array_rid_ = 0;
+    gdpt_device *rd_ = nullptr;
+    Denoising denoising_mode_ = PROGRESSIVE_RENDERING;
+    int max_depth_ = 5, cuda_ordinal_ = 0;
+    int shard_part_ = 0, shard_parts_ = 1, shard_band_ = 4;
+    int trace_segments_ = 0; uint32_t visits_per_ray_ = 0;
+    bool debug_steps_ = false, fused_frame_ = true;
+    uint32_t last_frame_count_ = 0;
+};
+
+} // namespace gdpt
+#endif
