@@ -94,6 +94,8 @@ CUDA_API = [
     ("gdpt_host_free", None, [c_void_p]),
     ("gdpt_device_stream", c_uint64, [c_void_p]),
     ("gdpt_shader_get_stats", c_int, [c_void_p, POINTER(FrameStats)]),
+    ("gdpt_shader_set_stage_timing", c_int, [c_void_p, c_int]),
+    ("gdpt_shader_get_stage_times", c_int, [c_void_p, c_void_p, c_int]),
     ("gdpt_shader_read_trace", c_int, [c_void_p, c_int, c_void_p, c_uint64]),
     ("gdpt_shader_read_visits", c_int, [c_void_p, c_void_p, c_uint32, c_uint64]),
 ]

@@ -5,6 +5,7 @@
 // pt_kernels.cu.  No CPU rendering path exists here: every entry point either
 // drives the GPU or fails.
 #include "gdpt.h"
+#include "derived_layout.h"
 #include "pt_kernels.cuh"
 
 #include <cuda_runtime.h>
@@ -66,6 +67,9 @@ struct gdpt_shader {
     int shard_part = 0, shard_parts = 1, shard_band = 4;
     gdpt_frame_stats stats;
     bool stats_valid = false;
+    bool stage_timing = false;          // record an event between the K1 stage launches
+    std::vector<cudaEvent_t> stage_ev;  // 2*max_depth + 1 events when enabled
+    int stage_count = 0;
 };
 
 namespace {
@@ -149,79 +153,24 @@ template <typename T> int dev_upload(gdpt_shader *s, const T **out, const std::v
     return GDPT_OK;
 }
 
-// Build WideNode / LeafRec / InstRec tables from the uploaded reference arrays.
+// Build WideNode / LeafRec / InstRec tables from the uploaded reference arrays and upload them.
 int build_derived_layout(gdpt_shader *s, const Resource &bvh_r, const Resource &blas_r, const Resource &tlas_r)
 {
     gdpt_device *d = s->dev;
-    const gdpt_bvh_node *bvh = reinterpret_cast<const gdpt_bvh_node *>(bvh_r.shadow.data());
-    const gdpt_blas_instance *blas = reinterpret_cast<const gdpt_blas_instance *>(blas_r.shadow.data());
-    const gdpt_tlas_node *tlas = reinterpret_cast<const gdpt_tlas_node *>(tlas_r.shadow.data());
-    const uint32_t n_nodes = (uint32_t)(bvh_r.size / sizeof(gdpt_bvh_node));
-    const uint32_t n_blas = (uint32_t)(blas_r.size / sizeof(gdpt_blas_instance));
-    const uint32_t n_tlas = (uint32_t)(tlas_r.size / sizeof(gdpt_tlas_node));
-    if (n_tlas == 0 || n_blas == 0) return fail(d, GDPT_ERR_BAD_BINDING, "empty TLAS / instance buffer");
-    if (n_nodes >= LINK_INDEX_MASK) return fail(d, GDPT_ERR_UNSUPPORTED, "too many BVH nodes");
-
-    // BLAS: internal nodes and leaves get their own dense numbering
-    std::vector<uint32_t> link(n_nodes);
-    uint32_t n_internal = 0, n_leaf = 0;
-    for (uint32_t i = 0; i < n_nodes; i++) link[i] = bvh[i].tri_count > 0 ? (LINK_LEAF | n_leaf++) : n_internal++;
-    std::vector<WideNode> wide(n_internal);
-    std::vector<LeafRec> leaves(n_leaf);
-    for (uint32_t i = 0; i < n_nodes; i++) {
-        const gdpt_bvh_node &n = bvh[i];
-        if (n.tri_count > 0) {
-            LeafRec &l = leaves[link[i] & LINK_INDEX_MASK];
-            l.first_tri = n.first_tri_index; l.tri_count = n.tri_count; l.orig = i; l.pad = 0;
-        } else {
-            if (n.left_child >= n_nodes || n.right_child >= n_nodes)
-                return fail(d, GDPT_ERR_BAD_BINDING, "BVH node %u has a child index out of range", i);
-            WideNode &w = wide[link[i]];
-            const gdpt_bvh_node &L = bvh[n.left_child], &R = bvh[n.right_child];
-            for (int k = 0; k < 3; k++) { w.lmin[k] = L.aabb_min[k]; w.lmax[k] = L.aabb_max[k]; w.rmin[k] = R.aabb_min[k]; w.rmax[k] = R.aabb_max[k]; }
-            w.left = link[n.left_child]; w.right = link[n.right_child]; w.orig = i; w.pad = 0;
-        }
-    }
-    // TLAS: same split; leaves index the instance table directly
-    std::vector<uint32_t> tlink(n_tlas);
-    uint32_t nt_internal = 0;
-    for (uint32_t i = 0; i < n_tlas; i++) {
-        if (tlas[i].left_right == 0) {
-            if (tlas[i].blas >= n_blas) return fail(d, GDPT_ERR_BAD_BINDING, "TLAS leaf %u names instance %u of %u", i, tlas[i].blas, n_blas);
-            tlink[i] = LINK_TLAS | LINK_LEAF | tlas[i].blas;
-        } else tlink[i] = LINK_TLAS | nt_internal++;
-    }
-    std::vector<WideNode> wtlas(nt_internal);
-    std::vector<InstRec> inst(n_blas);
-    for (uint32_t b = 0; b < n_blas; b++) {
-        if (blas[b].root >= n_nodes) return fail(d, GDPT_ERR_BAD_BINDING, "instance %u root out of range", b);
-        memcpy(inst[b].inv, blas[b].inverse_transform, sizeof(inst[b].inv));
-        inst[b].root_link = link[blas[b].root];
-        inst[b].root_orig = blas[b].root;
-        inst[b].tlas_orig = 0; inst[b].pad = 0;
-    }
-    for (uint32_t i = 0; i < n_tlas; i++) {
-        const gdpt_tlas_node &n = tlas[i];
-        if (n.left_right == 0) {
-            if (i > 0) inst[n.blas].tlas_orig = i; // leaves sit at 1..I in instance order (bvh.cpp:278-287)
-            continue;
-        }
-        const uint32_t l = n.left_right & 0xFFFFu, r = n.left_right >> 16;
-        if (l >= n_tlas || r >= n_tlas) return fail(d, GDPT_ERR_BAD_BINDING, "TLAS node %u has a child out of range", i);
-        WideNode &w = wtlas[tlink[i] & LINK_INDEX_MASK];
-        for (int k = 0; k < 3; k++) { w.lmin[k] = tlas[l].aabb_min[k]; w.lmax[k] = tlas[l].aabb_max[k]; w.rmin[k] = tlas[r].aabb_min[k]; w.rmax[k] = tlas[r].aabb_max[k]; }
-        w.left = tlink[l]; w.right = tlink[r]; w.orig = i; w.pad = 0;
-    }
-    // node 0 is a copy of the final root (bvh.cpp:316); with a single instance that root is
-    // itself the leaf, and the traversal pops it as node 0
-    if (tlas[0].left_right == 0) inst[tlas[0].blas].tlas_orig = 0;
-
+    DerivedLayout lay;
+    const std::string err = derive_layout(reinterpret_cast<const gdpt_bvh_node *>(bvh_r.shadow.data()),
+                                          (uint32_t)(bvh_r.size / sizeof(gdpt_bvh_node)),
+                                          reinterpret_cast<const gdpt_blas_instance *>(blas_r.shadow.data()),
+                                          (uint32_t)(blas_r.size / sizeof(gdpt_blas_instance)),
+                                          reinterpret_cast<const gdpt_tlas_node *>(tlas_r.shadow.data()),
+                                          (uint32_t)(tlas_r.size / sizeof(gdpt_tlas_node)), lay);
+    if (!err.empty()) return fail(d, GDPT_ERR_BAD_BINDING, "%s", err.c_str());
     int rc;
-    if ((rc = dev_upload(s, &s->args.sc.wide_nodes, wide))) return rc;
-    if ((rc = dev_upload(s, &s->args.sc.leaf_recs, leaves))) return rc;
-    if ((rc = dev_upload(s, &s->args.sc.wide_tlas, wtlas))) return rc;
-    if ((rc = dev_upload(s, &s->args.sc.inst_recs, inst))) return rc;
-    s->args.sc.tlas_root_link = tlink[0];
+    if ((rc = dev_upload(s, &s->args.sc.wide_nodes, lay.wide_nodes))) return rc;
+    if ((rc = dev_upload(s, &s->args.sc.leaf_recs, lay.leaf_recs))) return rc;
+    if ((rc = dev_upload(s, &s->args.sc.wide_tlas, lay.wide_tlas))) return rc;
+    if ((rc = dev_upload(s, &s->args.sc.inst_recs, lay.inst_recs))) return rc;
+    s->args.sc.tlas_root_link = lay.tlas_root_link;
     GDPT_CUDA(d, cudaStreamSynchronize(d->stream)); // host vectors die at return
     return GDPT_OK;
 }
@@ -335,13 +284,22 @@ int enqueue_k1(gdpt_shader *s)
     GDPT_CUDA(d, cudaMemsetAsync(a.counters, 0, sizeof(FrameCounters), d->stream));
     if (trace && a.trace) GDPT_CUDA(d, cudaMemsetAsync(a.trace, 0xFF, (size_t)a.trace_segments * a.width * a.height * sizeof(gdpt_trace_record), d->stream));
     if (trace && a.visits) GDPT_CUDA(d, cudaMemsetAsync(a.visits, 0xFF, (size_t)a.width * a.height * a.visits_per_ray * sizeof(uint32_t), d->stream));
+    const bool timing = s->stage_timing && !s->stage_ev.empty();
+    int ev = 0;
+    if (timing) GDPT_CUDA(d, cudaEventRecord(s->stage_ev[ev++], d->stream));
     launch_primary(a, trace, d->stream);
+    if (timing) GDPT_CUDA(d, cudaEventRecord(s->stage_ev[ev++], d->stream));
     if (!s->debug_steps) {
         for (int i = 0; i < a.max_depth; i++) {
             launch_shade(a, i, d->stream);
-            if (i + 1 < a.max_depth) launch_trace(a, i + 1, trace, d->stream);
+            if (timing) GDPT_CUDA(d, cudaEventRecord(s->stage_ev[ev++], d->stream));
+            if (i + 1 < a.max_depth) {
+                launch_trace(a, i + 1, trace, d->stream);
+                if (timing) GDPT_CUDA(d, cudaEventRecord(s->stage_ev[ev++], d->stream));
+            }
         }
     }
+    s->stage_count = timing ? ev - 1 : 0;
     GDPT_CUDA(d, cudaGetLastError());
     s->stats_valid = false;
     s->stats.kernel_launches = (uint32_t)k1_launch_count(a.max_depth, s->debug_steps);
@@ -480,6 +438,7 @@ void gdpt_shader_destroy(gdpt_shader *s)
     cudaSetDevice(d->ordinal);
     cudaStreamSynchronize(d->stream);
     for (void *p : s->derived) cudaFree(p);
+    for (cudaEvent_t e : s->stage_ev) cudaEventDestroy(e);
     for (gdpt_rid rid : s->owned) {
         Resource *r = find(d, rid);
         if (r) { cudaFree(r->dptr); d->resources.erase(rid); }
@@ -737,6 +696,30 @@ int gdpt_shader_get_stats(gdpt_shader *s, gdpt_frame_stats *out)
     }
     *out = s->stats;
     return GDPT_OK;
+}
+
+int gdpt_shader_set_stage_timing(gdpt_shader *s, int on)
+{
+    if (!s || s->kind != SHADER_MAIN) return GDPT_ERR_INVALID_ARG;
+    gdpt_device *d = s->dev;
+    cudaSetDevice(d->ordinal);
+    if (on && s->stage_ev.empty()) {
+        s->stage_ev.resize(2 * kMaxDepth + 1);
+        for (auto &e : s->stage_ev) GDPT_CUDA(d, cudaEventCreate(&e));
+    }
+    s->stage_timing = on != 0;
+    return GDPT_OK;
+}
+
+int gdpt_shader_get_stage_times(gdpt_shader *s, float *out_ms, int capacity)
+{
+    if (!s || !out_ms || s->kind != SHADER_MAIN) return GDPT_ERR_INVALID_ARG;
+    gdpt_device *d = s->dev;
+    cudaSetDevice(d->ordinal);
+    GDPT_CUDA(d, cudaStreamSynchronize(d->stream));
+    const int n = s->stage_count < capacity ? s->stage_count : capacity;
+    for (int i = 0; i < n; i++) GDPT_CUDA(d, cudaEventElapsedTime(&out_ms[i], s->stage_ev[i], s->stage_ev[i + 1]));
+    return n;
 }
 
 int gdpt_shader_read_trace(gdpt_shader *s, int segment, gdpt_trace_record *out, uint64_t capacity)

@@ -1,0 +1,74 @@
+"""Multi-GPU plumbing: one process per GPU (torch.distributed, NCCL over NVLink / NVSwitch).
+
+The path shards with NO collective inside a frame: pixels are independent and the seed depends
+only on (x, y, frame_index) (main.glsl:409), the scene is replicated.  Two partitions:
+
+  sample-index  rank r renders whole frames with frame_index = step * world + r + 1 and keeps its
+                own accumulation; a presented image needs one sum-reduce of the accumulations.
+  row bands     every rank renders the rows y with (y // band) % world == rank of the SAME frame
+                (bit-identical to the single-GPU frame); a presented image needs one all-gather
+                of the RGBA8 bands.
+
+PyTorch is used here for what it is good at -- wrapping device memory, NCCL process groups --
+not for any rendering.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+class _DevicePointer:
+    """Expose a raw device allocation to torch through __cuda_array_interface__ (zero copy)."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def as_tensor(ptr, shape, dtype, device):
+    typestr = {torch.uint8: "|u1", torch.float32: "<f4", torch.int32: "<i4"}[dtype]
+    return torch.as_tensor(_DevicePointer(ptr, shape, typestr), device=device)
+
+
+def band_rows(height, band, part, parts):
+    """Row indices owned by `part` (same rule as the kernels: (y // band) % parts == part)."""
+    y = np.arange(height)
+    return y[((y // band) % parts) == part]
+
+
+def init_process_group(backend=None):
+    import os
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        backend = backend or ("nccl" if torch.cuda.is_available() else "gloo")
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, local, world
+
+
+def gather_row_bands(frame, band, rank, world):
+    """frame: (H, W, 4) uint8 tensor holding this rank's rows; returns the assembled frame on every rank.
+    Ragged ownership (H not a multiple of band * world) is handled by padding each contribution to
+    the largest row count."""
+    if world == 1:
+        return frame
+    H = frame.shape[0]
+    rows = [torch.as_tensor(band_rows(H, band, r, world), device=frame.device) for r in range(world)]
+    most = max(len(r) for r in rows)
+    mine = torch.zeros((most,) + tuple(frame.shape[1:]), dtype=frame.dtype, device=frame.device)
+    mine[:len(rows[rank])] = frame[rows[rank]]
+    gathered = torch.empty((world,) + tuple(mine.shape), dtype=frame.dtype, device=frame.device)
+    dist.all_gather_into_tensor(gathered, mine)
+    out = torch.empty_like(frame)
+    for r in range(world):
+        out[rows[r]] = gathered[r, :len(rows[r])]
+    return out
+
+
+def reduce_accumulations(accum, dst=0):
+    """Sum the per-rank RGBA32F accumulation buffers onto `dst` (sample-index partition)."""
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.reduce(accum, dst=dst, op=dist.ReduceOp.SUM)
+    return accum

@@ -204,6 +204,12 @@ typedef struct gdpt_frame_stats {
 } gdpt_frame_stats;
 GDPT_API int  gdpt_shader_get_stats(gdpt_shader *main_shader, gdpt_frame_stats *out);
 
+/* Profiling aid: when on, an event is recorded between the stage kernels of every K1
+ * dispatch; get_stage_times returns the number of stages and their device times in launch
+ * order: primary, shade(0), trace(1), shade(1), ..., shade(D-1).  Blocks until the frame is done. */
+GDPT_API int  gdpt_shader_set_stage_timing(gdpt_shader *main_shader, int on);
+GDPT_API int  gdpt_shader_get_stage_times(gdpt_shader *main_shader, float *out_ms, int capacity);
+
 /* Under "#define GDPT_TRACE": per-pixel parity record of path segment `segment`
  * (0 = primary ray) of the last K1 dispatch; capacity in records (W*H needed).
  * Pixels whose path ended before `segment` have hit = 0xFFFFFFFF. */

@@ -42,7 +42,7 @@ def lib():
     if _orc is None:
         _orc = ctypes.CDLL(ORACLE_LIB)
         _orc.orc_path_trace.restype = c_int
-        _orc.orc_path_trace.argtypes = [POINTER(OrcScene), c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
+        _orc.orc_path_trace.argtypes = [POINTER(OrcScene), c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
                                         c_void_p, c_void_p, c_int, c_void_p, c_uint32, POINTER(OrcStats)]
         _orc.orc_progressive.restype = None
         _orc.orc_progressive.argtypes = [c_void_p, c_void_p, c_int, c_int, c_uint32]
@@ -104,7 +104,7 @@ class Scene:
 
 
 def path_trace(scene, width, height, camera_bytes, max_depth=5, debug_steps=False, threads=None, rows=None,
-               trace_segments=0, visits_per_ray=0):
+               trace_segments=0, visits_per_ray=0, row_step=1):
     """K1 on the CPU.  Returns dict(rgba8, depth, stats, trace, visits)."""
     threads = threads or hardware_threads()
     params = np.zeros(9, np.uint32)
@@ -116,7 +116,7 @@ def path_trace(scene, width, height, camera_bytes, max_depth=5, debug_steps=Fals
     visits = np.full((height * width, visits_per_ray), 0xFFFFFFFF, np.uint32) if visits_per_ray else None
     st = OrcStats()
     y0, y1 = rows if rows else (0, height)
-    lib().orc_path_trace(ctypes.byref(scene.c), _p(params), _p(cam), max_depth, 1 if debug_steps else 0, threads, y0, y1,
+    lib().orc_path_trace(ctypes.byref(scene.c), _p(params), _p(cam), max_depth, 1 if debug_steps else 0, threads, y0, y1, row_step,
                          _p(out), _p(depth), _p(trace) if trace is not None else None, trace_segments,
                          _p(visits) if visits is not None else None, visits_per_ray, ctypes.byref(st))
     stats = {k: getattr(st, k) for k, _ in OrcStats._fields_}
@@ -180,7 +180,7 @@ def reference_arrays(scene_desc, material_ids_per_instance):
     h, roots = reference_build(scene_desc)
     try:
         for inst, mids in zip(scene_desc.instances, material_ids_per_instance):
-            t = np.ascontiguousarray(inst.get("transform12"), np.float32)
+            t = np.ascontiguousarray(inst.get("transform12", [1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0]), np.float32)
             ids = np.ascontiguousarray(mids, np.int32)
             r.refbvh_add_instance(h, roots[inst["mesh"]], _p(ids), len(ids), _p(t))
         r.refbvh_build_tlas(h)

@@ -440,7 +440,7 @@ struct RenderJob {
     const gdpt_render_params *params;
     const gdpt_camera *cam;
     int max_depth, debug_steps;
-    int y_begin, y_end;
+    int y_begin, y_end, y_step;
     uint8_t *out_rgba8; float *out_depth;
     gdpt_trace_record *trace; int trace_segments;
     uint32_t *visits; uint32_t visits_per_ray;
@@ -457,7 +457,7 @@ static void render_rows(RenderJob *job)
     uint64_t rays = 0, phits = 0, pops = 0, boxes = 0, tris = 0, leaves = 0;
     uint32_t max_stack = 0; bool overflow = false;
     for (;;) {
-        int y = job->next_row.fetch_add(1);
+        int y = job->next_row.fetch_add(job->y_step);
         if (y >= job->y_end) break;
         for (int x = 0; x < W; x++) {
             const size_t pix = (size_t)y * W + x;
@@ -566,10 +566,10 @@ typedef struct orc_stats {
     uint32_t max_stack, stack_overflow;
 } orc_stats;
 
-// K1 on rows [y_begin, y_end) of the frame.  trace: [trace_segments][W*H] or NULL.
+// K1 on rows y_begin, y_begin + y_step, ... < y_end of the frame (y_step <= 1: every row).  trace: [trace_segments][W*H] or NULL.
 // visits: [W*H][visits_per_ray] (primary rays) or NULL.
 int orc_path_trace(const orc_scene *scene, const gdpt_render_params *params, const gdpt_camera *camera,
-                   int max_depth, int debug_steps, int n_threads, int y_begin, int y_end,
+                   int max_depth, int debug_steps, int n_threads, int y_begin, int y_end, int y_step,
                    uint8_t *out_rgba8, float *out_depth, gdpt_trace_record *trace, int trace_segments,
                    uint32_t *visits, uint32_t visits_per_ray, orc_stats *stats)
 {
@@ -585,7 +585,7 @@ int orc_path_trace(const orc_scene *scene, const gdpt_render_params *params, con
     job.max_depth = max_depth; job.debug_steps = debug_steps;
     if (y_begin < 0) y_begin = 0;
     if (y_end > params->height) y_end = params->height;
-    job.y_begin = y_begin; job.y_end = y_end;
+    job.y_begin = y_begin; job.y_end = y_end; job.y_step = y_step < 1 ? 1 : y_step;
     job.out_rgba8 = out_rgba8; job.out_depth = out_depth;
     job.trace = trace; job.trace_segments = trace_segments;
     job.visits = visits; job.visits_per_ray = visits_per_ray;

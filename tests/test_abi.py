@@ -1,0 +1,82 @@
+"""The C-ABI libraries load on a CPU-only box and export every symbol the headers declare;
+wire structs have the reference's sizes; without a GPU the backend fails loudly (no fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import REPO, has_gpu
+
+INCLUDE = os.path.join(REPO, "include")
+
+
+def declared(header):
+    text = open(os.path.join(INCLUDE, header)).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"GDPT_API\s+[\w\s\*]+?\b(gdpt_\w+)\s*\(", text)))
+
+
+def test_cuda_library_exports_every_declared_symbol():
+    names = declared("gdpt.h")
+    assert len(names) >= 25
+    lib = ctypes.CDLL(os.path.join(REPO, "gdpathtracing_b200", "libgdpt_cuda.so"))
+    for n in names:
+        assert hasattr(lib, n), f"libgdpt_cuda.so does not export {n}"
+    from gdpathtracing_b200 import _lib
+    assert sorted(n for n, _, _ in _lib.CUDA_API) == names, "ctypes table and gdpt.h disagree"
+
+
+def test_host_library_exports_every_declared_symbol():
+    names = declared("gdpt_host.h")
+    lib = ctypes.CDLL(os.path.join(REPO, "gdpathtracing_b200", "libgdpt_host.so"))
+    for n in names:
+        assert hasattr(lib, n), f"libgdpt_host.so does not export {n}"
+    from gdpathtracing_b200 import _lib
+    assert sorted(n for n, _, _ in _lib.HOST_API) == names
+
+
+def test_wire_struct_sizes_match_reference_layout(tmp_path):
+    """Compile a C probe against include/gdpt_wire.h (its static asserts are the check)."""
+    import subprocess
+    src = tmp_path / "probe.c"
+    src.write_text('#include "gdpt_wire.h"\n#include "gdpt.h"\n#include "gdpt_host.h"\n#include <stdio.h>\n'
+                   "int main(void){printf(\"%zu %zu %zu %zu %zu %zu %zu %zu\\n\", sizeof(gdpt_render_params), sizeof(gdpt_camera),"
+                   "sizeof(gdpt_bvh_node), sizeof(gdpt_tlas_node), sizeof(gdpt_blas_instance), sizeof(gdpt_triangle_geometry),"
+                   "sizeof(gdpt_triangle_data), sizeof(gdpt_material));return 0;}\n")
+    exe = tmp_path / "probe"
+    subprocess.run(["gcc", "-std=c11", "-I", INCLUDE, "-o", str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert [int(x) for x in out] == [36, 160, 48, 32, 176, 48, 80, 64]
+
+
+def test_reference_struct_sizes_agree():
+    from oracle import oracle
+    if not oracle.ref_available():
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    r = oracle.ref()
+    assert [r.refbvh_sizeof(i) for i in range(4)] == [48, 144, 176, 32]
+
+
+@pytest.mark.skipif(has_gpu(), reason="CPU-only behaviour")
+def test_no_gpu_means_loud_failure_not_fallback():
+    from gdpathtracing_b200 import PathTracingCamera, _lib, scenes
+    dev = ctypes.c_void_p()
+    rc = _lib.cuda.gdpt_device_create(0, ctypes.byref(dev))
+    assert rc == -1 and not dev.value
+    assert b"no CPU path" in _lib.cuda.gdpt_last_error(None)
+    cam = PathTracingCamera()
+    cam.geometry_group = scenes.populate(scenes.cornell32())
+    cam.set_window_size(64, 64)
+    with pytest.raises(_lib.GdptError):
+        cam.init()
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(REPO, "gdpathtracing_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                text = open(os.path.join(root, f), errors="ignore").read()
+                assert "oracle" not in text.replace("the oracle", "").replace("an oracle", "") or f in ("pt_math.cuh",), \
+                    f"{f} mentions the oracle package"

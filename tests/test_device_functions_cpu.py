@@ -1,0 +1,104 @@
+"""CPU tier: the backend's per-ray device functions (compiled for the host by tests/devcheck,
+see its header) against the oracle, bit for bit: hit records, node-visit order, per-ray work
+counters, colour, depth, and the K2 accumulate/tone-map arithmetic.  The GPU tier
+(test_gpu_parity.py) repeats these checks through the C-ABI on the real kernels."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from conftest import ptr, records_equal
+from gdpathtracing_b200 import nodes, scenes
+from oracle import oracle
+
+CASES = [
+    ("cornell32", lambda: scenes.cornell32(), 256, 256, 4, 4, 1),          # BASELINE config C1, full size
+    ("demo", lambda: scenes.demo_scene(), 240, 135, 8, 3, 1),
+    ("demo_frame7", lambda: scenes.demo_scene(), 160, 90, 5, 2, 7),
+    ("soup", lambda: scenes.triangle_soup(20000, seed=1), 96, 54, 2, 2, 1),
+    ("instanced", lambda: scenes.instanced_grid(3, 800, seed=3), 128, 72, 5, 2, 3),
+]
+
+
+def run_devcheck(devcheck, osc, cam_bytes, W, H, depth, segs, vis, debug=False):
+    params = np.zeros(9, np.uint32)
+    params[4], params[5] = W, H
+    cam = np.frombuffer(cam_bytes, np.uint8).copy()
+    out = np.zeros((H, W, 4), np.uint8)
+    dep = np.zeros((H, W), np.float32)
+    tr = np.zeros((segs, H * W), dtype=oracle.TRACE_DTYPE)
+    vs = np.full((H * W, vis), 0xFFFFFFFF, np.uint32)
+    rays = np.zeros(1, np.uint64)
+    rc = devcheck.devcheck_path_trace(ctypes.byref(osc.c), ptr(params), ptr(cam), depth, 1 if debug else 0, 0, H, ptr(out),
+                                      ptr(dep), ptr(tr), segs, ptr(vs), vis, ptr(rays))
+    assert rc == 0
+    return out, dep, tr, vs, int(rays[0])
+
+
+@pytest.mark.parametrize("name,make,W,H,depth,segs,frame", CASES, ids=[c[0] for c in CASES])
+def test_device_functions_match_oracle(devcheck, name, make, W, H, depth, segs, frame):
+    sc = make()
+    grp = scenes.populate(sc)
+    grp.build()
+    osc = oracle.Scene(grp.buffers(), grp.texture_layers())
+    cam = bytes(nodes.make_camera_block(sc.camera_transform12, sc.fov, W, H, frame))
+    ref = oracle.path_trace(osc, W, H, cam, max_depth=depth, trace_segments=segs, visits_per_ray=48)
+    out, dep, tr, vs, rays = run_devcheck(devcheck, osc, cam, W, H, depth, segs, 48)
+    assert ref["stats"]["stack_overflow"] == 0
+    assert rays == ref["stats"]["rays"]
+    assert ref["stats"]["primary_hits"] > 0, "scene/camera produced no hits: not a test"
+    for s in range(segs):
+        ok, why = records_equal(tr[s], ref["trace"][s])
+        assert ok, f"segment {s}: {why}"
+    assert np.array_equal(vs, ref["visits"]), "node-visit order differs"
+    assert np.array_equal(out, ref["rgba8"])
+    assert np.array_equal(dep.view(np.uint32), ref["depth"].view(np.uint32))
+
+
+def test_debug_steps_mode(devcheck):
+    sc = scenes.demo_scene()
+    grp = scenes.populate(sc)
+    grp.build()
+    osc = oracle.Scene(grp.buffers(), grp.texture_layers())
+    cam = bytes(nodes.make_camera_block(sc.camera_transform12, sc.fov, 160, 90, 1))
+    ref = oracle.path_trace(osc, 160, 90, cam, debug_steps=True)
+    out, dep, _, _, _ = run_devcheck(devcheck, osc, cam, 160, 90, 5, 1, 1, debug=True)
+    assert np.array_equal(out, ref["rgba8"]) and ref["rgba8"][..., 0].max() > 0
+    assert np.array_equal(dep.view(np.uint32), ref["depth"].view(np.uint32))
+
+
+def test_progressive_accumulation_arithmetic(devcheck):
+    """K2 (progressive_rendering.glsl:28-46) over 5 frames incl. the frame_count == 1 reset."""
+    rng = np.random.default_rng(3)
+    a_acc = np.zeros((40, 64, 4), np.float32)
+    b_acc = rng.random((40, 64, 4), dtype=np.float32)  # garbage that frame_count == 1 must ignore
+    a_acc[:] = b_acc
+    for fc in (1, 2, 3, 4, 5):
+        frame = rng.integers(0, 256, (40, 64, 4), dtype=np.uint8)
+        a, b = frame.copy(), frame.copy()
+        oracle.progressive(a, a_acc, fc)
+        devcheck.devcheck_progressive(ptr(b), ptr(b_acc), 64, 40, fc)
+        assert np.array_equal(a, b) and np.array_equal(a_acc.view(np.uint32), b_acc.view(np.uint32))
+        assert (a[..., 3] == 255).all()
+
+
+def test_tie_on_equal_t_last_tested_triangle_wins(devcheck):
+    """Quirk Q8 (main.glsl:247): `t > hit.t` rejects, so an equal-t duplicate tested later replaces the hit."""
+    sc = scenes.SceneDesc("dup", camera_transform12=scenes.transform12(None, (0, 0, 5)), fov=40.0)
+    sc.materials = [dict()]
+    sc.default_material = 0
+    tri = np.array([[-1, -1, 0], [0, 1, 0], [1, -1, 0]], np.float32)  # clockwise seen from +z
+    p = np.concatenate([tri, tri])
+    n = np.tile(np.array([0, 0, 1], np.float32), (6, 1))
+    sc.meshes = [[{"positions": p, "normals": n, "uvs": np.zeros((6, 2), np.float32), "indices": np.arange(6, dtype=np.int32)}]]
+    sc.instances = [dict(mesh=0)]
+    grp = scenes.populate(sc)
+    grp.build()
+    osc = oracle.Scene(grp.buffers(), grp.texture_layers())
+    cam = bytes(nodes.make_camera_block(sc.camera_transform12, sc.fov, 32, 32, 1))
+    ref = oracle.path_trace(osc, 32, 32, cam, max_depth=1, trace_segments=1)
+    hits = ref["trace"][0][ref["trace"][0]["hit"] == 1]
+    assert len(hits) > 0 and (hits["triangle"] == 1).all()
+    _, _, tr, _, _ = run_devcheck(devcheck, osc, cam, 32, 32, 1, 1, 1)
+    ok, why = records_equal(tr[0], ref["trace"][0])
+    assert ok, why

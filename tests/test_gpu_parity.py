@@ -1,0 +1,202 @@
+"""GPU tier: the CUDA kernels, driven through the C-ABI (libgdpt_cuda.so) by the host twins,
+against the oracle.  Bit-exact for hit ids, node-visit order, t/u/v, work counters, RGBA8
+frames, depth and the accumulation buffer (north_star asks for t within 1e-5 relative; we hold
+bit equality, which implies it)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from conftest import records_equal
+from gdpathtracing_b200 import PathTracingCamera, _lib, nodes, scenes
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def make_camera(sc, grp, W, H, depth, mode=PathTracingCamera.NONE, trace=0, visits=0, frame_index=0, fused=True,
+                debug=False, shard=None):
+    cam = PathTracingCamera()
+    cam.fov = sc.fov
+    cam.geometry_group = grp
+    cam.denoising_mode = mode
+    cam.set_window_size(W, H)
+    cam.set_global_transform(sc.camera_transform12)
+    cam.set_max_depth(depth)
+    cam.set_frame_index(frame_index)
+    cam.set_fused_frame(fused)
+    if trace:
+        cam.set_trace(trace, visits)
+    if debug:
+        cam.set_debug_steps(True)
+    if shard:
+        cam.set_shard(*shard)
+    cam.init()
+    return cam
+
+
+def oracle_scene(grp):
+    return oracle.Scene(grp.buffers(), grp.texture_layers())
+
+
+CASES = [
+    ("cornell32", lambda: scenes.cornell32(), 256, 256, 4, 4),            # BASELINE config C1 at full size
+    ("demo", lambda: scenes.demo_scene(), 480, 270, 8, 4),
+    ("soup", lambda: scenes.triangle_soup(20000, seed=1), 160, 90, 2, 2),
+    ("instanced", lambda: scenes.instanced_grid(3, 800, seed=3), 192, 108, 5, 3),
+]
+
+
+@pytest.mark.parametrize("name,make,W,H,depth,segs", CASES, ids=[c[0] for c in CASES])
+def test_trace_parity(name, make, W, H, depth, segs):
+    """Hit primitive ids, instance ids, t/u/v bits, visit-order hash + the first 48 visited
+    node ids, per-ray work counters, ray count, frame and depth: all identical to the oracle."""
+    sc = make()
+    grp = scenes.populate(sc)
+    cam = make_camera(sc, grp, W, H, depth, trace=segs, visits=48)
+    frame = cam.render().copy()
+    stats = cam.stats()
+    ref = oracle.path_trace(oracle_scene(grp), W, H, bytes(cam.camera_block()), max_depth=depth, trace_segments=segs,
+                            visits_per_ray=48)
+    assert ref["stats"]["primary_hits"] > 0
+    assert stats["rays"] == ref["stats"]["rays"]
+    assert stats["primary_hits"] == ref["stats"]["primary_hits"]
+    for k in ("node_pops", "box_tests", "tri_tests", "tlas_leaves", "max_stack"):
+        assert stats[k] == ref["stats"][k], k
+    for s in range(segs):
+        ok, why = records_equal(cam.read_trace(s), ref["trace"][s])
+        assert ok, f"segment {s}: {why}"
+    assert np.array_equal(cam.read_visits(), ref["visits"]), "node-visit order differs"
+    assert np.array_equal(frame, ref["rgba8"])
+    assert np.array_equal(cam.read_image("depth").view(np.uint32), ref["depth"].view(np.uint32))
+
+
+def test_fast_kernels_equal_traced_kernels():
+    """The un-instrumented instantiation (the one that is timed) produces the same frame."""
+    sc = scenes.demo_scene()
+    grp = scenes.populate(sc)
+    a = make_camera(sc, grp, 480, 270, 8).render().copy()
+    ref = oracle.path_trace(oracle_scene(grp), 480, 270,
+                            bytes(nodes.make_camera_block(sc.camera_transform12, sc.fov, 480, 270, 1)), max_depth=8)
+    assert np.array_equal(a, ref["rgba8"])
+
+
+def test_progressive_frames_and_both_call_sequences():
+    """Five accumulated frames: fused gdpt_render_frame == the reference's dispatch-by-dispatch sequence
+    (compute(main); compute(progressive); get_image) == oracle K1 + K2, including the accumulation buffer."""
+    sc = scenes.cornell32()
+    grp = scenes.populate(sc)
+    W = H = 256
+    fused = make_camera(sc, grp, W, H, 4, mode=PathTracingCamera.PROGRESSIVE_RENDERING, fused=True)
+    split = make_camera(sc, grp, W, H, 4, mode=PathTracingCamera.PROGRESSIVE_RENDERING, fused=False)
+    osc = oracle_scene(grp)
+    acc = np.zeros((H, W, 4), np.float32)
+    for f in range(1, 6):
+        a = fused.render().copy()
+        b = split.render().copy()
+        assert fused.camera_block().frame_index == f and fused.last_frame_count() == f == split.last_frame_count()
+        ref = oracle.path_trace(osc, W, H, bytes(fused.camera_block()), max_depth=4)
+        screen = ref["rgba8"].copy()
+        oracle.progressive(screen, acc, f)
+        assert np.array_equal(a, screen), f"fused frame {f}"
+        assert np.array_equal(b, screen), f"split frame {f}"
+    assert np.array_equal(fused.read_image("accum").view(np.uint32), acc.view(np.uint32))
+    assert np.array_equal(split.read_image("accum").view(np.uint32), acc.view(np.uint32))
+
+
+def test_frame_count_resets_when_camera_moves():
+    """progressive_rendering.cpp:53-60 (and quirk Q13: a camera sitting at the identity pose starts at 2)."""
+    sc = scenes.cornell32()
+    grp = scenes.populate(sc)
+    cam = make_camera(sc, grp, 64, 64, 2, mode=PathTracingCamera.PROGRESSIVE_RENDERING)
+    cam.render(); cam.render()
+    assert cam.last_frame_count() == 2
+    moved = sc.camera_transform12.copy()
+    moved[9] += 0.5
+    cam.set_global_transform(moved)
+    cam.render()
+    assert cam.last_frame_count() == 1
+    ident = make_camera(scenes.SceneDesc("x", fov=60.0), grp, 64, 64, 2, mode=PathTracingCamera.PROGRESSIVE_RENDERING)
+    ident.render()
+    assert ident.last_frame_count() == 2
+
+
+def test_debug_steps_define():
+    sc = scenes.demo_scene()
+    grp = scenes.populate(sc)
+    cam = make_camera(sc, grp, 320, 180, 5, debug=True)
+    frame = cam.render().copy()
+    ref = oracle.path_trace(oracle_scene(grp), 320, 180, bytes(cam.camera_block()), debug_steps=True)
+    assert np.array_equal(frame, ref["rgba8"]) and frame[..., 0].max() > 0
+
+
+def test_full_size_demo_frame_sampled_against_oracle():
+    """BASELINE config C2 at full size (1920x1080, depth 8): exact ray count, exact frame on a band
+    of rows the oracle renders, determinism (same frame_index twice -> identical bytes)."""
+    sc = scenes.demo_scene()
+    grp = scenes.populate(sc)
+    W, H = 1920, 1080
+    cam = make_camera(sc, grp, W, H, 8)
+    a = cam.render().copy()
+    rays = cam.stats()["rays"]
+    ref = oracle.path_trace(oracle_scene(grp), W, H, bytes(cam.camera_block()), max_depth=8)
+    assert rays == ref["stats"]["rays"]
+    assert np.array_equal(a, ref["rgba8"])
+    cam.set_frame_index(0)
+    assert np.array_equal(cam.render(), a), "same frame_index must reproduce the same bytes"
+
+
+def test_row_sharding_reassembles_the_unsharded_frame():
+    """Tile/row-band sharding (multi-GPU partition) is exact: the union of the parts' rows is the full frame,
+    rows outside a part are untouched, ray counts add up."""
+    sc = scenes.demo_scene()
+    grp = scenes.populate(sc)
+    W, H, parts, band = 480, 270, 3, 8
+    full_cam = make_camera(sc, grp, W, H, 6, mode=PathTracingCamera.PROGRESSIVE_RENDERING)
+    full = [full_cam.render().copy() for _ in range(3)][-1]
+    total_rays = full_cam.stats()["rays"]
+    assembled = np.zeros_like(full)
+    rays = 0
+    for p in range(parts):
+        cam = make_camera(sc, grp, W, H, 6, mode=PathTracingCamera.PROGRESSIVE_RENDERING, shard=(p, parts, band))
+        img = [cam.render().copy() for _ in range(3)][-1]
+        rays += cam.stats()["rays"]
+        own = ((np.arange(H) // band) % parts) == p
+        assert not img[~own].any(), "a shard wrote rows it does not own"
+        assembled[own] = img[own]
+    assert np.array_equal(assembled, full)
+    assert rays == total_rays
+
+
+def test_gdcs_style_error_behaviour():
+    """compute() before finish_create_uniforms is refused (gdcs.cpp:239-240,258-273); unknown shaders and bad
+    binding tables are reported through the status code + gdpt_last_error, never by crashing."""
+    dev = ctypes.c_void_p()
+    _lib.check(_lib.cuda.gdpt_device_create(0, ctypes.byref(dev)), None, "device_create")
+    sh = ctypes.c_void_p()
+    assert _lib.cuda.gdpt_shader_create(dev, b"res://nope.glsl", None, 0, ctypes.byref(sh)) == -5
+    _lib.check(_lib.cuda.gdpt_shader_create(dev, b"res://addons/jar_path_tracing/src/shaders/main.glsl", None, 0, ctypes.byref(sh)),
+               dev, "shader_create")
+    assert _lib.cuda.gdpt_shader_check_ready(sh) == 0
+    assert _lib.cuda.gdpt_shader_compute(sh, 1, 1, 1) == -4
+    assert _lib.cuda.gdpt_shader_finish_create_uniforms(sh) == -6
+    assert b"main.glsl needs" in _lib.cuda.gdpt_last_error(dev)
+    _lib.cuda.gdpt_shader_destroy(sh)
+    _lib.cuda.gdpt_device_destroy(dev)
+
+
+def test_storage_buffer_round_trip():
+    dev = ctypes.c_void_p()
+    _lib.check(_lib.cuda.gdpt_device_create(0, ctypes.byref(dev)), None, "device_create")
+    sh = ctypes.c_void_p()
+    _lib.check(_lib.cuda.gdpt_shader_create(dev, b"progressive_rendering.glsl", None, 0, ctypes.byref(sh)), dev, "create")
+    data = np.arange(64, dtype=np.uint32)
+    rid = _lib.cuda.gdpt_shader_create_storage_buffer_uniform(sh, data.ctypes.data_as(ctypes.c_void_p), data.nbytes, 0, 0)
+    assert rid != 0
+    upd = data[::-1].copy()
+    _lib.check(_lib.cuda.gdpt_shader_update_storage_buffer_uniform(sh, rid, upd.ctypes.data_as(ctypes.c_void_p), upd.nbytes), dev, "update")
+    back = np.zeros_like(data)
+    _lib.check(_lib.cuda.gdpt_shader_get_storage_buffer_uniform(sh, rid, back.ctypes.data_as(ctypes.c_void_p), back.nbytes), dev, "get")
+    assert np.array_equal(back, upd)
+    _lib.cuda.gdpt_shader_destroy(sh)
+    _lib.cuda.gdpt_device_destroy(dev)
