@@ -131,6 +131,7 @@ HOST_API = [
     ("gdpt_camera_set_shard", None, [c_void_p, c_int, c_int, c_int]),
     ("gdpt_camera_set_trace", None, [c_void_p, c_int, c_uint32]),
     ("gdpt_camera_set_debug_steps", None, [c_void_p, c_int]),
+    ("gdpt_camera_set_cull", None, [c_void_p, c_int]),
     ("gdpt_camera_set_fused_frame", None, [c_void_p, c_int]),
     ("gdpt_camera_init", c_int, [c_void_p]),
     ("gdpt_camera_render", None, [c_void_p]),

@@ -36,7 +36,7 @@ def _stale(target, deps):
 
 
 def _run(cmd):
-    print("+", " ".join(cmd), flush=True)
+    print("+", " ".join(cmd), file=sys.stderr, flush=True)
     subprocess.run(cmd, check=True)
 
 

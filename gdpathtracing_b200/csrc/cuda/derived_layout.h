@@ -6,6 +6,8 @@
 
 #include "pt_scene.cuh"
 
+#include <cfloat>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -21,18 +23,118 @@ struct DerivedLayout {
     uint32_t tlas_root_link = LINK_NONE;
 };
 
+struct TightBox { float lo[3], hi[3]; };
+
+inline TightBox tight_empty()
+{
+    TightBox b;
+    for (int k = 0; k < 3; k++) { b.lo[k] = FLT_MAX; b.hi[k] = -FLT_MAX; }
+    return b;
+}
+inline void tight_grow(TightBox &b, const float *p)
+{
+    for (int k = 0; k < 3; k++) { if (p[k] < b.lo[k]) b.lo[k] = p[k]; if (p[k] > b.hi[k]) b.hi[k] = p[k]; }
+}
+inline void tight_merge(TightBox &b, const TightBox &o)
+{
+    for (int k = 0; k < 3; k++) { if (o.lo[k] < b.lo[k]) b.lo[k] = o.lo[k]; if (o.hi[k] > b.hi[k]) b.hi[k] = o.hi[k]; }
+}
+inline float tight_extent(const TightBox &b)
+{
+    float e = 0.0f;
+    for (int k = 0; k < 3; k++) if (b.hi[k] - b.lo[k] > e) e = b.hi[k] - b.lo[k];
+    return e;
+}
+// Safety margin of a culling box: 1/256 of its own size plus 1/512 of the size of the BLAS it
+// belongs to.  The second term is what covers Moller-Trumbore's rounding (absolute error of
+// the order of 1e-6 x distance to the ray origin): it keeps a >10x reserve for rays that start
+// up to ~100 BLAS diameters away.  Non-finite input boxes become "everything" (never cull).
+inline TightBox tight_inflate(const TightBox &b, float owner_extent)
+{
+    TightBox r;
+    const float m = tight_extent(b) * (1.0f / 256.0f) + owner_extent * (1.0f / 512.0f) + 1e-30f;
+    bool finite = std::isfinite(m);
+    for (int k = 0; k < 3; k++) {
+        r.lo[k] = b.lo[k] - m; r.hi[k] = b.hi[k] + m;
+        finite = finite && std::isfinite(r.lo[k]) && std::isfinite(r.hi[k]) && b.lo[k] <= b.hi[k];
+    }
+    if (!finite)
+        for (int k = 0; k < 3; k++) { r.lo[k] = -FLT_MAX; r.hi[k] = FLT_MAX; }
+    return r;
+}
+
 // Returns "" on success, otherwise what is wrong with the input arrays.
 inline std::string derive_layout(const gdpt_bvh_node *bvh, uint32_t n_nodes, const gdpt_blas_instance *blas, uint32_t n_blas,
-                                 const gdpt_tlas_node *tlas, uint32_t n_tlas, DerivedLayout &out)
+                                 const gdpt_tlas_node *tlas, uint32_t n_tlas, const gdpt_triangle_geometry *tris,
+                                 uint32_t n_tris, DerivedLayout &out)
 {
     char msg[160];
     if (n_tlas == 0 || n_blas == 0) return "empty TLAS / instance buffer";
     if (n_nodes >= LINK_INDEX_MASK) return "too many BVH nodes";
 
-    // BLAS: internal nodes and leaves get their own dense numbering
+    // ---- BLAS: internal nodes and leaves get their own dense numbering
     std::vector<uint32_t> link(n_nodes);
     uint32_t n_internal = 0, n_leaf = 0;
-    for (uint32_t i = 0; i < n_nodes; i++) link[i] = bvh[i].tri_count > 0 ? (LINK_LEAF | n_leaf++) : n_internal++;
+    for (uint32_t i = 0; i < n_nodes; i++) {
+        const gdpt_bvh_node &n = bvh[i];
+        if (n.tri_count > 0) {
+            if ((uint64_t)n.first_tri_index + n.tri_count > n_tris) {
+                std::snprintf(msg, sizeof(msg), "BVH leaf %u references triangles beyond the triangle buffer", i);
+                return msg;
+            }
+            link[i] = LINK_LEAF | n_leaf++;
+        } else {
+            if (n.left_child >= n_nodes || n.right_child >= n_nodes) {
+                std::snprintf(msg, sizeof(msg), "BVH node %u has a child index out of range", i);
+                return msg;
+            }
+            link[i] = n_internal++;
+        }
+    }
+
+    // ---- true bounding boxes, bottom-up per BLAS (explicit post-order walk from every root)
+    std::vector<TightBox> raw(n_nodes, tight_empty());
+    std::vector<uint8_t> state(n_nodes, 0); // 0 unseen, 1 children pending, 2 done
+    std::vector<float> owner_extent(n_nodes, 0.0f);
+    std::vector<uint32_t> walk;
+    for (uint32_t b = 0; b < n_blas; b++) {
+        const uint32_t root = blas[b].root;
+        if (root >= n_nodes) {
+            std::snprintf(msg, sizeof(msg), "instance %u root out of range", b);
+            return msg;
+        }
+        if (state[root] == 2) continue;
+        walk.assign(1, root);
+        while (!walk.empty()) {
+            const uint32_t i = walk.back();
+            const gdpt_bvh_node &n = bvh[i];
+            if (n.tri_count > 0) {
+                TightBox t = tight_empty();
+                for (uint32_t k = 0; k < n.tri_count; k++)
+                    for (int v = 0; v < 3; v++) tight_grow(t, tris[n.first_tri_index + k].v[v]);
+                raw[i] = t; state[i] = 2; walk.pop_back();
+            } else if (state[i] == 0) {
+                state[i] = 1;
+                if (state[n.left_child] == 1 || state[n.right_child] == 1) return "BVH child links form a cycle";
+                if (state[n.left_child] == 0) walk.push_back(n.left_child);
+                if (state[n.right_child] == 0) walk.push_back(n.right_child);
+            } else {
+                TightBox t = raw[n.left_child];
+                tight_merge(t, raw[n.right_child]);
+                raw[i] = t; state[i] = 2; walk.pop_back();
+            }
+        }
+        // second walk: stamp the owning BLAS size on every node of this tree
+        const float ext = tight_extent(raw[root]);
+        walk.assign(1, root);
+        while (!walk.empty()) {
+            const uint32_t i = walk.back();
+            walk.pop_back();
+            owner_extent[i] = ext;
+            if (bvh[i].tri_count == 0) { walk.push_back(bvh[i].left_child); walk.push_back(bvh[i].right_child); }
+        }
+    }
+
     out.wide_nodes.assign(n_internal, WideNode());
     out.leaf_recs.assign(n_leaf, LeafRec());
     for (uint32_t i = 0; i < n_nodes; i++) {
@@ -42,20 +144,22 @@ inline std::string derive_layout(const gdpt_bvh_node *bvh, uint32_t n_nodes, con
             l.first_tri = n.first_tri_index; l.tri_count = n.tri_count; l.orig = i; l.pad = 0;
             continue;
         }
-        if (n.left_child >= n_nodes || n.right_child >= n_nodes) {
-            std::snprintf(msg, sizeof(msg), "BVH node %u has a child index out of range", i);
-            return msg;
-        }
         WideNode &w = out.wide_nodes[link[i]];
+        std::memset(&w, 0, sizeof(w));
         const gdpt_bvh_node &L = bvh[n.left_child], &R = bvh[n.right_child];
+        // nodes that no instance reaches keep an "everything" culling box
+        const TightBox tl = state[n.left_child] == 2 ? tight_inflate(raw[n.left_child], owner_extent[n.left_child]) : tight_inflate(tight_empty(), 0.0f);
+        const TightBox tr = state[n.right_child] == 2 ? tight_inflate(raw[n.right_child], owner_extent[n.right_child]) : tight_inflate(tight_empty(), 0.0f);
         for (int k = 0; k < 3; k++) {
             w.lmin[k] = L.aabb_min[k]; w.lmax[k] = L.aabb_max[k];
             w.rmin[k] = R.aabb_min[k]; w.rmax[k] = R.aabb_max[k];
+            w.tlmin[k] = tl.lo[k]; w.tlmax[k] = tl.hi[k];
+            w.trmin[k] = tr.lo[k]; w.trmax[k] = tr.hi[k];
         }
-        w.left = link[n.left_child]; w.right = link[n.right_child]; w.orig = i; w.pad = 0;
+        w.left = link[n.left_child]; w.right = link[n.right_child]; w.orig = i;
     }
 
-    // TLAS: same split; leaves index the instance table directly
+    // ---- TLAS: same split; leaves index the instance table directly
     std::vector<uint32_t> tlink(n_tlas);
     uint32_t nt_internal = 0;
     for (uint32_t i = 0; i < n_tlas; i++) {
@@ -65,20 +169,52 @@ inline std::string derive_layout(const gdpt_bvh_node *bvh, uint32_t n_nodes, con
                 return msg;
             }
             tlink[i] = LINK_TLAS | LINK_LEAF | tlas[i].blas;
-        } else tlink[i] = LINK_TLAS | nt_internal++;
+        } else {
+            const uint32_t l = tlas[i].left_right & 0xFFFFu, r = tlas[i].left_right >> 16;
+            if (l >= n_tlas || r >= n_tlas) {
+                std::snprintf(msg, sizeof(msg), "TLAS node %u has a child out of range", i);
+                return msg;
+            }
+            tlink[i] = LINK_TLAS | nt_internal++;
+        }
     }
     out.wide_tlas.assign(nt_internal, WideNode());
     out.inst_recs.assign(n_blas, InstRec());
+    std::vector<TightBox> world(n_blas);
     for (uint32_t b = 0; b < n_blas; b++) {
-        if (blas[b].root >= n_nodes) {
-            std::snprintf(msg, sizeof(msg), "instance %u root out of range", b);
-            return msg;
-        }
         InstRec &r = out.inst_recs[b];
+        std::memset(&r, 0, sizeof(r));
         std::memcpy(r.inv, blas[b].inverse_transform, sizeof(r.inv));
         r.root_link = link[blas[b].root];
         r.root_orig = blas[b].root;
-        r.tlas_orig = 0; r.pad = 0;
+        const TightBox obj = tight_inflate(raw[blas[b].root], owner_extent[blas[b].root]);
+        for (int k = 0; k < 3; k++) { r.tight_min[k] = obj.lo[k]; r.tight_max[k] = obj.hi[k]; }
+        // world-space culling box: the eight transformed corners of the object-space one, inflated again
+        TightBox w = tight_empty();
+        const float *m = blas[b].transform;
+        for (int c = 0; c < 8; c++) {
+            const double x = (c & 1) ? obj.hi[0] : obj.lo[0], y = (c & 2) ? obj.hi[1] : obj.lo[1], z = (c & 4) ? obj.hi[2] : obj.lo[2];
+            const float p[3] = { (float)(m[0] * x + m[4] * y + m[8] * z + m[12]), (float)(m[1] * x + m[5] * y + m[9] * z + m[13]),
+                                 (float)(m[2] * x + m[6] * y + m[10] * z + m[14]) };
+            tight_grow(w, p);
+        }
+        world[b] = tight_inflate(w, tight_extent(w));
+    }
+    // tight boxes of TLAS nodes, bottom-up (TLAS nodes are few: plain recursion-free fixpoint by depth)
+    std::vector<TightBox> traw(n_tlas, tight_empty());
+    std::vector<uint8_t> tdone(n_tlas, 0);
+    for (uint32_t i = 0; i < n_tlas; i++)
+        if (tlas[i].left_right == 0) { traw[i] = world[tlas[i].blas]; tdone[i] = 1; }
+    for (uint32_t pass = 0; pass < n_tlas; pass++) {
+        bool progress = false, all = true;
+        for (uint32_t i = 0; i < n_tlas; i++) {
+            if (tdone[i]) continue;
+            const uint32_t l = tlas[i].left_right & 0xFFFFu, r = tlas[i].left_right >> 16;
+            if (tdone[l] && tdone[r]) { traw[i] = traw[l]; tight_merge(traw[i], traw[r]); tdone[i] = 1; progress = true; }
+            else all = false;
+        }
+        if (all) break;
+        if (!progress) return "TLAS child links form a cycle";
     }
     for (uint32_t i = 0; i < n_tlas; i++) {
         const gdpt_tlas_node &n = tlas[i];
@@ -87,16 +223,15 @@ inline std::string derive_layout(const gdpt_bvh_node *bvh, uint32_t n_nodes, con
             continue;
         }
         const uint32_t l = n.left_right & 0xFFFFu, r = n.left_right >> 16;
-        if (l >= n_tlas || r >= n_tlas) {
-            std::snprintf(msg, sizeof(msg), "TLAS node %u has a child out of range", i);
-            return msg;
-        }
         WideNode &w = out.wide_tlas[tlink[i] & LINK_INDEX_MASK];
+        std::memset(&w, 0, sizeof(w));
         for (int k = 0; k < 3; k++) {
             w.lmin[k] = tlas[l].aabb_min[k]; w.lmax[k] = tlas[l].aabb_max[k];
             w.rmin[k] = tlas[r].aabb_min[k]; w.rmax[k] = tlas[r].aabb_max[k];
+            w.tlmin[k] = traw[l].lo[k]; w.tlmax[k] = traw[l].hi[k];
+            w.trmin[k] = traw[r].lo[k]; w.trmax[k] = traw[r].hi[k];
         }
-        w.left = tlink[l]; w.right = tlink[r]; w.orig = i; w.pad = 0;
+        w.left = tlink[l]; w.right = tlink[r]; w.orig = i;
     }
     // node 0 is a copy of the final root (bvh.cpp:316); with a single instance that root is
     // itself the leaf, and the traversal pops it as node 0

@@ -60,7 +60,8 @@ struct gdpt_shader {
     bool debug_steps = false;
     int trace_segments = 0;
     uint32_t visits_per_ray = 0;
-    int variant = 0;
+    int variant = -1; // "#define GDPT_VARIANT n": traversal schedule, -1 = default
+    int cull = -1;    // "#define GDPT_CULL n" / "#define GDPT_REFERENCE_ORDER": -1 = default
     // main-shader state built by finish_create_uniforms
     FrameArgs args;
     std::vector<void *> derived; // device allocations owned by this shader
@@ -154,7 +155,7 @@ template <typename T> int dev_upload(gdpt_shader *s, const T **out, const std::v
 }
 
 // Build WideNode / LeafRec / InstRec tables from the uploaded reference arrays and upload them.
-int build_derived_layout(gdpt_shader *s, const Resource &bvh_r, const Resource &blas_r, const Resource &tlas_r)
+int build_derived_layout(gdpt_shader *s, const Resource &bvh_r, const Resource &blas_r, const Resource &tlas_r, const Resource &tri_r)
 {
     gdpt_device *d = s->dev;
     DerivedLayout lay;
@@ -163,7 +164,9 @@ int build_derived_layout(gdpt_shader *s, const Resource &bvh_r, const Resource &
                                           reinterpret_cast<const gdpt_blas_instance *>(blas_r.shadow.data()),
                                           (uint32_t)(blas_r.size / sizeof(gdpt_blas_instance)),
                                           reinterpret_cast<const gdpt_tlas_node *>(tlas_r.shadow.data()),
-                                          (uint32_t)(tlas_r.size / sizeof(gdpt_tlas_node)), lay);
+                                          (uint32_t)(tlas_r.size / sizeof(gdpt_tlas_node)),
+                                          reinterpret_cast<const gdpt_triangle_geometry *>(tri_r.shadow.data()),
+                                          (uint32_t)(tri_r.size / sizeof(gdpt_triangle_geometry)), lay);
     if (!err.empty()) return fail(d, GDPT_ERR_BAD_BINDING, "%s", err.c_str());
     int rc;
     if ((rc = dev_upload(s, &s->args.sc.wide_nodes, lay.wide_nodes))) return rc;
@@ -231,7 +234,7 @@ int finish_main(gdpt_shader *s)
     a.sc.n_blas = (uint32_t)(blas->size / sizeof(gdpt_blas_instance));
     a.sc.n_tlas = (uint32_t)(tlas->size / sizeof(gdpt_tlas_node));
     a.sc.n_materials = (uint32_t)(mat->size / sizeof(gdpt_material));
-    int rc = build_derived_layout(s, *bvh, *blas, *tlas);
+    int rc = build_derived_layout(s, *bvh, *blas, *tlas, *tg);
     if (rc) return rc;
 
     a.camera = static_cast<const gdpt_camera *>(camera->dptr);
@@ -243,7 +246,12 @@ int finish_main(gdpt_shader *s)
     if ((rc = dev_alloc(s, &a.queue[1], (size_t)a.queue_cap * 5))) return rc;
     if ((rc = dev_alloc(s, &a.hit_list, (size_t)a.queue_cap))) return rc;
     if ((rc = dev_alloc(s, &a.counters, 1))) return rc;
-    a.refill_below = 20; a.burst = 4;
+    a.schedule = s->variant >= 0 ? s->variant : 1;
+    // culling (pt_scene.cuh) is the default for rendering; parity traces keep the full reference visit order
+    a.cull = s->cull >= 0 ? s->cull : (s->trace_segments > 0 ? 0 : 1);
+    if (const char *e = getenv("GDPT_CULL")) { if (s->cull < 0 && s->trace_segments == 0) a.cull = atoi(e) != 0; }
+    a.refill_below = 24; a.burst = a.schedule == 0 ? 4 : 16;
+    if (const char *e = getenv("GDPT_SCHEDULE")) a.schedule = atoi(e);
     if (const char *e = getenv("GDPT_REFILL_BELOW")) a.refill_below = atoi(e);
     if (const char *e = getenv("GDPT_BURST")) a.burst = atoi(e);
     if (a.refill_below < 1) a.refill_below = 1;
@@ -418,6 +426,8 @@ int gdpt_shader_create(gdpt_device *d, const char *shader_path, const char *cons
         else if (name == "GDPT_TRACE") s->trace_segments = has_value ? (int)value : 1;
         else if (name == "GDPT_TRACE_VISITS" && has_value) s->visits_per_ray = (uint32_t)value;
         else if (name == "GDPT_VARIANT" && has_value) s->variant = (int)value;
+        else if (name == "GDPT_CULL" && has_value) s->cull = value != 0 ? 1 : 0;
+        else if (name == "GDPT_REFERENCE_ORDER") s->cull = 0;
     }
     if (s->max_depth < 1 || s->max_depth > kMaxDepth) {
         delete s;

@@ -34,8 +34,8 @@ constexpr int kTraceThreads = 128;
 constexpr int kSmemStack = 16;
 constexpr int kShadeThreads = 128;
 constexpr unsigned kFull = 0xFFFFFFFFu;
-constexpr uint32_t kChunkPrimary = 256; // 8 tiles of 8x4 pixels
-constexpr uint32_t kChunkBounce = 64;
+constexpr uint32_t kChunkPrimary = 32; // one 8x4-pixel tile: small chunks keep the expensive tiles spread over many warps
+constexpr uint32_t kChunkBounce = 32;
 
 struct SmemStack {
     uint32_t *col;   // this thread's column of the CTA's shared stack array
@@ -87,7 +87,7 @@ __device__ __forceinline__ void write_trace_record(const FrameArgs &a, int segme
 }
 
 // MODE 0: primary rays generated from pixel work items.  MODE 1: rays read from queue `src`.
-template <bool TRACE, int MODE>
+template <bool TRACE, int MODE, bool CULL>
 __global__ void __launch_bounds__(kTraceThreads) k_trace(const FrameArgs a, const int segment, const int src)
 {
     __shared__ uint32_t s_stack[kSmemStack * kTraceThreads];
@@ -117,6 +117,7 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(const FrameArgs a, cons
     TraceCounters tc;
     if (TRACE) counters_init(tc, nullptr, 0);
 
+    uint32_t tri_next = 0, tri_end = 0;     // pending triangle range of the leaf being tested (schedule 1)
     uint32_t chunk_next = 0, chunk_end = 0; // warp-uniform
     bool exhausted = (total == 0u);
     unsigned long long my_pops = 0, my_boxes = 0, my_tris = 0, my_leaves = 0, my_phits = 0;
@@ -176,18 +177,41 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(const FrameArgs a, cons
 
         // ---------------- traverse ----------------
         const int keep_going = exhausted ? 1 : refill_below;
-        for (int it = 0; it < a.burst; ++it) {
-            while (link_is_blas_internal(r.cur)) step_blas_internal<TRACE>(a.sc, r, st, &tc);
-            if (r.cur != LINK_NONE) {
-                if (link_is_blas_leaf(r.cur)) step_blas_leaf<TRACE>(a.sc, r, st, &tc);
-                else step_tlas<TRACE>(a.sc, r, st, &tc);
+        if (a.schedule == 0) {
+            // while-while: descend internal nodes in a tight loop, then one leaf / TLAS step
+            for (int it = 0; it < a.burst; ++it) {
+                while (link_is_blas_internal(r.cur)) step_blas_internal<TRACE, CULL>(a.sc, r, st, &tc);
+                if (r.cur != LINK_NONE) {
+                    if (link_is_blas_leaf(r.cur)) step_blas_leaf<TRACE>(a.sc, r, st, &tc);
+                    else step_tlas<TRACE, CULL>(a.sc, r, st, &tc);
+                }
+                const unsigned walking = __ballot_sync(kFull, r.cur != LINK_NONE);
+                if (__popc(walking) < keep_going) break;
             }
-            const unsigned walking = __ballot_sync(kFull, r.cur != LINK_NONE);
-            if (__popc(walking) < keep_going) break;
+        } else {
+            // phase voting: every lane is in one of three phases (L: one triangle test, I: one
+            // internal node = two box tests, T: one TLAS-level entry).  Each iteration the warp
+            // executes only the phase most lanes are in, so an instruction stream is not issued
+            // for a handful of lanes while the rest could have joined it a step later.
+            for (int it = 0; it < a.burst; ++it) {
+                const bool in_l = tri_next < tri_end || link_is_blas_leaf(r.cur);
+                const bool in_i = !in_l && link_is_blas_internal(r.cur);
+                const bool in_t = !in_l && !in_i && r.cur != LINK_NONE;
+                const int n_l = __popc(__ballot_sync(kFull, in_l)), n_i = __popc(__ballot_sync(kFull, in_i)),
+                          n_t = __popc(__ballot_sync(kFull, in_t));
+                if (n_l + n_i + n_t < keep_going) break;
+                if (n_l >= n_i && n_l >= n_t) {
+                    if (in_l) step_blas_leaf_one<TRACE>(a.sc, r, st, &tc, tri_next, tri_end);
+                } else if (n_i >= n_t) {
+                    if (in_i) step_blas_internal<TRACE, CULL>(a.sc, r, st, &tc);
+                } else {
+                    if (in_t) step_tlas<TRACE, CULL>(a.sc, r, st, &tc);
+                }
+            }
         }
 
         // ---------------- retire finished rays ----------------
-        const bool fin = has && r.cur == LINK_NONE;
+        const bool fin = has && r.cur == LINK_NONE && tri_next == tri_end;
         const bool is_hit = fin && r.t < 1e9f;
         if (MODE == 0) {
             // hits join the path queue
@@ -387,11 +411,31 @@ __global__ void __launch_bounds__(256) k_progressive(uint32_t *__restrict__ scre
 struct Shapes {
     bool ready = false;
     int sms = 148;
-    int trace_blocks[2][2] = { { 0, 0 }, { 0, 0 } }; // [TRACE][MODE]
+    int trace_blocks[2][2][2] = {}; // [TRACE][MODE][CULL]
     int shade_blocks = 0;
     int prog_blocks = 0;
 };
 Shapes g_shapes[16];
+
+template <bool TRACE, int MODE, bool CULL> int trace_grid(int sms)
+{
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<TRACE, MODE, CULL>, kTraceThreads, 0);
+    return sms * (per_sm > 0 ? per_sm : 1);
+}
+
+template <int MODE> void launch_trace_kernel(const Shapes &sh, const FrameArgs &a, bool trace, int segment, int src, cudaStream_t s)
+{
+    const bool cull = a.cull != 0;
+    const int blocks = sh.trace_blocks[trace ? 1 : 0][MODE][cull ? 1 : 0];
+    if (trace) {
+        if (cull) k_trace<true, MODE, true><<<blocks, kTraceThreads, 0, s>>>(a, segment, src);
+        else k_trace<true, MODE, false><<<blocks, kTraceThreads, 0, s>>>(a, segment, src);
+    } else {
+        if (cull) k_trace<false, MODE, true><<<blocks, kTraceThreads, 0, s>>>(a, segment, src);
+        else k_trace<false, MODE, false><<<blocks, kTraceThreads, 0, s>>>(a, segment, src);
+    }
+}
 
 } // namespace
 
@@ -402,11 +446,11 @@ void init_launch_shapes(int device)
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, device);
     s.sms = prop.multiProcessorCount;
+    s.trace_blocks[0][0][0] = trace_grid<false, 0, false>(s.sms); s.trace_blocks[0][0][1] = trace_grid<false, 0, true>(s.sms);
+    s.trace_blocks[0][1][0] = trace_grid<false, 1, false>(s.sms); s.trace_blocks[0][1][1] = trace_grid<false, 1, true>(s.sms);
+    s.trace_blocks[1][0][0] = trace_grid<true, 0, false>(s.sms); s.trace_blocks[1][0][1] = trace_grid<true, 0, true>(s.sms);
+    s.trace_blocks[1][1][0] = trace_grid<true, 1, false>(s.sms); s.trace_blocks[1][1][1] = trace_grid<true, 1, true>(s.sms);
     int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<false, 0>, kTraceThreads, 0); s.trace_blocks[0][0] = s.sms * (per_sm > 0 ? per_sm : 1);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<false, 1>, kTraceThreads, 0); s.trace_blocks[0][1] = s.sms * (per_sm > 0 ? per_sm : 1);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<true, 0>, kTraceThreads, 0); s.trace_blocks[1][0] = s.sms * (per_sm > 0 ? per_sm : 1);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<true, 1>, kTraceThreads, 0); s.trace_blocks[1][1] = s.sms * (per_sm > 0 ? per_sm : 1);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_shade, kShadeThreads, 0); s.shade_blocks = s.sms * (per_sm > 0 ? per_sm : 1);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_progressive, 256, 0); s.prog_blocks = s.sms * (per_sm > 0 ? per_sm : 1);
     s.ready = true;
@@ -422,9 +466,7 @@ static Shapes &shapes_for_current_device()
 
 void launch_primary(const FrameArgs &a, bool trace, cudaStream_t s)
 {
-    Shapes &sh = shapes_for_current_device();
-    if (trace) k_trace<true, 0><<<sh.trace_blocks[1][0], kTraceThreads, 0, s>>>(a, 0, 0);
-    else k_trace<false, 0><<<sh.trace_blocks[0][0], kTraceThreads, 0, s>>>(a, 0, 0);
+    launch_trace_kernel<0>(shapes_for_current_device(), a, trace, 0, 0, s);
 }
 
 void launch_shade(const FrameArgs &a, int segment, cudaStream_t s)
@@ -435,10 +477,8 @@ void launch_shade(const FrameArgs &a, int segment, cudaStream_t s)
 
 void launch_trace(const FrameArgs &a, int segment, bool trace, cudaStream_t s)
 {
-    Shapes &sh = shapes_for_current_device();
     // rays of segment i were written by shade(i-1) into queue (i-1)&1 ^ 1 == i&1
-    if (trace) k_trace<true, 1><<<sh.trace_blocks[1][1], kTraceThreads, 0, s>>>(a, segment, segment & 1);
-    else k_trace<false, 1><<<sh.trace_blocks[0][1], kTraceThreads, 0, s>>>(a, segment, segment & 1);
+    launch_trace_kernel<1>(shapes_for_current_device(), a, trace, segment, segment & 1, s);
 }
 
 void launch_progressive(uint32_t *screen_rgba8, float4 *accum, const gdpt_progressive_params *params_dev, int width,

@@ -40,6 +40,8 @@ struct FrameArgs {
     // scheduling knobs (results do not depend on them)
     int refill_below;  // refill idle lanes when fewer than this many lanes are traversing
     int burst;         // node steps between refill checks
+    int schedule;      // 0: while-while descent, 1: phase voting (see k_trace)
+    int cull;          // 1: skip children whose tight box the ray misses (pt_scene.cuh); results identical
     // parity outputs (TRACE builds only)
     gdpt_trace_record *trace; int trace_segments;
     uint32_t *visits; uint32_t visits_per_ray;

@@ -8,15 +8,27 @@
 // incoherent rays every such read is its own L1 wavefront, which bounds
 // traversal long before issue slots do.  We keep node identity and visiting
 // order exactly as in the reference, but store, per INTERNAL node, both child
-// boxes and both child links in one 64 B record (4 x 128-bit loads from one
-// 128 B line), and per LEAF a 16 B descriptor.  Child links are pre-encoded so
-// a popped entry says which table it indexes without another load.
+// boxes and both child links in one 128 B record (one cache line), and per LEAF
+// a 16 B descriptor.  Child links are pre-encoded so a popped entry says which
+// table it indexes without another load.
 //
 //   link bits: [31] TLAS level   [30] leaf   [29:0] index into the table
 //     BLAS internal -> wide_nodes[]     BLAS leaf -> leaf_recs[]
 //     TLAS internal -> wide_tlas[]      TLAS leaf -> inst_recs[]
 //
 // `orig` fields carry the reference node index for the parity trace.
+//
+// Tight boxes (culling).  The reference's boxes all contain the planes y=0, z=0
+// of their mesh (quirk Q1, bvh.cpp:6-10), so a ray near those planes walks
+// thousands of nodes whose triangles it cannot hit.  Next to each reference box
+// we keep the TRUE bounding box of the child's triangles, inflated by a safety
+// margin.  A child whose tight box the ray misses cannot contain an accepted
+// triangle hit, so skipping it changes neither hit.t nor any later decision:
+// ordering (d1 < d2) and pruning (d < hit.t) of the surviving children still use
+// the reference boxes, and the surviving nodes are visited in reference order.
+// Hit records and images are bit-identical; only the visit list gets shorter.
+// Trace/parity mode does not cull (the full reference visit order is observable
+// there).
 #ifndef GDPT_PT_SCENE_CUH
 #define GDPT_PT_SCENE_CUH
 
@@ -32,15 +44,19 @@ enum : uint32_t {
     LINK_NONE = 0xFFFFFFFFu
 };
 
-// 64 B, 64 B-aligned.  Boxes of the left (L) and right (R) child:
+// 128 B, 128 B-aligned: eight 128-bit quads.
 //   q0 = Lmin.x Lmin.y Lmin.z Lmax.x   q1 = Lmax.y Lmax.z Rmin.x Rmin.y
 //   q2 = Rmin.z Rmax.x Rmax.y Rmax.z   q3 = left_link right_link orig_id 0
-struct __attribute__((aligned(64))) WideNode {
+//   q4..q6 = the same 12 floats for the tight (culling) boxes   q7 = padding
+struct __attribute__((aligned(128))) WideNode {
     float lmin[3]; float lmax[3];
     float rmin[3]; float rmax[3];
     uint32_t left, right, orig, pad;
+    float tlmin[3]; float tlmax[3];
+    float trmin[3]; float trmax[3];
+    uint32_t pad2[4];
 };
-static_assert(sizeof(WideNode) == 64, "WideNode is one half cache line");
+static_assert(sizeof(WideNode) == 128, "WideNode is one cache line");
 
 struct __attribute__((aligned(16))) LeafRec {
     uint32_t first_tri, tri_count, orig, pad;
@@ -54,8 +70,10 @@ struct __attribute__((aligned(16))) InstRec {
     uint32_t tlas_orig;     // reference TLAS node index of this leaf
     uint32_t root_orig;     // reference BVH node index of the root
     uint32_t pad;
+    float tight_min[4];     // tight box of the whole BLAS, object space (w unused)
+    float tight_max[4];
 };
-static_assert(sizeof(InstRec) == 80, "InstRec is five 128-bit loads");
+static_assert(sizeof(InstRec) == 112, "InstRec is seven 128-bit loads");
 
 struct SceneView {
     // uploaded reference buffers (set 1 bindings 0..5, set 2 binding 0)

@@ -148,10 +148,12 @@ template <class Stack> GDPT_HD uint32_t stack_pop(RayState &r, Stack &st)
 }
 
 // Shared tail of an internal-node visit: children tests done, pick what comes next.
+// keep_l / keep_r: false when the culling box of that child is missed (always true without CULL).
 template <bool TRACE, class Stack>
-GDPT_HD void choose_next(RayState &r, Stack &st, float d1, float d2, uint32_t left, uint32_t right, TraceCounters *tc)
+GDPT_HD void choose_next(RayState &r, Stack &st, float d1, float d2, uint32_t left, uint32_t right, bool keep_l, bool keep_r,
+                         TraceCounters *tc)
 {
-    const bool lv = d1 < r.t, rv = d2 < r.t;
+    const bool lv = d1 < r.t && keep_l, rv = d2 < r.t && keep_r;
     const bool left_first = d1 < d2;
     const uint32_t first = left_first ? left : right, second = left_first ? right : left;
     const bool fv = left_first ? lv : rv, sv = left_first ? rv : lv;
@@ -170,19 +172,48 @@ GDPT_HD void choose_next(RayState &r, Stack &st, float d1, float d2, uint32_t le
     }
 }
 
-// One BLAS internal node (main.glsl:285-300).
-template <bool TRACE, class Stack>
-GDPT_HD void step_blas_internal(const SceneView &sc, RayState &r, Stack &st, TraceCounters *tc)
+// Does the ray touch the (inflated) culling box at all?  Same slab arithmetic; NaNs from
+// 0 * inf are dropped by minNum/maxNum, which errs on the side of "touches".
+GDPT_HD bool slab_touches(const RayState &r, float nx, float ny, float nz, float xx, float xy, float xz)
 {
-    const uint32_t idx = r.cur & LINK_INDEX_MASK;
-    const q4f q0 = ldq(sc.wide_nodes, idx * 4u + 0u);
-    const q4f q1 = ldq(sc.wide_nodes, idx * 4u + 1u);
-    const q4f q2 = ldq(sc.wide_nodes, idx * 4u + 2u);
-    const q4u q3 = ldqu(sc.wide_nodes, idx * 4u + 3u);
-    if (TRACE) counters_visit(*tc, q3.z);
+    const float tx1 = (nx - r.o.x) * r.rd.x, tx2 = (xx - r.o.x) * r.rd.x;
+    float tmin = min_num(tx1, tx2), tmax = max_num(tx1, tx2);
+    const float ty1 = (ny - r.o.y) * r.rd.y, ty2 = (xy - r.o.y) * r.rd.y;
+    tmin = max_num(tmin, min_num(ty1, ty2)); tmax = min_num(tmax, max_num(ty1, ty2));
+    const float tz1 = (nz - r.o.z) * r.rd.z, tz2 = (xz - r.o.z) * r.rd.z;
+    tmin = max_num(tmin, min_num(tz1, tz2)); tmax = min_num(tmax, max_num(tz1, tz2));
+    return !(tmax < tmin) && !(tmax < 0.0f);
+}
+
+// The two children of a WideNode record: reference distances, and (CULL) whether each child's
+// culling box is touched.
+template <bool TRACE, bool CULL, class Stack>
+GDPT_HD void visit_wide(const void *table, uint32_t idx, uint32_t tag, RayState &r, Stack &st, TraceCounters *tc)
+{
+    const q4f q0 = ldq(table, idx * 8u + 0u);
+    const q4f q1 = ldq(table, idx * 8u + 1u);
+    const q4f q2 = ldq(table, idx * 8u + 2u);
+    const q4u q3 = ldqu(table, idx * 8u + 3u);
+    if (TRACE) counters_visit(*tc, q3.z | tag);
     const float d1 = slab_test(r, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y);
     const float d2 = slab_test(r, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w);
-    choose_next<TRACE>(r, st, d1, d2, q3.x, q3.y, tc);
+    bool keep_l = true, keep_r = true;
+    if (CULL) {
+        const q4f q4 = ldq(table, idx * 8u + 4u);
+        const q4f q5 = ldq(table, idx * 8u + 5u);
+        const q4f q6 = ldq(table, idx * 8u + 6u);
+        keep_l = slab_touches(r, q4.x, q4.y, q4.z, q4.w, q5.x, q5.y);
+        keep_r = slab_touches(r, q5.z, q5.w, q6.x, q6.y, q6.z, q6.w);
+        if (TRACE) tc->box_tests += 2u; // executed-work accounting: the two extra box tests
+    }
+    choose_next<TRACE>(r, st, d1, d2, q3.x, q3.y, keep_l, keep_r, tc);
+}
+
+// One BLAS internal node (main.glsl:285-300).
+template <bool TRACE, bool CULL, class Stack>
+GDPT_HD void step_blas_internal(const SceneView &sc, RayState &r, Stack &st, TraceCounters *tc)
+{
+    visit_wide<TRACE, CULL>(sc.wide_nodes, r.cur & LINK_INDEX_MASK, 0u, r, st, tc);
 }
 
 // One BLAS leaf (main.glsl:280-284).
@@ -195,9 +226,27 @@ GDPT_HD void step_blas_leaf(const SceneView &sc, RayState &r, Stack &st, TraceCo
     r.cur = stack_pop(r, st);
 }
 
+// Leaf handling split into single-triangle steps, for schedulers that interleave lanes:
+// entering the leaf (visit + range fetch + next link) is merged with its first
+// triangle test; later calls test one more triangle of the pending range.  The
+// next link sits in `cur` but is not processed before the range is exhausted, so
+// every test still sees the hit.t the reference would have at that point.
+template <bool TRACE, class Stack>
+GDPT_HD void step_blas_leaf_one(const SceneView &sc, RayState &r, Stack &st, TraceCounters *tc, uint32_t &tri_next,
+                                uint32_t &tri_end)
+{
+    if (tri_next == tri_end) {
+        const q4u leaf = ldqu(sc.leaf_recs, r.cur & LINK_INDEX_MASK);
+        if (TRACE) { counters_visit(*tc, leaf.z); tc->tri_tests += leaf.y; }
+        tri_next = leaf.x; tri_end = leaf.x + leaf.y;
+        r.cur = stack_pop(r, st);
+    }
+    if (tri_next < tri_end) triangle_test(sc, r, tri_next++);
+}
+
 // One TLAS-level entry: leave the instance we were in (if any), then either
 // enter an instance (main.glsl:316-323) or test the two TLAS children (:330-346).
-template <bool TRACE, class Stack>
+template <bool TRACE, bool CULL, class Stack>
 GDPT_HD void step_tlas(const SceneView &sc, RayState &r, Stack &st, TraceCounters *tc)
 {
     if (r.inst != GDPT_NO_INSTANCE) {
@@ -207,11 +256,11 @@ GDPT_HD void step_tlas(const SceneView &sc, RayState &r, Stack &st, TraceCounter
     }
     const uint32_t idx = r.cur & LINK_INDEX_MASK;
     if (r.cur & LINK_LEAF) {
-        const q4f c0 = ldq(sc.inst_recs, idx * 5u + 0u);
-        const q4f c1 = ldq(sc.inst_recs, idx * 5u + 1u);
-        const q4f c2 = ldq(sc.inst_recs, idx * 5u + 2u);
-        const q4f c3 = ldq(sc.inst_recs, idx * 5u + 3u);
-        const q4u tail = ldqu(sc.inst_recs, idx * 5u + 4u);
+        const q4f c0 = ldq(sc.inst_recs, idx * 7u + 0u);
+        const q4f c1 = ldq(sc.inst_recs, idx * 7u + 1u);
+        const q4f c2 = ldq(sc.inst_recs, idx * 7u + 2u);
+        const q4f c3 = ldq(sc.inst_recs, idx * 7u + 3u);
+        const q4u tail = ldqu(sc.inst_recs, idx * 7u + 4u);
         if (TRACE) {
             counters_visit(*tc, tail.y | GDPT_VISIT_TLAS_TAG);
             tc->tlas_leaves++;
@@ -227,16 +276,17 @@ GDPT_HD void step_tlas(const SceneView &sc, RayState &r, Stack &st, TraceCounter
         r.rd = rcp3(r.d);
         r.inst = idx;
         r.cur = tail.x;
+        if (CULL) {
+            // the BLAS root is never box-tested upstream (main.glsl:274); with culling, an instance whose
+            // true bounds the local ray misses is left again at once (nothing in it can be hit)
+            const q4f tmin4 = ldq(sc.inst_recs, idx * 7u + 5u);
+            const q4f tmax4 = ldq(sc.inst_recs, idx * 7u + 6u);
+            if (TRACE) tc->box_tests += 1u;
+            if (!slab_touches(r, tmin4.x, tmin4.y, tmin4.z, tmax4.x, tmax4.y, tmax4.z)) r.cur = stack_pop(r, st);
+        }
         return;
     }
-    const q4f q0 = ldq(sc.wide_tlas, idx * 4u + 0u);
-    const q4f q1 = ldq(sc.wide_tlas, idx * 4u + 1u);
-    const q4f q2 = ldq(sc.wide_tlas, idx * 4u + 2u);
-    const q4u q3 = ldqu(sc.wide_tlas, idx * 4u + 3u);
-    if (TRACE) counters_visit(*tc, q3.z | GDPT_VISIT_TLAS_TAG);
-    const float d1 = slab_test(r, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y);
-    const float d2 = slab_test(r, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w);
-    choose_next<TRACE>(r, st, d1, d2, q3.x, q3.y, tc);
+    visit_wide<TRACE, CULL>(sc.wide_tlas, idx, GDPT_VISIT_TLAS_TAG, r, st, tc);
 }
 
 GDPT_HD bool link_is_blas_internal(uint32_t l) { return (l & (LINK_TLAS | LINK_LEAF)) == 0u; }
@@ -244,13 +294,25 @@ GDPT_HD bool link_is_blas_leaf(uint32_t l) { return (l & (LINK_TLAS | LINK_LEAF)
 
 // Whole traversal of one ray, one node per iteration (used where no warp-level
 // scheduling is wanted, and by the host-side unit check).
-template <bool TRACE, class Stack>
+template <bool TRACE, bool CULL, class Stack>
 GDPT_HD void trace_ray(const SceneView &sc, RayState &r, Stack &st, TraceCounters *tc)
 {
     while (r.cur != LINK_NONE) {
-        if (link_is_blas_internal(r.cur)) step_blas_internal<TRACE>(sc, r, st, tc);
+        if (link_is_blas_internal(r.cur)) step_blas_internal<TRACE, CULL>(sc, r, st, tc);
         else if (link_is_blas_leaf(r.cur)) step_blas_leaf<TRACE>(sc, r, st, tc);
-        else step_tlas<TRACE>(sc, r, st, tc);
+        else step_tlas<TRACE, CULL>(sc, r, st, tc);
+    }
+}
+
+// Same traversal with leaves taken one triangle per step (the order a phase-voting warp uses).
+template <bool TRACE, bool CULL, class Stack>
+GDPT_HD void trace_ray_stepwise(const SceneView &sc, RayState &r, Stack &st, TraceCounters *tc)
+{
+    uint32_t tri_next = 0, tri_end = 0;
+    while (r.cur != LINK_NONE || tri_next < tri_end) {
+        if (tri_next < tri_end || link_is_blas_leaf(r.cur)) step_blas_leaf_one<TRACE>(sc, r, st, tc, tri_next, tri_end);
+        else if (link_is_blas_internal(r.cur)) step_blas_internal<TRACE, CULL>(sc, r, st, tc);
+        else step_tlas<TRACE, CULL>(sc, r, st, tc);
     }
 }
 

@@ -97,6 +97,7 @@ bool PathTracingCamera::init()
     if (debug_steps_) defines.push_back("#define DEBUG_STEPS");
     if (trace_segments_ > 0) defines.push_back("#define GDPT_TRACE " + std::to_string(trace_segments_));
     if (visits_per_ray_ > 0) defines.push_back("#define GDPT_TRACE_VISITS " + std::to_string(visits_per_ray_));
+    if (cull_ >= 0) defines.push_back("#define GDPT_CULL " + std::to_string(cull_));
     cs_ = new ComputeShader("res://addons/jar_path_tracing/src/shaders/main.glsl", rd_, defines);
 
     render_parameters_rid_ = cs_->create_storage_buffer_uniform(&render_parameters_, sizeof(render_parameters_), 2, 0);

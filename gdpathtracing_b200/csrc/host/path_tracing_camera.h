@@ -70,6 +70,8 @@ public:
     void set_shard(int part, int parts, int band_rows) { shard_part_ = part; shard_parts_ = parts; shard_band_ = band_rows; }
     void set_trace(int segments, uint32_t visits_per_ray) { trace_segments_ = segments; visits_per_ray_ = visits_per_ray; }
     void set_debug_steps(bool on) { debug_steps_ = on; }
+    // -1 backend default (cull when rendering, reference order when tracing), 0 reference order, 1 cull
+    void set_cull(int mode) { cull_ = mode; }
     // true: one gdpt_render_frame call per frame; false: the reference's dispatch-by-dispatch sequence
     void set_fused_frame(bool on) { fused_frame_ = on; }
 
@@ -109,6 +111,7 @@ private:
     int shard_part_ = 0, shard_parts_ = 1, shard_band_ = 4;
     int trace_segments_ = 0; uint32_t visits_per_ray_ = 0;
     bool debug_steps_ = false, fused_frame_ = true;
+    int cull_ = -1;
     uint32_t last_frame_count_ = 0;
 };
 

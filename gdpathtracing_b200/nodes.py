@@ -178,6 +178,10 @@ class PathTracingCamera:
     def set_debug_steps(self, on):
         host.gdpt_camera_set_debug_steps(self._h, 1 if on else 0)
 
+    def set_cull(self, mode):
+        """-1 backend default, 0 reference visit order, 1 tight-box culling (bit-identical results)."""
+        host.gdpt_camera_set_cull(self._h, int(mode))
+
     def set_fused_frame(self, on):
         host.gdpt_camera_set_fused_frame(self._h, 1 if on else 0)
 

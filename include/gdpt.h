@@ -100,6 +100,9 @@ GDPT_API uint32_t gdpt_abi_version(void);
  *   "#define MAX_DEPTH n"      path segments; default 5 = main.glsl:377
  *   "#define GDPT_TRACE"       also emit per-ray parity records (gdpt_shader_read_trace)
  *   "#define GDPT_VARIANT n"   kernel schedule variant; results identical
+ *   "#define GDPT_REFERENCE_ORDER"  visit every node the reference visits (no tight-box culling);
+ *                              results are identical either way, only the work differs.  Implied
+ *                              by GDPT_TRACE unless "#define GDPT_CULL 1" is also given
  * Unknown defines are ignored, as a GLSL compiler would ignore an unused macro. */
 GDPT_API int  gdpt_shader_create(gdpt_device *device, const char *shader_path,
                                  const char *const *args, int n_args,

@@ -77,6 +77,8 @@ GDPT_API void  gdpt_camera_set_frame_index(gdpt_camera_node *c, uint32_t frame_i
 GDPT_API void  gdpt_camera_set_shard(gdpt_camera_node *c, int part, int n_parts, int band_rows);
 GDPT_API void  gdpt_camera_set_trace(gdpt_camera_node *c, int segments, uint32_t visits_per_ray);
 GDPT_API void  gdpt_camera_set_debug_steps(gdpt_camera_node *c, int on);
+/* -1 backend default, 0 reference visit order, 1 tight-box culling (results identical) */
+GDPT_API void  gdpt_camera_set_cull(gdpt_camera_node *c, int mode);
 GDPT_API void  gdpt_camera_set_fused_frame(gdpt_camera_node *c, int on);
 /* init() / render() (path_tracing_camera.cpp:111-232); init returns 1 when check_ready() */
 GDPT_API int   gdpt_camera_init(gdpt_camera_node *c);

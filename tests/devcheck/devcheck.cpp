@@ -27,7 +27,21 @@ struct HostStack {
 };
 } // namespace
 
+static int g_stepwise = 0;
+static int g_cull = 0;
+
+template <bool CULL> static void run_ray(const SceneView &sc, RayState &r, HostStack &st, TraceCounters *tc)
+{
+    if (g_stepwise) trace_ray_stepwise<true, CULL>(sc, r, st, tc);
+    else trace_ray<true, CULL>(sc, r, st, tc);
+}
+
 extern "C" {
+
+// 0: node-at-a-time traversal, 1: leaves split into single-triangle steps (phase-voting order)
+void devcheck_set_stepwise(int on) { g_stepwise = on; }
+// 0: reference visit order, 1: tight-box culling (hit records must not change)
+void devcheck_set_cull(int on) { g_cull = on; }
 
 struct devcheck_scene {
     const void *tri_geom; uint64_t n_tris;
@@ -47,7 +61,8 @@ int devcheck_path_trace(const devcheck_scene *in, const gdpt_render_params *para
 {
     DerivedLayout lay;
     const std::string err = derive_layout((const gdpt_bvh_node *)in->bvh, (uint32_t)in->n_nodes, (const gdpt_blas_instance *)in->blas,
-                                          (uint32_t)in->n_blas, (const gdpt_tlas_node *)in->tlas, (uint32_t)in->n_tlas, lay);
+                                          (uint32_t)in->n_blas, (const gdpt_tlas_node *)in->tlas, (uint32_t)in->n_tlas,
+                                          (const gdpt_triangle_geometry *)in->tri_geom, (uint32_t)in->n_tris, lay);
     if (!err.empty()) return -1;
     SceneView sc;
     std::memset(&sc, 0, sizeof(sc));
@@ -77,7 +92,8 @@ int devcheck_path_trace(const devcheck_scene *in, const gdpt_render_params *para
                 ray_begin(r, sc, o, d);
                 TraceCounters tc;
                 counters_init(tc, (visits && i == 0) ? visits + (size_t)pixel * visits_per_ray : nullptr, visits_per_ray);
-                trace_ray<true>(sc, r, st, &tc);
+                if (g_cull) run_ray<true>(sc, r, st, &tc);
+                else run_ray<false>(sc, r, st, &tc);
                 rays++;
                 const bool hit = r.t < 1e9f;
                 if (trace && i < trace_segments) {

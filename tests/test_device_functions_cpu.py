@@ -35,8 +35,10 @@ def run_devcheck(devcheck, osc, cam_bytes, W, H, depth, segs, vis, debug=False):
     return out, dep, tr, vs, int(rays[0])
 
 
+@pytest.mark.parametrize("stepwise", [0, 1], ids=["node_steps", "triangle_steps"])
 @pytest.mark.parametrize("name,make,W,H,depth,segs,frame", CASES, ids=[c[0] for c in CASES])
-def test_device_functions_match_oracle(devcheck, name, make, W, H, depth, segs, frame):
+def test_device_functions_match_oracle(devcheck, name, make, W, H, depth, segs, frame, stepwise):
+    devcheck.devcheck_set_stepwise(stepwise)
     sc = make()
     grp = scenes.populate(sc)
     grp.build()
@@ -53,6 +55,46 @@ def test_device_functions_match_oracle(devcheck, name, make, W, H, depth, segs, 
     assert np.array_equal(vs, ref["visits"]), "node-visit order differs"
     assert np.array_equal(out, ref["rgba8"])
     assert np.array_equal(dep.view(np.uint32), ref["depth"].view(np.uint32))
+
+
+HIT_FIELDS = ("hit", "triangle", "blas", "front", "t", "u", "v")
+
+
+@pytest.mark.parametrize("stepwise", [0, 1], ids=["node_steps", "triangle_steps"])
+@pytest.mark.parametrize("name,make,W,H,depth,segs,frame", CASES, ids=[c[0] for c in CASES])
+def test_tight_box_culling_changes_no_result(devcheck, name, make, W, H, depth, segs, frame, stepwise):
+    """Culling (pt_scene.cuh) may only shorten the visit list: hit records, ray counts, colour and depth
+    stay bit-identical to the oracle's full reference traversal, and it must actually save work."""
+    devcheck.devcheck_set_stepwise(stepwise)
+    devcheck.devcheck_set_cull(1)
+    try:
+        sc = make()
+        grp = scenes.populate(sc)
+        grp.build()
+        osc = oracle.Scene(grp.buffers(), grp.texture_layers())
+        cam = bytes(nodes.make_camera_block(sc.camera_transform12, sc.fov, W, H, frame))
+        ref = oracle.path_trace(osc, W, H, cam, max_depth=depth, trace_segments=segs)
+        out, dep, tr, _, rays = run_devcheck(devcheck, osc, cam, W, H, depth, segs, 1)
+    finally:
+        devcheck.devcheck_set_cull(0)
+    assert rays == ref["stats"]["rays"]
+    pops_ref = pops_cull = 0
+    for s in range(segs):
+        a, b = tr[s], ref["trace"][s]
+        assert np.array_equal(a["hit"], b["hit"])
+        live = b["hit"] != 0xFFFFFFFF
+        for f in HIT_FIELDS:
+            x, y = a[f][live], b[f][live]
+            if x.dtype == np.float32:
+                x, y = x.view(np.uint32), y.view(np.uint32)
+            assert np.array_equal(x, y), f"segment {s} field {f}"
+        assert (a["tri_tests"][live] <= b["tri_tests"][live]).all() and (a["node_pops"][live] <= b["node_pops"][live]).all()
+        pops_ref += int(b["node_pops"][live].sum()); pops_cull += int(a["node_pops"][live].sum())
+    assert np.array_equal(out, ref["rgba8"])
+    assert np.array_equal(dep.view(np.uint32), ref["depth"].view(np.uint32))
+    if name != "cornell32":  # every Cornell-32 BLAS is a single leaf: nothing to cull below the TLAS
+        assert pops_cull < pops_ref
+    print(f"{name}: node pops {pops_ref} -> {pops_cull}")
 
 
 def test_debug_steps_mode(devcheck):

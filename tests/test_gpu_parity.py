@@ -71,6 +71,42 @@ def test_trace_parity(name, make, W, H, depth, segs):
     assert np.array_equal(cam.read_image("depth").view(np.uint32), ref["depth"].view(np.uint32))
 
 
+@pytest.mark.parametrize("name,make,W,H,depth,segs", CASES, ids=[c[0] for c in CASES])
+def test_culled_traversal_gives_identical_hits(name, make, W, H, depth, segs):
+    """Tight-box culling (the default when rendering) only shortens the visit list: per-segment hit
+    records (hit, triangle, instance, front, t/u/v bits), frame and depth equal the oracle's full traversal."""
+    sc = make()
+    grp = scenes.populate(sc)
+    cam = make_camera(sc, grp, W, H, depth, trace=segs)
+    cam2 = PathTracingCamera()  # same, but instrumented kernels with culling forced on
+    cam2.fov = sc.fov
+    cam2.geometry_group = grp
+    cam2.denoising_mode = PathTracingCamera.NONE
+    cam2.set_window_size(W, H)
+    cam2.set_global_transform(sc.camera_transform12)
+    cam2.set_max_depth(depth)
+    cam2.set_trace(segs, 0)
+    cam2.set_cull(1)
+    cam2.init()
+    frame = cam2.render().copy()
+    st = cam2.stats()
+    ref = oracle.path_trace(oracle_scene(grp), W, H, bytes(cam2.camera_block()), max_depth=depth, trace_segments=segs)
+    assert st["rays"] == ref["stats"]["rays"] and st["primary_hits"] == ref["stats"]["primary_hits"]
+    assert st["node_pops"] <= ref["stats"]["node_pops"] and st["tri_tests"] <= ref["stats"]["tri_tests"]
+    for s in range(segs):
+        a, b = cam2.read_trace(s), ref["trace"][s]
+        assert np.array_equal(a["hit"], b["hit"])
+        live = b["hit"] != 0xFFFFFFFF
+        for f in ("triangle", "blas", "front", "t", "u", "v"):
+            x, y = a[f][live], b[f][live]
+            if x.dtype == np.float32:
+                x, y = x.view(np.uint32), y.view(np.uint32)
+            assert np.array_equal(x, y), f"segment {s} field {f}"
+    assert np.array_equal(frame, ref["rgba8"])
+    assert np.array_equal(cam2.read_image("depth").view(np.uint32), ref["depth"].view(np.uint32))
+    del cam
+
+
 def test_fast_kernels_equal_traced_kernels():
     """The un-instrumented instantiation (the one that is timed) produces the same frame."""
     sc = scenes.demo_scene()
