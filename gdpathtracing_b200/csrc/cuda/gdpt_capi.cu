@@ -246,14 +246,20 @@ int finish_main(gdpt_shader *s)
     if ((rc = dev_alloc(s, &a.queue[1], (size_t)a.queue_cap * 5))) return rc;
     if ((rc = dev_alloc(s, &a.hit_list, (size_t)a.queue_cap))) return rc;
     if ((rc = dev_alloc(s, &a.counters, 1))) return rc;
-    a.schedule = s->variant >= 0 ? s->variant : 1;
-    // culling (pt_scene.cuh) is the default for rendering; parity traces keep the full reference visit order
-    a.cull = s->cull >= 0 ? s->cull : (s->trace_segments > 0 ? 0 : 1);
-    if (const char *e = getenv("GDPT_CULL")) { if (s->cull < 0 && s->trace_segments == 0) a.cull = atoi(e) != 0; }
-    a.refill_below = 24; a.burst = a.schedule == 0 ? 4 : 16;
-    if (const char *e = getenv("GDPT_SCHEDULE")) a.schedule = atoi(e);
+    a.schedule = s->variant >= 0 ? s->variant : 2;
+    if (const char *e = getenv("GDPT_SCHEDULE")) { if (s->variant < 0) a.schedule = atoi(e); }
+    if (a.schedule < 0 || a.schedule > 2) a.schedule = 2;
+    // culling (pt_scene.cuh) is the default for rendering; parity traces and the DEBUG_STEPS heat map
+    // keep the full reference visit order (their output IS the reference's work)
+    const bool observes_work = s->trace_segments > 0 || s->debug_steps;
+    a.cull = s->cull >= 0 ? s->cull : (observes_work ? 0 : 1);
+    if (const char *e = getenv("GDPT_CULL")) { if (s->cull < 0 && !observes_work) a.cull = atoi(e) != 0; }
+    a.refill_below = a.schedule == 2 ? 24 : 20;
+    a.burst = a.schedule == 0 ? 8 : 16;
+    a.shade_at = 8;
     if (const char *e = getenv("GDPT_REFILL_BELOW")) a.refill_below = atoi(e);
     if (const char *e = getenv("GDPT_BURST")) a.burst = atoi(e);
+    if (const char *e = getenv("GDPT_SHADE_AT")) a.shade_at = atoi(e);
     if (a.refill_below < 1) a.refill_below = 1;
     if (a.refill_below > 32) a.refill_below = 32;
     if (a.burst < 1) a.burst = 1;
@@ -295,6 +301,15 @@ int enqueue_k1(gdpt_shader *s)
     const bool timing = s->stage_timing && !s->stage_ev.empty();
     int ev = 0;
     if (timing) GDPT_CUDA(d, cudaEventRecord(s->stage_ev[ev++], d->stream));
+    if (a.schedule == 2) {
+        launch_path(a, trace, d->stream);
+        if (timing) GDPT_CUDA(d, cudaEventRecord(s->stage_ev[ev++], d->stream));
+        s->stage_count = timing ? ev - 1 : 0;
+        GDPT_CUDA(d, cudaGetLastError());
+        s->stats_valid = false;
+        s->stats.kernel_launches = 1;
+        return GDPT_OK;
+    }
     launch_primary(a, trace, d->stream);
     if (timing) GDPT_CUDA(d, cudaEventRecord(s->stage_ev[ev++], d->stream));
     if (!s->debug_steps) {
@@ -334,7 +349,8 @@ int collect_stats(gdpt_shader *s)
     GDPT_CUDA(d, cudaStreamSynchronize(d->stream));
     gdpt_frame_stats &st = s->stats;
     uint64_t rays = (uint64_t)s->args.width * s->args.local_rows;
-    if (!s->debug_steps)
+    if (s->args.schedule == 2) rays = c.rays;
+    else if (!s->debug_steps)
         for (int i = 1; i < s->args.max_depth; i++) rays += c.qcount[i];
     st.rays = rays;
     st.primary_hits = c.primary_hits;

@@ -305,6 +305,165 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(const FrameArgs a, cons
     if (my_overflow) atomicOr(&cnt->overflow, 1u);
 }
 
+// Single-kernel schedule: every lane carries one whole path (main.glsl:372-401) from its camera ray
+// to termination, so there is no barrier between bounces and no queue traffic.  A warp is a small
+// scheduler over five phases -- L (one triangle test), I (one internal node), T (one TLAS-level
+// entry), S (shade the finished segment and start the next, or finish the path) and R (refill idle
+// lanes with new pixels).  Each iteration it executes the one phase that pays most: S once
+// `shade_at` lanes hold a finished ray (or nothing is walking), R once enough lanes are idle,
+// otherwise the traversal phase most lanes are in.
+template <bool TRACE, bool CULL>
+__global__ void __launch_bounds__(kTraceThreads) k_path(const FrameArgs a)
+{
+    __shared__ uint32_t s_stack[kSmemStack * kTraceThreads];
+    __shared__ gdpt_camera s_cam;
+    uint32_t spill[GDPT_MAX_STACK - kSmemStack];
+    SmemStack st;
+    st.col = s_stack + threadIdx.x;
+    st.spill = spill;
+    if (threadIdx.x < sizeof(gdpt_camera) / 4u)
+        reinterpret_cast<uint32_t *>(&s_cam)[threadIdx.x] = reinterpret_cast<const uint32_t *>(a.camera)[threadIdx.x];
+    __syncthreads();
+    const gdpt_camera &cam = s_cam;
+
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lanemask_lt = (1u << lane) - 1u;
+    FrameCounters *cnt = a.counters;
+    const uint32_t total = a.n_work;
+    const int refill_below = max(a.refill_below, 1);
+    const int shade_at = min(max(a.shade_at, 1), 32);
+    const int last_segment = a.debug_steps ? 0 : a.max_depth - 1;
+
+    RayState r;
+    r.cur = LINK_NONE; r.sp = 0; r.overflow = 0; r.t = 1e9f;
+    f3 throughput = mk3(1.0f, 1.0f, 1.0f), radiance = mk3(0.0f, 0.0f, 0.0f);
+    u2 seed; seed.x = seed.y = 0u;
+    uint32_t pixel = 0;
+    int segment = 0;
+    bool has = false;
+    uint32_t tri_next = 0, tri_end = 0;
+    TraceCounters tc;
+    if (TRACE) counters_init(tc, nullptr, 0);
+    uint32_t chunk_next = 0, chunk_end = 0;
+    bool exhausted = (total == 0u);
+    unsigned long long my_rays = 0, my_phits = 0, my_pops = 0, my_boxes = 0, my_tris = 0, my_leaves = 0;
+    uint32_t my_max_stack = 0, my_overflow = 0;
+
+    for (;;) {
+        const bool in_l = has && (tri_next < tri_end || link_is_blas_leaf(r.cur));
+        const bool in_i = has && !in_l && link_is_blas_internal(r.cur);
+        const bool in_t = has && !in_l && !in_i && r.cur != LINK_NONE;
+        const bool fin = has && !in_l && !in_i && !in_t;
+        const int n_l = __popc(__ballot_sync(kFull, in_l)), n_i = __popc(__ballot_sync(kFull, in_i)),
+                  n_t = __popc(__ballot_sync(kFull, in_t)), n_fin = __popc(__ballot_sync(kFull, fin));
+        const unsigned idle = __ballot_sync(kFull, !has);
+        const int n_walk = n_l + n_i + n_t, n_idle = __popc(idle);
+
+        if (n_fin > 0 && (n_fin >= shade_at || n_walk == 0)) {
+            // ---------------- S: finish a segment ----------------
+            if (fin) {
+                const bool hit = r.t < 1e9f;
+                my_rays++;
+                if (segment == 0 && hit) my_phits++;
+                if (TRACE) {
+                    write_trace_record(a, segment, pixel, r, tc);
+                    my_pops += tc.node_pops; my_boxes += tc.box_tests; my_tris += tc.tri_tests; my_leaves += tc.tlas_leaves;
+                    if (tc.max_stack > my_max_stack) my_max_stack = tc.max_stack;
+                }
+                my_overflow |= r.overflow;
+                bool alive = false;
+                if (a.debug_steps) { // main.glsl:358-361,423-427
+                    float e = TRACE ? (float)tc.tri_tests / 256.0f : 0.0f;
+                    e = e < 0.0f ? 0.0f : (e > 1.0f ? 1.0f : e);
+                    radiance = mk3(e, e, e);
+                    a.out_depth[pixel] = encode_depth(cam, cam.z_far);
+                } else if (!hit) {
+                    radiance = radiance + throughput * sample_sky(r.wd);
+                    if (segment == 0) a.out_depth[pixel] = encode_depth(cam, cam.z_far);
+                } else {
+                    const BounceResult br = shade_and_bounce(a.sc, r.wo, r.wd, r.t, r.u, r.v, r.tri, r.blas_front, radiance,
+                                                             throughput, seed);
+                    radiance = br.radiance;
+                    if (segment == 0) a.out_depth[pixel] = encode_depth(cam, br.first_hit_distance);
+                    alive = br.alive && segment < last_segment;
+                    if (alive) {
+                        throughput = br.throughput;
+                        ray_begin(r, a.sc, br.next_o, br.next_d);
+                        segment++;
+                        if (TRACE) counters_init(tc, nullptr, 0);
+                    }
+                }
+                if (!alive) {
+                    a.out_rgba8[pixel] = pack_rgba8(radiance);
+                    has = false;
+                }
+            }
+            continue;
+        }
+        if (!exhausted && n_idle > 0 && (32 - n_idle < refill_below || n_walk + n_fin == 0)) {
+            // ---------------- R: new camera rays for idle lanes ----------------
+            if (chunk_next == chunk_end) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(&cnt->cursor[0], kChunkPrimary);
+                base = __shfl_sync(kFull, base, 0);
+                if (base >= total) { exhausted = true; continue; }
+                chunk_next = base;
+                chunk_end = min(base + kChunkPrimary, total);
+            }
+            const uint32_t avail = chunk_end - chunk_next;
+            const uint32_t rank = __popc(idle & lanemask_lt);
+            if (!has && rank < avail) {
+                int px, py;
+                if (work_to_pixel(a, chunk_next + rank, &px, &py)) {
+                    f3 o, d;
+                    seed = generate_primary_ray(cam, a.width, a.height, px, py, &o, &d);
+                    pixel = (uint32_t)py * (uint32_t)a.width + (uint32_t)px;
+                    throughput = mk3(1.0f, 1.0f, 1.0f); radiance = mk3(0.0f, 0.0f, 0.0f);
+                    segment = 0;
+                    ray_begin(r, a.sc, o, d);
+                    has = true;
+                    if (TRACE) counters_init(tc, a.visits ? a.visits + (size_t)pixel * a.visits_per_ray : nullptr, a.visits_per_ray);
+                }
+            }
+            chunk_next += min((uint32_t)n_idle, avail);
+            continue;
+        }
+        if (n_walk == 0) {
+            if (exhausted && n_fin == 0) break;
+            continue;
+        }
+        // ---------------- L / I / T: one traversal step of the most popular phase ----------------
+        if (n_l >= n_i && n_l >= n_t) {
+            if (in_l) step_blas_leaf_one<TRACE>(a.sc, r, st, &tc, tri_next, tri_end);
+        } else if (n_i >= n_t) {
+            if (in_i) step_blas_internal<TRACE, CULL>(a.sc, r, st, &tc);
+        } else {
+            if (in_t) step_tlas<TRACE, CULL>(a.sc, r, st, &tc);
+        }
+    }
+
+    for (int off = 16; off > 0; off >>= 1) {
+        my_rays += __shfl_down_sync(kFull, my_rays, off);
+        my_phits += __shfl_down_sync(kFull, my_phits, off);
+    }
+    if (lane == 0) { atomicAdd(&cnt->rays, my_rays); atomicAdd(&cnt->primary_hits, my_phits); }
+    if (TRACE) {
+        for (int off = 16; off > 0; off >>= 1) {
+            my_pops += __shfl_down_sync(kFull, my_pops, off);
+            my_boxes += __shfl_down_sync(kFull, my_boxes, off);
+            my_tris += __shfl_down_sync(kFull, my_tris, off);
+            my_leaves += __shfl_down_sync(kFull, my_leaves, off);
+            my_max_stack = max(my_max_stack, __shfl_down_sync(kFull, my_max_stack, off));
+        }
+        if (lane == 0) {
+            atomicAdd(&cnt->node_pops, my_pops); atomicAdd(&cnt->box_tests, my_boxes);
+            atomicAdd(&cnt->tri_tests, my_tris); atomicAdd(&cnt->tlas_leaves, my_leaves);
+            atomicMax(&cnt->max_stack, my_max_stack);
+        }
+    }
+    if (my_overflow) atomicOr(&cnt->overflow, 1u);
+}
+
 // shade(segment): entries come from queue `src` (through the hit list for segment > 0),
 // continuation rays go to queue `src ^ 1`.
 __global__ void __launch_bounds__(kShadeThreads) k_shade(const FrameArgs a, const int segment, const int src)
@@ -412,6 +571,7 @@ struct Shapes {
     bool ready = false;
     int sms = 148;
     int trace_blocks[2][2][2] = {}; // [TRACE][MODE][CULL]
+    int path_blocks[2][2] = {};     // [TRACE][CULL]
     int shade_blocks = 0;
     int prog_blocks = 0;
 };
@@ -451,6 +611,10 @@ void init_launch_shapes(int device)
     s.trace_blocks[1][0][0] = trace_grid<true, 0, false>(s.sms); s.trace_blocks[1][0][1] = trace_grid<true, 0, true>(s.sms);
     s.trace_blocks[1][1][0] = trace_grid<true, 1, false>(s.sms); s.trace_blocks[1][1][1] = trace_grid<true, 1, true>(s.sms);
     int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_path<false, false>, kTraceThreads, 0); s.path_blocks[0][0] = s.sms * (per_sm > 0 ? per_sm : 1);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_path<false, true>, kTraceThreads, 0); s.path_blocks[0][1] = s.sms * (per_sm > 0 ? per_sm : 1);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_path<true, false>, kTraceThreads, 0); s.path_blocks[1][0] = s.sms * (per_sm > 0 ? per_sm : 1);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_path<true, true>, kTraceThreads, 0); s.path_blocks[1][1] = s.sms * (per_sm > 0 ? per_sm : 1);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_shade, kShadeThreads, 0); s.shade_blocks = s.sms * (per_sm > 0 ? per_sm : 1);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_progressive, 256, 0); s.prog_blocks = s.sms * (per_sm > 0 ? per_sm : 1);
     s.ready = true;
@@ -462,6 +626,20 @@ static Shapes &shapes_for_current_device()
     cudaGetDevice(&dev);
     init_launch_shapes(dev);
     return g_shapes[dev & 15];
+}
+
+void launch_path(const FrameArgs &a, bool trace, cudaStream_t s)
+{
+    Shapes &sh = shapes_for_current_device();
+    const bool cull = a.cull != 0;
+    const int blocks = sh.path_blocks[trace ? 1 : 0][cull ? 1 : 0];
+    if (trace) {
+        if (cull) k_path<true, true><<<blocks, kTraceThreads, 0, s>>>(a);
+        else k_path<true, false><<<blocks, kTraceThreads, 0, s>>>(a);
+    } else {
+        if (cull) k_path<false, true><<<blocks, kTraceThreads, 0, s>>>(a);
+        else k_path<false, false><<<blocks, kTraceThreads, 0, s>>>(a);
+    }
 }
 
 void launch_primary(const FrameArgs &a, bool trace, cudaStream_t s)

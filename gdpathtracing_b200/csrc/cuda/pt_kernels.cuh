@@ -17,6 +17,7 @@ struct FrameCounters {
     uint32_t max_stack;
     uint32_t overflow;                  // a ray exceeded the reference's stack capacity
     unsigned long long primary_hits;
+    unsigned long long rays;            // ray_trace() calls, counted by the single-kernel schedule
     unsigned long long node_pops, box_tests, tri_tests, tlas_leaves; // TRACE builds only
 };
 
@@ -40,7 +41,8 @@ struct FrameArgs {
     // scheduling knobs (results do not depend on them)
     int refill_below;  // refill idle lanes when fewer than this many lanes are traversing
     int burst;         // node steps between refill checks
-    int schedule;      // 0: while-while descent, 1: phase voting (see k_trace)
+    int schedule;      // 0: wavefront + while-while descent, 1: wavefront + phase voting, 2: single path kernel
+    int shade_at;      // schedule 2: shade once this many lanes wait with a finished ray
     int cull;          // 1: skip children whose tight box the ray misses (pt_scene.cuh); results identical
     // parity outputs (TRACE builds only)
     gdpt_trace_record *trace; int trace_segments;
@@ -51,6 +53,8 @@ struct FrameArgs {
 struct LaunchShape { int blocks; int threads; };
 
 // K1 stages.  `trace` selects the instrumented instantiation.
+// Single-kernel schedule (a.schedule == 2): whole paths per lane, no stage barriers.
+void launch_path(const FrameArgs &a, bool trace, cudaStream_t s);
 void launch_primary(const FrameArgs &a, bool trace, cudaStream_t s);
 void launch_shade(const FrameArgs &a, int segment, cudaStream_t s);
 void launch_trace(const FrameArgs &a, int segment, bool trace, cudaStream_t s);
