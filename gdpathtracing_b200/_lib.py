@@ -96,6 +96,8 @@ CUDA_API = [
     ("gdpt_shader_get_stats", c_int, [c_void_p, POINTER(FrameStats)]),
     ("gdpt_shader_set_stage_timing", c_int, [c_void_p, c_int]),
     ("gdpt_shader_get_stage_times", c_int, [c_void_p, c_void_p, c_int]),
+    ("gdpt_shader_set_warp_profile", c_int, [c_void_p, c_int]),
+    ("gdpt_shader_read_warp_profile", ctypes.c_int64, [c_void_p, c_void_p, c_uint64]),
     ("gdpt_shader_read_trace", c_int, [c_void_p, c_int, c_void_p, c_uint64]),
     ("gdpt_shader_read_visits", c_int, [c_void_p, c_void_p, c_uint32, c_uint64]),
 ]

@@ -68,6 +68,8 @@ struct gdpt_shader {
     int shard_part = 0, shard_parts = 1, shard_band = 4;
     gdpt_frame_stats stats;
     bool stats_valid = false;
+    bool warp_profile = false;          // per-warp schedule profile of the path kernel
+    size_t warp_prof_warps = 0;
     bool stage_timing = false;          // record an event between the K1 stage launches
     std::vector<cudaEvent_t> stage_ev;  // 2*max_depth + 1 events when enabled
     int stage_count = 0;
@@ -192,6 +194,17 @@ void compute_shard(gdpt_shader *s)
     a.n_work = tiles_x * tiles_y * 32u;
 }
 
+int alloc_warp_profile(gdpt_shader *s)
+{
+    FrameArgs &a = s->args;
+    if (a.warp_prof || a.schedule < 2) return GDPT_OK;
+    s->warp_prof_warps = path_kernel_warps(a);
+    int rc = dev_alloc(s, &a.warp_prof, s->warp_prof_warps * 8);
+    if (rc) return rc;
+    GDPT_CUDA(s->dev, cudaMemsetAsync(a.warp_prof, 0, s->warp_prof_warps * 8 * sizeof(unsigned long long), s->dev->stream));
+    return GDPT_OK;
+}
+
 int finish_main(gdpt_shader *s)
 {
     gdpt_device *d = s->dev;
@@ -244,22 +257,38 @@ int finish_main(gdpt_shader *s)
     a.queue_cap = (uint32_t)((size_t)rp.width * rp.height);
     if ((rc = dev_alloc(s, &a.queue[0], (size_t)a.queue_cap * 5))) return rc;
     if ((rc = dev_alloc(s, &a.queue[1], (size_t)a.queue_cap * 5))) return rc;
-    if ((rc = dev_alloc(s, &a.hit_list, (size_t)a.queue_cap))) return rc;
+    a.heavy_cap = a.queue_cap / 8u > 1024u ? a.queue_cap / 8u : 1024u;
+    if ((rc = dev_alloc(s, &a.hit_list, (size_t)a.queue_cap + (size_t)(kCostClasses - 1) * a.heavy_cap))) return rc;
+    if ((rc = dev_alloc(s, &a.cost, (size_t)a.queue_cap))) return rc;
+    GDPT_CUDA(d, cudaMemsetAsync(a.cost, 0, (size_t)a.queue_cap * sizeof(uint32_t), d->stream));
     if ((rc = dev_alloc(s, &a.counters, 1))) return rc;
-    a.schedule = s->variant >= 0 ? s->variant : 2;
+    a.schedule = s->variant >= 0 ? s->variant : 3;
     if (const char *e = getenv("GDPT_SCHEDULE")) { if (s->variant < 0) a.schedule = atoi(e); }
-    if (a.schedule < 0 || a.schedule > 2) a.schedule = 2;
+    if (a.schedule < 0 || a.schedule > 4) a.schedule = 3;
     // culling (pt_scene.cuh) is the default for rendering; parity traces and the DEBUG_STEPS heat map
     // keep the full reference visit order (their output IS the reference's work)
     const bool observes_work = s->trace_segments > 0 || s->debug_steps;
     a.cull = s->cull >= 0 ? s->cull : (observes_work ? 0 : 1);
     if (const char *e = getenv("GDPT_CULL")) { if (s->cull < 0 && !observes_work) a.cull = atoi(e) != 0; }
-    a.refill_below = a.schedule == 2 ? 24 : 20;
+    // the classification kernel is a tight-box test and writes no parity records
+    if (a.schedule >= 3 && (!a.cull || observes_work)) a.schedule = 2;
+    a.mux_k = 2;
+    if (const char *e = getenv("GDPT_MUX_K")) a.mux_k = atoi(e);
+    if (a.mux_k < 1 || a.mux_k > 4) a.mux_k = 2;
+    init_launch_shapes(d->ordinal);
+    if (a.schedule == 4 && (rc = dev_alloc(s, &a.path_recs, mux_path_record_quads()))) return rc;
+    a.refill_below = a.schedule >= 2 ? 24 : 20;
     a.burst = a.schedule == 0 ? 8 : 16;
     a.shade_at = 8;
     if (const char *e = getenv("GDPT_REFILL_BELOW")) a.refill_below = atoi(e);
     if (const char *e = getenv("GDPT_BURST")) a.burst = atoi(e);
     if (const char *e = getenv("GDPT_SHADE_AT")) a.shade_at = atoi(e);
+    a.blocks_per_sm = 0;
+    if (const char *e = getenv("GDPT_BLOCKS_PER_SM")) a.blocks_per_sm = atoi(e);
+    a.path_minb = 4;
+    if (const char *e = getenv("GDPT_PATH_MINB")) a.path_minb = atoi(e);
+    a.lead_min = 0;
+    if (const char *e = getenv("GDPT_LEAD_MIN")) a.lead_min = atoi(e);
     if (a.refill_below < 1) a.refill_below = 1;
     if (a.refill_below > 32) a.refill_below = 32;
     if (a.burst < 1) a.burst = 1;
@@ -272,7 +301,7 @@ int finish_main(gdpt_shader *s)
         if (s->visits_per_ray > 0 && (rc = dev_alloc(s, &a.visits, (size_t)rp.width * rp.height * s->visits_per_ray))) return rc;
     }
     compute_shard(s);
-    init_launch_shapes(d->ordinal);
+    if (s->warp_profile) return alloc_warp_profile(s);
     return GDPT_OK;
 }
 
@@ -301,13 +330,20 @@ int enqueue_k1(gdpt_shader *s)
     const bool timing = s->stage_timing && !s->stage_ev.empty();
     int ev = 0;
     if (timing) GDPT_CUDA(d, cudaEventRecord(s->stage_ev[ev++], d->stream));
-    if (a.schedule == 2) {
-        launch_path(a, trace, d->stream);
+    if (a.schedule >= 2) {
+        if (a.schedule >= 3) {
+            launch_primary_cull(a, d->stream);
+            if (timing) GDPT_CUDA(d, cudaEventRecord(s->stage_ev[ev++], d->stream));
+            if (a.schedule == 4) launch_path_mux(a, d->stream);
+            else launch_path_list(a, trace, d->stream);
+        } else {
+            launch_path(a, trace, d->stream);
+        }
         if (timing) GDPT_CUDA(d, cudaEventRecord(s->stage_ev[ev++], d->stream));
         s->stage_count = timing ? ev - 1 : 0;
         GDPT_CUDA(d, cudaGetLastError());
         s->stats_valid = false;
-        s->stats.kernel_launches = 1;
+        s->stats.kernel_launches = (uint32_t)k1_launch_count(a.schedule, a.max_depth, s->debug_steps);
         return GDPT_OK;
     }
     launch_primary(a, trace, d->stream);
@@ -325,7 +361,7 @@ int enqueue_k1(gdpt_shader *s)
     s->stage_count = timing ? ev - 1 : 0;
     GDPT_CUDA(d, cudaGetLastError());
     s->stats_valid = false;
-    s->stats.kernel_launches = (uint32_t)k1_launch_count(a.max_depth, s->debug_steps);
+    s->stats.kernel_launches = (uint32_t)k1_launch_count(a.schedule, a.max_depth, s->debug_steps);
     return GDPT_OK;
 }
 
@@ -349,7 +385,7 @@ int collect_stats(gdpt_shader *s)
     GDPT_CUDA(d, cudaStreamSynchronize(d->stream));
     gdpt_frame_stats &st = s->stats;
     uint64_t rays = (uint64_t)s->args.width * s->args.local_rows;
-    if (s->args.schedule == 2) rays = c.rays;
+    if (s->args.schedule >= 2) rays = c.rays;
     else if (!s->debug_steps)
         for (int i = 1; i < s->args.max_depth; i++) rays += c.qcount[i];
     st.rays = rays;
@@ -735,6 +771,28 @@ int gdpt_shader_set_stage_timing(gdpt_shader *s, int on)
     }
     s->stage_timing = on != 0;
     return GDPT_OK;
+}
+
+int gdpt_shader_set_warp_profile(gdpt_shader *s, int on)
+{
+    if (!s || s->kind != SHADER_MAIN) return GDPT_ERR_INVALID_ARG;
+    s->warp_profile = on != 0;
+    if (!on) { s->args.warp_prof = nullptr; return GDPT_OK; } // the allocation stays with the shader
+    if (s->uniforms_ready) { cudaSetDevice(s->dev->ordinal); return alloc_warp_profile(s); }
+    return GDPT_OK;
+}
+
+int64_t gdpt_shader_read_warp_profile(gdpt_shader *s, uint64_t *out, uint64_t capacity_words)
+{
+    if (!s || !out || s->kind != SHADER_MAIN) return GDPT_ERR_INVALID_ARG;
+    gdpt_device *d = s->dev;
+    if (!gdpt_shader_check_ready(s) || !s->args.warp_prof) return fail(d, GDPT_ERR_NOT_READY, "warp profile is not enabled for this shader");
+    const size_t words = s->warp_prof_warps * 8;
+    if (capacity_words < words) return fail(d, GDPT_ERR_INVALID_ARG, "warp profile needs %llu words", (unsigned long long)words);
+    cudaSetDevice(d->ordinal);
+    GDPT_CUDA(d, cudaMemcpyAsync(out, s->args.warp_prof, words * sizeof(uint64_t), cudaMemcpyDeviceToHost, d->stream));
+    GDPT_CUDA(d, cudaStreamSynchronize(d->stream));
+    return (int64_t)s->warp_prof_warps;
 }
 
 int gdpt_shader_get_stage_times(gdpt_shader *s, float *out_ms, int capacity)

@@ -36,6 +36,8 @@ constexpr int kShadeThreads = 128;
 constexpr unsigned kFull = 0xFFFFFFFFu;
 constexpr uint32_t kChunkPrimary = 32; // one 8x4-pixel tile: small chunks keep the expensive tiles spread over many warps
 constexpr uint32_t kChunkBounce = 32;
+constexpr uint32_t kChunkHeavy = 4;  // work items taken at a time while the long-path classes last
+constexpr int kLeafTris = 4;         // triangle tests per leaf step of the path kernel
 
 struct SmemStack {
     uint32_t *col;   // this thread's column of the CTA's shared stack array
@@ -66,6 +68,62 @@ __device__ __forceinline__ bool work_to_pixel(const FrameArgs &a, uint32_t w, in
     *px = lx; *py = y;
     return true;
 }
+
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Optional out-of-line form of the cold code (shading, ray generation).  Measured on the demo frame:
+// the call ABI's register spills cost more (k_path 1.67 -> 2.04 ms) than the smaller hot-loop
+// footprint saves, so it is off; kept for the compact-loop rework.
+constexpr bool kOutOfLineCold = false;
+__device__ __noinline__ void shade_and_bounce_ool(const SceneView *sc, const f3 *wo, const f3 *wd, float t, float u, float v,
+                                                  uint32_t tri, uint32_t blas_front, const f3 *radiance, const f3 *throughput,
+                                                  u2 *seed, BounceResult *out)
+{
+    *out = shade_and_bounce(*sc, *wo, *wd, t, u, v, tri, blas_front, *radiance, *throughput, *seed);
+}
+__device__ __noinline__ void generate_primary_ray_ool(const gdpt_camera *cam, int width, int height, int px, int py, f3 *o, f3 *d,
+                                                      u2 *seed)
+{
+    *seed = generate_primary_ray(*cam, width, height, px, py, o, d);
+}
+
+__device__ __forceinline__ uint32_t class_base(const FrameArgs &a, int c)
+{
+    return c == 0 ? 0u : a.queue_cap + (uint32_t)(c - 1) * a.heavy_cap;
+}
+__device__ __forceinline__ int cost_class(uint32_t cost)
+{
+    return cost >= 1024u ? 4 : (cost >= 512u ? 3 : (cost >= 256u ? 2 : (cost >= 128u ? 1 : 0)));
+}
+// Work item w of the survivor lists, heaviest class first.  end[c] = items in classes >= c... see k_path.
+struct SurvivorLists {
+    uint32_t n[kCostClasses];
+    uint32_t total, heavy_total;
+    __device__ __forceinline__ void load(const FrameArgs &a)
+    {
+        total = 0u;
+#pragma unroll
+        for (int c = 0; c < kCostClasses; c++) {
+            n[c] = min(a.counters->qcount[c], c == 0 ? a.queue_cap : a.heavy_cap);
+            total += n[c];
+        }
+        heavy_total = total - n[0];
+    }
+    __device__ __forceinline__ uint32_t pixel(const FrameArgs &a, uint32_t w) const
+    {
+#pragma unroll
+        for (int c = kCostClasses - 1; c > 0; c--) {
+            if (w < n[c]) return a.hit_list[class_base(a, c) + w];
+            w -= n[c];
+        }
+        return a.hit_list[w];
+    }
+};
 
 __device__ __forceinline__ float4 *plane(const FrameArgs &a, int q, int p) { return a.queue[q] + (size_t)p * a.queue_cap; }
 
@@ -312,8 +370,11 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(const FrameArgs a, cons
 // lanes with new pixels).  Each iteration it executes the one phase that pays most: S once
 // `shade_at` lanes hold a finished ray (or nothing is walking), R once enough lanes are idle,
 // otherwise the traversal phase most lanes are in.
-template <bool TRACE, bool CULL>
-__global__ void __launch_bounds__(kTraceThreads) k_path(const FrameArgs a)
+//
+// SRC 0: work items are 8x4-pixel tiles of the whole (sharded) image.  SRC 1: work items are the
+// pixels k_primary_cull left in `hit_list` (camera rays that touch some instance's tight box).
+template <bool TRACE, bool CULL, int SRC, int MINB = 4>
+__global__ void __launch_bounds__(kTraceThreads, MINB) k_path(const FrameArgs a)
 {
     __shared__ uint32_t s_stack[kSmemStack * kTraceThreads];
     __shared__ gdpt_camera s_cam;
@@ -329,9 +390,14 @@ __global__ void __launch_bounds__(kTraceThreads) k_path(const FrameArgs a)
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lanemask_lt = (1u << lane) - 1u;
     FrameCounters *cnt = a.counters;
-    const uint32_t total = a.n_work;
+    SurvivorLists lists;
+    if (SRC == 1) lists.load(a);
+    const uint32_t total = (SRC == 0) ? a.n_work : lists.total;
     const int refill_below = max(a.refill_below, 1);
     const int shade_at = min(max(a.shade_at, 1), 32);
+    const uint32_t lead_min = a.lead_min > 0 ? (uint32_t)a.lead_min : 0xFFFFFFFFu;
+    uint32_t steps = 0; // scheduler iterations this lane's current path took part in
+    bool heavy_done = false; // warp-uniform: the heavy classes are handed out
     const int last_segment = a.debug_steps ? 0 : a.max_depth - 1;
 
     RayState r;
@@ -348,6 +414,9 @@ __global__ void __launch_bounds__(kTraceThreads) k_path(const FrameArgs a)
     bool exhausted = (total == 0u);
     unsigned long long my_rays = 0, my_phits = 0, my_pops = 0, my_boxes = 0, my_tris = 0, my_leaves = 0;
     uint32_t my_max_stack = 0, my_overflow = 0;
+    const bool prof = a.warp_prof != nullptr;
+    const unsigned long long t_start = prof ? global_ns() : 0ull;
+    uint32_t it_i = 0, it_l = 0, it_t = 0, it_f = 0, it_e = 0, n_started = 0;
 
     for (;;) {
         const bool in_l = has && (tri_next < tri_end || link_is_blas_leaf(r.cur));
@@ -358,9 +427,21 @@ __global__ void __launch_bounds__(kTraceThreads) k_path(const FrameArgs a)
                   n_t = __popc(__ballot_sync(kFull, in_t)), n_fin = __popc(__ballot_sync(kFull, fin));
         const unsigned idle = __ballot_sync(kFull, !has);
         const int n_walk = n_l + n_i + n_t, n_idle = __popc(idle);
+        // critical-path-first: once some path is long, the longest one picks the phase, so the path
+        // that decides when the kernel ends moves every iteration
+        int lead_phase = -1; // 0 L, 1 I, 2 T, 3 finished
+        {
+            const uint32_t key = has ? steps : 0u;
+            const uint32_t most = __reduce_max_sync(kFull, key);
+            if (most >= lead_min) {
+                const unsigned who = __ballot_sync(kFull, has && steps == most);
+                lead_phase = __shfl_sync(kFull, in_l ? 0 : (in_i ? 1 : (in_t ? 2 : 3)), __ffs(who) - 1);
+            }
+        }
 
-        if (n_fin > 0 && (n_fin >= shade_at || n_walk == 0)) {
+        if (n_fin > 0 && (n_fin >= shade_at || n_walk == 0 || lead_phase == 3)) {
             // ---------------- S: finish a segment ----------------
+            it_f++;
             if (fin) {
                 const bool hit = r.t < 1e9f;
                 my_rays++;
@@ -381,8 +462,9 @@ __global__ void __launch_bounds__(kTraceThreads) k_path(const FrameArgs a)
                     radiance = radiance + throughput * sample_sky(r.wd);
                     if (segment == 0) a.out_depth[pixel] = encode_depth(cam, cam.z_far);
                 } else {
-                    const BounceResult br = shade_and_bounce(a.sc, r.wo, r.wd, r.t, r.u, r.v, r.tri, r.blas_front, radiance,
-                                                             throughput, seed);
+                    BounceResult br;
+                    if (TRACE || !kOutOfLineCold) br = shade_and_bounce(a.sc, r.wo, r.wd, r.t, r.u, r.v, r.tri, r.blas_front, radiance, throughput, seed);
+                    else shade_and_bounce_ool(&a.sc, &r.wo, &r.wd, r.t, r.u, r.v, r.tri, r.blas_front, &radiance, &throughput, &seed, &br);
                     radiance = br.radiance;
                     if (segment == 0) a.out_depth[pixel] = encode_depth(cam, br.first_hit_distance);
                     alive = br.alive && segment < last_segment;
@@ -395,6 +477,7 @@ __global__ void __launch_bounds__(kTraceThreads) k_path(const FrameArgs a)
                 }
                 if (!alive) {
                     a.out_rgba8[pixel] = pack_rgba8(radiance);
+                    if (SRC == 1) a.cost[pixel] = steps;
                     has = false;
                 }
             }
@@ -402,29 +485,54 @@ __global__ void __launch_bounds__(kTraceThreads) k_path(const FrameArgs a)
         }
         if (!exhausted && n_idle > 0 && (32 - n_idle < refill_below || n_walk + n_fin == 0)) {
             // ---------------- R: new camera rays for idle lanes ----------------
+            it_e++;
             if (chunk_next == chunk_end) {
-                uint32_t base = 0;
-                if (lane == 0) base = atomicAdd(&cnt->cursor[0], kChunkPrimary);
+                uint32_t base = 0, len = kChunkPrimary;
+                if (lane == 0) {
+                    if (SRC == 1 && !heavy_done) { // the long paths (front of the survivor order) are dealt a few per warp
+                        base = atomicAdd(&cnt->cursor[0], kChunkHeavy);
+                        len = kChunkHeavy;
+                        if (base >= lists.heavy_total) base = 0xFFFFFFFFu;
+                        else if (base + len > lists.heavy_total) len = lists.heavy_total - base;
+                    }
+                    if (SRC == 0 || heavy_done || base == 0xFFFFFFFFu) {
+                        const uint32_t first = (SRC == 1) ? lists.heavy_total : 0u;
+                        base = first + atomicAdd(&cnt->cursor[1], kChunkPrimary);
+                        len = kChunkPrimary | 0x80000000u; // flag: came from the light cursor
+                    }
+                }
                 base = __shfl_sync(kFull, base, 0);
+                len = __shfl_sync(kFull, len, 0);
+                if (len & 0x80000000u) { heavy_done = true; len &= 0x7FFFFFFFu; }
                 if (base >= total) { exhausted = true; continue; }
                 chunk_next = base;
-                chunk_end = min(base + kChunkPrimary, total);
+                chunk_end = min(base + len, total);
             }
             const uint32_t avail = chunk_end - chunk_next;
             const uint32_t rank = __popc(idle & lanemask_lt);
             if (!has && rank < avail) {
-                int px, py;
-                if (work_to_pixel(a, chunk_next + rank, &px, &py)) {
+                int px = 0, py = 0;
+                bool valid;
+                if (SRC == 0) valid = work_to_pixel(a, chunk_next + rank, &px, &py);
+                else {
+                    const uint32_t p = lists.pixel(a, chunk_next + rank);
+                    py = (int)(p / (uint32_t)a.width); px = (int)(p - (uint32_t)py * (uint32_t)a.width);
+                    valid = true;
+                }
+                if (valid) {
                     f3 o, d;
-                    seed = generate_primary_ray(cam, a.width, a.height, px, py, &o, &d);
+                    if (TRACE || !kOutOfLineCold) seed = generate_primary_ray(cam, a.width, a.height, px, py, &o, &d);
+                    else generate_primary_ray_ool(&cam, a.width, a.height, px, py, &o, &d, &seed);
                     pixel = (uint32_t)py * (uint32_t)a.width + (uint32_t)px;
                     throughput = mk3(1.0f, 1.0f, 1.0f); radiance = mk3(0.0f, 0.0f, 0.0f);
                     segment = 0;
+                    steps = 0;
                     ray_begin(r, a.sc, o, d);
                     has = true;
                     if (TRACE) counters_init(tc, a.visits ? a.visits + (size_t)pixel * a.visits_per_ray : nullptr, a.visits_per_ray);
                 }
             }
+            n_started += min((uint32_t)n_idle, avail);
             chunk_next += min((uint32_t)n_idle, avail);
             continue;
         }
@@ -432,14 +540,23 @@ __global__ void __launch_bounds__(kTraceThreads) k_path(const FrameArgs a)
             if (exhausted && n_fin == 0) break;
             continue;
         }
-        // ---------------- L / I / T: one traversal step of the most popular phase ----------------
-        if (n_l >= n_i && n_l >= n_t) {
-            if (in_l) step_blas_leaf_one<TRACE>(a.sc, r, st, &tc, tri_next, tri_end);
-        } else if (n_i >= n_t) {
-            if (in_i) step_blas_internal<TRACE, CULL>(a.sc, r, st, &tc);
+        // ---------------- L / I / T: one traversal step of the leading path's phase, else the most popular ----------------
+        int run = (n_l >= n_i && n_l >= n_t) ? 0 : (n_i >= n_t ? 1 : 2);
+        if (lead_phase >= 0 && lead_phase < 3) run = lead_phase;
+        if (run == 0) {
+            it_l++;
+            if (in_l) { step_blas_leaf_some<TRACE, kLeafTris>(a.sc, r, st, &tc, tri_next, tri_end); steps++; }
+        } else if (run == 1) {
+            it_i++;
+            if (in_i) { step_blas_internal<TRACE, CULL>(a.sc, r, st, &tc); steps++; }
         } else {
-            if (in_t) step_tlas<TRACE, CULL>(a.sc, r, st, &tc);
+            it_t++;
+            if (in_t) { step_tlas<TRACE, CULL>(a.sc, r, st, &tc); steps++; }
         }
+    }
+    if (prof && lane == 0) {
+        unsigned long long *w = a.warp_prof + (size_t)((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 8u;
+        w[0] = t_start; w[1] = global_ns(); w[2] = it_i; w[3] = it_l; w[4] = it_t; w[5] = it_f; w[6] = it_e; w[7] = n_started;
     }
 
     for (int off = 16; off > 0; off >>= 1) {
@@ -461,6 +578,362 @@ __global__ void __launch_bounds__(kTraceThreads) k_path(const FrameArgs a)
             atomicMax(&cnt->max_stack, my_max_stack);
         }
     }
+    if (my_overflow) atomicOr(&cnt->overflow, 1u);
+}
+
+// Camera-ray classification (first kernel of the two-kernel schedule): one thread per pixel in
+// 8x4-tile order, so a warp is one tile and runs in lockstep.  The thread generates its camera ray
+// (main.glsl:405-421) and walks the TLAS level with tight-box culling.  A ray that reaches no
+// instance whose tight box it touches cannot hit anything: it is finished here (sky colour +
+// far depth, main.glsl:366-369,430-435) exactly as the full traversal would finish it.  The other
+// pixels are appended, warp-aggregated, to `hit_list` for k_path<SRC=1>, which restarts them from
+// the camera (the seed and the ray are functions of (pixel, frame_index) only).
+__global__ void __launch_bounds__(kTraceThreads) k_primary_cull(const FrameArgs a)
+{
+    __shared__ uint32_t s_stack[kSmemStack * kTraceThreads];
+    __shared__ gdpt_camera s_cam;
+    uint32_t spill[GDPT_MAX_STACK - kSmemStack];
+    SmemStack st;
+    st.col = s_stack + threadIdx.x;
+    st.spill = spill;
+    if (threadIdx.x < sizeof(gdpt_camera) / 4u)
+        reinterpret_cast<uint32_t *>(&s_cam)[threadIdx.x] = reinterpret_cast<const uint32_t *>(a.camera)[threadIdx.x];
+    __syncthreads();
+    const gdpt_camera &cam = s_cam;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lanemask_lt = (1u << lane) - 1u;
+    FrameCounters *cnt = a.counters;
+    unsigned long long my_done = 0;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t w0 = blockIdx.x * blockDim.x; w0 < a.n_work; w0 += stride) { // warp-uniform trip count
+        const uint32_t w = w0 + threadIdx.x;
+        int px, py;
+        const bool valid = w < a.n_work && work_to_pixel(a, w, &px, &py);
+        bool survivor = false;
+        uint32_t pixel = 0;
+        if (valid) {
+            f3 o, d;
+            generate_primary_ray(cam, a.width, a.height, px, py, &o, &d);
+            pixel = (uint32_t)py * (uint32_t)a.width + (uint32_t)px;
+            RayState r;
+            ray_begin(r, a.sc, o, d);
+            while (r.cur != LINK_NONE && (r.cur & LINK_TLAS)) step_tlas<false, true>(a.sc, r, st, nullptr);
+            survivor = r.cur != LINK_NONE;
+            if (!survivor) {
+                a.out_rgba8[pixel] = pack_rgba8(mk3(0.0f, 0.0f, 0.0f) + mk3(1.0f, 1.0f, 1.0f) * sample_sky(d));
+                a.out_depth[pixel] = encode_depth(cam, cam.z_far);
+                my_done++;
+            }
+        }
+        // append to the list of the pixel's cost class (previous frame), one atomic per class present in the warp
+        int cls = survivor ? cost_class(a.cost[pixel]) : -1;
+#pragma unroll
+        for (int pass = 0; pass < 2; pass++) { // pass 1: lanes whose heavy list was full fall back to the light list
+            const unsigned peers = __match_any_sync(kFull, cls);
+            if (cls >= 0) {
+                const int leader = __ffs(peers) - 1;
+                uint32_t base = 0;
+                if ((int)lane == leader) base = atomicAdd(&cnt->qcount[cls], (uint32_t)__popc(peers));
+                base = __shfl_sync(peers, base, leader);
+                const uint32_t slot = base + __popc(peers & lanemask_lt);
+                const uint32_t cap = cls == 0 ? a.queue_cap : a.heavy_cap;
+                if (slot < cap) { a.hit_list[class_base(a, cls) + slot] = pixel; cls = -1; }
+                else cls = 0;
+            }
+        }
+    }
+    for (int off = 16; off > 0; off >>= 1) my_done += __shfl_down_sync(kFull, my_done, off);
+    if (lane == 0 && my_done) atomicAdd(&cnt->rays, my_done);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Lane-multiplexed path kernel (second kernel of schedule 4).
+//
+// k_path keeps one path per lane in registers; a warp then issues every traversal instruction for
+// the handful of lanes that happen to be in the phase being executed (ncu: ~7 of 32 lanes in the
+// box/triangle code) and its 114 registers leave 4 warps per scheduler to hide a dependent ALU
+// chain.  Here every lane owns K path contexts ("slots") that live in shared memory -- word f of
+// slot k of thread t sits at s_state[(f*K + k)*kMuxThreads + t], so a lane only ever touches bank
+// (t mod 32) whatever slot it picks: conflict-free without any coordination.  Each iteration the
+// warp counts, with one REDUX, how many lanes own a slot in each phase
+//     I  one internal node (BLAS, or TLAS while outside an instance): two reference + two tight box tests
+//     L  one triangle test of the pending leaf range
+//     T  instance bookkeeping: leave the current instance and/or enter the popped one
+//     F  segment finished: shade + sample the continuation ray, or finish the pixel
+//     E  empty: take the next surviving pixel from k_primary_cull's list
+// executes the phase most lanes can join, and every lane works on its first slot in that phase.
+// A lane idles only when none of its K slots is in the chosen phase.  Registers hold no path state
+// between iterations.  The steps are the same device functions (same node order, same float ops)
+// the other schedules and the CPU unit check use, so results stay bit-identical.
+//
+// Cold per-path state (world ray, throughput, radiance, seed, pixel, segment) is an 80 B record in
+// global memory (L2-resident), touched at T and F steps only.
+constexpr int kMuxThreads = 128;
+constexpr int kMuxStack = 8; // smem-resident stack entries per slot; deeper entries go to local memory
+enum MuxField { MF_OX, MF_OY, MF_OZ, MF_DX, MF_DY, MF_DZ, MF_RX, MF_RY, MF_RZ, MF_T, MF_U, MF_V, MF_TRI, MF_BF,
+                MF_CUR, MF_SP, MF_INST, MF_TN, MF_TE, MF_STEPS, MF_STACK, MF_COUNT = MF_STACK + kMuxStack };
+enum MuxPhase : uint32_t { PH_E = 0, PH_I = 1, PH_L = 2, PH_T = 3, PH_F = 4 };
+
+template <int K> struct MuxSlot {
+    uint32_t *base; // &s_state[k * kMuxThreads + tid]
+    uint32_t *spill;
+    __device__ __forceinline__ uint32_t ldu(int f) const { return base[f * K * kMuxThreads]; }
+    __device__ __forceinline__ float ldf(int f) const { return __uint_as_float(base[f * K * kMuxThreads]); }
+    __device__ __forceinline__ void stu(int f, uint32_t v) const { base[f * K * kMuxThreads] = v; }
+    __device__ __forceinline__ void stf(int f, float v) const { base[f * K * kMuxThreads] = __float_as_uint(v); }
+    // stack interface of pt_trace.cuh
+    __device__ __forceinline__ void store(uint32_t i, uint32_t v)
+    {
+        if (i < (uint32_t)kMuxStack) base[(MF_STACK + i) * K * kMuxThreads] = v; else spill[i - kMuxStack] = v;
+    }
+    __device__ __forceinline__ uint32_t load(uint32_t i) const
+    {
+        return (i < (uint32_t)kMuxStack) ? base[(MF_STACK + i) * K * kMuxThreads] : spill[i - kMuxStack];
+    }
+};
+
+__device__ __forceinline__ uint32_t mux_phase_of(uint32_t cur, bool pending, uint32_t inst)
+{
+    if (pending || link_is_blas_leaf(cur)) return PH_L;
+    if (cur == LINK_NONE) return PH_F;
+    if (cur & LINK_TLAS) return (inst != GDPT_NO_INSTANCE || (cur & LINK_LEAF)) ? PH_T : PH_I;
+    return PH_I;
+}
+
+// global path record: five 128-bit quads
+//   q0 = wo.xyz, pixel   q1 = wd.xyz, segment   q2 = wrd.xyz, seed.x   q3 = throughput.rgb, seed.y   q4 = radiance.rgb, -
+template <int K>
+__device__ __forceinline__ void mux_begin_segment(const SceneView &sc, const MuxSlot<K> &m, float4 *rec, f3 o, f3 d, f3 thr, f3 rad,
+                                                  u2 seed, uint32_t pixel, uint32_t segment)
+{
+    const f3 rd = rcp3(d);
+    rec[0] = make_float4(o.x, o.y, o.z, __uint_as_float(pixel));
+    rec[1] = make_float4(d.x, d.y, d.z, __uint_as_float(segment));
+    rec[2] = make_float4(rd.x, rd.y, rd.z, __uint_as_float(seed.x));
+    rec[3] = make_float4(thr.x, thr.y, thr.z, __uint_as_float(seed.y));
+    rec[4] = make_float4(rad.x, rad.y, rad.z, 0.0f);
+    m.stf(MF_OX, o.x); m.stf(MF_OY, o.y); m.stf(MF_OZ, o.z);
+    m.stf(MF_DX, d.x); m.stf(MF_DY, d.y); m.stf(MF_DZ, d.z);
+    m.stf(MF_RX, rd.x); m.stf(MF_RY, rd.y); m.stf(MF_RZ, rd.z);
+    m.stf(MF_T, 1e9f); m.stf(MF_U, 0.0f); m.stf(MF_V, 0.0f); m.stu(MF_TRI, 0u); m.stu(MF_BF, 0u);
+    m.stu(MF_CUR, sc.tlas_root_link); m.stu(MF_SP, 0u); m.stu(MF_INST, GDPT_NO_INSTANCE);
+    m.stu(MF_TN, 0u); m.stu(MF_TE, 0u);
+    if (segment == 0u) m.stu(MF_STEPS, 0u);
+}
+
+template <int K, int MINB>
+__global__ void __launch_bounds__(kMuxThreads, MINB) k_path_mux(const FrameArgs a)
+{
+    extern __shared__ uint32_t s_state[]; // MF_COUNT * K * kMuxThreads words
+    __shared__ gdpt_camera s_cam;
+    uint32_t spill[K * (GDPT_MAX_STACK - kMuxStack)];
+    if (threadIdx.x < sizeof(gdpt_camera) / 4u)
+        reinterpret_cast<uint32_t *>(&s_cam)[threadIdx.x] = reinterpret_cast<const uint32_t *>(a.camera)[threadIdx.x];
+    __syncthreads();
+    const gdpt_camera &cam = s_cam;
+    const SceneView &sc = a.sc;
+
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lanemask_lt = (1u << lane) - 1u;
+    FrameCounters *cnt = a.counters;
+    SurvivorLists lists;
+    lists.load(a);
+    const uint32_t total = lists.total;
+    float4 *my_recs = a.path_recs + ((size_t)blockIdx.x * kMuxThreads + threadIdx.x) * (size_t)(K * 5);
+    const int last_segment = a.max_depth - 1;
+    const int refill_at = min(max(a.refill_below, 1), 32); // R once this many lanes own an empty slot
+    const int shade_at = min(max(a.shade_at, 1), 32);      // F once this many lanes own a finished segment
+
+    uint32_t ph = 0u; // 4 bits per slot, all PH_E
+    uint32_t chunk_next = 0, chunk_end = 0;
+    bool exhausted = (total == 0u);
+    unsigned long long my_rays = 0, my_phits = 0;
+    uint32_t my_overflow = 0;
+    const bool prof = a.warp_prof != nullptr;
+    const unsigned long long t_start = prof ? global_ns() : 0ull;
+    uint32_t it_count[5] = { 0, 0, 0, 0, 0 }, n_started = 0; // indexed by MuxPhase
+
+    for (;;) {
+        // ---- which phases do my slots offer?  one REDUX gives the per-phase lane counts
+        uint32_t offer = 0u; // bit p: some slot of this lane is in phase p
+#pragma unroll
+        for (int k = 0; k < K; k++) offer |= 1u << ((ph >> (4 * k)) & 15u);
+        uint32_t packed = 0u;
+#pragma unroll
+        for (int p = 0; p < 5; p++) packed |= ((offer >> p) & 1u) << (6 * p);
+        packed = __reduce_add_sync(kFull, packed);
+        const int n_e = (int)(packed & 63u), n_i = (int)((packed >> 6) & 63u), n_l = (int)((packed >> 12) & 63u),
+                  n_t = (int)((packed >> 18) & 63u), n_f = (int)((packed >> 24) & 63u);
+        const bool can_fill = !exhausted && n_e > 0;
+        const int n_walk_best = max(n_i, max(n_l, n_t));
+
+        uint32_t phase;
+        if (can_fill && (n_e >= refill_at || (n_walk_best == 0 && n_f == 0))) phase = PH_E;
+        else if (n_f > 0 && (n_f >= shade_at || n_walk_best == 0)) phase = PH_F;
+        else if (n_walk_best == 0) break; // nothing walking, nothing to shade, no work left
+        else if (n_l >= n_i && n_l >= n_t) phase = PH_L;
+        else if (n_i >= n_t) phase = PH_I;
+        else phase = PH_T;
+        if (prof) {
+#pragma unroll
+            for (int p = 0; p < 5; p++) it_count[p] += (phase == (uint32_t)p) ? 1u : 0u;
+        }
+
+        // ---- my first slot in that phase
+        int k = -1;
+#pragma unroll
+        for (int j = K - 1; j >= 0; j--)
+            if (((ph >> (4 * j)) & 15u) == phase) k = j;
+        MuxSlot<K> m;
+        m.base = s_state + (k < 0 ? 0 : k) * kMuxThreads + threadIdx.x;
+        m.spill = spill + (k < 0 ? 0 : k) * (GDPT_MAX_STACK - kMuxStack);
+        uint32_t next_phase = phase;
+
+        if (phase == PH_I) {
+            if (k >= 0) {
+                RayState r;
+                r.o = mk3(m.ldf(MF_OX), m.ldf(MF_OY), m.ldf(MF_OZ));
+                r.rd = mk3(m.ldf(MF_RX), m.ldf(MF_RY), m.ldf(MF_RZ));
+                r.t = m.ldf(MF_T); r.cur = m.ldu(MF_CUR); r.sp = m.ldu(MF_SP); r.overflow = 0u;
+                const void *table = (r.cur & LINK_TLAS) ? (const void *)sc.wide_tlas : (const void *)sc.wide_nodes;
+                visit_wide<false, true>(table, r.cur & LINK_INDEX_MASK, 0u, r, m, nullptr);
+                m.stu(MF_CUR, r.cur); m.stu(MF_SP, r.sp);
+                my_overflow |= r.overflow;
+                uint32_t inst = GDPT_NO_INSTANCE;
+                if (r.cur != LINK_NONE && (r.cur & LINK_TLAS)) inst = m.ldu(MF_INST);
+                next_phase = mux_phase_of(r.cur, false, inst);
+            }
+        } else if (phase == PH_L) {
+            if (k >= 0) {
+                RayState r;
+                uint32_t tn = m.ldu(MF_TN), te = m.ldu(MF_TE);
+                r.cur = m.ldu(MF_CUR);
+                r.inst = m.ldu(MF_INST);
+                if (tn == te) { // entering the leaf: fetch its range, pop what comes after it
+                    r.sp = m.ldu(MF_SP);
+                    const q4u leaf = ldqu(sc.leaf_recs, r.cur & LINK_INDEX_MASK);
+                    tn = leaf.x; te = leaf.x + leaf.y;
+                    r.cur = stack_pop(r, m);
+                    m.stu(MF_CUR, r.cur); m.stu(MF_SP, r.sp); m.stu(MF_TE, te);
+                }
+                if (tn < te) {
+                    r.o = mk3(m.ldf(MF_OX), m.ldf(MF_OY), m.ldf(MF_OZ));
+                    r.d = mk3(m.ldf(MF_DX), m.ldf(MF_DY), m.ldf(MF_DZ));
+                    r.t = m.ldf(MF_T); r.blas_front = m.ldu(MF_BF); r.tri = 0xFFFFFFFFu;
+                    triangle_test(sc, r, tn);
+                    if (r.tri != 0xFFFFFFFFu) { // accepted
+                        m.stf(MF_T, r.t); m.stf(MF_U, r.u); m.stf(MF_V, r.v); m.stu(MF_TRI, r.tri); m.stu(MF_BF, r.blas_front);
+                    }
+                    tn++;
+                }
+                m.stu(MF_TN, tn);
+                next_phase = mux_phase_of(r.cur, tn < te, r.inst);
+            }
+        } else if (phase == PH_T) {
+            if (k >= 0) {
+                RayState r;
+                r.cur = m.ldu(MF_CUR); r.sp = m.ldu(MF_SP); r.inst = m.ldu(MF_INST); r.overflow = 0u;
+                float4 *rec = my_recs + k * 5;
+                if (r.inst != GDPT_NO_INSTANCE) { // back to world space (main.glsl:316-327: the TLAS loop uses `ray`)
+                    const float4 q0 = rec[0], q1 = rec[1], q2 = rec[2];
+                    r.o = mk3(q0.x, q0.y, q0.z); r.d = mk3(q1.x, q1.y, q1.z); r.rd = mk3(q2.x, q2.y, q2.z);
+                    r.inst = GDPT_NO_INSTANCE;
+                    if (!(r.cur & LINK_LEAF)) {
+                        m.stf(MF_OX, r.o.x); m.stf(MF_OY, r.o.y); m.stf(MF_OZ, r.o.z);
+                        m.stf(MF_DX, r.d.x); m.stf(MF_DY, r.d.y); m.stf(MF_DZ, r.d.z);
+                        m.stf(MF_RX, r.rd.x); m.stf(MF_RY, r.rd.y); m.stf(MF_RZ, r.rd.z);
+                    }
+                } else {
+                    r.o = mk3(m.ldf(MF_OX), m.ldf(MF_OY), m.ldf(MF_OZ));
+                    r.d = mk3(m.ldf(MF_DX), m.ldf(MF_DY), m.ldf(MF_DZ));
+                }
+                if (r.cur & LINK_LEAF) {
+                    r.wo = r.o; r.wd = r.d;
+                    r.t = m.ldf(MF_T); // distance culling of the instance's tight box
+                    step_tlas<false, true>(sc, r, m, nullptr); // inst == NONE here: enters the instance (and may leave it at once)
+                    m.stf(MF_OX, r.o.x); m.stf(MF_OY, r.o.y); m.stf(MF_OZ, r.o.z);
+                    m.stf(MF_DX, r.d.x); m.stf(MF_DY, r.d.y); m.stf(MF_DZ, r.d.z);
+                    m.stf(MF_RX, r.rd.x); m.stf(MF_RY, r.rd.y); m.stf(MF_RZ, r.rd.z);
+                }
+                m.stu(MF_CUR, r.cur); m.stu(MF_SP, r.sp); m.stu(MF_INST, r.inst);
+                my_overflow |= r.overflow;
+                next_phase = mux_phase_of(r.cur, false, r.inst);
+            }
+        } else if (phase == PH_F) {
+            if (k >= 0) {
+                float4 *rec = my_recs + k * 5;
+                const float4 q0 = rec[0], q1 = rec[1], q2 = rec[2], q3 = rec[3], q4 = rec[4];
+                const f3 wo = mk3(q0.x, q0.y, q0.z), wd = mk3(q1.x, q1.y, q1.z);
+                const uint32_t pixel = __float_as_uint(q0.w);
+                const int segment = (int)__float_as_uint(q1.w);
+                u2 seed; seed.x = __float_as_uint(q2.w); seed.y = __float_as_uint(q3.w);
+                f3 throughput = mk3(q3.x, q3.y, q3.z), radiance = mk3(q4.x, q4.y, q4.z);
+                const float t = m.ldf(MF_T);
+                const bool hit = t < 1e9f;
+                my_rays++;
+                if (segment == 0 && hit) my_phits++;
+                bool alive = false;
+                if (!hit) {
+                    radiance = radiance + throughput * sample_sky(wd);
+                    if (segment == 0) a.out_depth[pixel] = encode_depth(cam, cam.z_far);
+                } else {
+                    BounceResult br;
+                    if (kOutOfLineCold) shade_and_bounce_ool(&sc, &wo, &wd, t, m.ldf(MF_U), m.ldf(MF_V), m.ldu(MF_TRI), m.ldu(MF_BF), &radiance, &throughput, &seed, &br);
+                    else br = shade_and_bounce(sc, wo, wd, t, m.ldf(MF_U), m.ldf(MF_V), m.ldu(MF_TRI), m.ldu(MF_BF), radiance, throughput, seed);
+                    radiance = br.radiance;
+                    if (segment == 0) a.out_depth[pixel] = encode_depth(cam, br.first_hit_distance);
+                    alive = br.alive && segment < last_segment;
+                    if (alive) mux_begin_segment<K>(sc, m, rec, br.next_o, br.next_d, br.throughput, radiance, seed, pixel, (uint32_t)segment + 1u);
+                }
+                if (!alive) {
+                    a.out_rgba8[pixel] = pack_rgba8(radiance);
+                    a.cost[pixel] = m.ldu(MF_STEPS);
+                    next_phase = PH_E;
+                } else {
+                    next_phase = mux_phase_of(sc.tlas_root_link, false, GDPT_NO_INSTANCE);
+                }
+            }
+        } else { // PH_E: one new pixel for every lane that owns an empty slot
+            if (chunk_next == chunk_end) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(&cnt->cursor[1], kChunkPrimary);
+                base = __shfl_sync(kFull, base, 0);
+                if (base >= total) { exhausted = true; continue; }
+                chunk_next = base;
+                chunk_end = min(base + kChunkPrimary, total);
+            }
+            const unsigned want = __ballot_sync(kFull, k >= 0);
+            const uint32_t avail = chunk_end - chunk_next;
+            const uint32_t rank = __popc(want & lanemask_lt);
+            if (k >= 0 && rank < avail) {
+                const uint32_t pixel = lists.pixel(a, chunk_next + rank);
+                const int py = (int)(pixel / (uint32_t)a.width), px = (int)(pixel - (uint32_t)py * (uint32_t)a.width);
+                f3 o, d;
+                u2 seed;
+                if (kOutOfLineCold) generate_primary_ray_ool(&cam, a.width, a.height, px, py, &o, &d, &seed);
+                else seed = generate_primary_ray(cam, a.width, a.height, px, py, &o, &d);
+                mux_begin_segment<K>(sc, m, my_recs + k * 5, o, d, mk3(1.0f, 1.0f, 1.0f), mk3(0.0f, 0.0f, 0.0f), seed, pixel, 0u);
+                next_phase = mux_phase_of(sc.tlas_root_link, false, GDPT_NO_INSTANCE);
+            }
+            n_started += min((uint32_t)__popc(want), avail);
+            chunk_next += min((uint32_t)__popc(want), avail);
+        }
+        if (k >= 0) {
+            ph = (ph & ~(15u << (4 * k))) | (next_phase << (4 * k));
+            if (phase >= PH_I && phase <= PH_T) m.stu(MF_STEPS, m.ldu(MF_STEPS) + 1u);
+        }
+    }
+    if (prof && lane == 0) {
+        unsigned long long *w = a.warp_prof + (size_t)((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 8u;
+        w[0] = t_start; w[1] = global_ns(); w[2] = it_count[PH_I]; w[3] = it_count[PH_L]; w[4] = it_count[PH_T];
+        w[5] = it_count[PH_F]; w[6] = it_count[PH_E]; w[7] = n_started;
+    }
+
+    for (int off = 16; off > 0; off >>= 1) {
+        my_rays += __shfl_down_sync(kFull, my_rays, off);
+        my_phits += __shfl_down_sync(kFull, my_phits, off);
+    }
+    if (lane == 0) { atomicAdd(&cnt->rays, my_rays); atomicAdd(&cnt->primary_hits, my_phits); }
     if (my_overflow) atomicOr(&cnt->overflow, 1u);
 }
 
@@ -571,7 +1044,11 @@ struct Shapes {
     bool ready = false;
     int sms = 148;
     int trace_blocks[2][2][2] = {}; // [TRACE][MODE][CULL]
-    int path_blocks[2][2] = {};     // [TRACE][CULL]
+    int path_blocks[2][2] = {};     // [TRACE][CULL], SRC 0
+    int path_list_blocks[2] = {};   // [TRACE], CULL, SRC 1
+    int path_list_blocks_minb[9] = {}; // untraced, by MINB (register cap variants)
+    int mux_blocks[5] = {};         // k_path_mux<K>, index K
+    int cull_blocks_per_sm = 1;
     int shade_blocks = 0;
     int prog_blocks = 0;
 };
@@ -581,6 +1058,16 @@ template <bool TRACE, int MODE, bool CULL> int trace_grid(int sms)
 {
     int per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<TRACE, MODE, CULL>, kTraceThreads, 0);
+    return sms * (per_sm > 0 ? per_sm : 1);
+}
+
+constexpr size_t mux_smem_bytes(int k) { return (size_t)MF_COUNT * k * kMuxThreads * sizeof(uint32_t); }
+
+template <int K, int MINB> int mux_grid(int sms)
+{
+    cudaFuncSetAttribute(k_path_mux<K, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mux_smem_bytes(K));
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_path_mux<K, MINB>, kMuxThreads, mux_smem_bytes(K));
     return sms * (per_sm > 0 ? per_sm : 1);
 }
 
@@ -611,10 +1098,26 @@ void init_launch_shapes(int device)
     s.trace_blocks[1][0][0] = trace_grid<true, 0, false>(s.sms); s.trace_blocks[1][0][1] = trace_grid<true, 0, true>(s.sms);
     s.trace_blocks[1][1][0] = trace_grid<true, 1, false>(s.sms); s.trace_blocks[1][1][1] = trace_grid<true, 1, true>(s.sms);
     int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_path<false, false>, kTraceThreads, 0); s.path_blocks[0][0] = s.sms * (per_sm > 0 ? per_sm : 1);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_path<false, true>, kTraceThreads, 0); s.path_blocks[0][1] = s.sms * (per_sm > 0 ? per_sm : 1);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_path<true, false>, kTraceThreads, 0); s.path_blocks[1][0] = s.sms * (per_sm > 0 ? per_sm : 1);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_path<true, true>, kTraceThreads, 0); s.path_blocks[1][1] = s.sms * (per_sm > 0 ? per_sm : 1);
+    auto grid_of = [&](auto kernel, int threads) {
+        per_sm = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0);
+        return s.sms * (per_sm > 0 ? per_sm : 1);
+    };
+    s.path_blocks[0][0] = grid_of(k_path<false, false, 0>, kTraceThreads);
+    s.path_blocks[0][1] = grid_of(k_path<false, true, 0>, kTraceThreads);
+    s.path_blocks[1][0] = grid_of(k_path<true, false, 0>, kTraceThreads);
+    s.path_blocks[1][1] = grid_of(k_path<true, true, 0>, kTraceThreads);
+    s.path_list_blocks[0] = grid_of(k_path<false, true, 1>, kTraceThreads);
+    s.path_list_blocks[1] = grid_of(k_path<true, true, 1>, kTraceThreads);
+    s.path_list_blocks_minb[5] = grid_of(k_path<false, true, 1, 5>, kTraceThreads);
+    s.path_list_blocks_minb[6] = grid_of(k_path<false, true, 1, 6>, kTraceThreads);
+    s.path_list_blocks_minb[8] = grid_of(k_path<false, true, 1, 8>, kTraceThreads);
+    s.mux_blocks[1] = mux_grid<1, 8>(s.sms);
+    s.mux_blocks[2] = mux_grid<2, 8>(s.sms);
+    s.mux_blocks[3] = mux_grid<3, 5>(s.sms);
+    s.mux_blocks[4] = mux_grid<4, 4>(s.sms);
+    grid_of(k_primary_cull, kTraceThreads);
+    s.cull_blocks_per_sm = per_sm > 0 ? per_sm : 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_shade, kShadeThreads, 0); s.shade_blocks = s.sms * (per_sm > 0 ? per_sm : 1);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_progressive, 256, 0); s.prog_blocks = s.sms * (per_sm > 0 ? per_sm : 1);
     s.ready = true;
@@ -634,12 +1137,37 @@ void launch_path(const FrameArgs &a, bool trace, cudaStream_t s)
     const bool cull = a.cull != 0;
     const int blocks = sh.path_blocks[trace ? 1 : 0][cull ? 1 : 0];
     if (trace) {
-        if (cull) k_path<true, true><<<blocks, kTraceThreads, 0, s>>>(a);
-        else k_path<true, false><<<blocks, kTraceThreads, 0, s>>>(a);
+        if (cull) k_path<true, true, 0><<<blocks, kTraceThreads, 0, s>>>(a);
+        else k_path<true, false, 0><<<blocks, kTraceThreads, 0, s>>>(a);
     } else {
-        if (cull) k_path<false, true><<<blocks, kTraceThreads, 0, s>>>(a);
-        else k_path<false, false><<<blocks, kTraceThreads, 0, s>>>(a);
+        if (cull) k_path<false, true, 0><<<blocks, kTraceThreads, 0, s>>>(a);
+        else k_path<false, false, 0><<<blocks, kTraceThreads, 0, s>>>(a);
     }
+}
+
+// grid of a persistent kernel: all resident blocks, or a.blocks_per_sm per SM when that is smaller
+static int persistent_grid(const Shapes &sh, const FrameArgs &a, int resident)
+{
+    if (a.blocks_per_sm > 0 && a.blocks_per_sm * sh.sms < resident) return a.blocks_per_sm * sh.sms;
+    return resident;
+}
+
+void launch_primary_cull(const FrameArgs &a, cudaStream_t s)
+{
+    Shapes &sh = shapes_for_current_device();
+    const int needed = (int)((a.n_work + kTraceThreads - 1) / kTraceThreads);
+    const int resident = sh.sms * sh.cull_blocks_per_sm;
+    k_primary_cull<<<needed < resident ? (needed > 0 ? needed : 1) : resident, kTraceThreads, 0, s>>>(a);
+}
+
+void launch_path_list(const FrameArgs &a, bool trace, cudaStream_t s)
+{
+    Shapes &sh = shapes_for_current_device();
+    if (trace) k_path<true, true, 1><<<persistent_grid(sh, a, sh.path_list_blocks[1]), kTraceThreads, 0, s>>>(a);
+    else if (a.path_minb == 5) k_path<false, true, 1, 5><<<persistent_grid(sh, a, sh.path_list_blocks_minb[5]), kTraceThreads, 0, s>>>(a);
+    else if (a.path_minb == 6) k_path<false, true, 1, 6><<<persistent_grid(sh, a, sh.path_list_blocks_minb[6]), kTraceThreads, 0, s>>>(a);
+    else if (a.path_minb == 8) k_path<false, true, 1, 8><<<persistent_grid(sh, a, sh.path_list_blocks_minb[8]), kTraceThreads, 0, s>>>(a);
+    else k_path<false, true, 1><<<persistent_grid(sh, a, sh.path_list_blocks[0]), kTraceThreads, 0, s>>>(a);
 }
 
 void launch_primary(const FrameArgs &a, bool trace, cudaStream_t s)
@@ -667,8 +1195,47 @@ void launch_progressive(uint32_t *screen_rgba8, float4 *accum, const gdpt_progre
                                                  shard_band);
 }
 
-int k1_launch_count(int max_depth, bool debug_steps)
+void launch_path_mux(const FrameArgs &a, cudaStream_t s)
 {
+    Shapes &sh = shapes_for_current_device();
+    const int k = (a.mux_k >= 1 && a.mux_k <= 4) ? a.mux_k : 2;
+    const int grid = persistent_grid(sh, a, sh.mux_blocks[k]);
+    switch (k) {
+    case 1: k_path_mux<1, 8><<<grid, kMuxThreads, mux_smem_bytes(1), s>>>(a); break;
+    case 3: k_path_mux<3, 5><<<grid, kMuxThreads, mux_smem_bytes(3), s>>>(a); break;
+    case 4: k_path_mux<4, 4><<<grid, kMuxThreads, mux_smem_bytes(4), s>>>(a); break;
+    default: k_path_mux<2, 8><<<grid, kMuxThreads, mux_smem_bytes(2), s>>>(a); break;
+    }
+}
+
+size_t mux_path_record_quads()
+{
+    Shapes &sh = shapes_for_current_device();
+    size_t most = 0;
+    for (int k = 1; k <= 4; k++) {
+        const size_t n = (size_t)sh.mux_blocks[k] * kMuxThreads * k * 5;
+        if (n > most) most = n;
+    }
+    return most;
+}
+
+size_t path_kernel_warps(const FrameArgs &a)
+{
+    Shapes &sh = shapes_for_current_device();
+    if (a.schedule == 3 && (a.path_minb == 5 || a.path_minb == 6 || a.path_minb == 8)) return (size_t)sh.path_list_blocks_minb[a.path_minb] * (kTraceThreads / 32);
+    if (a.schedule == 4) return (size_t)sh.mux_blocks[(a.mux_k >= 1 && a.mux_k <= 4) ? a.mux_k : 2] * (kMuxThreads / 32);
+    int most = 0;
+    for (int t = 0; t < 2; t++) {
+        for (int c = 0; c < 2; c++) most = most > sh.path_blocks[t][c] ? most : sh.path_blocks[t][c];
+        most = most > sh.path_list_blocks[t] ? most : sh.path_list_blocks[t];
+    }
+    return (size_t)most * (kTraceThreads / 32);
+}
+
+int k1_launch_count(int schedule, int max_depth, bool debug_steps)
+{
+    if (schedule == 2) return 1;
+    if (schedule == 3 || schedule == 4) return 2;
     if (debug_steps) return 1;
     return 1 + max_depth + (max_depth - 1); // primary + shade(0..D-1) + trace(1..D-1)
 }

@@ -8,6 +8,9 @@
 namespace gdpt {
 
 enum { kMaxDepth = 32 };
+// Surviving pixels are binned by the cost their path had in the previous frame (longest first):
+// class 0 = light (< 128 iterations or unknown), 1: >=128, 2: >=256, 3: >=512, 4: >=1024.
+enum { kCostClasses = 5 };
 
 // Device-resident counters of one frame; zeroed with one memset per dispatch.
 struct FrameCounters {
@@ -36,14 +39,27 @@ struct FrameArgs {
     float *out_depth;                        // bound R32F image
     float4 *queue[2];
     uint32_t queue_cap;
-    uint32_t *hit_list;
+    uint32_t *hit_list;                      // schedules 3/4: surviving pixels, kCostClasses lists (see class_base)
+    uint32_t heavy_cap;                      // capacity of each of the heavy-class lists behind the light list
+    uint32_t *cost;                          // per pixel: scheduler iterations its path took in the previous frame
+    int blocks_per_sm;                       // schedules 3/4: cap on resident path-kernel blocks per SM (0 = occupancy limit)
+    int path_minb;                           // schedule 3: min-blocks-per-SM variant of the path kernel (register cap)
+    int lead_min;                            // the path with the most iterations picks the phase once it has this many
+    float4 *path_recs;                       // schedule 4: 5 quads per path context
+    int mux_k;                               // schedule 4: path contexts per lane (1..4)
     FrameCounters *counters;
     // scheduling knobs (results do not depend on them)
     int refill_below;  // refill idle lanes when fewer than this many lanes are traversing
     int burst;         // node steps between refill checks
-    int schedule;      // 0: wavefront + while-while descent, 1: wavefront + phase voting, 2: single path kernel
+    int schedule;      // 0: wavefront + while-while descent, 1: wavefront + phase voting, 2: single path kernel,
+                       // 3: camera-ray classification kernel + path kernel over the surviving pixels,
+                       // 4: classification kernel + lane-multiplexed path kernel
     int shade_at;      // schedule 2: shade once this many lanes wait with a finished ray
     int cull;          // 1: skip children whose tight box the ray misses (pt_scene.cuh); results identical
+    // optional per-warp schedule profile (gdpt_shader_set_warp_profile): 8 x u64 per warp of the path kernel
+    //   [0] globaltimer at start (ns)  [1] globaltimer at end  [2..6] iterations spent in phase I, L, T, F(shade), E(refill)
+    //   [7] paths started
+    unsigned long long *warp_prof;
     // parity outputs (TRACE builds only)
     gdpt_trace_record *trace; int trace_segments;
     uint32_t *visits; uint32_t visits_per_ray;
@@ -55,6 +71,15 @@ struct LaunchShape { int blocks; int threads; };
 // K1 stages.  `trace` selects the instrumented instantiation.
 // Single-kernel schedule (a.schedule == 2): whole paths per lane, no stage barriers.
 void launch_path(const FrameArgs &a, bool trace, cudaStream_t s);
+// Two-kernel schedule (a.schedule == 3, needs a.cull): camera-ray classification against the tight
+// boxes, then whole paths per lane for the pixels that can hit something.
+void launch_primary_cull(const FrameArgs &a, cudaStream_t s);
+void launch_path_list(const FrameArgs &a, bool trace, cudaStream_t s);
+// Schedule 4: the same classification kernel, then the lane-multiplexed path kernel (a.mux_k
+// path contexts per lane, kept in shared memory; a.path_recs holds their cold state).
+void launch_path_mux(const FrameArgs &a, cudaStream_t s);
+size_t mux_path_record_quads(); // float4 elements a.path_recs must provide on the current device
+size_t path_kernel_warps(const FrameArgs &a); // warps of the path kernel enqueue_k1 would launch for `a`
 void launch_primary(const FrameArgs &a, bool trace, cudaStream_t s);
 void launch_shade(const FrameArgs &a, int segment, cudaStream_t s);
 void launch_trace(const FrameArgs &a, int segment, bool trace, cudaStream_t s);
@@ -62,7 +87,7 @@ void launch_trace(const FrameArgs &a, int segment, bool trace, cudaStream_t s);
 void launch_progressive(uint32_t *screen_rgba8, float4 *accum, const gdpt_progressive_params *params_dev,
                         int width, int height, int shard_part, int shard_parts, int shard_band, cudaStream_t s);
 // Number of kernels one K1 dispatch launches for a given depth.
-int k1_launch_count(int max_depth, bool debug_steps);
+int k1_launch_count(int schedule, int max_depth, bool debug_steps);
 // One-time per device: query SM count / occupancy for the persistent grids.
 void init_launch_shapes(int device);
 

@@ -109,11 +109,8 @@ GDPT_HD float slab_test(const RayState &r, float nx, float ny, float nz, float x
 
 // intersectTriangle (main.glsl:224-257).  `position`/`out_dir` are not stored:
 // the shading stage recomputes them from (ray, t) with the same operations.
-GDPT_HD void triangle_test(const SceneView &sc, RayState &r, uint32_t tri_index)
+GDPT_HD void triangle_test_loaded(RayState &r, uint32_t tri_index, const q4f a, const q4f b, const q4f c)
 {
-    const q4f a = ldq(sc.tri_geom, tri_index * 3u + 0u);
-    const q4f b = ldq(sc.tri_geom, tri_index * 3u + 1u);
-    const q4f c = ldq(sc.tri_geom, tri_index * 3u + 2u);
     const f3 v0 = mk3(a.x, a.y, a.z);
     const f3 e1 = mk3(b.x, b.y, b.z) - v0, e2 = mk3(c.x, c.y, c.z) - v0;
     const f3 pvec = cross3(r.d, e2);
@@ -133,6 +130,13 @@ GDPT_HD void triangle_test(const SceneView &sc, RayState &r, uint32_t tri_index)
     const uint32_t blas = (t < r.t) ? r.inst : (r.blas_front & ~GDPT_FRONT_BIT);
     const uint32_t front = dot3(cross3(e1, e2), r.d) > 0.0f ? GDPT_FRONT_BIT : 0u;
     r.t = t; r.u = u; r.v = v; r.tri = tri_index; r.blas_front = blas | front;
+}
+GDPT_HD void triangle_test(const SceneView &sc, RayState &r, uint32_t tri_index)
+{
+    const q4f a = ldq(sc.tri_geom, tri_index * 3u + 0u);
+    const q4f b = ldq(sc.tri_geom, tri_index * 3u + 1u);
+    const q4f c = ldq(sc.tri_geom, tri_index * 3u + 2u);
+    triangle_test_loaded(r, tri_index, a, b, c);
 }
 
 template <class Stack> GDPT_HD void stack_push(RayState &r, Stack &st, uint32_t link)
@@ -172,8 +176,10 @@ GDPT_HD void choose_next(RayState &r, Stack &st, float d1, float d2, uint32_t le
     }
 }
 
-// Does the ray touch the (inflated) culling box at all?  Same slab arithmetic; NaNs from
-// 0 * inf are dropped by minNum/maxNum, which errs on the side of "touches".
+// Can the subtree inside this (inflated) culling box still change the hit?  Not if the ray misses
+// the box, and not if it enters the box beyond the current hit.t: every triangle in there would be
+// rejected by `t > hit.t` (main.glsl:247), and hit.t only ever decreases.  Same slab arithmetic;
+// NaNs from 0 * inf are dropped by minNum/maxNum, which errs on the side of "touches".
 GDPT_HD bool slab_touches(const RayState &r, float nx, float ny, float nz, float xx, float xy, float xz)
 {
     const float tx1 = (nx - r.o.x) * r.rd.x, tx2 = (xx - r.o.x) * r.rd.x;
@@ -182,7 +188,7 @@ GDPT_HD bool slab_touches(const RayState &r, float nx, float ny, float nz, float
     tmin = max_num(tmin, min_num(ty1, ty2)); tmax = min_num(tmax, max_num(ty1, ty2));
     const float tz1 = (nz - r.o.z) * r.rd.z, tz2 = (xz - r.o.z) * r.rd.z;
     tmin = max_num(tmin, min_num(tz1, tz2)); tmax = min_num(tmax, max_num(tz1, tz2));
-    return !(tmax < tmin) && !(tmax < 0.0f);
+    return !(tmax < tmin) && !(tmax < 0.0f) && !(tmin > r.t);
 }
 
 // The two children of a WideNode record: reference distances, and (CULL) whether each child's
@@ -242,6 +248,30 @@ GDPT_HD void step_blas_leaf_one(const SceneView &sc, RayState &r, Stack &st, Tra
         r.cur = stack_pop(r, st);
     }
     if (tri_next < tri_end) triangle_test(sc, r, tri_next++);
+}
+
+// Same, up to N triangles per step: their vertex loads are issued together, the tests then run
+// in index order on the running hit.t, so the outcome is that of N single steps.
+template <bool TRACE, int N, class Stack>
+GDPT_HD void step_blas_leaf_some(const SceneView &sc, RayState &r, Stack &st, TraceCounters *tc, uint32_t &tri_next,
+                                 uint32_t &tri_end)
+{
+    if (tri_next == tri_end) {
+        const q4u leaf = ldqu(sc.leaf_recs, r.cur & LINK_INDEX_MASK);
+        if (TRACE) { counters_visit(*tc, leaf.z); tc->tri_tests += leaf.y; }
+        tri_next = leaf.x; tri_end = leaf.x + leaf.y;
+        r.cur = stack_pop(r, st);
+    }
+    q4f va[N], vb[N], vc[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        const uint32_t ti = (tri_next + (uint32_t)i < tri_end) ? tri_next + (uint32_t)i : tri_next; // clamp: a valid address
+        va[i] = ldq(sc.tri_geom, ti * 3u + 0u); vb[i] = ldq(sc.tri_geom, ti * 3u + 1u); vc[i] = ldq(sc.tri_geom, ti * 3u + 2u);
+    }
+#pragma unroll
+    for (int i = 0; i < N; i++)
+        if (tri_next + (uint32_t)i < tri_end) triangle_test_loaded(r, tri_next + (uint32_t)i, va[i], vb[i], vc[i]);
+    tri_next = (tri_end - tri_next > (uint32_t)N) ? tri_next + (uint32_t)N : tri_end;
 }
 
 // One TLAS-level entry: leave the instance we were in (if any), then either

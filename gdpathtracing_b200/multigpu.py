@@ -59,8 +59,9 @@ def gather_row_bands(frame, band, rank, world):
     most = max(len(r) for r in rows)
     mine = torch.zeros((most,) + tuple(frame.shape[1:]), dtype=frame.dtype, device=frame.device)
     mine[:len(rows[rank])] = frame[rows[rank]]
-    gathered = torch.empty((world,) + tuple(mine.shape), dtype=frame.dtype, device=frame.device)
-    dist.all_gather_into_tensor(gathered, mine)
+    flat = torch.empty((world * most,) + tuple(mine.shape[1:]), dtype=frame.dtype, device=frame.device)
+    dist.all_gather_into_tensor(flat, mine)  # concatenated along dim 0: the form NCCL and gloo both accept
+    gathered = flat.view((world,) + tuple(mine.shape))
     out = torch.empty_like(frame)
     for r in range(world):
         out[rows[r]] = gathered[r, :len(rows[r])]

@@ -213,6 +213,14 @@ GDPT_API int  gdpt_shader_get_stats(gdpt_shader *main_shader, gdpt_frame_stats *
 GDPT_API int  gdpt_shader_set_stage_timing(gdpt_shader *main_shader, int on);
 GDPT_API int  gdpt_shader_get_stage_times(gdpt_shader *main_shader, float *out_ms, int capacity);
 
+/* Profiling aid: when on, the path kernel of every K1 dispatch then
+ * leaves one 8 x uint64 record per warp: globaltimer ns at start and end, the number of scheduler
+ * iterations it spent on internal nodes, triangle tests, instance entries/exits, shading and
+ * refilling, and the number of paths it started.  read_warp_profile returns the number of warps
+ * (or a negative gdpt_status) and blocks until the frame is done. */
+GDPT_API int  gdpt_shader_set_warp_profile(gdpt_shader *main_shader, int on);
+GDPT_API int64_t gdpt_shader_read_warp_profile(gdpt_shader *main_shader, uint64_t *out, uint64_t capacity_words);
+
 /* Under "#define GDPT_TRACE": per-pixel parity record of path segment `segment`
  * (0 = primary ray) of the last K1 dispatch; capacity in records (W*H needed).
  * Pixels whose path ended before `segment` have hit = 0xFFFFFFFF. */
