@@ -257,25 +257,48 @@ def run_ours(args, rank, local, world):
     clocks = sampler.stop() if rank == 0 else None
     dev_ms += gather_ms
 
-    # ---- end-to-end leg: host camera block in, RGBA8 frame back in (pinned) host memory, every step
+    # ---- end-to-end leg: host camera block in, RGBA8 frame back in (pinned) host memory, every step.
+    # (a) the reference's blocking render(): one frame at a time; (b) the pipelined form of the same call
+    # (render_begin / render_wait, two frames in flight: frame N's read-back overlaps frame N+1's kernels).
+    # Every step of both does its own H2D camera upload and its own full-frame D2H.
     barrier()
-    e2e_rays = 0
+    sync_rays = 0
     t0 = time.perf_counter()
     for s in range(args.steps):
         set_index(args.warmup + args.steps + s)
         cam.render()  # gdpt_render_frame: H2D camera, K1, K2, D2H frame; blocking
-        e2e_rays += cam.stats()["rays"]
+        sync_rays += cam.stats()["rays"]
+    barrier()
+    sync_s = time.perf_counter() - t0
+
+    for s in range(2):  # untimed: first use of the pipelined path
+        set_index(s)
+        cam.render_begin(); cam.render_wait()
+    barrier()
+    e2e_rays, in_flight, touched = 0, 0, 0
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        set_index(args.warmup + 2 * args.steps + s)
+        cam.render_begin()
+        in_flight += 1
+        if in_flight == 2:
+            img, fst = cam.render_wait()
+            e2e_rays += fst["rays"]; touched += int(img[0, 0, 3]); in_flight -= 1
+    while in_flight:
+        img, fst = cam.render_wait()
+        e2e_rays += fst["rays"]; touched += int(img[0, 0, 3]); in_flight -= 1
     barrier()
     e2e_s = time.perf_counter() - t0
+    assert touched == 255 * args.steps, "a pipelined frame came back without pixels"
 
     # ---- reduce over ranks: slowest rank's time, everybody's rays
     if world > 1:
-        t = torch.tensor([dev_ms, e2e_s, wall_ms], dtype=torch.float64, device=dev_t)
+        t = torch.tensor([dev_ms, e2e_s, wall_ms, sync_s], dtype=torch.float64, device=dev_t)
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-        r = torch.tensor([rays_total, e2e_rays], dtype=torch.int64, device=dev_t)
+        r = torch.tensor([rays_total, e2e_rays, sync_rays], dtype=torch.int64, device=dev_t)
         torch.distributed.all_reduce(r, op=torch.distributed.ReduceOp.SUM)
-        dev_ms, e2e_s, wall_ms = [float(x) for x in t.tolist()]
-        rays_total, e2e_rays = [int(x) for x in r.tolist()]
+        dev_ms, e2e_s, wall_ms, sync_s = [float(x) for x in t.tolist()]
+        rays_total, e2e_rays, sync_rays = [int(x) for x in r.tolist()]
     if rank != 0:
         return
 
@@ -332,8 +355,11 @@ def run_ours(args, rank, local, world):
         "clocks": clocks,
         "e2e": {"value": e2e_rays / e2e_s / 1e6, "unit": "Mrays/s", "ms_per_step": e2e_s / args.steps * 1e3,
                 "h2d_bytes_per_step": 160 + 12, "d2h_bytes_per_step": W * H * 4,
-                "api": "PathTracingCamera.render() -> gdpt_render_frame (host camera block in, pinned host RGBA8 frame out)"},
-        "gpu_launches": int(launches_per_frame * args.steps * 2),  # device-timed leg + end-to-end leg
+                "api": "PathTracingCamera.render_begin()/render_wait() -> gdpt_render_frame_begin/_wait: host camera block in, "
+                       "pinned host RGBA8 frame out, every step; two frames in flight",
+                "blocking_render": {"value": sync_rays / sync_s / 1e6, "ms_per_step": sync_s / args.steps * 1e3,
+                                    "api": "PathTracingCamera.render() -> gdpt_render_frame, one frame at a time"}},
+        "gpu_launches": int(launches_per_frame * args.steps * 3),  # device-timed leg + the two end-to-end legs
         "roofline": roofline, "roofline_accumulate": roofline_k2,
     }
     if cpu:

@@ -88,6 +88,8 @@ CUDA_API = [
     ("gdpt_render_frame", c_int, [c_void_p, c_void_p, POINTER(Camera), c_int, c_uint32, c_void_p, c_void_p]),
     ("gdpt_render_frame_async", c_int, [c_void_p, c_void_p, POINTER(Camera), c_int, c_uint32]),
     ("gdpt_device_synchronize", c_int, [c_void_p]),
+    ("gdpt_render_frame_begin", c_int, [c_void_p, c_void_p, POINTER(Camera), c_int, c_uint32, c_void_p, c_void_p]),
+    ("gdpt_render_frame_wait", c_int, [c_void_p, POINTER(FrameStats)]),
     ("gdpt_shader_set_shard", c_int, [c_void_p, c_int, c_int, c_int]),
     ("gdpt_rid_device_pointer", c_int, [c_void_p, c_uint64, POINTER(c_uint64), POINTER(c_uint64)]),
     ("gdpt_host_alloc", c_void_p, [c_uint64]),
@@ -138,6 +140,8 @@ HOST_API = [
     ("gdpt_camera_init", c_int, [c_void_p]),
     ("gdpt_camera_render", None, [c_void_p]),
     ("gdpt_camera_render_device_only", None, [c_void_p]),
+    ("gdpt_camera_render_begin", c_int, [c_void_p]),
+    ("gdpt_camera_render_wait", c_void_p, [c_void_p, POINTER(FrameStats)]),
     ("gdpt_camera_output_image", c_void_p, [c_void_p]),
     ("gdpt_camera_main_shader", c_void_p, [c_void_p]),
     ("gdpt_camera_progressive_shader", c_void_p, [c_void_p]),

@@ -47,6 +47,12 @@ struct gdpt_device {
     gdpt_rid next_rid = 1;
     void *pinned_staging = nullptr; // small H2D staging (camera, params)
     cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
+    // pipelined frames: read-backs run on their own stream; per-frame H2D blocks come from a ring
+    cudaStream_t copy_stream = nullptr;
+    uint8_t *ring = nullptr;            // kRingSlots x 512 B of pinned memory
+    cudaEvent_t ring_ev[8] = {};        // slot i may be rewritten once ring_ev[i] has completed
+    bool ring_used[8] = {};
+    unsigned ring_next = 0;
 };
 
 struct gdpt_shader {
@@ -68,6 +74,17 @@ struct gdpt_shader {
     int shard_part = 0, shard_parts = 1, shard_band = 4;
     gdpt_frame_stats stats;
     bool stats_valid = false;
+    // frames in flight of gdpt_render_frame_begin / _wait
+    struct FrameSlot {
+        FrameCounters *dcnt = nullptr;   // device counters of this frame
+        FrameCounters *hcnt = nullptr;   // pinned host copy, valid once `done` has completed
+        void *stage_rgba8 = nullptr;     // device copies the read-back streams from, so the next K1 may overwrite the images
+        float *stage_depth = nullptr;
+        cudaEvent_t k_done = nullptr, done = nullptr, t0 = nullptr, t1 = nullptr, t2 = nullptr, t3 = nullptr;
+        bool pending = false, with_k2 = false;
+        uint32_t launches = 0;
+    } slots[2];
+    unsigned slot_head = 0, slot_tail = 0; // begin fills slots[head % 2], wait drains slots[tail % 2]
     bool warp_profile = false;          // per-warp schedule profile of the path kernel
     size_t warp_prof_warps = 0;
     bool stage_timing = false;          // record an event between the K1 stage launches
@@ -194,6 +211,8 @@ void compute_shard(gdpt_shader *s)
     a.n_work = tiles_x * tiles_y * 32u;
 }
 
+int ensure_slot(gdpt_shader *m, gdpt_shader::FrameSlot &sl, bool want_depth);
+
 int alloc_warp_profile(gdpt_shader *s)
 {
     FrameArgs &a = s->args;
@@ -278,14 +297,14 @@ int finish_main(gdpt_shader *s)
     init_launch_shapes(d->ordinal);
     if (a.schedule == 4 && (rc = dev_alloc(s, &a.path_recs, mux_path_record_quads()))) return rc;
     a.refill_below = a.schedule >= 2 ? 24 : 20;
-    a.burst = a.schedule == 0 ? 8 : 16;
+    a.burst = a.schedule == 0 ? 8 : (a.schedule == 3 ? 4 : 16);
     a.shade_at = 8;
     if (const char *e = getenv("GDPT_REFILL_BELOW")) a.refill_below = atoi(e);
     if (const char *e = getenv("GDPT_BURST")) a.burst = atoi(e);
     if (const char *e = getenv("GDPT_SHADE_AT")) a.shade_at = atoi(e);
     a.blocks_per_sm = 0;
     if (const char *e = getenv("GDPT_BLOCKS_PER_SM")) a.blocks_per_sm = atoi(e);
-    a.path_minb = 4;
+    a.path_minb = 1; // 1: compact loop (default); 4/5/6/8: the first-generation loop at that occupancy; 2: compact, 6 blocks/SM
     if (const char *e = getenv("GDPT_PATH_MINB")) a.path_minb = atoi(e);
     a.lead_min = 0;
     if (const char *e = getenv("GDPT_LEAD_MIN")) a.lead_min = atoi(e);
@@ -301,6 +320,11 @@ int finish_main(gdpt_shader *s)
         if (s->visits_per_ray > 0 && (rc = dev_alloc(s, &a.visits, (size_t)rp.width * rp.height * s->visits_per_ray))) return rc;
     }
     compute_shard(s);
+    // the two frame slots of gdpt_render_frame_begin are set up here, not on the first pipelined frame
+    for (auto &sl : s->slots) {
+        sl.dcnt = nullptr; sl.stage_rgba8 = nullptr; sl.stage_depth = nullptr; // (re)allocated with the derived buffers
+        if ((rc = ensure_slot(s, sl, false))) return rc;
+    }
     if (s->warp_profile) return alloc_warp_profile(s);
     return GDPT_OK;
 }
@@ -423,6 +447,13 @@ int gdpt_device_create(int cuda_ordinal, gdpt_device **out_device)
         return GDPT_ERR_CUDA;
     }
     for (int i = 0; i < 4; i++) cudaEventCreate(&d->ev[i]);
+    if (cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaHostAlloc(reinterpret_cast<void **>(&d->ring), 8 * 512, cudaHostAllocDefault) != cudaSuccess) {
+        fail(nullptr, GDPT_ERR_CUDA, "device %d: copy stream / staging ring setup failed: %s", cuda_ordinal, cudaGetErrorString(cudaGetLastError()));
+        gdpt_device_destroy(d);
+        return GDPT_ERR_CUDA;
+    }
+    for (int i = 0; i < 8; i++) cudaEventCreateWithFlags(&d->ring_ev[i], cudaEventDisableTiming);
     init_launch_shapes(cuda_ordinal);
     *out_device = d;
     return GDPT_OK;
@@ -436,6 +467,9 @@ void gdpt_device_destroy(gdpt_device *d)
     for (auto &kv : d->resources) cudaFree(kv.second.dptr);
     for (int i = 0; i < 4; i++) if (d->ev[i]) cudaEventDestroy(d->ev[i]);
     if (d->pinned_staging) cudaFreeHost(d->pinned_staging);
+    if (d->copy_stream) { cudaStreamSynchronize(d->copy_stream); cudaStreamDestroy(d->copy_stream); }
+    if (d->ring) cudaFreeHost(d->ring);
+    for (int i = 0; i < 8; i++) if (d->ring_ev[i]) cudaEventDestroy(d->ring_ev[i]);
     cudaStreamDestroy(d->stream);
     delete d;
 }
@@ -499,8 +533,13 @@ void gdpt_shader_destroy(gdpt_shader *s)
     gdpt_device *d = s->dev;
     cudaSetDevice(d->ordinal);
     cudaStreamSynchronize(d->stream);
+    if (d->copy_stream) cudaStreamSynchronize(d->copy_stream);
     for (void *p : s->derived) cudaFree(p);
     for (cudaEvent_t e : s->stage_ev) cudaEventDestroy(e);
+    for (auto &sl : s->slots) {
+        if (sl.hcnt) cudaFreeHost(sl.hcnt);
+        for (cudaEvent_t e : { sl.k_done, sl.done, sl.t0, sl.t1, sl.t2, sl.t3 }) if (e) cudaEventDestroy(e);
+    }
     for (gdpt_rid rid : s->owned) {
         Resource *r = find(d, rid);
         if (r) { cudaFree(r->dptr); d->resources.erase(rid); }
@@ -835,3 +874,133 @@ int gdpt_shader_read_visits(gdpt_shader *s, uint32_t *out, uint32_t max_per_ray,
 }
 
 } // extern "C"
+
+// ---- pipelined frames -------------------------------------------------------------------------
+namespace {
+
+// 512 B of pinned memory that stays untouched until the copies enqueued from it have run
+int ring_take(gdpt_device *d, uint8_t **out, unsigned *slot_out)
+{
+    const unsigned i = d->ring_next++ & 7u;
+    if (d->ring_used[i]) GDPT_CUDA(d, cudaEventSynchronize(d->ring_ev[i]));
+    *out = d->ring + (size_t)i * 512u;
+    *slot_out = i;
+    return GDPT_OK;
+}
+
+int ensure_slot(gdpt_shader *m, gdpt_shader::FrameSlot &sl, bool want_depth)
+{
+    gdpt_device *d = m->dev;
+    const size_t n = (size_t)m->args.width * m->args.height;
+    int rc;
+    if (!sl.dcnt) {
+        if ((rc = dev_alloc(m, &sl.dcnt, 1))) return rc;
+        uint32_t *stage = nullptr;
+        if ((rc = dev_alloc(m, &stage, n))) return rc;
+        sl.stage_rgba8 = stage;
+    }
+    if (!sl.hcnt) {
+        GDPT_CUDA(d, cudaHostAlloc(reinterpret_cast<void **>(&sl.hcnt), sizeof(FrameCounters), cudaHostAllocDefault));
+        for (cudaEvent_t *e : { &sl.t0, &sl.t1, &sl.t2, &sl.t3 }) GDPT_CUDA(d, cudaEventCreate(e));
+        GDPT_CUDA(d, cudaEventCreateWithFlags(&sl.k_done, cudaEventDisableTiming));
+        GDPT_CUDA(d, cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+    }
+    if (want_depth && !sl.stage_depth && (rc = dev_alloc(m, &sl.stage_depth, n))) return rc;
+    return GDPT_OK;
+}
+
+} // namespace
+
+extern "C" int gdpt_render_frame_begin(gdpt_shader *m, gdpt_shader *p, const gdpt_camera *camera, gdpt_denoising mode,
+                                       uint32_t frame_count, void *out_rgba8, float *out_depth)
+{
+    if (!m || m->kind != SHADER_MAIN || !camera || !out_rgba8) return GDPT_ERR_INVALID_ARG;
+    gdpt_device *d = m->dev;
+    if (!gdpt_shader_check_ready(m)) return fail(d, GDPT_ERR_NOT_READY, "main shader is not ready");
+    if (mode == GDPT_DENOISE_TEMPORAL_REPROJECTION) return fail(d, GDPT_ERR_UNSUPPORTED, "temporal reprojection is not implemented yet");
+    if (mode == GDPT_DENOISE_PROGRESSIVE_RENDERING) {
+        if (!p || p->kind != SHADER_PROGRESSIVE || p->dev != d || !gdpt_shader_check_ready(p)) return fail(d, GDPT_ERR_NOT_READY, "progressive shader missing or not ready");
+        if (bound(p, 0, 1) != bound(m, 0, 0)) return fail(d, GDPT_ERR_BAD_BINDING, "progressive shader must share the main shader's output image (add_existing_buffer)");
+    }
+    gdpt_shader::FrameSlot &sl = m->slots[m->slot_head & 1u];
+    if (sl.pending) return fail(d, GDPT_ERR_NOT_READY, "two frames are already in flight: call gdpt_render_frame_wait first");
+    cudaSetDevice(d->ordinal);
+    int rc;
+    if ((rc = ensure_slot(m, sl, out_depth != nullptr))) return rc;
+
+    // per-frame H2D blocks come from the pinned ring: nothing here waits for the GPU
+    uint8_t *stage = nullptr; unsigned ring_slot = 0;
+    if ((rc = ring_take(d, &stage, &ring_slot))) return rc;
+    memcpy(stage, camera, sizeof(gdpt_camera));
+    Resource *cam_r = bound(m, 0, 3);
+    const size_t cam_bytes = cam_r->size < sizeof(gdpt_camera) ? cam_r->size : sizeof(gdpt_camera);
+    memcpy(cam_r->shadow.data(), camera, cam_bytes);
+    GDPT_CUDA(d, cudaMemcpyAsync(cam_r->dptr, stage, cam_bytes, cudaMemcpyHostToDevice, d->stream));
+    sl.with_k2 = (mode == GDPT_DENOISE_PROGRESSIVE_RENDERING);
+    if (sl.with_k2) {
+        Resource *pp = bound(p, 0, 0);
+        gdpt_progressive_params host_pp = { m->args.width, m->args.height, frame_count };
+        memcpy(stage + 256, &host_pp, sizeof(host_pp));
+        memcpy(pp->shadow.data(), &host_pp, sizeof(host_pp));
+        GDPT_CUDA(d, cudaMemcpyAsync(pp->dptr, stage + 256, sizeof(host_pp), cudaMemcpyHostToDevice, d->stream));
+    }
+    GDPT_CUDA(d, cudaEventRecord(d->ring_ev[ring_slot], d->stream));
+    d->ring_used[ring_slot] = true;
+
+    FrameCounters *const classic = m->args.counters;
+    m->args.counters = sl.dcnt; // this frame counts into its own block
+    GDPT_CUDA(d, cudaEventRecord(sl.t0, d->stream));
+    rc = enqueue_k1(m);
+    m->args.counters = classic;
+    if (rc) return rc;
+    sl.launches = m->stats.kernel_launches;
+    GDPT_CUDA(d, cudaEventRecord(sl.t1, d->stream));
+    if (sl.with_k2) {
+        GDPT_CUDA(d, cudaEventRecord(sl.t2, d->stream));
+        if ((rc = enqueue_k2(p, m->shard_part, m->shard_parts, m->shard_band))) return rc;
+        GDPT_CUDA(d, cudaEventRecord(sl.t3, d->stream));
+    }
+    const size_t n = (size_t)m->args.width * m->args.height;
+    GDPT_CUDA(d, cudaMemcpyAsync(sl.stage_rgba8, m->args.out_rgba8, n * 4, cudaMemcpyDeviceToDevice, d->stream));
+    if (out_depth) GDPT_CUDA(d, cudaMemcpyAsync(sl.stage_depth, m->args.out_depth, n * 4, cudaMemcpyDeviceToDevice, d->stream));
+    GDPT_CUDA(d, cudaMemcpyAsync(sl.hcnt, sl.dcnt, sizeof(FrameCounters), cudaMemcpyDeviceToHost, d->stream));
+    GDPT_CUDA(d, cudaEventRecord(sl.k_done, d->stream));
+    // the read-back leaves on the copy stream while the compute stream starts the next frame
+    GDPT_CUDA(d, cudaStreamWaitEvent(d->copy_stream, sl.k_done, 0));
+    GDPT_CUDA(d, cudaMemcpyAsync(out_rgba8, sl.stage_rgba8, n * 4, cudaMemcpyDeviceToHost, d->copy_stream));
+    if (out_depth) GDPT_CUDA(d, cudaMemcpyAsync(out_depth, sl.stage_depth, n * 4, cudaMemcpyDeviceToHost, d->copy_stream));
+    GDPT_CUDA(d, cudaEventRecord(sl.done, d->copy_stream));
+    sl.pending = true;
+    m->slot_head++;
+    m->stats_valid = false;
+    return GDPT_OK;
+}
+
+extern "C" int gdpt_render_frame_wait(gdpt_shader *m, gdpt_frame_stats *out_stats)
+{
+    if (!m || m->kind != SHADER_MAIN) return GDPT_ERR_INVALID_ARG;
+    gdpt_device *d = m->dev;
+    gdpt_shader::FrameSlot &sl = m->slots[m->slot_tail & 1u];
+    if (!sl.pending) return fail(d, GDPT_ERR_NOT_READY, "no frame in flight");
+    cudaSetDevice(d->ordinal);
+    GDPT_CUDA(d, cudaEventSynchronize(sl.done));
+    sl.pending = false;
+    m->slot_tail++;
+    const FrameCounters &c = *sl.hcnt;
+    if (c.overflow) return fail(d, GDPT_ERR_UNSUPPORTED, "a ray exceeded the reference's 64+64 traversal stack entries");
+    if (out_stats) {
+        memset(out_stats, 0, sizeof(*out_stats));
+        uint64_t rays = (uint64_t)m->args.width * m->args.local_rows;
+        if (m->args.schedule >= 2) rays = c.rays;
+        else if (!m->debug_steps)
+            for (int i = 1; i < m->args.max_depth; i++) rays += c.qcount[i];
+        out_stats->rays = rays;
+        out_stats->primary_hits = c.primary_hits;
+        out_stats->node_pops = c.node_pops; out_stats->box_tests = c.box_tests; out_stats->tri_tests = c.tri_tests;
+        out_stats->tlas_leaves = c.tlas_leaves; out_stats->max_stack = c.max_stack;
+        out_stats->kernel_launches = sl.launches;
+        cudaEventElapsedTime(&out_stats->k1_ms, sl.t0, sl.t1);
+        if (sl.with_k2) cudaEventElapsedTime(&out_stats->k2_ms, sl.t2, sl.t3);
+    }
+    return GDPT_OK;
+}

@@ -26,6 +26,10 @@
 
 #include <cstdio>
 
+#ifndef GDPT_OOL_COLD
+#define GDPT_OOL_COLD 1
+#endif
+
 namespace gdpt {
 
 namespace {
@@ -79,17 +83,16 @@ __device__ __forceinline__ unsigned long long global_ns()
 // Optional out-of-line form of the cold code (shading, ray generation).  Measured on the demo frame:
 // the call ABI's register spills cost more (k_path 1.67 -> 2.04 ms) than the smaller hot-loop
 // footprint saves, so it is off; kept for the compact-loop rework.
-constexpr bool kOutOfLineCold = false;
-__device__ __noinline__ void shade_and_bounce_ool(const SceneView *sc, const f3 *wo, const f3 *wd, float t, float u, float v,
-                                                  uint32_t tri, uint32_t blas_front, const f3 *radiance, const f3 *throughput,
-                                                  u2 *seed, BounceResult *out)
+constexpr bool kOutOfLineCold = GDPT_OOL_COLD != 0;
+struct PrimaryRay { f3 o, d; u2 seed; };
+__device__ __noinline__ void shade_and_bounce_ool(const SceneView *sc, f3 wo, f3 wd, float t, float u, float v, uint32_t tri,
+                                                  uint32_t blas_front, f3 radiance, f3 throughput, u2 *seed, BounceResult *out)
 {
-    *out = shade_and_bounce(*sc, *wo, *wd, t, u, v, tri, blas_front, *radiance, *throughput, *seed);
+    *out = shade_and_bounce(*sc, wo, wd, t, u, v, tri, blas_front, radiance, throughput, *seed);
 }
-__device__ __noinline__ void generate_primary_ray_ool(const gdpt_camera *cam, int width, int height, int px, int py, f3 *o, f3 *d,
-                                                      u2 *seed)
+__device__ __noinline__ void generate_primary_ray_ool(const gdpt_camera *cam, int width, int height, int px, int py, PrimaryRay *out)
 {
-    *seed = generate_primary_ray(*cam, width, height, px, py, o, d);
+    out->seed = generate_primary_ray(*cam, width, height, px, py, &out->o, &out->d);
 }
 
 __device__ __forceinline__ uint32_t class_base(const FrameArgs &a, int c)
@@ -373,7 +376,11 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(const FrameArgs a, cons
 //
 // SRC 0: work items are 8x4-pixel tiles of the whole (sharded) image.  SRC 1: work items are the
 // pixels k_primary_cull left in `hit_list` (camera rays that touch some instance's tight box).
-template <bool TRACE, bool CULL, int SRC, int MINB = 4>
+// COMPACT: the hot loop is written for the instruction cache (32 KB L1.5, ~6 KB L0): one copy of the
+// box code serves BLAS and TLAS internal nodes, leaves run one triangle-test body in a short loop,
+// instance entry/exit is its own small phase, the phase census is one REDUX, and shading / ray
+// generation are called out of line with by-value arguments.
+template <bool TRACE, bool CULL, int SRC, int MINB = 4, bool COMPACT = false>
 __global__ void __launch_bounds__(kTraceThreads, MINB) k_path(const FrameArgs a)
 {
     __shared__ uint32_t s_stack[kSmemStack * kTraceThreads];
@@ -397,6 +404,7 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path(const FrameArgs a)
     const int shade_at = min(max(a.shade_at, 1), 32);
     const uint32_t lead_min = a.lead_min > 0 ? (uint32_t)a.lead_min : 0xFFFFFFFFu;
     uint32_t steps = 0; // scheduler iterations this lane's current path took part in
+    uint32_t pred = 0;  // what its pixel's path cost in the previous frame (0 = unknown / light)
     bool heavy_done = false; // warp-uniform: the heavy classes are handed out
     const int last_segment = a.debug_steps ? 0 : a.max_depth - 1;
 
@@ -420,17 +428,34 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path(const FrameArgs a)
 
     for (;;) {
         const bool in_l = has && (tri_next < tri_end || link_is_blas_leaf(r.cur));
-        const bool in_i = has && !in_l && link_is_blas_internal(r.cur);
+        const bool in_i = has && !in_l && (COMPACT ? link_is_node_step(r.cur, r.inst) : link_is_blas_internal(r.cur));
         const bool in_t = has && !in_l && !in_i && r.cur != LINK_NONE;
         const bool fin = has && !in_l && !in_i && !in_t;
-        const int n_l = __popc(__ballot_sync(kFull, in_l)), n_i = __popc(__ballot_sync(kFull, in_i)),
-                  n_t = __popc(__ballot_sync(kFull, in_t)), n_fin = __popc(__ballot_sync(kFull, fin));
-        const unsigned idle = __ballot_sync(kFull, !has);
-        const int n_walk = n_l + n_i + n_t, n_idle = __popc(idle);
+        int n_l, n_i, n_t, n_fin, n_idle;
+        unsigned idle;
+        if (COMPACT) {
+            // one REDUX: every lane adds 1 into the 6-bit field of its phase
+            const uint32_t census = __reduce_add_sync(kFull, 1u << (in_l ? 0 : (in_i ? 6 : (in_t ? 12 : (fin ? 18 : 24)))));
+            n_l = (int)(census & 63u); n_i = (int)((census >> 6) & 63u); n_t = (int)((census >> 12) & 63u);
+            n_fin = (int)((census >> 18) & 63u); n_idle = (int)(census >> 24);
+            idle = 0u; // taken by ballot only where it is needed (refill)
+        } else {
+            n_l = __popc(__ballot_sync(kFull, in_l)); n_i = __popc(__ballot_sync(kFull, in_i));
+            n_t = __popc(__ballot_sync(kFull, in_t)); n_fin = __popc(__ballot_sync(kFull, fin));
+            idle = __ballot_sync(kFull, !has);
+            n_idle = __popc(idle);
+        }
+        const int n_walk = n_l + n_i + n_t;
         // critical-path-first: once some path is long, the longest one picks the phase, so the path
         // that decides when the kernel ends moves every iteration
         int lead_phase = -1; // 0 L, 1 I, 2 T, 3 finished
-        {
+        if (COMPACT) {
+            // the lane whose path is expected to run longest (previous frame's cost) picks the phase, so the
+            // path that decides when this warp ends advances every iteration instead of every other one
+            const uint32_t key = (has && pred >= lead_min) ? ((pred << 5) | lane) : 0u; // pred < 2^27: unique per lane
+            const uint32_t most = __reduce_max_sync(kFull, key);
+            if (most != 0u) lead_phase = __shfl_sync(kFull, in_l ? 0 : (in_i ? 1 : (in_t ? 2 : 3)), most & 31u);
+        } else {
             const uint32_t key = has ? steps : 0u;
             const uint32_t most = __reduce_max_sync(kFull, key);
             if (most >= lead_min) {
@@ -463,8 +488,13 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path(const FrameArgs a)
                     if (segment == 0) a.out_depth[pixel] = encode_depth(cam, cam.z_far);
                 } else {
                     BounceResult br;
-                    if (TRACE || !kOutOfLineCold) br = shade_and_bounce(a.sc, r.wo, r.wd, r.t, r.u, r.v, r.tri, r.blas_front, radiance, throughput, seed);
-                    else shade_and_bounce_ool(&a.sc, &r.wo, &r.wd, r.t, r.u, r.v, r.tri, r.blas_front, &radiance, &throughput, &seed, &br);
+                    if (COMPACT && kOutOfLineCold) {
+                        u2 sd = seed; // by value: nothing the hot loop keeps in registers has its address taken
+                        shade_and_bounce_ool(&a.sc, r.wo, r.wd, r.t, r.u, r.v, r.tri, r.blas_front, radiance, throughput, &sd, &br);
+                        seed = sd;
+                    } else {
+                        br = shade_and_bounce(a.sc, r.wo, r.wd, r.t, r.u, r.v, r.tri, r.blas_front, radiance, throughput, seed);
+                    }
                     radiance = br.radiance;
                     if (segment == 0) a.out_depth[pixel] = encode_depth(cam, br.first_hit_distance);
                     alive = br.alive && segment < last_segment;
@@ -508,6 +538,7 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path(const FrameArgs a)
                 chunk_next = base;
                 chunk_end = min(base + len, total);
             }
+            if (COMPACT) idle = __ballot_sync(kFull, !has);
             const uint32_t avail = chunk_end - chunk_next;
             const uint32_t rank = __popc(idle & lanemask_lt);
             if (!has && rank < avail) {
@@ -517,12 +548,18 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path(const FrameArgs a)
                 else {
                     const uint32_t p = lists.pixel(a, chunk_next + rank);
                     py = (int)(p / (uint32_t)a.width); px = (int)(p - (uint32_t)py * (uint32_t)a.width);
+                    pred = min(a.cost[p], (1u << 27) - 1u);
                     valid = true;
                 }
                 if (valid) {
                     f3 o, d;
-                    if (TRACE || !kOutOfLineCold) seed = generate_primary_ray(cam, a.width, a.height, px, py, &o, &d);
-                    else generate_primary_ray_ool(&cam, a.width, a.height, px, py, &o, &d, &seed);
+                    if (COMPACT && kOutOfLineCold) {
+                        PrimaryRay pr;
+                        generate_primary_ray_ool(&cam, a.width, a.height, px, py, &pr);
+                        o = pr.o; d = pr.d; seed = pr.seed;
+                    } else {
+                        seed = generate_primary_ray(cam, a.width, a.height, px, py, &o, &d);
+                    }
                     pixel = (uint32_t)py * (uint32_t)a.width + (uint32_t)px;
                     throughput = mk3(1.0f, 1.0f, 1.0f); radiance = mk3(0.0f, 0.0f, 0.0f);
                     segment = 0;
@@ -543,15 +580,45 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path(const FrameArgs a)
         // ---------------- L / I / T: one traversal step of the leading path's phase, else the most popular ----------------
         int run = (n_l >= n_i && n_l >= n_t) ? 0 : (n_i >= n_t ? 1 : 2);
         if (lead_phase >= 0 && lead_phase < 3) run = lead_phase;
+        if (COMPACT && run == 1 && a.burst > 1) {
+            // node burst: keep descending while at least half of the lanes that started stay on internal nodes
+            // (no census in between): the long paths spend most of their steps here
+            it_i++;
+            bool go = in_i;
+            int need = (n_i + 1) >> 1;
+#pragma unroll 1
+            for (int b = 0; b < a.burst; b++) {
+                if (go) { step_node<TRACE, CULL>(a.sc, r, st, &tc); steps++; go = link_is_node_step(r.cur, r.inst); }
+                if (__popc(__ballot_sync(kFull, go)) < need) break;
+            }
+            continue;
+        }
         if (run == 0) {
             it_l++;
-            if (in_l) { step_blas_leaf_some<TRACE, kLeafTris>(a.sc, r, st, &tc, tri_next, tri_end); steps++; }
+            if (in_l) {
+                if (COMPACT) {
+                    step_blas_leaf_one<TRACE>(a.sc, r, st, &tc, tri_next, tri_end); // enters the leaf if needed + first test
+#pragma unroll 1
+                    for (int i = 1; i < kLeafTris && tri_next < tri_end; i++) triangle_test(a.sc, r, tri_next++);
+                } else {
+                    step_blas_leaf_some<TRACE, kLeafTris>(a.sc, r, st, &tc, tri_next, tri_end);
+                }
+                steps++;
+            }
         } else if (run == 1) {
             it_i++;
-            if (in_i) { step_blas_internal<TRACE, CULL>(a.sc, r, st, &tc); steps++; }
+            if (in_i) {
+                if (COMPACT) step_node<TRACE, CULL>(a.sc, r, st, &tc);
+                else step_blas_internal<TRACE, CULL>(a.sc, r, st, &tc);
+                steps++;
+            }
         } else {
             it_t++;
-            if (in_t) { step_tlas<TRACE, CULL>(a.sc, r, st, &tc); steps++; }
+            if (in_t) {
+                if (COMPACT) step_instance<TRACE, CULL>(a.sc, r, st, &tc);
+                else step_tlas<TRACE, CULL>(a.sc, r, st, &tc);
+                steps++;
+            }
         }
     }
     if (prof && lane == 0) {
@@ -878,7 +945,7 @@ __global__ void __launch_bounds__(kMuxThreads, MINB) k_path_mux(const FrameArgs 
                     if (segment == 0) a.out_depth[pixel] = encode_depth(cam, cam.z_far);
                 } else {
                     BounceResult br;
-                    if (kOutOfLineCold) shade_and_bounce_ool(&sc, &wo, &wd, t, m.ldf(MF_U), m.ldf(MF_V), m.ldu(MF_TRI), m.ldu(MF_BF), &radiance, &throughput, &seed, &br);
+                    if (kOutOfLineCold) shade_and_bounce_ool(&sc, wo, wd, t, m.ldf(MF_U), m.ldf(MF_V), m.ldu(MF_TRI), m.ldu(MF_BF), radiance, throughput, &seed, &br);
                     else br = shade_and_bounce(sc, wo, wd, t, m.ldf(MF_U), m.ldf(MF_V), m.ldu(MF_TRI), m.ldu(MF_BF), radiance, throughput, seed);
                     radiance = br.radiance;
                     if (segment == 0) a.out_depth[pixel] = encode_depth(cam, br.first_hit_distance);
@@ -910,8 +977,13 @@ __global__ void __launch_bounds__(kMuxThreads, MINB) k_path_mux(const FrameArgs 
                 const int py = (int)(pixel / (uint32_t)a.width), px = (int)(pixel - (uint32_t)py * (uint32_t)a.width);
                 f3 o, d;
                 u2 seed;
-                if (kOutOfLineCold) generate_primary_ray_ool(&cam, a.width, a.height, px, py, &o, &d, &seed);
-                else seed = generate_primary_ray(cam, a.width, a.height, px, py, &o, &d);
+                if (kOutOfLineCold) {
+                    PrimaryRay pr;
+                    generate_primary_ray_ool(&cam, a.width, a.height, px, py, &pr);
+                    o = pr.o; d = pr.d; seed = pr.seed;
+                } else {
+                    seed = generate_primary_ray(cam, a.width, a.height, px, py, &o, &d);
+                }
                 mux_begin_segment<K>(sc, m, my_recs + k * 5, o, d, mk3(1.0f, 1.0f, 1.0f), mk3(0.0f, 0.0f, 0.0f), seed, pixel, 0u);
                 next_phase = mux_phase_of(sc.tlas_root_link, false, GDPT_NO_INSTANCE);
             }
@@ -1109,6 +1181,8 @@ void init_launch_shapes(int device)
     s.path_blocks[1][1] = grid_of(k_path<true, true, 0>, kTraceThreads);
     s.path_list_blocks[0] = grid_of(k_path<false, true, 1>, kTraceThreads);
     s.path_list_blocks[1] = grid_of(k_path<true, true, 1>, kTraceThreads);
+    s.path_list_blocks_minb[1] = grid_of(k_path<false, true, 1, 4, true>, kTraceThreads);
+    s.path_list_blocks_minb[2] = grid_of(k_path<false, true, 1, 6, true>, kTraceThreads);
     s.path_list_blocks_minb[5] = grid_of(k_path<false, true, 1, 5>, kTraceThreads);
     s.path_list_blocks_minb[6] = grid_of(k_path<false, true, 1, 6>, kTraceThreads);
     s.path_list_blocks_minb[8] = grid_of(k_path<false, true, 1, 8>, kTraceThreads);
@@ -1164,6 +1238,8 @@ void launch_path_list(const FrameArgs &a, bool trace, cudaStream_t s)
 {
     Shapes &sh = shapes_for_current_device();
     if (trace) k_path<true, true, 1><<<persistent_grid(sh, a, sh.path_list_blocks[1]), kTraceThreads, 0, s>>>(a);
+    else if (a.path_minb == 1) k_path<false, true, 1, 4, true><<<persistent_grid(sh, a, sh.path_list_blocks_minb[1]), kTraceThreads, 0, s>>>(a);
+    else if (a.path_minb == 2) k_path<false, true, 1, 6, true><<<persistent_grid(sh, a, sh.path_list_blocks_minb[2]), kTraceThreads, 0, s>>>(a);
     else if (a.path_minb == 5) k_path<false, true, 1, 5><<<persistent_grid(sh, a, sh.path_list_blocks_minb[5]), kTraceThreads, 0, s>>>(a);
     else if (a.path_minb == 6) k_path<false, true, 1, 6><<<persistent_grid(sh, a, sh.path_list_blocks_minb[6]), kTraceThreads, 0, s>>>(a);
     else if (a.path_minb == 8) k_path<false, true, 1, 8><<<persistent_grid(sh, a, sh.path_list_blocks_minb[8]), kTraceThreads, 0, s>>>(a);
@@ -1222,7 +1298,7 @@ size_t mux_path_record_quads()
 size_t path_kernel_warps(const FrameArgs &a)
 {
     Shapes &sh = shapes_for_current_device();
-    if (a.schedule == 3 && (a.path_minb == 5 || a.path_minb == 6 || a.path_minb == 8)) return (size_t)sh.path_list_blocks_minb[a.path_minb] * (kTraceThreads / 32);
+    if (a.schedule == 3 && (a.path_minb == 1 || a.path_minb == 2 || a.path_minb == 5 || a.path_minb == 6 || a.path_minb == 8)) return (size_t)sh.path_list_blocks_minb[a.path_minb] * (kTraceThreads / 32);
     if (a.schedule == 4) return (size_t)sh.mux_blocks[(a.mux_k >= 1 && a.mux_k <= 4) ? a.mux_k : 2] * (kMuxThreads / 32);
     int most = 0;
     for (int t = 0; t < 2; t++) {

@@ -274,49 +274,79 @@ GDPT_HD void step_blas_leaf_some(const SceneView &sc, RayState &r, Stack &st, Tr
     tri_next = (tri_end - tri_next > (uint32_t)N) ? tri_next + (uint32_t)N : tri_end;
 }
 
+// Back to world space after an instance (main.glsl:316-327: the TLAS loop keeps using `ray`).
+template <bool TRACE>
+GDPT_HD void leave_instance(RayState &r, TraceCounters *tc)
+{
+    r.o = r.wo; r.d = r.wd; r.rd = rcp3(r.wd);
+    r.inst = GDPT_NO_INSTANCE;
+    if (TRACE) tc->level_base = 0u;
+}
+
+// r.cur is a TLAS leaf and the ray is in world space: enter the instance (main.glsl:316-323).
+template <bool TRACE, bool CULL, class Stack>
+GDPT_HD void enter_instance(const SceneView &sc, RayState &r, Stack &st, TraceCounters *tc)
+{
+    const uint32_t idx = r.cur & LINK_INDEX_MASK;
+    const q4f c0 = ldq(sc.inst_recs, idx * 7u + 0u);
+    const q4f c1 = ldq(sc.inst_recs, idx * 7u + 1u);
+    const q4f c2 = ldq(sc.inst_recs, idx * 7u + 2u);
+    const q4f c3 = ldq(sc.inst_recs, idx * 7u + 3u);
+    const q4u tail = ldqu(sc.inst_recs, idx * 7u + 4u);
+    if (TRACE) {
+        counters_visit(*tc, tail.y | GDPT_VISIT_TLAS_TAG);
+        tc->tlas_leaves++;
+        tc->level_base = r.sp; // BLAS stack starts empty; its root push counts 1 (<= max_stack init)
+    }
+    // b_ray = inverse_transform * (ray.o, 1), * (ray.d, 0); d is NOT renormalised, so t is shared
+    r.o = mk3(((c0.x * r.wo.x + c1.x * r.wo.y) + c2.x * r.wo.z) + c3.x * 1.0f,
+              ((c0.y * r.wo.x + c1.y * r.wo.y) + c2.y * r.wo.z) + c3.y * 1.0f,
+              ((c0.z * r.wo.x + c1.z * r.wo.y) + c2.z * r.wo.z) + c3.z * 1.0f);
+    r.d = mk3(((c0.x * r.wd.x + c1.x * r.wd.y) + c2.x * r.wd.z) + c3.x * 0.0f,
+              ((c0.y * r.wd.x + c1.y * r.wd.y) + c2.y * r.wd.z) + c3.y * 0.0f,
+              ((c0.z * r.wd.x + c1.z * r.wd.y) + c2.z * r.wd.z) + c3.z * 0.0f);
+    r.rd = rcp3(r.d);
+    r.inst = idx;
+    r.cur = tail.x;
+    if (CULL) {
+        // the BLAS root is never box-tested upstream (main.glsl:274); with culling, an instance whose
+        // true bounds the local ray misses is left again at once (nothing in it can be hit)
+        const q4f tmin4 = ldq(sc.inst_recs, idx * 7u + 5u);
+        const q4f tmax4 = ldq(sc.inst_recs, idx * 7u + 6u);
+        if (TRACE) tc->box_tests += 1u;
+        if (!slab_touches(r, tmin4.x, tmin4.y, tmin4.z, tmax4.x, tmax4.y, tmax4.z)) r.cur = stack_pop(r, st);
+    }
+}
+
 // One TLAS-level entry: leave the instance we were in (if any), then either
 // enter an instance (main.glsl:316-323) or test the two TLAS children (:330-346).
 template <bool TRACE, bool CULL, class Stack>
 GDPT_HD void step_tlas(const SceneView &sc, RayState &r, Stack &st, TraceCounters *tc)
 {
-    if (r.inst != GDPT_NO_INSTANCE) {
-        r.o = r.wo; r.d = r.wd; r.rd = rcp3(r.wd);
-        r.inst = GDPT_NO_INSTANCE;
-        if (TRACE) tc->level_base = 0u;
-    }
-    const uint32_t idx = r.cur & LINK_INDEX_MASK;
-    if (r.cur & LINK_LEAF) {
-        const q4f c0 = ldq(sc.inst_recs, idx * 7u + 0u);
-        const q4f c1 = ldq(sc.inst_recs, idx * 7u + 1u);
-        const q4f c2 = ldq(sc.inst_recs, idx * 7u + 2u);
-        const q4f c3 = ldq(sc.inst_recs, idx * 7u + 3u);
-        const q4u tail = ldqu(sc.inst_recs, idx * 7u + 4u);
-        if (TRACE) {
-            counters_visit(*tc, tail.y | GDPT_VISIT_TLAS_TAG);
-            tc->tlas_leaves++;
-            tc->level_base = r.sp; // BLAS stack starts empty; its root push counts 1 (<= max_stack init)
-        }
-        // b_ray = inverse_transform * (ray.o, 1), * (ray.d, 0); d is NOT renormalised, so t is shared
-        r.o = mk3(((c0.x * r.wo.x + c1.x * r.wo.y) + c2.x * r.wo.z) + c3.x * 1.0f,
-                  ((c0.y * r.wo.x + c1.y * r.wo.y) + c2.y * r.wo.z) + c3.y * 1.0f,
-                  ((c0.z * r.wo.x + c1.z * r.wo.y) + c2.z * r.wo.z) + c3.z * 1.0f);
-        r.d = mk3(((c0.x * r.wd.x + c1.x * r.wd.y) + c2.x * r.wd.z) + c3.x * 0.0f,
-                  ((c0.y * r.wd.x + c1.y * r.wd.y) + c2.y * r.wd.z) + c3.y * 0.0f,
-                  ((c0.z * r.wd.x + c1.z * r.wd.y) + c2.z * r.wd.z) + c3.z * 0.0f);
-        r.rd = rcp3(r.d);
-        r.inst = idx;
-        r.cur = tail.x;
-        if (CULL) {
-            // the BLAS root is never box-tested upstream (main.glsl:274); with culling, an instance whose
-            // true bounds the local ray misses is left again at once (nothing in it can be hit)
-            const q4f tmin4 = ldq(sc.inst_recs, idx * 7u + 5u);
-            const q4f tmax4 = ldq(sc.inst_recs, idx * 7u + 6u);
-            if (TRACE) tc->box_tests += 1u;
-            if (!slab_touches(r, tmin4.x, tmin4.y, tmin4.z, tmax4.x, tmax4.y, tmax4.z)) r.cur = stack_pop(r, st);
-        }
-        return;
-    }
-    visit_wide<TRACE, CULL>(sc.wide_tlas, idx, GDPT_VISIT_TLAS_TAG, r, st, tc);
+    if (r.inst != GDPT_NO_INSTANCE) leave_instance<TRACE>(r, tc);
+    if (r.cur & LINK_LEAF) { enter_instance<TRACE, CULL>(sc, r, st, tc); return; }
+    visit_wide<TRACE, CULL>(sc.wide_tlas, r.cur & LINK_INDEX_MASK, GDPT_VISIT_TLAS_TAG, r, st, tc);
+}
+
+// The compact scheduler's split of the same work: `step_node` takes any internal node -- BLAS, or
+// TLAS while the ray is in world space -- through ONE copy of the box code; `step_instance` does the
+// space changes (leave and/or enter) and leaves a TLAS-internal link for the next `step_node`.
+GDPT_HD bool link_is_node_step(uint32_t l, uint32_t inst)
+{
+    return (l & LINK_LEAF) == 0u && l != LINK_NONE && ((l & LINK_TLAS) == 0u || inst == GDPT_NO_INSTANCE);
+}
+template <bool TRACE, bool CULL, class Stack>
+GDPT_HD void step_node(const SceneView &sc, RayState &r, Stack &st, TraceCounters *tc)
+{
+    const bool top = (r.cur & LINK_TLAS) != 0u;
+    const void *table = top ? static_cast<const void *>(sc.wide_tlas) : static_cast<const void *>(sc.wide_nodes);
+    visit_wide<TRACE, CULL>(table, r.cur & LINK_INDEX_MASK, top ? GDPT_VISIT_TLAS_TAG : 0u, r, st, tc);
+}
+template <bool TRACE, bool CULL, class Stack>
+GDPT_HD void step_instance(const SceneView &sc, RayState &r, Stack &st, TraceCounters *tc)
+{
+    if (r.inst != GDPT_NO_INSTANCE) leave_instance<TRACE>(r, tc);
+    if (r.cur & LINK_LEAF) enter_instance<TRACE, CULL>(sc, r, st, tc);
 }
 
 GDPT_HD bool link_is_blas_internal(uint32_t l) { return (l & (LINK_TLAS | LINK_LEAF)) == 0u; }
@@ -343,6 +373,18 @@ GDPT_HD void trace_ray_stepwise(const SceneView &sc, RayState &r, Stack &st, Tra
         if (tri_next < tri_end || link_is_blas_leaf(r.cur)) step_blas_leaf_one<TRACE>(sc, r, st, tc, tri_next, tri_end);
         else if (link_is_blas_internal(r.cur)) step_blas_internal<TRACE, CULL>(sc, r, st, tc);
         else step_tlas<TRACE, CULL>(sc, r, st, tc);
+    }
+}
+
+// The order the compact path kernel uses: node steps / instance steps / single-triangle steps.
+template <bool TRACE, bool CULL, class Stack>
+GDPT_HD void trace_ray_compact(const SceneView &sc, RayState &r, Stack &st, TraceCounters *tc)
+{
+    uint32_t tri_next = 0, tri_end = 0;
+    while (r.cur != LINK_NONE || tri_next < tri_end) {
+        if (tri_next < tri_end || link_is_blas_leaf(r.cur)) step_blas_leaf_one<TRACE>(sc, r, st, tc, tri_next, tri_end);
+        else if (link_is_node_step(r.cur, r.inst)) step_node<TRACE, CULL>(sc, r, st, tc);
+        else step_instance<TRACE, CULL>(sc, r, st, tc);
     }
 }
 

@@ -114,6 +114,8 @@ void gdpt_camera_set_fused_frame(gdpt_camera_node *c, int on) { c->impl.set_fuse
 int gdpt_camera_init(gdpt_camera_node *c) { return c->impl.init() ? 1 : 0; }
 void gdpt_camera_render(gdpt_camera_node *c) { c->impl.render(); }
 void gdpt_camera_render_device_only(gdpt_camera_node *c) { c->impl.render_device_only(); }
+int gdpt_camera_render_begin(gdpt_camera_node *c) { return c->impl.render_begin() ? 1 : 0; }
+const uint8_t *gdpt_camera_render_wait(gdpt_camera_node *c, gdpt_frame_stats *stats) { return c->impl.render_wait(stats); }
 const uint8_t *gdpt_camera_output_image(const gdpt_camera_node *c) { return c->impl.get_output_image(); }
 gdpt_shader *gdpt_camera_main_shader(const gdpt_camera_node *c) { return c->impl.compute_shader() ? c->impl.compute_shader()->handle() : nullptr; }
 gdpt_shader *gdpt_camera_progressive_shader(const gdpt_camera_node *c)

@@ -63,6 +63,7 @@ PathTracingCamera::~PathTracingCamera()
     delete progressive_renderer_;
     delete cs_;
     if (output_image_) gdpt_host_free(output_image_);
+    if (pipeline_image_[1]) gdpt_host_free(pipeline_image_[1]); // [0] is output_image_
     if (rd_) gdpt_device_destroy(rd_);
 }
 
@@ -161,6 +162,48 @@ void PathTracingCamera::render_device_only()
     last_frame_count_ = frame_count;
     if (gdpt_render_frame_async(cs_->handle(), prog, &camera_, (gdpt_denoising)denoising_mode_, frame_count) != GDPT_OK)
         std::fprintf(stderr, "render_frame_async: %s\n", gdpt_last_error(rd_));
+}
+
+bool PathTracingCamera::render_begin()
+{
+    if (cs_ == nullptr || !cs_->check_ready()) return false;
+    if (pipe_head_ - pipe_tail_ >= 2) {
+        std::fprintf(stderr, "render_begin: two frames are already in flight\n");
+        return false;
+    }
+    if (!pipeline_image_[1]) {
+        pipeline_image_[0] = output_image_;
+        pipeline_image_[1] = static_cast<uint8_t *>(gdpt_host_alloc((size_t)window_w_ * window_h_ * 4));
+        if (!pipeline_image_[1]) return false;
+    }
+    camera_.set_camera_transform(global_transform_, projection_matrix_);
+    camera_.frame_index++;
+    gdpt_shader *prog = nullptr;
+    uint32_t frame_count = 0;
+    if (denoising_mode_ == PROGRESSIVE_RENDERING) {
+        ensure_progressive();
+        frame_count = progressive_renderer_->advance(global_transform_);
+        prog = progressive_renderer_->shader()->handle();
+    }
+    last_frame_count_ = frame_count;
+    if (gdpt_render_frame_begin(cs_->handle(), prog, &camera_, (gdpt_denoising)denoising_mode_, frame_count,
+                                pipeline_image_[pipe_head_ & 1u], nullptr) != GDPT_OK) {
+        std::fprintf(stderr, "render_frame_begin: %s\n", gdpt_last_error(rd_));
+        return false;
+    }
+    pipe_head_++;
+    return true;
+}
+
+const uint8_t *PathTracingCamera::render_wait(gdpt_frame_stats *stats)
+{
+    if (cs_ == nullptr || pipe_head_ == pipe_tail_) return nullptr;
+    if (gdpt_render_frame_wait(cs_->handle(), stats) != GDPT_OK) {
+        std::fprintf(stderr, "render_frame_wait: %s\n", gdpt_last_error(rd_));
+        pipe_tail_++;
+        return nullptr;
+    }
+    return pipeline_image_[pipe_tail_++ & 1u];
 }
 
 void PathTracingCamera::render()

@@ -80,6 +80,11 @@ public:
     void render();
     // render without the device->host read-back (frame stays in the output RID)
     void render_device_only();
+    // pipelined render(): begin() enqueues a frame including its read-back and returns; wait() blocks until the
+    // oldest frame in flight (at most two) is in host memory and returns it (nullptr if none / on error).
+    // Frame N's read-back overlaps frame N+1's kernels.
+    bool render_begin();
+    const uint8_t *render_wait(gdpt_frame_stats *stats = nullptr);
 
     ComputeShader *compute_shader() const { return cs_; }
     ProgressiveRendering *progressive() const { return progressive_renderer_; }
@@ -97,6 +102,8 @@ private:
     ProgressiveRendering *progressive_renderer_ = nullptr;
     GeometryGroup3D *geometry_group_ = nullptr;
     uint8_t *output_image_ = nullptr; // pinned, W*H*4
+    uint8_t *pipeline_image_[2] = { nullptr, nullptr }; // pinned targets of the frames in flight
+    unsigned pipe_head_ = 0, pipe_tail_ = 0;
     gdpt_render_params render_parameters_ = {};
     CameraBlock camera_;
     Mat4 projection_matrix_;

@@ -201,13 +201,34 @@ class PathTracingCamera:
     def render_device_only(self):
         host.gdpt_camera_render_device_only(self._h)
 
+    def render_begin(self):
+        """Pipelined render(): enqueue one frame including its read-back; at most two may be in flight."""
+        if host.gdpt_camera_render_begin(self._h) != 1:
+            raise _lib.GdptError("render_begin failed: " + (cuda.gdpt_last_error(self.device) or b"").decode())
+
+    def render_wait(self):
+        """Block for the oldest frame in flight.  Returns (image, stats): the image is a zero-copy view of the
+        page-locked buffer the frame was read back into, valid until two more frames have been begun."""
+        st = _lib.FrameStats()
+        p = host.gdpt_camera_render_wait(self._h, ctypes.byref(st))
+        if not p:
+            raise _lib.GdptError("render_wait failed: " + (cuda.gdpt_last_error(self.device) or b"").decode())
+        return self._pinned_view(p), {k: getattr(st, k) for k, _ in _lib.FrameStats._fields_}
+
+    def _pinned_view(self, address):
+        """numpy view of one of this camera's page-locked frame buffers; the view keeps the camera alive."""
+        n = self._w * self._h_px * 4
+        buf = (ctypes.c_uint8 * n).from_address(address)
+        buf._owner = self  # the array's base is `buf`: the buffers are not freed under a live view
+        return np.ctypeslib.as_array(buf).reshape(self._h_px, self._w, 4)
+
     def synchronize(self):
         _lib.check(cuda.gdpt_device_synchronize(self.device), self.device, "synchronize")
 
     def output_image(self):
-        p = host.gdpt_camera_output_image(self._h)
-        n = self._w * self._h_px * 4
-        return np.frombuffer(ctypes.string_at(p, n), np.uint8).reshape(self._h_px, self._w, 4)
+        """Zero-copy view of the page-locked buffer render() reads the frame back into (overwritten by the
+        next render(); copy it to keep it)."""
+        return self._pinned_view(host.gdpt_camera_output_image(self._h))
 
     # introspection for tests / bench ----------------------------------------------------------
     @property

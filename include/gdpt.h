@@ -176,6 +176,18 @@ GDPT_API int  gdpt_render_frame_async(gdpt_shader *main_shader, gdpt_shader *pro
                                  uint32_t frame_count);
 GDPT_API int  gdpt_device_synchronize(gdpt_device *device);
 
+/* Pipelined form of gdpt_render_frame: `begin` enqueues the camera upload, K1, the post process AND the
+ * read-back of the finished frame into out_rgba8 / out_depth (page-locked memory from gdpt_host_alloc
+ * keeps the copy asynchronous), then returns without waiting.  The read-back runs on a second stream from
+ * a device-side copy of the images, so the next frame's kernels overlap it.  At most two frames may be in
+ * flight; `wait` blocks until the OLDEST of them is complete in its caller buffers and reports its stats
+ * (out_stats may be NULL).  Results are byte-identical to gdpt_render_frame called frame by frame. */
+struct gdpt_frame_stats;
+GDPT_API int  gdpt_render_frame_begin(gdpt_shader *main_shader, gdpt_shader *progressive,
+                                 const gdpt_camera *camera, gdpt_denoising mode, uint32_t frame_count,
+                                 void *out_rgba8, float *out_depth);
+GDPT_API int  gdpt_render_frame_wait(gdpt_shader *main_shader, struct gdpt_frame_stats *out_stats);
+
 /* Restrict K1/K2 to image rows [row_begin,row_end) interleaved in bands:
  * a pixel row y is rendered iff ((y / band_rows) % n_parts) == part.  Used to
  * tile-shard a frame over several GPUs; (0,1) restores the full frame. */

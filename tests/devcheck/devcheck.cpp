@@ -32,13 +32,15 @@ static int g_cull = 0;
 
 template <bool CULL> static void run_ray(const SceneView &sc, RayState &r, HostStack &st, TraceCounters *tc)
 {
-    if (g_stepwise) trace_ray_stepwise<true, CULL>(sc, r, st, tc);
+    if (g_stepwise == 2) trace_ray_compact<true, CULL>(sc, r, st, tc);
+    else if (g_stepwise) trace_ray_stepwise<true, CULL>(sc, r, st, tc);
     else trace_ray<true, CULL>(sc, r, st, tc);
 }
 
 extern "C" {
 
-// 0: node-at-a-time traversal, 1: leaves split into single-triangle steps (phase-voting order)
+// 0: node-at-a-time traversal, 1: leaves split into single-triangle steps (phase-voting order),
+// 2: the compact scheduler's node / instance / triangle steps
 void devcheck_set_stepwise(int on) { g_stepwise = on; }
 // 0: reference visit order, 1: tight-box culling (hit records must not change)
 void devcheck_set_cull(int on) { g_cull = on; }

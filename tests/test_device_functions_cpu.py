@@ -35,7 +35,7 @@ def run_devcheck(devcheck, osc, cam_bytes, W, H, depth, segs, vis, debug=False):
     return out, dep, tr, vs, int(rays[0])
 
 
-@pytest.mark.parametrize("stepwise", [0, 1], ids=["node_steps", "triangle_steps"])
+@pytest.mark.parametrize("stepwise", [0, 1, 2], ids=["node_steps", "triangle_steps", "compact_steps"])
 @pytest.mark.parametrize("name,make,W,H,depth,segs,frame", CASES, ids=[c[0] for c in CASES])
 def test_device_functions_match_oracle(devcheck, name, make, W, H, depth, segs, frame, stepwise):
     devcheck.devcheck_set_stepwise(stepwise)
@@ -60,7 +60,7 @@ def test_device_functions_match_oracle(devcheck, name, make, W, H, depth, segs, 
 HIT_FIELDS = ("hit", "triangle", "blas", "front", "t", "u", "v")
 
 
-@pytest.mark.parametrize("stepwise", [0, 1], ids=["node_steps", "triangle_steps"])
+@pytest.mark.parametrize("stepwise", [0, 1, 2], ids=["node_steps", "triangle_steps", "compact_steps"])
 @pytest.mark.parametrize("name,make,W,H,depth,segs,frame", CASES, ids=[c[0] for c in CASES])
 def test_tight_box_culling_changes_no_result(devcheck, name, make, W, H, depth, segs, frame, stepwise):
     """Culling (pt_scene.cuh) may only shorten the visit list: hit records, ray counts, colour and depth
