@@ -187,6 +187,7 @@ inline std::string derive_layout(const gdpt_bvh_node *bvh, uint32_t n_nodes, con
         std::memcpy(r.inv, blas[b].inverse_transform, sizeof(r.inv));
         r.root_link = link[blas[b].root];
         r.root_orig = blas[b].root;
+        r.fast_root = LINK_NONE; // filled by the closest-hit builder (fast_bvh.h)
         const TightBox obj = tight_inflate(raw[blas[b].root], owner_extent[blas[b].root]);
         for (int k = 0; k < 3; k++) { r.tight_min[k] = obj.lo[k]; r.tight_max[k] = obj.hi[k]; }
         // world-space culling box: the eight transformed corners of the object-space one, inflated again

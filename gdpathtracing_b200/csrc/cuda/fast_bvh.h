@@ -1,0 +1,274 @@
+// fast_bvh.h -- host-side construction of the CLOSEST-HIT tables (pt_fast.cuh).
+//
+// The reference traversal (main.glsl:270-350) returns, for one ray, the triangle with the smallest
+// accepted t among the triangles it reaches; on equal t the one tested last wins (main.glsl:247).
+// Which triangles it reaches depends on its visiting order only through ties and through box tests
+// that sit exactly on the current hit distance.  The rendering kernels therefore answer a ray in two
+// steps (pt_fast.cuh):
+//   1. an order-free closest-hit search over OUR OWN acceleration structure -- a binned-SAH BVH over
+//      the same triangles with true (inflated) bounds, built here -- that evaluates the reference's
+//      Moller-Trumbore arithmetic on the reference's vertices and the reference's instance-local ray,
+//      and notices ties;
+//   2. a proof that the reference traversal reaches that triangle: the reference box of the triangle's
+//      leaf (and of its instance's TLAS leaf) is entered strictly before the hit.  Reference boxes
+//      are nested (a child's box is computed from a subset of its parent's triangles, bvh.cpp:24-37,
+//      108-127; TLAS boxes are unions, bvh.cpp:299-304) and the slab arithmetic is monotone in the box,
+//      so every ancestor is then entered no later, i.e. pushed while hit.t is still larger.
+// A ray whose proof fails (or that saw a tie) is re-traced with the exact reference-order traversal
+// (pt_trace.cuh), so results are bit-identical either way; only the amount of work differs.
+// The nesting the proof relies on is verified here for every edge of the uploaded arrays; if it does
+// not hold (hand-made arrays), `ok` is false and the kernels use the reference-order traversal only.
+//
+// Pure C++ (no CUDA) so tests/devcheck can reuse it.
+#ifndef GDPT_FAST_BVH_H
+#define GDPT_FAST_BVH_H
+
+#include "derived_layout.h"
+
+#include <algorithm>
+
+namespace gdpt {
+
+struct FastLayout {
+    std::vector<FastNode> nodes;     // internal nodes of every BLAS
+    std::vector<FastTri> tris;       // triangle copies in leaf order
+    std::vector<FastNode> tlas;      // TLAS internal nodes: reference topology, true world boxes
+    std::vector<uint32_t> tri_leaf;  // per reference triangle index: reference node index of the leaf that holds it
+    std::vector<uint32_t> inst_root; // per instance: link of the root of its BLAS in `nodes`/`tris`
+    uint32_t tlas_root_link = LINK_NONE;
+    uint32_t max_depth = 0;          // deepest root-to-leaf chain of our trees (stack bound)
+    bool ok = false;
+    std::string why_not;
+};
+
+namespace fastbvh {
+
+constexpr int kBins = 16;
+constexpr uint32_t kLeafMax = 4;
+
+struct Prim { float lo[3], hi[3], c[3]; uint32_t orig; };
+
+inline TightBox bounds_of(const std::vector<Prim> &p, uint32_t b, uint32_t e)
+{
+    TightBox t = tight_empty();
+    for (uint32_t i = b; i < e; i++) { tight_grow(t, p[i].lo); tight_grow(t, p[i].hi); }
+    return t;
+}
+inline float half_area(const TightBox &b)
+{
+    const float x = b.hi[0] - b.lo[0], y = b.hi[1] - b.lo[1], z = b.hi[2] - b.lo[2];
+    return x * y + y * z + z * x;
+}
+
+struct Builder {
+    const gdpt_triangle_geometry *tris;
+    std::vector<Prim> prims;
+    FastLayout *out;
+    float owner_extent = 0.0f;
+    uint32_t depth_seen = 0;
+
+    // builds [b, e) and returns its link; *box receives the true bounds
+    uint32_t build(uint32_t b, uint32_t e, uint32_t depth, TightBox *box)
+    {
+        if (depth > depth_seen) depth_seen = depth;
+        *box = bounds_of(prims, b, e);
+        const uint32_t n = e - b;
+        if (n <= kLeafMax) {
+            const uint32_t first = (uint32_t)out->tris.size();
+            for (uint32_t i = b; i < e; i++) {
+                FastTri t;
+                std::memset(&t, 0, sizeof(t));
+                const gdpt_triangle_geometry &g = tris[prims[i].orig];
+                for (int k = 0; k < 3; k++) { t.v0[k] = g.v[0][k]; t.v1[k] = g.v[1][k]; t.v2[k] = g.v[2][k]; }
+                t.orig = prims[i].orig;
+                out->tris.push_back(t);
+            }
+            return LINK_LEAF | ((n - 1u) << FAST_LEAF_COUNT_SHIFT) | first;
+        }
+        // binned SAH over the centroid bounds, three axes
+        TightBox cb = tight_empty();
+        for (uint32_t i = b; i < e; i++) tight_grow(cb, prims[i].c);
+        int best_axis = -1, best_bin = -1;
+        float best_cost = FLT_MAX;
+        for (int axis = 0; axis < 3; axis++) {
+            const float lo = cb.lo[axis], ext = cb.hi[axis] - cb.lo[axis];
+            if (!(ext > 0.0f) || !std::isfinite(ext)) continue;
+            TightBox bb[kBins];
+            uint32_t cnt[kBins];
+            for (int k = 0; k < kBins; k++) { bb[k] = tight_empty(); cnt[k] = 0; }
+            const float scale = (float)kBins / ext;
+            for (uint32_t i = b; i < e; i++) {
+                int k = (int)((prims[i].c[axis] - lo) * scale);
+                k = k < 0 ? 0 : (k >= kBins ? kBins - 1 : k);
+                cnt[k]++; tight_grow(bb[k], prims[i].lo); tight_grow(bb[k], prims[i].hi);
+            }
+            float right_area[kBins];
+            uint32_t right_cnt[kBins];
+            TightBox acc = tight_empty();
+            uint32_t c = 0;
+            for (int k = kBins - 1; k > 0; k--) {
+                if (cnt[k]) tight_merge(acc, bb[k]);
+                c += cnt[k];
+                right_area[k] = c ? half_area(acc) : 0.0f; right_cnt[k] = c;
+            }
+            acc = tight_empty(); c = 0;
+            for (int k = 0; k < kBins - 1; k++) {
+                if (cnt[k]) tight_merge(acc, bb[k]);
+                c += cnt[k];
+                if (c == 0 || right_cnt[k + 1] == 0) continue;
+                const float cost = half_area(acc) * (float)c + right_area[k + 1] * (float)right_cnt[k + 1];
+                if (cost < best_cost) { best_cost = cost; best_axis = axis; best_bin = k; }
+            }
+        }
+        uint32_t mid = b;
+        if (best_axis >= 0) {
+            const float lo = cb.lo[best_axis], scale = (float)kBins / (cb.hi[best_axis] - cb.lo[best_axis]);
+            const int axis = best_axis, bin = best_bin;
+            auto it = std::partition(prims.begin() + b, prims.begin() + e, [&](const Prim &p) {
+                int k = (int)((p.c[axis] - lo) * scale);
+                k = k < 0 ? 0 : (k >= kBins ? kBins - 1 : k);
+                return k <= bin;
+            });
+            mid = (uint32_t)(it - prims.begin());
+        }
+        if (mid == b || mid == e) { // all centroids coincide (or non-finite input): split the index range
+            int axis = 0;
+            for (int k = 1; k < 3; k++) if (cb.hi[k] - cb.lo[k] > cb.hi[axis] - cb.lo[axis]) axis = k;
+            mid = b + n / 2;
+            std::nth_element(prims.begin() + b, prims.begin() + mid, prims.begin() + e,
+                             [axis](const Prim &x, const Prim &y) { return x.c[axis] < y.c[axis]; });
+        }
+        const uint32_t idx = (uint32_t)out->nodes.size();
+        out->nodes.push_back(FastNode());
+        TightBox lb, rb;
+        const uint32_t l = build(b, mid, depth + 1, &lb);
+        const uint32_t r = build(mid, e, depth + 1, &rb);
+        FastNode &nd = out->nodes[idx];
+        std::memset(&nd, 0, sizeof(nd));
+        const TightBox li = tight_inflate(lb, owner_extent), ri = tight_inflate(rb, owner_extent);
+        for (int k = 0; k < 3; k++) { nd.lmin[k] = li.lo[k]; nd.lmax[k] = li.hi[k]; nd.rmin[k] = ri.lo[k]; nd.rmax[k] = ri.hi[k]; }
+        nd.left = l; nd.right = r;
+        return idx;
+    }
+};
+
+inline bool box_inside(const float *cmin, const float *cmax, const float *pmin, const float *pmax)
+{
+    for (int k = 0; k < 3; k++)
+        if (!(cmin[k] >= pmin[k]) || !(cmax[k] <= pmax[k])) return false; // NaN fails
+    return true;
+}
+
+} // namespace fastbvh
+
+// `lay` is the derived layout of the same arrays (its TLAS records carry the true world boxes).
+inline void build_fast_layout(const gdpt_bvh_node *bvh, uint32_t n_nodes, const gdpt_blas_instance *blas, uint32_t n_blas,
+                              const gdpt_tlas_node *tlas, uint32_t n_tlas, const gdpt_triangle_geometry *tris, uint32_t n_tris,
+                              const DerivedLayout &lay, FastLayout &out)
+{
+    out = FastLayout();
+    out.tri_leaf.assign(n_tris, 0xFFFFFFFFu);
+    out.inst_root.assign(n_blas, LINK_NONE);
+    if (n_tris >= (1u << FAST_LEAF_COUNT_SHIFT)) { out.why_not = "too many triangles for the leaf link encoding"; return; }
+
+    // ---- one tree per distinct BLAS root
+    std::vector<uint32_t> root_link(n_nodes, 0xFFFFFFFEu); // 0xFFFFFFFE = not built
+    std::vector<uint32_t> walk;
+    std::vector<uint32_t> depth_of(n_nodes, 0);
+    for (uint32_t b = 0; b < n_blas; b++) {
+        const uint32_t root = blas[b].root;
+        if (root_link[root] != 0xFFFFFFFEu) { out.inst_root[b] = root_link[root]; continue; }
+        fastbvh::Builder bld;
+        bld.tris = tris; bld.out = &out;
+        uint32_t ref_depth = 0;
+        walk.assign(1, root);
+        depth_of[root] = 0;
+        while (!walk.empty()) {
+            const uint32_t i = walk.back();
+            walk.pop_back();
+            const gdpt_bvh_node &n = bvh[i];
+            if (depth_of[i] > ref_depth) ref_depth = depth_of[i];
+            if (depth_of[i] > 4096u) { out.why_not = "reference BVH deeper than 4096 levels"; return; }
+            if (n.tri_count > 0) {
+                for (uint32_t k = 0; k < n.tri_count; k++) {
+                    const uint32_t t = n.first_tri_index + k;
+                    if (out.tri_leaf[t] != 0xFFFFFFFFu) { out.why_not = "a triangle belongs to two reference leaves"; return; }
+                    out.tri_leaf[t] = i;
+                    fastbvh::Prim p;
+                    for (int a = 0; a < 3; a++) {
+                        const float x = tris[t].v[0][a], y = tris[t].v[1][a], z = tris[t].v[2][a];
+                        p.lo[a] = std::min(x, std::min(y, z)); p.hi[a] = std::max(x, std::max(y, z));
+                        p.c[a] = (x + y + z) * (1.0f / 3.0f);
+                    }
+                    p.orig = t;
+                    bld.prims.push_back(p);
+                }
+                continue;
+            }
+            for (int side = 0; side < 2; side++) {
+                const uint32_t c = side ? n.right_child : n.left_child;
+                // the proof in pt_fast.cuh needs child boxes nested in their parent's (true for bvh.cpp's output)
+                if (i != root && !fastbvh::box_inside(bvh[c].aabb_min, bvh[c].aabb_max, n.aabb_min, n.aabb_max)) {
+                    out.why_not = "reference BVH boxes are not nested";
+                    return;
+                }
+                depth_of[c] = depth_of[i] + 1;
+                walk.push_back(c);
+            }
+        }
+        // the reference keeps 64 stack entries per level without a check (main.glsl:272); a tree this shallow cannot exceed them
+        if (ref_depth >= 60u) { out.why_not = "reference BVH too deep to bound its stack use"; return; }
+        uint32_t link = LINK_NONE;
+        if (!bld.prims.empty()) {
+            const TightBox all = fastbvh::bounds_of(bld.prims, 0, (uint32_t)bld.prims.size());
+            bld.owner_extent = tight_extent(all);
+            TightBox box;
+            link = bld.build(0, (uint32_t)bld.prims.size(), 0, &box);
+            if (bld.depth_seen > out.max_depth) out.max_depth = bld.depth_seen;
+        }
+        root_link[root] = link;
+        out.inst_root[b] = link;
+    }
+    // children of a BLAS root are tested against nothing above them, but they must still nest below the root's children:
+    // handled above for every non-root parent; a root's children need no condition (the root is never box-tested).
+
+    // ---- TLAS: reference topology with the true world boxes; nesting of the reference boxes verified per edge
+    out.tlas.assign(lay.wide_tlas.size(), FastNode());
+    uint32_t tlas_depth = 0;
+    {
+        std::vector<uint32_t> d(n_tlas, 0);
+        walk.assign(1, 0u);
+        uint32_t visited = 0;
+        while (!walk.empty()) {
+            const uint32_t i = walk.back();
+            walk.pop_back();
+            if (++visited > 2u * n_tlas + 2u) { out.why_not = "TLAS links do not form a tree"; return; }
+            if (d[i] > tlas_depth) tlas_depth = d[i];
+            if (tlas[i].left_right == 0) continue;
+            const uint32_t l = tlas[i].left_right & 0xFFFFu, r = tlas[i].left_right >> 16;
+            for (uint32_t c : { l, r }) {
+                if (i != 0 && !fastbvh::box_inside(tlas[c].aabb_min, tlas[c].aabb_max, tlas[i].aabb_min, tlas[i].aabb_max)) {
+                    out.why_not = "reference TLAS boxes are not nested";
+                    return;
+                }
+                d[c] = d[i] + 1;
+                walk.push_back(c);
+            }
+        }
+        if (tlas_depth >= 60u) { out.why_not = "reference TLAS too deep to bound its stack use"; return; }
+    }
+    for (size_t i = 0; i < lay.wide_tlas.size(); i++) {
+        const WideNode &w = lay.wide_tlas[i];
+        FastNode &f = out.tlas[i];
+        std::memset(&f, 0, sizeof(f));
+        for (int k = 0; k < 3; k++) { f.lmin[k] = w.tlmin[k]; f.lmax[k] = w.tlmax[k]; f.rmin[k] = w.trmin[k]; f.rmax[k] = w.trmax[k]; }
+        f.left = w.left; f.right = w.right;
+    }
+    out.tlas_root_link = lay.tlas_root_link;
+    out.max_depth += tlas_depth + 2u;
+    if (out.max_depth >= GDPT_FAST_MAX_DEPTH) { out.why_not = "closest-hit tree deeper than the traversal stack"; return; }
+    out.ok = true;
+}
+
+} // namespace gdpt
+#endif

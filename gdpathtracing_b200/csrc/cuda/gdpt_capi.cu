@@ -6,6 +6,7 @@
 // drives the GPU or fails.
 #include "gdpt.h"
 #include "derived_layout.h"
+#include "fast_bvh.h"
 #include "pt_kernels.cuh"
 
 #include <cuda_runtime.h>
@@ -68,6 +69,8 @@ struct gdpt_shader {
     uint32_t visits_per_ray = 0;
     int variant = -1; // "#define GDPT_VARIANT n": traversal schedule, -1 = default
     int cull = -1;    // "#define GDPT_CULL n" / "#define GDPT_REFERENCE_ORDER": -1 = default
+    int record_hits = 0; // "#define GDPT_RECORD_HITS n": hit records of the first n segments from the rendering kernels
+    std::string fast_why_not; // why the closest-hit tables are not in use ("" = in use)
     // main-shader state built by finish_create_uniforms
     FrameArgs args;
     std::vector<void *> derived; // device allocations owned by this shader
@@ -188,6 +191,22 @@ int build_derived_layout(gdpt_shader *s, const Resource &bvh_r, const Resource &
                                           (uint32_t)(tri_r.size / sizeof(gdpt_triangle_geometry)), lay);
     if (!err.empty()) return fail(d, GDPT_ERR_BAD_BINDING, "%s", err.c_str());
     int rc;
+    // closest-hit tables (fast_bvh.h): our own BVH over the same triangles + what the proof of pt_fast.cuh reads
+    FastLayout fast;
+    build_fast_layout(reinterpret_cast<const gdpt_bvh_node *>(bvh_r.shadow.data()), (uint32_t)(bvh_r.size / sizeof(gdpt_bvh_node)),
+                      reinterpret_cast<const gdpt_blas_instance *>(blas_r.shadow.data()), (uint32_t)(blas_r.size / sizeof(gdpt_blas_instance)),
+                      reinterpret_cast<const gdpt_tlas_node *>(tlas_r.shadow.data()), (uint32_t)(tlas_r.size / sizeof(gdpt_tlas_node)),
+                      reinterpret_cast<const gdpt_triangle_geometry *>(tri_r.shadow.data()),
+                      (uint32_t)(tri_r.size / sizeof(gdpt_triangle_geometry)), lay, fast);
+    s->args.sc.fast_ok = fast.ok ? 1u : 0u;
+    s->fast_why_not = fast.why_not;
+    if (fast.ok) {
+        for (size_t b = 0; b < lay.inst_recs.size(); b++) lay.inst_recs[b].fast_root = fast.inst_root[b];
+        if ((rc = dev_upload(s, &s->args.sc.fast_nodes, fast.nodes))) return rc;
+        if ((rc = dev_upload(s, &s->args.sc.fast_tlas, fast.tlas))) return rc;
+        if ((rc = dev_upload(s, &s->args.sc.fast_tris, fast.tris))) return rc;
+        if ((rc = dev_upload(s, &s->args.sc.tri_leaf, fast.tri_leaf))) return rc;
+    }
     if ((rc = dev_upload(s, &s->args.sc.wide_nodes, lay.wide_nodes))) return rc;
     if ((rc = dev_upload(s, &s->args.sc.leaf_recs, lay.leaf_recs))) return rc;
     if ((rc = dev_upload(s, &s->args.sc.wide_tlas, lay.wide_tlas))) return rc;
@@ -281,9 +300,10 @@ int finish_main(gdpt_shader *s)
     if ((rc = dev_alloc(s, &a.cost, (size_t)a.queue_cap))) return rc;
     GDPT_CUDA(d, cudaMemsetAsync(a.cost, 0, (size_t)a.queue_cap * sizeof(uint32_t), d->stream));
     if ((rc = dev_alloc(s, &a.counters, 1))) return rc;
-    a.schedule = s->variant >= 0 ? s->variant : 3;
+    a.schedule = s->variant >= 0 ? s->variant : 5;
     if (const char *e = getenv("GDPT_SCHEDULE")) { if (s->variant < 0) a.schedule = atoi(e); }
-    if (a.schedule < 0 || a.schedule > 4) a.schedule = 3;
+    if (a.schedule < 0 || a.schedule > 5) a.schedule = 5;
+    if (a.schedule == 5 && !a.sc.fast_ok) a.schedule = 3; // closest-hit tables unavailable for these arrays (fast_bvh.h)
     // culling (pt_scene.cuh) is the default for rendering; parity traces and the DEBUG_STEPS heat map
     // keep the full reference visit order (their output IS the reference's work)
     const bool observes_work = s->trace_segments > 0 || s->debug_steps;
@@ -297,7 +317,7 @@ int finish_main(gdpt_shader *s)
     init_launch_shapes(d->ordinal);
     if (a.schedule == 4 && (rc = dev_alloc(s, &a.path_recs, mux_path_record_quads()))) return rc;
     a.refill_below = a.schedule >= 2 ? 24 : 20;
-    a.burst = a.schedule == 0 ? 8 : (a.schedule == 3 ? 4 : 16);
+    a.burst = a.schedule == 0 ? 8 : (a.schedule == 3 || a.schedule == 5 ? 4 : 16);
     a.shade_at = 8;
     if (const char *e = getenv("GDPT_REFILL_BELOW")) a.refill_below = atoi(e);
     if (const char *e = getenv("GDPT_BURST")) a.burst = atoi(e);
@@ -314,8 +334,9 @@ int finish_main(gdpt_shader *s)
     a.debug_steps = s->debug_steps ? 1 : 0;
     a.trace_segments = s->trace_segments;
     a.visits_per_ray = s->visits_per_ray;
-    if (s->trace_segments > 0) {
-        const size_t n = (size_t)s->trace_segments * rp.width * rp.height;
+    if (s->record_hits > 0 && !observes_work) a.trace_segments = s->record_hits < s->max_depth ? s->record_hits : s->max_depth;
+    if (a.trace_segments > 0) {
+        const size_t n = (size_t)a.trace_segments * rp.width * rp.height;
         if ((rc = dev_alloc(s, &a.trace, n))) return rc;
         if (s->visits_per_ray > 0 && (rc = dev_alloc(s, &a.visits, (size_t)rp.width * rp.height * s->visits_per_ray))) return rc;
     }
@@ -348,8 +369,9 @@ int enqueue_k1(gdpt_shader *s)
     gdpt_device *d = s->dev;
     FrameArgs &a = s->args;
     const bool trace = s->trace_segments > 0 || s->debug_steps;
+    const bool rec = !trace && a.trace != nullptr; // "#define GDPT_RECORD_HITS": hit records from the rendering kernels
     GDPT_CUDA(d, cudaMemsetAsync(a.counters, 0, sizeof(FrameCounters), d->stream));
-    if (trace && a.trace) GDPT_CUDA(d, cudaMemsetAsync(a.trace, 0xFF, (size_t)a.trace_segments * a.width * a.height * sizeof(gdpt_trace_record), d->stream));
+    if ((trace || rec) && a.trace) GDPT_CUDA(d, cudaMemsetAsync(a.trace, 0xFF, (size_t)a.trace_segments * a.width * a.height * sizeof(gdpt_trace_record), d->stream));
     if (trace && a.visits) GDPT_CUDA(d, cudaMemsetAsync(a.visits, 0xFF, (size_t)a.width * a.height * a.visits_per_ray * sizeof(uint32_t), d->stream));
     const bool timing = s->stage_timing && !s->stage_ev.empty();
     int ev = 0;
@@ -359,7 +381,8 @@ int enqueue_k1(gdpt_shader *s)
             launch_primary_cull(a, d->stream);
             if (timing) GDPT_CUDA(d, cudaEventRecord(s->stage_ev[ev++], d->stream));
             if (a.schedule == 4) launch_path_mux(a, d->stream);
-            else launch_path_list(a, trace, d->stream);
+            else if (a.schedule == 5) launch_path_fast(a, rec, d->stream);
+            else launch_path_list(a, trace || rec, d->stream);
         } else {
             launch_path(a, trace, d->stream);
         }
@@ -414,6 +437,7 @@ int collect_stats(gdpt_shader *s)
         for (int i = 1; i < s->args.max_depth; i++) rays += c.qcount[i];
     st.rays = rays;
     st.primary_hits = c.primary_hits;
+    st.retraced = c.retraced;
     st.node_pops = c.node_pops; st.box_tests = c.box_tests; st.tri_tests = c.tri_tests; st.tlas_leaves = c.tlas_leaves;
     st.max_stack = c.max_stack;
     if (c.overflow) return fail(d, GDPT_ERR_UNSUPPORTED, "a ray exceeded the reference's 64+64 traversal stack entries");
@@ -514,6 +538,7 @@ int gdpt_shader_create(gdpt_device *d, const char *shader_path, const char *cons
         else if (name == "GDPT_VARIANT" && has_value) s->variant = (int)value;
         else if (name == "GDPT_CULL" && has_value) s->cull = value != 0 ? 1 : 0;
         else if (name == "GDPT_REFERENCE_ORDER") s->cull = 0;
+        else if (name == "GDPT_RECORD_HITS" && has_value) s->record_hits = (int)value;
     }
     if (s->max_depth < 1 || s->max_depth > kMaxDepth) {
         delete s;
@@ -996,6 +1021,7 @@ extern "C" int gdpt_render_frame_wait(gdpt_shader *m, gdpt_frame_stats *out_stat
             for (int i = 1; i < m->args.max_depth; i++) rays += c.qcount[i];
         out_stats->rays = rays;
         out_stats->primary_hits = c.primary_hits;
+        out_stats->retraced = c.retraced;
         out_stats->node_pops = c.node_pops; out_stats->box_tests = c.box_tests; out_stats->tri_tests = c.tri_tests;
         out_stats->tlas_leaves = c.tlas_leaves; out_stats->max_stack = c.max_stack;
         out_stats->kernel_launches = sl.launches;

@@ -1,0 +1,217 @@
+// pt_fast.cuh -- closest-hit search over the tables of fast_bvh.h, plus the proof that the
+// reference traversal (main.glsl:270-350) returns the same record.
+//
+// What the reference returns for one ray: among the (instance, triangle) pairs it tests, the one
+// with the smallest accepted t; on equal t the pair tested last (main.glsl:247 rejects only t > hit.t).
+// Every per-pair quantity -- the instance-local ray (main.glsl:316-321), det/u/v/t/front
+// (main.glsl:224-257) -- is a function of the ray and the pair alone, so an order-free search that
+// evaluates the same expressions gets the same numbers.  The search here finds the minimum t over ALL
+// pairs (its boxes are true bounds with a margin) and records whether a second pair reaches exactly that
+// t (`RAY_TIE`).  With a unique minimum at pair w, the reference returns w iff it tests w, because
+// nothing it tests can have a smaller or equal t:  hit.t stays > t_w until w is tested, so every box
+// on the way to w that is entered at d < t_w passes the reference's `d < hit.t` push test
+// (main.glsl:293-299, 339-345).  Reference boxes are nested and the slab arithmetic is monotone in the
+// box, so it is enough to check the deepest box of each level: the leaf that holds the triangle and
+// the TLAS leaf of its instance (`fast_proves_reference_hit`).  Roots are never box-tested upstream.
+// A miss of the complete search is a miss of the reference, which tests a subset of the pairs.
+// Rays that fail the proof are re-traced in reference order by the caller.
+#ifndef GDPT_PT_FAST_CUH
+#define GDPT_PT_FAST_CUH
+
+#include "pt_trace.cuh"
+
+namespace gdpt {
+
+#define RAY_OVERFLOW 1u /* RayState.overflow bit 0: traversal stack exceeded */
+#define RAY_TIE 2u      /* RayState.overflow bit 1: a second pair reached the current minimum t (or t was NaN) */
+
+GDPT_HD void fast_ray_begin(RayState &r, const SceneView &sc, f3 o, f3 d)
+{
+    ray_begin(r, sc, o, d);
+}
+
+// true box of a child: entry distance and whether the subtree can still hold a hit with t <= r.t
+GDPT_HD bool fast_slab(const RayState &r, float nx, float ny, float nz, float xx, float xy, float xz, float *entry)
+{
+    const float tx1 = (nx - r.o.x) * r.rd.x, tx2 = (xx - r.o.x) * r.rd.x;
+    float tmin = min_num(tx1, tx2), tmax = max_num(tx1, tx2);
+    const float ty1 = (ny - r.o.y) * r.rd.y, ty2 = (xy - r.o.y) * r.rd.y;
+    tmin = max_num(tmin, min_num(ty1, ty2)); tmax = min_num(tmax, max_num(ty1, ty2));
+    const float tz1 = (nz - r.o.z) * r.rd.z, tz2 = (xz - r.o.z) * r.rd.z;
+    tmin = max_num(tmin, min_num(tz1, tz2)); tmax = min_num(tmax, max_num(tz1, tz2));
+    *entry = tmin;
+    return !(tmax < tmin) && !(tmax < 0.0f) && !(tmin > r.t);
+}
+
+// One internal node of either level: nearer child next, farther child pushed.
+template <class Stack> GDPT_HD void fast_step_node(const SceneView &sc, RayState &r, Stack &st)
+{
+    const void *table = (r.cur & LINK_TLAS) ? static_cast<const void *>(sc.fast_tlas) : static_cast<const void *>(sc.fast_nodes);
+    const uint32_t idx = r.cur & LINK_INDEX_MASK;
+    const q4f q0 = ldq(table, idx * 4u + 0u);
+    const q4f q1 = ldq(table, idx * 4u + 1u);
+    const q4f q2 = ldq(table, idx * 4u + 2u);
+    const q4u q3 = ldqu(table, idx * 4u + 3u);
+    float dl, dr;
+    const bool hl = fast_slab(r, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, &dl);
+    const bool hr = fast_slab(r, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, &dr);
+    const bool left_first = dl <= dr;
+    const uint32_t first = left_first ? q3.x : q3.y, second = left_first ? q3.y : q3.x;
+    const bool fv = left_first ? hl : hr, sv = left_first ? hr : hl;
+    if (fv) {
+        if (sv) stack_push(r, st, second);
+        r.cur = first;
+    } else if (sv) {
+        r.cur = second;
+    } else {
+        r.cur = stack_pop(r, st);
+    }
+}
+
+// intersectTriangle (main.glsl:224-257), same operations as triangle_test_loaded; the running minimum
+// replaces hit.t, and a pair that reaches the minimum exactly is recorded instead of accepted.
+GDPT_HD void fast_triangle_test(RayState &r, const q4f a, const q4f b, const q4f c)
+{
+    const f3 v0 = mk3(a.x, a.y, a.z);
+    const f3 e1 = mk3(b.x, b.y, b.z) - v0, e2 = mk3(c.x, c.y, c.z) - v0;
+    const f3 pvec = cross3(r.d, e2);
+    const float det = dot3(e1, pvec);
+    if (fabsf(det) < 1e-5f) return;
+    const float inv_det = 1.0f / det;
+    const f3 tvec = r.o - v0;
+    const float u = dot3(tvec, pvec) * inv_det;
+    if (u < 0.0f || u > 1.0f) return;
+    const f3 qvec = cross3(tvec, e1);
+    const float v = dot3(r.d, qvec) * inv_det;
+    if (v < 0.0f || u + v > 1.0f) return;
+    const float t = dot3(e2, qvec) * inv_det;
+    if (t < 0.0f || t > r.t) return;
+    if (t < r.t) {
+        const uint32_t front = dot3(cross3(e1, e2), r.d) > 0.0f ? GDPT_FRONT_BIT : 0u;
+#if defined(__CUDA_ARCH__)
+        r.tri = __float_as_uint(a.w);
+#else
+        memcpy(&r.tri, &a.w, 4);
+#endif
+        r.t = t; r.u = u; r.v = v; r.blas_front = r.inst | front;
+        r.overflow &= ~RAY_TIE;
+    } else {
+        r.overflow |= RAY_TIE; // t == r.t (or NaN): the reference's answer would depend on its visiting order
+    }
+}
+
+// One leaf: up to four triangles, loads issued together.
+template <class Stack> GDPT_HD void fast_step_leaf(const SceneView &sc, RayState &r, Stack &st)
+{
+    const uint32_t first = r.cur & FAST_LEAF_FIRST_MASK, count = ((r.cur >> FAST_LEAF_COUNT_SHIFT) & 7u) + 1u;
+    r.cur = stack_pop(r, st);
+    q4f va[4], vb[4], vc[4];
+#pragma unroll
+    for (uint32_t i = 0; i < 4u; i++) {
+        const uint32_t ti = first + (i < count ? i : 0u);
+        va[i] = ldq(sc.fast_tris, ti * 3u + 0u); vb[i] = ldq(sc.fast_tris, ti * 3u + 1u); vc[i] = ldq(sc.fast_tris, ti * 3u + 2u);
+    }
+#pragma unroll
+    for (uint32_t i = 0; i < 4u; i++)
+        if (i < count) fast_triangle_test(r, va[i], vb[i], vc[i]);
+}
+
+// b_ray of main.glsl:316-321 for instance record `c0..c3` (inverse transform columns)
+GDPT_HD void fast_local_ray(const q4f c0, const q4f c1, const q4f c2, const q4f c3, f3 wo, f3 wd, f3 *o, f3 *d)
+{
+    *o = mk3(((c0.x * wo.x + c1.x * wo.y) + c2.x * wo.z) + c3.x * 1.0f,
+             ((c0.y * wo.x + c1.y * wo.y) + c2.y * wo.z) + c3.y * 1.0f,
+             ((c0.z * wo.x + c1.z * wo.y) + c2.z * wo.z) + c3.z * 1.0f);
+    *d = mk3(((c0.x * wd.x + c1.x * wd.y) + c2.x * wd.z) + c3.x * 0.0f,
+             ((c0.y * wd.x + c1.y * wd.y) + c2.y * wd.z) + c3.y * 0.0f,
+             ((c0.z * wd.x + c1.z * wd.y) + c2.z * wd.z) + c3.z * 0.0f);
+}
+
+// Space changes: back to world space after an instance and/or into the instance `cur` names.
+template <class Stack> GDPT_HD void fast_step_instance(const SceneView &sc, RayState &r, Stack &st)
+{
+    if (r.inst != GDPT_NO_INSTANCE) {
+        r.o = r.wo; r.d = r.wd; r.rd = rcp3(r.wd);
+        r.inst = GDPT_NO_INSTANCE;
+    }
+    if ((r.cur & LINK_LEAF) == 0u) return;
+    const uint32_t idx = r.cur & LINK_INDEX_MASK;
+    const q4f c0 = ldq(sc.inst_recs, idx * 7u + 0u);
+    const q4f c1 = ldq(sc.inst_recs, idx * 7u + 1u);
+    const q4f c2 = ldq(sc.inst_recs, idx * 7u + 2u);
+    const q4f c3 = ldq(sc.inst_recs, idx * 7u + 3u);
+    const q4u tail = ldqu(sc.inst_recs, idx * 7u + 4u);
+    const q4f tmin4 = ldq(sc.inst_recs, idx * 7u + 5u);
+    const q4f tmax4 = ldq(sc.inst_recs, idx * 7u + 6u);
+    fast_local_ray(c0, c1, c2, c3, r.wo, r.wd, &r.o, &r.d);
+    r.rd = rcp3(r.d);
+    r.inst = idx;
+    float entry;
+    const bool touches = fast_slab(r, tmin4.x, tmin4.y, tmin4.z, tmax4.x, tmax4.y, tmax4.z, &entry);
+    r.cur = (touches && tail.w != LINK_NONE) ? tail.w : stack_pop(r, st);
+}
+
+GDPT_HD bool fast_link_is_leaf(uint32_t l) { return (l & (LINK_TLAS | LINK_LEAF)) == LINK_LEAF; }
+GDPT_HD bool fast_link_is_node(uint32_t l, uint32_t inst)
+{
+    return (l & LINK_LEAF) == 0u && l != LINK_NONE && ((l & LINK_TLAS) == 0u || inst == GDPT_NO_INSTANCE);
+}
+
+// Whole search of one ray (no warp-level scheduling): used by k_primary-style callers and the host check.
+template <class Stack> GDPT_HD void fast_trace_ray(const SceneView &sc, RayState &r, Stack &st)
+{
+    while (r.cur != LINK_NONE) {
+        if (fast_link_is_leaf(r.cur)) fast_step_leaf(sc, r, st);
+        else if (fast_link_is_node(r.cur, r.inst)) fast_step_node(sc, r, st);
+        else fast_step_instance(sc, r, st);
+    }
+}
+
+// The search ended with a hit (r.t < 1e9) and no tie.  Does the reference traversal test this pair?
+// Sufficient condition: with the reference's own box arithmetic (slab_test == intersectAABB,
+// main.glsl:259-268), the TLAS leaf of the instance (world ray) and the BLAS leaf of the triangle
+// (instance-local ray) are entered strictly before r.t.  Rays with a zero direction component are
+// sent to the exact traversal: 0 * inf in a slab would void the monotonicity argument.
+GDPT_HD bool fast_proves_reference_hit(const SceneView &sc, const RayState &r)
+{
+    const uint32_t inst = r.blas_front & ~GDPT_FRONT_BIT;
+    const q4f c0 = ldq(sc.inst_recs, inst * 7u + 0u);
+    const q4f c1 = ldq(sc.inst_recs, inst * 7u + 1u);
+    const q4f c2 = ldq(sc.inst_recs, inst * 7u + 2u);
+    const q4f c3 = ldq(sc.inst_recs, inst * 7u + 3u);
+    const q4u tail = ldqu(sc.inst_recs, inst * 7u + 4u);
+    RayState w;
+    w.o = r.wo; w.rd = rcp3(r.wd);
+    bool ok = r.wd.x != 0.0f && r.wd.y != 0.0f && r.wd.z != 0.0f;
+    if ((sc.tlas_root_link & LINK_LEAF) == 0u) {
+        const q4f n0 = ldq(sc.tlas, tail.y * 2u + 0u);
+        const q4f n1 = ldq(sc.tlas, tail.y * 2u + 1u);
+        ok = ok && slab_test(w, n0.x, n0.y, n0.z, n1.x, n1.y, n1.z) < r.t;
+    }
+    f3 ld;
+    fast_local_ray(c0, c1, c2, c3, r.wo, r.wd, &w.o, &ld);
+    w.rd = rcp3(ld);
+    ok = ok && ld.x != 0.0f && ld.y != 0.0f && ld.z != 0.0f;
+#if defined(__CUDA_ARCH__)
+    const uint32_t leaf = __ldg(sc.tri_leaf + r.tri);
+#else
+    const uint32_t leaf = sc.tri_leaf[r.tri];
+#endif
+    if (leaf != tail.z) { // a root that is itself the leaf is never box-tested (main.glsl:274)
+        const q4f b0 = ldq(sc.bvh, leaf * 3u + 0u);
+        const q4f b1 = ldq(sc.bvh, leaf * 3u + 1u);
+        ok = ok && slab_test(w, b0.x, b0.y, b0.z, b1.x, b1.y, b1.z) < r.t;
+    }
+    return ok;
+}
+
+// Verdict on a finished search: true = the record in `r` is the reference's record.
+GDPT_HD bool fast_result_is_reference(const SceneView &sc, const RayState &r)
+{
+    if (r.overflow & RAY_TIE) return false;
+    if (!(r.t < 1e9f)) return true;
+    return fast_proves_reference_hit(sc, r);
+}
+
+} // namespace gdpt
+#endif

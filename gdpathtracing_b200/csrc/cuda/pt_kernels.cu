@@ -21,6 +21,7 @@
 // entries at a common reconvergence point, and re-checks the number of live
 // lanes with a ballot every step to decide when to refill.
 #include "pt_kernels.cuh"
+#include "pt_fast.cuh"
 #include "pt_shade.cuh"
 #include "pt_trace.cuh"
 
@@ -648,6 +649,230 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path(const FrameArgs a)
     if (my_overflow) atomicOr(&cnt->overflow, 1u);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Path kernel of schedule 5: k_path's scheduler (whole paths per lane, phase census, longest path
+// first) over the closest-hit tables.  A ray is answered by the order-free search of pt_fast.cuh --
+// I: one internal node (two true-box tests, four LDG.128), L: one leaf (<= 4 triangles), T: instance
+// entry/exit -- and, when the search ends, by the proof that the reference traversal returns the same
+// record.  The few rays without a proof (ties, hits that sit on a reference box face) are re-traced in
+// reference order by an out-of-line call, so every record equals the reference's bit for bit.
+struct LocalStack {
+    uint32_t *slots;
+    __device__ __forceinline__ void store(uint32_t i, uint32_t v) { slots[i] = v; }
+    __device__ __forceinline__ uint32_t load(uint32_t i) const { return slots[i]; }
+};
+struct ExactHit { float t, u, v; uint32_t tri, blas_front, overflow; };
+__device__ __noinline__ void exact_retrace(const SceneView *sc, f3 wo, f3 wd, ExactHit *out)
+{
+    uint32_t slots[GDPT_MAX_STACK];
+    LocalStack st;
+    st.slots = slots;
+    RayState r;
+    ray_begin(r, *sc, wo, wd);
+    trace_ray_compact<false, true>(*sc, r, st, nullptr);
+    out->t = r.t; out->u = r.u; out->v = r.v; out->tri = r.tri; out->blas_front = r.blas_front; out->overflow = r.overflow;
+}
+
+__device__ __forceinline__ void write_hit_record(const FrameArgs &a, int segment, uint32_t pixel, float t, float u, float v, uint32_t tri,
+                                                 uint32_t blas_front)
+{
+    if (segment >= a.trace_segments) return;
+    gdpt_trace_record rec;
+    const bool hit = t < 1e9f;
+    rec.hit = hit ? 1u : 0u;
+    rec.triangle = hit ? tri : 0u;
+    rec.blas = hit ? (blas_front & ~GDPT_FRONT_BIT) : 0u;
+    rec.front = hit ? (blas_front >> 31) : 0u;
+    rec.t = t; rec.u = hit ? u : 0.0f; rec.v = hit ? v : 0.0f;
+    rec.node_pops = rec.box_tests = rec.tri_tests = rec.tlas_leaves = rec.max_stack = 0u;
+    rec.visit_hash_lo = rec.visit_hash_hi = 0u;
+    a.trace[(size_t)segment * a.width * a.height + pixel] = rec;
+}
+
+template <bool REC, int MINB>
+__global__ void __launch_bounds__(kTraceThreads, MINB) k_path_fast(const FrameArgs a)
+{
+    __shared__ uint32_t s_stack[kSmemStack * kTraceThreads];
+    __shared__ gdpt_camera s_cam;
+    uint32_t spill[GDPT_MAX_STACK - kSmemStack];
+    SmemStack st;
+    st.col = s_stack + threadIdx.x;
+    st.spill = spill;
+    if (threadIdx.x < sizeof(gdpt_camera) / 4u)
+        reinterpret_cast<uint32_t *>(&s_cam)[threadIdx.x] = reinterpret_cast<const uint32_t *>(a.camera)[threadIdx.x];
+    __syncthreads();
+    const gdpt_camera &cam = s_cam;
+
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lanemask_lt = (1u << lane) - 1u;
+    FrameCounters *cnt = a.counters;
+    SurvivorLists lists;
+    lists.load(a);
+    const uint32_t total = lists.total;
+    const int refill_below = max(a.refill_below, 1);
+    const int shade_at = min(max(a.shade_at, 1), 32);
+    const uint32_t lead_min = a.lead_min > 0 ? (uint32_t)a.lead_min : 0xFFFFFFFFu;
+    uint32_t steps = 0, pred = 0;
+    bool heavy_done = false;
+    const int last_segment = a.max_depth - 1;
+
+    RayState r;
+    r.cur = LINK_NONE; r.sp = 0; r.overflow = 0; r.t = 1e9f; r.inst = GDPT_NO_INSTANCE;
+    f3 throughput = mk3(1.0f, 1.0f, 1.0f), radiance = mk3(0.0f, 0.0f, 0.0f);
+    u2 seed; seed.x = seed.y = 0u;
+    uint32_t pixel = 0;
+    int segment = 0;
+    bool has = false;
+    uint32_t chunk_next = 0, chunk_end = 0;
+    bool exhausted = (total == 0u);
+    unsigned long long my_rays = 0, my_phits = 0, my_retraced = 0;
+    uint32_t my_overflow = 0;
+    const bool prof = a.warp_prof != nullptr;
+    const unsigned long long t_start = prof ? global_ns() : 0ull;
+    uint32_t it_i = 0, it_l = 0, it_t = 0, it_f = 0, it_e = 0, n_started = 0;
+
+    for (;;) {
+        const bool in_l = has && fast_link_is_leaf(r.cur);
+        const bool in_i = has && !in_l && fast_link_is_node(r.cur, r.inst);
+        const bool in_t = has && !in_l && !in_i && r.cur != LINK_NONE;
+        const bool fin = has && r.cur == LINK_NONE;
+        const uint32_t census = __reduce_add_sync(kFull, 1u << (in_l ? 0 : (in_i ? 6 : (in_t ? 12 : (fin ? 18 : 24)))));
+        const int n_l = (int)(census & 63u), n_i = (int)((census >> 6) & 63u), n_t = (int)((census >> 12) & 63u),
+                  n_fin = (int)((census >> 18) & 63u), n_idle = (int)(census >> 24);
+        const int n_walk = n_l + n_i + n_t;
+        int lead_phase = -1; // 0 L, 1 I, 2 T, 3 finished
+        {
+            const uint32_t key = (has && pred >= lead_min) ? ((pred << 5) | lane) : 0u;
+            const uint32_t most = __reduce_max_sync(kFull, key);
+            if (most != 0u) lead_phase = __shfl_sync(kFull, in_l ? 0 : (in_i ? 1 : (in_t ? 2 : 3)), most & 31u);
+        }
+
+        if (n_fin > 0 && (n_fin >= shade_at || n_walk == 0 || lead_phase == 3)) {
+            // ---------------- S: prove, then finish the segment ----------------
+            it_f++;
+            if (fin) {
+                if (!fast_result_is_reference(a.sc, r)) { // rare: exact reference-order traversal of this ray
+                    ExactHit eh;
+                    exact_retrace(&a.sc, r.wo, r.wd, &eh);
+                    r.t = eh.t; r.u = eh.u; r.v = eh.v; r.tri = eh.tri; r.blas_front = eh.blas_front; r.overflow = eh.overflow & RAY_OVERFLOW;
+                    my_retraced++;
+                }
+                const bool hit = r.t < 1e9f;
+                my_rays++;
+                if (segment == 0 && hit) my_phits++;
+                if (REC) write_hit_record(a, segment, pixel, r.t, r.u, r.v, r.tri, r.blas_front);
+                my_overflow |= r.overflow & RAY_OVERFLOW;
+                bool alive = false;
+                if (!hit) {
+                    radiance = radiance + throughput * sample_sky(r.wd);
+                    if (segment == 0) a.out_depth[pixel] = encode_depth(cam, cam.z_far);
+                } else {
+                    BounceResult br;
+                    u2 sd = seed;
+                    shade_and_bounce_ool(&a.sc, r.wo, r.wd, r.t, r.u, r.v, r.tri, r.blas_front, radiance, throughput, &sd, &br);
+                    seed = sd;
+                    radiance = br.radiance;
+                    if (segment == 0) a.out_depth[pixel] = encode_depth(cam, br.first_hit_distance);
+                    alive = br.alive && segment < last_segment;
+                    if (alive) {
+                        throughput = br.throughput;
+                        fast_ray_begin(r, a.sc, br.next_o, br.next_d);
+                        segment++;
+                    }
+                }
+                if (!alive) {
+                    a.out_rgba8[pixel] = pack_rgba8(radiance);
+                    a.cost[pixel] = steps;
+                    has = false;
+                }
+            }
+            continue;
+        }
+        if (!exhausted && n_idle > 0 && (32 - n_idle < refill_below || n_walk + n_fin == 0)) {
+            // ---------------- R: new camera rays for idle lanes ----------------
+            it_e++;
+            if (chunk_next == chunk_end) {
+                uint32_t base = 0, len = kChunkPrimary;
+                if (lane == 0) {
+                    if (!heavy_done) {
+                        base = atomicAdd(&cnt->cursor[0], kChunkHeavy);
+                        len = kChunkHeavy;
+                        if (base >= lists.heavy_total) base = 0xFFFFFFFFu;
+                        else if (base + len > lists.heavy_total) len = lists.heavy_total - base;
+                    }
+                    if (heavy_done || base == 0xFFFFFFFFu) {
+                        base = lists.heavy_total + atomicAdd(&cnt->cursor[1], kChunkPrimary);
+                        len = kChunkPrimary | 0x80000000u;
+                    }
+                }
+                base = __shfl_sync(kFull, base, 0);
+                len = __shfl_sync(kFull, len, 0);
+                if (len & 0x80000000u) { heavy_done = true; len &= 0x7FFFFFFFu; }
+                if (base >= total) { exhausted = true; continue; }
+                chunk_next = base;
+                chunk_end = min(base + len, total);
+            }
+            const unsigned idle = __ballot_sync(kFull, !has);
+            const uint32_t avail = chunk_end - chunk_next;
+            const uint32_t rank = __popc(idle & lanemask_lt);
+            if (!has && rank < avail) {
+                const uint32_t p = lists.pixel(a, chunk_next + rank);
+                const int py = (int)(p / (uint32_t)a.width), px = (int)(p - (uint32_t)py * (uint32_t)a.width);
+                pred = min(a.cost[p], (1u << 27) - 1u);
+                PrimaryRay pr;
+                generate_primary_ray_ool(&cam, a.width, a.height, px, py, &pr);
+                seed = pr.seed;
+                pixel = p;
+                throughput = mk3(1.0f, 1.0f, 1.0f); radiance = mk3(0.0f, 0.0f, 0.0f);
+                segment = 0;
+                steps = 0;
+                fast_ray_begin(r, a.sc, pr.o, pr.d);
+                has = true;
+            }
+            n_started += min((uint32_t)n_idle, avail);
+            chunk_next += min((uint32_t)n_idle, avail);
+            continue;
+        }
+        if (n_walk == 0) {
+            if (exhausted && n_fin == 0) break;
+            continue;
+        }
+        // ---------------- L / I / T: one step of the leading path's phase, else of the most popular ----------------
+        int run = (n_l >= n_i && n_l >= n_t) ? 0 : (n_i >= n_t ? 1 : 2);
+        if (lead_phase >= 0 && lead_phase < 3) run = lead_phase;
+        if (run == 1) {
+            it_i++;
+            bool go = in_i;
+            const int need = (n_i + 1) >> 1;
+#pragma unroll 1
+            for (int b = 0; b < a.burst; b++) { // node burst: no census while at least half of the starters stay on internal nodes
+                if (go) { fast_step_node(a.sc, r, st); steps++; go = fast_link_is_node(r.cur, r.inst); }
+                if (__popc(__ballot_sync(kFull, go)) < need) break;
+            }
+        } else if (run == 0) {
+            it_l++;
+            if (in_l) { fast_step_leaf(a.sc, r, st); steps++; }
+        } else {
+            it_t++;
+            if (in_t) { fast_step_instance(a.sc, r, st); steps++; }
+        }
+    }
+    if (prof && lane == 0) {
+        unsigned long long *w = a.warp_prof + (size_t)((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 8u;
+        w[0] = t_start; w[1] = global_ns(); w[2] = it_i; w[3] = it_l; w[4] = it_t; w[5] = it_f; w[6] = it_e; w[7] = n_started;
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        my_rays += __shfl_down_sync(kFull, my_rays, off);
+        my_phits += __shfl_down_sync(kFull, my_phits, off);
+        my_retraced += __shfl_down_sync(kFull, my_retraced, off);
+    }
+    if (lane == 0) {
+        atomicAdd(&cnt->rays, my_rays); atomicAdd(&cnt->primary_hits, my_phits);
+        if (my_retraced) atomicAdd(&cnt->retraced, my_retraced);
+    }
+    if (my_overflow) atomicOr(&cnt->overflow, 1u);
+}
+
 // Camera-ray classification (first kernel of the two-kernel schedule): one thread per pixel in
 // 8x4-tile order, so a warp is one tile and runs in lockstep.  The thread generates its camera ray
 // (main.glsl:405-421) and walks the TLAS level with tight-box culling.  A ray that reaches no
@@ -689,6 +914,7 @@ __global__ void __launch_bounds__(kTraceThreads) k_primary_cull(const FrameArgs 
             if (!survivor) {
                 a.out_rgba8[pixel] = pack_rgba8(mk3(0.0f, 0.0f, 0.0f) + mk3(1.0f, 1.0f, 1.0f) * sample_sky(d));
                 a.out_depth[pixel] = encode_depth(cam, cam.z_far);
+                if (a.trace) write_hit_record(a, 0, pixel, 1e9f, 0.0f, 0.0f, 0u, 0u); // GDPT_RECORD_HITS: a miss
                 my_done++;
             }
         }
@@ -1120,6 +1346,7 @@ struct Shapes {
     int path_list_blocks[2] = {};   // [TRACE], CULL, SRC 1
     int path_list_blocks_minb[9] = {}; // untraced, by MINB (register cap variants)
     int mux_blocks[5] = {};         // k_path_mux<K>, index K
+    int fast_blocks[2][9] = {};     // k_path_fast<REC, MINB>
     int cull_blocks_per_sm = 1;
     int shade_blocks = 0;
     int prog_blocks = 0;
@@ -1186,6 +1413,11 @@ void init_launch_shapes(int device)
     s.path_list_blocks_minb[5] = grid_of(k_path<false, true, 1, 5>, kTraceThreads);
     s.path_list_blocks_minb[6] = grid_of(k_path<false, true, 1, 6>, kTraceThreads);
     s.path_list_blocks_minb[8] = grid_of(k_path<false, true, 1, 8>, kTraceThreads);
+    s.fast_blocks[0][4] = grid_of(k_path_fast<false, 4>, kTraceThreads);
+    s.fast_blocks[0][5] = grid_of(k_path_fast<false, 5>, kTraceThreads);
+    s.fast_blocks[0][6] = grid_of(k_path_fast<false, 6>, kTraceThreads);
+    s.fast_blocks[0][8] = grid_of(k_path_fast<false, 8>, kTraceThreads);
+    s.fast_blocks[1][4] = grid_of(k_path_fast<true, 4>, kTraceThreads);
     s.mux_blocks[1] = mux_grid<1, 8>(s.sms);
     s.mux_blocks[2] = mux_grid<2, 8>(s.sms);
     s.mux_blocks[3] = mux_grid<3, 5>(s.sms);
@@ -1271,6 +1503,22 @@ void launch_progressive(uint32_t *screen_rgba8, float4 *accum, const gdpt_progre
                                                  shard_band);
 }
 
+static int fast_minb(const FrameArgs &a) { return (a.path_minb == 5 || a.path_minb == 6 || a.path_minb == 8) ? a.path_minb : 4; }
+
+void launch_path_fast(const FrameArgs &a, bool record, cudaStream_t s)
+{
+    Shapes &sh = shapes_for_current_device();
+    if (record) { k_path_fast<true, 4><<<persistent_grid(sh, a, sh.fast_blocks[1][4]), kTraceThreads, 0, s>>>(a); return; }
+    const int m = fast_minb(a);
+    const int grid = persistent_grid(sh, a, sh.fast_blocks[0][m]);
+    switch (m) {
+    case 5: k_path_fast<false, 5><<<grid, kTraceThreads, 0, s>>>(a); break;
+    case 6: k_path_fast<false, 6><<<grid, kTraceThreads, 0, s>>>(a); break;
+    case 8: k_path_fast<false, 8><<<grid, kTraceThreads, 0, s>>>(a); break;
+    default: k_path_fast<false, 4><<<grid, kTraceThreads, 0, s>>>(a); break;
+    }
+}
+
 void launch_path_mux(const FrameArgs &a, cudaStream_t s)
 {
     Shapes &sh = shapes_for_current_device();
@@ -1299,6 +1547,7 @@ size_t path_kernel_warps(const FrameArgs &a)
 {
     Shapes &sh = shapes_for_current_device();
     if (a.schedule == 3 && (a.path_minb == 1 || a.path_minb == 2 || a.path_minb == 5 || a.path_minb == 6 || a.path_minb == 8)) return (size_t)sh.path_list_blocks_minb[a.path_minb] * (kTraceThreads / 32);
+    if (a.schedule == 5) return (size_t)sh.fast_blocks[0][fast_minb(a)] * (kTraceThreads / 32);
     if (a.schedule == 4) return (size_t)sh.mux_blocks[(a.mux_k >= 1 && a.mux_k <= 4) ? a.mux_k : 2] * (kMuxThreads / 32);
     int most = 0;
     for (int t = 0; t < 2; t++) {
@@ -1311,7 +1560,7 @@ size_t path_kernel_warps(const FrameArgs &a)
 int k1_launch_count(int schedule, int max_depth, bool debug_steps)
 {
     if (schedule == 2) return 1;
-    if (schedule == 3 || schedule == 4) return 2;
+    if (schedule >= 3) return 2;
     if (debug_steps) return 1;
     return 1 + max_depth + (max_depth - 1); // primary + shade(0..D-1) + trace(1..D-1)
 }

@@ -22,6 +22,7 @@ struct FrameCounters {
     unsigned long long primary_hits;
     unsigned long long rays;            // ray_trace() calls, counted by the single-kernel schedule
     unsigned long long node_pops, box_tests, tri_tests, tlas_leaves; // TRACE builds only
+    unsigned long long retraced;        // schedule 5: rays re-traced in reference order (proof failed or tie)
 };
 
 // Path queue: structure-of-arrays of five 16 B planes per entry.
@@ -75,6 +76,10 @@ void launch_path(const FrameArgs &a, bool trace, cudaStream_t s);
 // boxes, then whole paths per lane for the pixels that can hit something.
 void launch_primary_cull(const FrameArgs &a, cudaStream_t s);
 void launch_path_list(const FrameArgs &a, bool trace, cudaStream_t s);
+// Schedule 5 (default when rendering): the same classification kernel, then whole paths per lane whose rays
+// are answered by the closest-hit search of pt_fast.cuh (+ proof, exact re-trace where it fails).
+// `record` also writes the hit records of the first a.trace_segments segments (no work counters).
+void launch_path_fast(const FrameArgs &a, bool record, cudaStream_t s);
 // Schedule 4: the same classification kernel, then the lane-multiplexed path kernel (a.mux_k
 // path contexts per lane, kept in shared memory; a.path_recs holds their cold state).
 void launch_path_mux(const FrameArgs &a, cudaStream_t s);

@@ -69,11 +69,34 @@ struct __attribute__((aligned(16))) InstRec {
     uint32_t root_link;     // pre-encoded link of BLASInstance.root
     uint32_t tlas_orig;     // reference TLAS node index of this leaf
     uint32_t root_orig;     // reference BVH node index of the root
-    uint32_t pad;
+    uint32_t fast_root;     // link of this BLAS's root in the closest-hit tables (fast_bvh.h)
     float tight_min[4];     // tight box of the whole BLAS, object space (w unused)
     float tight_max[4];
 };
 static_assert(sizeof(InstRec) == 112, "InstRec is seven 128-bit loads");
+
+// ---- closest-hit tables (fast_bvh.h / pt_fast.cuh) -------------------------------------------
+// 64 B, four 128-bit quads: both children's true (inflated) boxes and their links.
+//   q0 = Lmin.x Lmin.y Lmin.z Lmax.x   q1 = Lmax.y Lmax.z Rmin.x Rmin.y
+//   q2 = Rmin.z Rmax.x Rmax.y Rmax.z   q3 = left right - -
+// Links: [31] TLAS level, [30] leaf.  BLAS leaf = LINK_LEAF | (count-1) << 27 | first FastTri;
+// TLAS leaf = LINK_TLAS | LINK_LEAF | instance; internal = index into fast_nodes / fast_tlas.
+struct __attribute__((aligned(64))) FastNode {
+    float lmin[3]; float lmax[3];
+    float rmin[3]; float rmax[3];
+    uint32_t left, right, pad[2];
+};
+static_assert(sizeof(FastNode) == 64, "FastNode is four 128-bit loads");
+// 48 B: the reference's vertices (bit copies) and the triangle's index in the reference arrays.
+struct __attribute__((aligned(16))) FastTri {
+    float v0[3]; uint32_t orig;
+    float v1[3]; uint32_t pad1;
+    float v2[3]; uint32_t pad2;
+};
+static_assert(sizeof(FastTri) == 48, "FastTri is three 128-bit loads");
+#define FAST_LEAF_COUNT_SHIFT 27
+#define FAST_LEAF_FIRST_MASK 0x07FFFFFFu
+#define GDPT_FAST_MAX_DEPTH 120u
 
 struct SceneView {
     // uploaded reference buffers (set 1 bindings 0..5, set 2 binding 0)
@@ -92,6 +115,12 @@ struct SceneView {
     const WideNode *wide_tlas;
     const InstRec *inst_recs;
     uint32_t tlas_root_link;
+    // closest-hit tables; fast_ok == 0 means "use the reference-order traversal only"
+    const FastNode *fast_nodes;
+    const FastNode *fast_tlas;
+    const FastTri *fast_tris;
+    const uint32_t *tri_leaf;
+    uint32_t fast_ok;
 };
 
 } // namespace gdpt

@@ -141,7 +141,7 @@ GDPT_HD void triangle_test(const SceneView &sc, RayState &r, uint32_t tri_index)
 
 template <class Stack> GDPT_HD void stack_push(RayState &r, Stack &st, uint32_t link)
 {
-    if (r.sp < GDPT_MAX_STACK) st.store(r.sp, link); else r.overflow = 1u;
+    if (r.sp < GDPT_MAX_STACK) st.store(r.sp, link); else r.overflow |= 1u;
     r.sp++;
 }
 template <class Stack> GDPT_HD uint32_t stack_pop(RayState &r, Stack &st)

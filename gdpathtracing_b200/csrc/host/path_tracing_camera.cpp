@@ -99,6 +99,8 @@ bool PathTracingCamera::init()
     if (trace_segments_ > 0) defines.push_back("#define GDPT_TRACE " + std::to_string(trace_segments_));
     if (visits_per_ray_ > 0) defines.push_back("#define GDPT_TRACE_VISITS " + std::to_string(visits_per_ray_));
     if (cull_ >= 0) defines.push_back("#define GDPT_CULL " + std::to_string(cull_));
+    if (variant_ >= 0) defines.push_back("#define GDPT_VARIANT " + std::to_string(variant_));
+    if (record_hits_ > 0) defines.push_back("#define GDPT_RECORD_HITS " + std::to_string(record_hits_));
     cs_ = new ComputeShader("res://addons/jar_path_tracing/src/shaders/main.glsl", rd_, defines);
 
     render_parameters_rid_ = cs_->create_storage_buffer_uniform(&render_parameters_, sizeof(render_parameters_), 2, 0);

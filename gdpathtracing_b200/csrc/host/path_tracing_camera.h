@@ -72,6 +72,10 @@ public:
     void set_debug_steps(bool on) { debug_steps_ = on; }
     // -1 backend default (cull when rendering, reference order when tracing), 0 reference order, 1 cull
     void set_cull(int mode) { cull_ = mode; }
+    // hit records (no work counters) of the first n segments, written by the RENDERING kernels (parity check of the fast path)
+    void set_record_hits(int segments) { record_hits_ = segments; }
+    // kernel schedule ("#define GDPT_VARIANT n", include/gdpt.h); -1 = backend default.  Results do not depend on it.
+    void set_variant(int variant) { variant_ = variant; }
     // true: one gdpt_render_frame call per frame; false: the reference's dispatch-by-dispatch sequence
     void set_fused_frame(bool on) { fused_frame_ = on; }
 
@@ -119,6 +123,8 @@ private:
     int trace_segments_ = 0; uint32_t visits_per_ray_ = 0;
     bool debug_steps_ = false, fused_frame_ = true;
     int cull_ = -1;
+    int record_hits_ = 0;
+    int variant_ = -1;
     uint32_t last_frame_count_ = 0;
 };
 

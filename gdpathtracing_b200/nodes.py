@@ -178,6 +178,14 @@ class PathTracingCamera:
     def set_debug_steps(self, on):
         host.gdpt_camera_set_debug_steps(self._h, 1 if on else 0)
 
+    def set_variant(self, variant):
+        """Kernel schedule (include/gdpt.h GDPT_VARIANT); -1 backend default.  Results are identical for every value."""
+        host.gdpt_camera_set_variant(self._h, int(variant))
+
+    def set_record_hits(self, segments):
+        """Hit records of the first n segments from the rendering kernels (no work counters)."""
+        host.gdpt_camera_set_record_hits(self._h, int(segments))
+
     def set_cull(self, mode):
         """-1 backend default, 0 reference visit order, 1 tight-box culling (bit-identical results)."""
         host.gdpt_camera_set_cull(self._h, int(mode))

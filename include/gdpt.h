@@ -103,6 +103,11 @@ GDPT_API uint32_t gdpt_abi_version(void);
  *   "#define GDPT_REFERENCE_ORDER"  visit every node the reference visits (no tight-box culling);
  *                              results are identical either way, only the work differs.  Implied
  *                              by GDPT_TRACE unless "#define GDPT_CULL 1" is also given
+ *   "#define GDPT_RECORD_HITS n"  the rendering kernels themselves also write the hit records (no work
+ *                              counters) of the first n segments; read with gdpt_shader_read_trace
+ *   "#define GDPT_VARIANT 3"   keep the reference visiting order (with culling) when rendering; the default
+ *                              (variant 5) answers rays with an order-free closest-hit search plus a proof that the
+ *                              reference reaches the same triangle, and re-traces the rest; identical results
  * Unknown defines are ignored, as a GLSL compiler would ignore an unused macro. */
 GDPT_API int  gdpt_shader_create(gdpt_device *device, const char *shader_path,
                                  const char *const *args, int n_args,
@@ -216,6 +221,7 @@ typedef struct gdpt_frame_stats {
     uint32_t max_stack;
     float    k1_ms;         /* CUDA-event time of the last K1 dispatch */
     float    k2_ms;
+    uint64_t retraced;      /* rays the closest-hit search handed to the exact reference-order traversal */
 } gdpt_frame_stats;
 GDPT_API int  gdpt_shader_get_stats(gdpt_shader *main_shader, gdpt_frame_stats *out);
 

@@ -79,6 +79,11 @@ GDPT_API void  gdpt_camera_set_trace(gdpt_camera_node *c, int segments, uint32_t
 GDPT_API void  gdpt_camera_set_debug_steps(gdpt_camera_node *c, int on);
 /* -1 backend default, 0 reference visit order, 1 tight-box culling (results identical) */
 GDPT_API void  gdpt_camera_set_cull(gdpt_camera_node *c, int mode);
+/* hit records (gdpt_trace_record without work counters) of the first `segments` path segments, written by the
+ * rendering kernels themselves; read back with gdpt_shader_read_trace */
+GDPT_API void  gdpt_camera_set_record_hits(gdpt_camera_node *c, int segments);
+/* kernel schedule ("#define GDPT_VARIANT n", gdpt.h); -1 = backend default; results are identical for every value */
+GDPT_API void  gdpt_camera_set_variant(gdpt_camera_node *c, int variant);
 GDPT_API void  gdpt_camera_set_fused_frame(gdpt_camera_node *c, int on);
 /* init() / render() (path_tracing_camera.cpp:111-232); init returns 1 when check_ready() */
 GDPT_API int   gdpt_camera_init(gdpt_camera_node *c);

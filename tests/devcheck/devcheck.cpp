@@ -10,6 +10,8 @@
 // tests/devcheck/_build/ by tests/conftest.py and only the "not gpu" tests call it.  The
 // kernel-level scheduling (queues, refill, atomics) is covered by the GPU tests.
 #include "derived_layout.h"
+#include "fast_bvh.h"
+#include "pt_fast.cuh"
 #include "pt_shade.cuh"
 #include "pt_trace.cuh"
 
@@ -29,21 +31,24 @@ struct HostStack {
 
 static int g_stepwise = 0;
 static int g_cull = 0;
+static int g_fast = 0;
+static uint64_t g_fast_rays = 0, g_fast_retraced = 0, g_fast_ties = 0;
 
 template <bool CULL> static void run_ray(const SceneView &sc, RayState &r, HostStack &st, TraceCounters *tc)
 {
+    if (g_fast && sc.fast_ok) {
+        // closest-hit search + proof; rays that fail it are re-traced in reference order (what the kernels do)
+        RayState f = r;
+        fast_trace_ray(sc, f, st);
+        __atomic_add_fetch(&g_fast_rays, 1, __ATOMIC_RELAXED);
+        if (fast_result_is_reference(sc, f)) { r = f; return; }
+        __atomic_add_fetch(&g_fast_retraced, 1, __ATOMIC_RELAXED);
+        if (f.overflow & RAY_TIE) __atomic_add_fetch(&g_fast_ties, 1, __ATOMIC_RELAXED);
+    }
     if (g_stepwise == 2) trace_ray_compact<true, CULL>(sc, r, st, tc);
     else if (g_stepwise) trace_ray_stepwise<true, CULL>(sc, r, st, tc);
     else trace_ray<true, CULL>(sc, r, st, tc);
 }
-
-extern "C" {
-
-// 0: node-at-a-time traversal, 1: leaves split into single-triangle steps (phase-voting order),
-// 2: the compact scheduler's node / instance / triangle steps
-void devcheck_set_stepwise(int on) { g_stepwise = on; }
-// 0: reference visit order, 1: tight-box culling (hit records must not change)
-void devcheck_set_cull(int on) { g_cull = on; }
 
 struct devcheck_scene {
     const void *tri_geom; uint64_t n_tris;
@@ -54,6 +59,38 @@ struct devcheck_scene {
     const void *tlas; uint64_t n_tlas;
     const uint8_t *textures; int32_t tex_w, tex_h, tex_layers, _pad;
 };
+
+static void make_view(const devcheck_scene *in, DerivedLayout &lay, FastLayout &fast, SceneView &sc)
+{
+    std::memset(&sc, 0, sizeof(sc));
+    sc.tri_geom = (const gdpt_triangle_geometry *)in->tri_geom; sc.tri_data = (const gdpt_triangle_data *)in->tri_data;
+    sc.materials = (const gdpt_material *)in->materials; sc.bvh = (const gdpt_bvh_node *)in->bvh;
+    sc.blas = (const gdpt_blas_instance *)in->blas; sc.tlas = (const gdpt_tlas_node *)in->tlas;
+    sc.textures = in->textures; sc.tex_w = in->tex_w; sc.tex_h = in->tex_h; sc.tex_layers = in->tex_layers;
+    if (g_fast) {
+        build_fast_layout(sc.bvh, (uint32_t)in->n_nodes, sc.blas, (uint32_t)in->n_blas, sc.tlas, (uint32_t)in->n_tlas, sc.tri_geom,
+                          (uint32_t)in->n_tris, lay, fast);
+        for (size_t b = 0; b < lay.inst_recs.size(); b++) lay.inst_recs[b].fast_root = fast.inst_root[b];
+        sc.fast_nodes = fast.nodes.data(); sc.fast_tlas = fast.tlas.data(); sc.fast_tris = fast.tris.data();
+        sc.tri_leaf = fast.tri_leaf.data(); sc.fast_ok = fast.ok ? 1u : 0u;
+        if (!fast.ok) std::fprintf(stderr, "devcheck: closest-hit tables unavailable: %s\n", fast.why_not.c_str());
+    }
+    sc.wide_nodes = lay.wide_nodes.data(); sc.leaf_recs = lay.leaf_recs.data();
+    sc.wide_tlas = lay.wide_tlas.data(); sc.inst_recs = lay.inst_recs.data();
+    sc.tlas_root_link = lay.tlas_root_link;
+}
+
+extern "C" {
+
+// 0: node-at-a-time traversal, 1: leaves split into single-triangle steps (phase-voting order),
+// 2: the compact scheduler's node / instance / triangle steps
+void devcheck_set_stepwise(int on) { g_stepwise = on; }
+// 0: reference visit order, 1: tight-box culling (hit records must not change)
+void devcheck_set_cull(int on) { g_cull = on; }
+// 1: closest-hit search + proof, exact re-trace where the proof fails (pt_fast.cuh); hit records must not change
+void devcheck_set_fast(int on) { g_fast = on; g_fast_rays = g_fast_retraced = g_fast_ties = 0; }
+void devcheck_fast_counts(uint64_t *out3) { out3[0] = g_fast_rays; out3[1] = g_fast_retraced; out3[2] = g_fast_ties; }
+
 
 // Renders rows [y_begin, y_end) with the device functions.  Same outputs as orc_path_trace.
 int devcheck_path_trace(const devcheck_scene *in, const gdpt_render_params *params, const gdpt_camera *cam, int max_depth,
@@ -66,15 +103,9 @@ int devcheck_path_trace(const devcheck_scene *in, const gdpt_render_params *para
                                           (uint32_t)in->n_blas, (const gdpt_tlas_node *)in->tlas, (uint32_t)in->n_tlas,
                                           (const gdpt_triangle_geometry *)in->tri_geom, (uint32_t)in->n_tris, lay);
     if (!err.empty()) return -1;
+    FastLayout fast;
     SceneView sc;
-    std::memset(&sc, 0, sizeof(sc));
-    sc.tri_geom = (const gdpt_triangle_geometry *)in->tri_geom; sc.tri_data = (const gdpt_triangle_data *)in->tri_data;
-    sc.materials = (const gdpt_material *)in->materials; sc.bvh = (const gdpt_bvh_node *)in->bvh;
-    sc.blas = (const gdpt_blas_instance *)in->blas; sc.tlas = (const gdpt_tlas_node *)in->tlas;
-    sc.textures = in->textures; sc.tex_w = in->tex_w; sc.tex_h = in->tex_h; sc.tex_layers = in->tex_layers;
-    sc.wide_nodes = lay.wide_nodes.data(); sc.leaf_recs = lay.leaf_recs.data();
-    sc.wide_tlas = lay.wide_tlas.data(); sc.inst_recs = lay.inst_recs.data();
-    sc.tlas_root_link = lay.tlas_root_link;
+    make_view(in, lay, fast, sc);
 
     const int W = params->width, H = params->height;
     uint64_t rays = 0;
@@ -156,3 +187,63 @@ void devcheck_progressive(uint8_t *screen, float *accum, int width, int height, 
 }
 
 } // extern "C"
+
+// Analysis hook (tools/path_cost_model.py): per-pixel step counts of the culled, compact-order traversal --
+// node steps, leaf entries, triangle tests, instance steps, segments, and the largest leaf met.
+extern "C" int devcheck_path_costs(const devcheck_scene *in, const gdpt_render_params *params, const gdpt_camera *cam, int max_depth,
+                                   int y_begin, int y_end, uint32_t *out6)
+{
+    DerivedLayout lay;
+    const std::string err = derive_layout((const gdpt_bvh_node *)in->bvh, (uint32_t)in->n_nodes, (const gdpt_blas_instance *)in->blas,
+                                          (uint32_t)in->n_blas, (const gdpt_tlas_node *)in->tlas, (uint32_t)in->n_tlas,
+                                          (const gdpt_triangle_geometry *)in->tri_geom, (uint32_t)in->n_tris, lay);
+    if (!err.empty()) return -1;
+    FastLayout fast;
+    SceneView sc;
+    make_view(in, lay, fast, sc);
+    const int W = params->width, H = params->height;
+    HostStack st;
+    for (int y = y_begin; y < y_end && y < H; y++) {
+        for (int x = 0; x < W; x++) {
+            uint32_t *c = out6 + ((size_t)y * W + x) * 6;
+            for (int k = 0; k < 6; k++) c[k] = 0;
+            f3 o, d;
+            u2 seed = generate_primary_ray(*cam, W, H, x, y, &o, &d);
+            f3 radiance = mk3(0, 0, 0), throughput = mk3(1, 1, 1);
+            for (int i = 0; i < max_depth; i++) {
+                RayState r;
+                ray_begin(r, sc, o, d);
+                TraceCounters tc;
+                counters_init(tc, nullptr, 0);
+                uint32_t tri_next = 0, tri_end = 0;
+                if (g_fast && sc.fast_ok) { // step counts of the closest-hit search (c[5] = exact re-traces)
+                    while (r.cur != LINK_NONE) {
+                        if (fast_link_is_leaf(r.cur)) { c[1]++; c[2] += ((r.cur >> FAST_LEAF_COUNT_SHIFT) & 7u) + 1u; fast_step_leaf(sc, r, st); }
+                        else if (fast_link_is_node(r.cur, r.inst)) { c[0]++; fast_step_node(sc, r, st); }
+                        else { c[3]++; fast_step_instance(sc, r, st); }
+                    }
+                    if (!fast_result_is_reference(sc, r)) { c[5]++; ray_begin(r, sc, o, d); trace_ray_compact<true, true>(sc, r, st, &tc); }
+                }
+                while (r.cur != LINK_NONE || tri_next < tri_end) {
+                    if (tri_next < tri_end || link_is_blas_leaf(r.cur)) {
+                        if (tri_next == tri_end) {
+                            c[1]++;
+                            const q4u leaf = ldqu(sc.leaf_recs, r.cur & LINK_INDEX_MASK);
+                            if (leaf.y > c[5]) c[5] = leaf.y;
+                        }
+                        step_blas_leaf_one<true>(sc, r, st, &tc, tri_next, tri_end);
+                        c[2]++;
+                    } else if (link_is_node_step(r.cur, r.inst)) { step_node<true, true>(sc, r, st, &tc); c[0]++; }
+                    else { step_instance<true, true>(sc, r, st, &tc); c[3]++; }
+                }
+                c[4]++;
+                if (!(r.t < 1e9f)) break;
+                BounceResult br = shade_and_bounce(sc, o, d, r.t, r.u, r.v, r.tri, r.blas_front, radiance, throughput, seed);
+                radiance = br.radiance;
+                if (!br.alive) break;
+                throughput = br.throughput; o = br.next_o; d = br.next_d;
+            }
+        }
+    }
+    return 0;
+}

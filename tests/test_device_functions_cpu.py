@@ -144,3 +144,74 @@ def test_tie_on_equal_t_last_tested_triangle_wins(devcheck):
     _, _, tr, _, _ = run_devcheck(devcheck, osc, cam, 32, 32, 1, 1, 1)
     ok, why = records_equal(tr[0], ref["trace"][0])
     assert ok, why
+
+
+def fast_counts(devcheck):
+    c = np.zeros(3, np.uint64)
+    devcheck.devcheck_fast_counts(ptr(c))
+    return dict(rays=int(c[0]), retraced=int(c[1]), ties=int(c[2]))
+
+
+FAST_CASES = CASES + [
+    ("demo_wide", lambda: scenes.demo_scene(), 320, 180, 8, 8, 3),
+    ("soup_dense", lambda: scenes.triangle_soup(60000, seed=5), 96, 54, 3, 3, 2),
+]
+
+
+@pytest.mark.parametrize("name,make,W,H,depth,segs,frame", FAST_CASES, ids=[c[0] for c in FAST_CASES])
+def test_closest_hit_search_with_proof_equals_reference_traversal(devcheck, name, make, W, H, depth, segs, frame):
+    """pt_fast.cuh: an order-free closest-hit search over our own BVH plus the proof that the reference
+    reaches that triangle (exact re-trace where the proof fails) returns the reference's hit records, bit for bit."""
+    devcheck.devcheck_set_fast(1)
+    try:
+        sc = make()
+        grp = scenes.populate(sc)
+        grp.build()
+        osc = oracle.Scene(grp.buffers(), grp.texture_layers())
+        cam = bytes(nodes.make_camera_block(sc.camera_transform12, sc.fov, W, H, frame))
+        ref = oracle.path_trace(osc, W, H, cam, max_depth=depth, trace_segments=segs)
+        out, dep, tr, _, rays = run_devcheck(devcheck, osc, cam, W, H, depth, segs, 1)
+        counts = fast_counts(devcheck)
+    finally:
+        devcheck.devcheck_set_fast(0)
+    assert rays == ref["stats"]["rays"]
+    assert counts["rays"] == rays, "the closest-hit tables were not used"
+    for s in range(segs):
+        a, b = tr[s], ref["trace"][s]
+        assert np.array_equal(a["hit"], b["hit"])
+        live = b["hit"] != 0xFFFFFFFF
+        for f in HIT_FIELDS:
+            x, y = a[f][live], b[f][live]
+            if x.dtype == np.float32:
+                x, y = x.view(np.uint32), y.view(np.uint32)
+            assert np.array_equal(x, y), f"segment {s} field {f}"
+    assert np.array_equal(out, ref["rgba8"])
+    assert np.array_equal(dep.view(np.uint32), ref["depth"].view(np.uint32))
+    print(f"{name}: {counts}")
+
+
+def test_closest_hit_search_sends_ties_to_the_exact_traversal(devcheck):
+    """Equal-t duplicates (quirk Q8): the search must notice the tie and fall back, not pick a winner."""
+    sc = scenes.SceneDesc("dup", camera_transform12=scenes.transform12(None, (0, 0, 5)), fov=40.0)
+    sc.materials = [dict()]
+    sc.default_material = 0
+    tri = np.array([[-1, -1, 0], [0, 1, 0], [1, -1, 0]], np.float32)
+    p = np.concatenate([tri, tri])
+    n = np.tile(np.array([0, 0, 1], np.float32), (6, 1))
+    sc.meshes = [[{"positions": p, "normals": n, "uvs": np.zeros((6, 2), np.float32), "indices": np.arange(6, dtype=np.int32)}]]
+    sc.instances = [dict(mesh=0)]
+    grp = scenes.populate(sc)
+    grp.build()
+    osc = oracle.Scene(grp.buffers(), grp.texture_layers())
+    cam = bytes(nodes.make_camera_block(sc.camera_transform12, sc.fov, 32, 32, 1))
+    ref = oracle.path_trace(osc, 32, 32, cam, max_depth=1, trace_segments=1)
+    devcheck.devcheck_set_fast(1)
+    try:
+        _, _, tr, _, _ = run_devcheck(devcheck, osc, cam, 32, 32, 1, 1, 1)
+        counts = fast_counts(devcheck)
+    finally:
+        devcheck.devcheck_set_fast(0)
+    hits = ref["trace"][0]["hit"] == 1
+    assert counts["ties"] == int(hits.sum()) > 0
+    for f in HIT_FIELDS:
+        assert np.array_equal(tr[0][f][hits].view(np.uint32), ref["trace"][0][f][hits].view(np.uint32)), f

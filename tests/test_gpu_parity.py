@@ -107,6 +107,46 @@ def test_culled_traversal_gives_identical_hits(name, make, W, H, depth, segs):
     del cam
 
 
+@pytest.mark.parametrize("variant", [5, 3], ids=["closest_hit_plus_proof", "reference_order_culled"])
+@pytest.mark.parametrize("name,make,W,H,depth,segs", CASES, ids=[c[0] for c in CASES])
+def test_rendering_kernels_record_the_reference_hits(name, make, W, H, depth, segs, variant):
+    """The kernels that are timed (schedule 5: closest-hit search + proof + exact re-trace, pt_fast.cuh;
+    schedule 3: culled reference order) write their own hit records: hit, triangle, instance, front and the
+    t/u/v bits of every segment equal the oracle's full reference traversal, as do frame, depth and ray count."""
+    sc = make()
+    grp = scenes.populate(sc)
+    cam = PathTracingCamera()
+    cam.fov = sc.fov
+    cam.geometry_group = grp
+    cam.denoising_mode = PathTracingCamera.NONE
+    cam.set_window_size(W, H)
+    cam.set_global_transform(sc.camera_transform12)
+    cam.set_max_depth(depth)
+    cam.set_record_hits(depth)
+    cam.set_variant(variant)
+    cam.init()
+    frame = cam.render().copy()
+    st = cam.stats()
+    ref = oracle.path_trace(oracle_scene(grp), W, H, bytes(cam.camera_block()), max_depth=depth, trace_segments=depth)
+    assert st["rays"] == ref["stats"]["rays"] and st["primary_hits"] == ref["stats"]["primary_hits"]
+    for s in range(depth):
+        a, b = cam.read_trace(s), ref["trace"][s]
+        assert np.array_equal(a["hit"], b["hit"]), f"segment {s}: hit flags"
+        live = b["hit"] != 0xFFFFFFFF
+        for f in ("triangle", "blas", "front", "t", "u", "v"):
+            x, y = a[f][live], b[f][live]
+            if x.dtype == np.float32:
+                x, y = x.view(np.uint32), y.view(np.uint32)
+            assert np.array_equal(x, y), f"segment {s} field {f}: {(x != y).sum()} differ"
+    assert np.array_equal(frame, ref["rgba8"])
+    assert np.array_equal(cam.read_image("depth").view(np.uint32), ref["depth"].view(np.uint32))
+    if variant == 5:
+        assert st["retraced"] * 20 < st["rays"], "the proof should fail for a small minority of rays only"
+        print(f"{name}: {st['retraced']} of {st['rays']} rays re-traced in reference order")
+    else:
+        assert st["retraced"] == 0
+
+
 def test_fast_kernels_equal_traced_kernels():
     """The un-instrumented instantiation (the one that is timed) produces the same frame."""
     sc = scenes.demo_scene()
