@@ -317,8 +317,8 @@ int finish_main(gdpt_shader *s)
     init_launch_shapes(d->ordinal);
     if (a.schedule == 4 && (rc = dev_alloc(s, &a.path_recs, mux_path_record_quads()))) return rc;
     a.refill_below = a.schedule >= 2 ? 24 : 20;
-    a.burst = a.schedule == 0 ? 8 : (a.schedule == 3 || a.schedule == 5 ? 4 : 16);
-    a.shade_at = 8;
+    a.burst = a.schedule == 0 ? 8 : (a.schedule == 3 ? 4 : (a.schedule == 5 ? 8 : 16));
+    a.shade_at = a.schedule == 5 ? 16 : 8;
     if (const char *e = getenv("GDPT_REFILL_BELOW")) a.refill_below = atoi(e);
     if (const char *e = getenv("GDPT_BURST")) a.burst = atoi(e);
     if (const char *e = getenv("GDPT_SHADE_AT")) a.shade_at = atoi(e);

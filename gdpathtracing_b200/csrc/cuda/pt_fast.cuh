@@ -100,11 +100,15 @@ GDPT_HD void fast_triangle_test(RayState &r, const q4f a, const q4f b, const q4f
     }
 }
 
-// One leaf: up to four triangles, loads issued together.
-template <class Stack> GDPT_HD void fast_step_leaf(const SceneView &sc, RayState &r, Stack &st)
+// One leaf: up to four triangles.  GDPT_FAST_LEAF_UNROLL 4 issues all loads together (more registers, 4 copies of
+// the test in the instruction stream); 1 keeps one copy of the test in a short loop (instruction-cache friendly).
+#ifndef GDPT_FAST_LEAF_UNROLL
+#define GDPT_FAST_LEAF_UNROLL 1
+#endif
+GDPT_HD void fast_leaf_tests(const SceneView &sc, RayState &r, uint32_t leaf_link)
 {
-    const uint32_t first = r.cur & FAST_LEAF_FIRST_MASK, count = ((r.cur >> FAST_LEAF_COUNT_SHIFT) & 7u) + 1u;
-    r.cur = stack_pop(r, st);
+    const uint32_t first = leaf_link & FAST_LEAF_FIRST_MASK, count = ((leaf_link >> FAST_LEAF_COUNT_SHIFT) & 7u) + 1u;
+#if GDPT_FAST_LEAF_UNROLL == 4
     q4f va[4], vb[4], vc[4];
 #pragma unroll
     for (uint32_t i = 0; i < 4u; i++) {
@@ -114,6 +118,23 @@ template <class Stack> GDPT_HD void fast_step_leaf(const SceneView &sc, RayState
 #pragma unroll
     for (uint32_t i = 0; i < 4u; i++)
         if (i < count) fast_triangle_test(r, va[i], vb[i], vc[i]);
+#else
+    // software-pipelined by one triangle: the next triangle's vertices are in flight during the current test
+    q4f a = ldq(sc.fast_tris, first * 3u + 0u), b = ldq(sc.fast_tris, first * 3u + 1u), c = ldq(sc.fast_tris, first * 3u + 2u);
+#pragma unroll 1
+    for (uint32_t i = 0; i < count; i++) {
+        const uint32_t tn = first + (i + 1u < count ? i + 1u : i);
+        const q4f na = ldq(sc.fast_tris, tn * 3u + 0u), nb = ldq(sc.fast_tris, tn * 3u + 1u), nc = ldq(sc.fast_tris, tn * 3u + 2u);
+        fast_triangle_test(r, a, b, c);
+        a = na; b = nb; c = nc;
+    }
+#endif
+}
+template <class Stack> GDPT_HD void fast_step_leaf(const SceneView &sc, RayState &r, Stack &st)
+{
+    const uint32_t leaf = r.cur;
+    r.cur = stack_pop(r, st);
+    fast_leaf_tests(sc, r, leaf);
 }
 
 // b_ray of main.glsl:316-321 for instance record `c0..c3` (inverse transform columns)
@@ -127,6 +148,7 @@ GDPT_HD void fast_local_ray(const q4f c0, const q4f c1, const q4f c2, const q4f 
              ((c0.z * wd.x + c1.z * wd.y) + c2.z * wd.z) + c3.z * 0.0f);
 }
 
+template <class Stack> GDPT_HD void fast_enter_instance(const SceneView &sc, RayState &r, Stack &st);
 // Space changes: back to world space after an instance and/or into the instance `cur` names.
 template <class Stack> GDPT_HD void fast_step_instance(const SceneView &sc, RayState &r, Stack &st)
 {
@@ -135,6 +157,11 @@ template <class Stack> GDPT_HD void fast_step_instance(const SceneView &sc, RayS
         r.inst = GDPT_NO_INSTANCE;
     }
     if ((r.cur & LINK_LEAF) == 0u) return;
+    fast_enter_instance(sc, r, st);
+}
+// r is in world space and r.cur names an instance: into its space (main.glsl:316-321), or past it if its true box is missed
+template <class Stack> GDPT_HD void fast_enter_instance(const SceneView &sc, RayState &r, Stack &st)
+{
     const uint32_t idx = r.cur & LINK_INDEX_MASK;
     const q4f c0 = ldq(sc.inst_recs, idx * 7u + 0u);
     const q4f c1 = ldq(sc.inst_recs, idx * 7u + 1u);

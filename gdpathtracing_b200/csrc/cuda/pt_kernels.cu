@@ -689,6 +689,30 @@ __device__ __forceinline__ void write_hit_record(const FrameArgs &a, int segment
     a.trace[(size_t)segment * a.width * a.height + pixel] = rec;
 }
 
+// Verdict on a finished search, out of line: executed once per ray, not per step.
+__device__ __noinline__ bool fast_verdict_ool(const SceneView *sc, f3 wo, f3 wd, float t, uint32_t tri, uint32_t blas_front, uint32_t flags)
+{
+    RayState r;
+    r.wo = wo; r.wd = wd; r.t = t; r.tri = tri; r.blas_front = blas_front; r.overflow = flags;
+    return fast_result_is_reference(*sc, r);
+}
+
+// Scheduler phases of k_path_fast.  A lane may be able to join more than one: a leaf it reaches is parked in
+// `pend` (speculative traversal: the search is order-free, so the leaf can wait) and the lane keeps descending;
+// the warp runs the leaf phase when enough lanes hold one.
+//   I  one internal node of either level (back to world space first if the link is a TLAS one)
+//   L  one leaf (the parked one, else the current link): <= 4 triangle tests
+//   T  enter the instance the current link names
+__device__ __forceinline__ bool lane_can_node(uint32_t cur, uint32_t pend)
+{
+    return cur != LINK_NONE && (cur & LINK_LEAF) == 0u && ((cur & LINK_TLAS) == 0u || pend == LINK_NONE);
+}
+__device__ __forceinline__ bool lane_can_enter(uint32_t cur, uint32_t pend)
+{
+    return cur != LINK_NONE && (cur & (LINK_TLAS | LINK_LEAF)) == (LINK_TLAS | LINK_LEAF) && pend == LINK_NONE;
+}
+__device__ __forceinline__ bool lane_can_leaf(uint32_t cur, uint32_t pend) { return pend != LINK_NONE || fast_link_is_leaf(cur); }
+
 template <bool REC, int MINB>
 __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_fast(const FrameArgs a)
 {
@@ -718,6 +742,8 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_fast(const FrameAr
 
     RayState r;
     r.cur = LINK_NONE; r.sp = 0; r.overflow = 0; r.t = 1e9f; r.inst = GDPT_NO_INSTANCE;
+    f3 wrd = mk3(0.0f, 0.0f, 0.0f);   // 1 / world direction (ray.rD, main.glsl:421)
+    uint32_t pend = LINK_NONE;        // parked leaf (instance-local: flushed before the space changes)
     f3 throughput = mk3(1.0f, 1.0f, 1.0f), radiance = mk3(0.0f, 0.0f, 0.0f);
     u2 seed; seed.x = seed.y = 0u;
     uint32_t pixel = 0;
@@ -732,27 +758,28 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_fast(const FrameAr
     uint32_t it_i = 0, it_l = 0, it_t = 0, it_f = 0, it_e = 0, n_started = 0;
 
     for (;;) {
-        const bool in_l = has && fast_link_is_leaf(r.cur);
-        const bool in_i = has && !in_l && fast_link_is_node(r.cur, r.inst);
-        const bool in_t = has && !in_l && !in_i && r.cur != LINK_NONE;
-        const bool fin = has && r.cur == LINK_NONE;
-        const uint32_t census = __reduce_add_sync(kFull, 1u << (in_l ? 0 : (in_i ? 6 : (in_t ? 12 : (fin ? 18 : 24)))));
-        const int n_l = (int)(census & 63u), n_i = (int)((census >> 6) & 63u), n_t = (int)((census >> 12) & 63u),
+        const bool can_i = has && lane_can_node(r.cur, pend);
+        const bool can_l = has && lane_can_leaf(r.cur, pend);
+        const bool can_t = has && lane_can_enter(r.cur, pend);
+        const bool fin = has && r.cur == LINK_NONE && pend == LINK_NONE;
+        const uint32_t census = __reduce_add_sync(kFull, (can_i ? 1u : 0u) | (can_l ? 1u << 6 : 0u) | (can_t ? 1u << 12 : 0u) |
+                                                             (fin ? 1u << 18 : 0u) | (has ? 0u : 1u << 24));
+        const int n_i = (int)(census & 63u), n_l = (int)((census >> 6) & 63u), n_t = (int)((census >> 12) & 63u),
                   n_fin = (int)((census >> 18) & 63u), n_idle = (int)(census >> 24);
-        const int n_walk = n_l + n_i + n_t;
-        int lead_phase = -1; // 0 L, 1 I, 2 T, 3 finished
+        const int n_walk = 32 - n_idle - n_fin;
+        int lead_phase = -1; // 0 L, 1 I, 2 T, 3 finished: what the path expected to run longest needs next
         {
             const uint32_t key = (has && pred >= lead_min) ? ((pred << 5) | lane) : 0u;
             const uint32_t most = __reduce_max_sync(kFull, key);
-            if (most != 0u) lead_phase = __shfl_sync(kFull, in_l ? 0 : (in_i ? 1 : (in_t ? 2 : 3)), most & 31u);
+            if (most != 0u) lead_phase = __shfl_sync(kFull, fin ? 3 : (can_i ? 1 : (can_l ? 0 : 2)), most & 31u);
         }
 
         if (n_fin > 0 && (n_fin >= shade_at || n_walk == 0 || lead_phase == 3)) {
             // ---------------- S: prove, then finish the segment ----------------
             it_f++;
             if (fin) {
-                if (!fast_result_is_reference(a.sc, r)) { // rare: exact reference-order traversal of this ray
-                    ExactHit eh;
+                if (!fast_verdict_ool(&a.sc, r.wo, r.wd, r.t, r.tri, r.blas_front, r.overflow)) {
+                    ExactHit eh; // rare: exact reference-order traversal of this ray
                     exact_retrace(&a.sc, r.wo, r.wd, &eh);
                     r.t = eh.t; r.u = eh.u; r.v = eh.v; r.tri = eh.tri; r.blas_front = eh.blas_front; r.overflow = eh.overflow & RAY_OVERFLOW;
                     my_retraced++;
@@ -777,6 +804,7 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_fast(const FrameAr
                     if (alive) {
                         throughput = br.throughput;
                         fast_ray_begin(r, a.sc, br.next_o, br.next_d);
+                        wrd = r.rd;
                         segment++;
                     }
                 }
@@ -827,6 +855,7 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_fast(const FrameAr
                 segment = 0;
                 steps = 0;
                 fast_ray_begin(r, a.sc, pr.o, pr.d);
+                wrd = r.rd;
                 has = true;
             }
             n_started += min((uint32_t)n_idle, avail);
@@ -837,24 +866,42 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_fast(const FrameAr
             if (exhausted && n_fin == 0) break;
             continue;
         }
-        // ---------------- L / I / T: one step of the leading path's phase, else of the most popular ----------------
-        int run = (n_l >= n_i && n_l >= n_t) ? 0 : (n_i >= n_t ? 1 : 2);
+        // ---------------- I / L / T: the phase that advances most lanes per instruction, or the leading path's ----------------
+        int run = (n_i * 3 >= n_l && n_i * 3 >= n_t * 2) ? 1 : (n_l >= n_t * 2 ? 0 : 2);
         if (lead_phase >= 0 && lead_phase < 3) run = lead_phase;
         if (run == 1) {
             it_i++;
-            bool go = in_i;
+            bool go = can_i;
             const int need = (n_i + 1) >> 1;
 #pragma unroll 1
             for (int b = 0; b < a.burst; b++) { // node burst: no census while at least half of the starters stay on internal nodes
-                if (go) { fast_step_node(a.sc, r, st); steps++; go = fast_link_is_node(r.cur, r.inst); }
+                if (go) {
+                    if ((r.cur & LINK_TLAS) != 0u && r.inst != GDPT_NO_INSTANCE) { // back to world space (main.glsl:316-327)
+                        r.o = r.wo; r.d = r.wd; r.rd = wrd; r.inst = GDPT_NO_INSTANCE;
+                    }
+                    fast_step_node(a.sc, r, st);
+                    steps++;
+                    if (pend == LINK_NONE && fast_link_is_leaf(r.cur)) { pend = r.cur; r.cur = stack_pop(r, st); } // park the leaf, keep descending
+                    go = lane_can_node(r.cur, pend);
+                }
                 if (__popc(__ballot_sync(kFull, go)) < need) break;
             }
         } else if (run == 0) {
             it_l++;
-            if (in_l) { fast_step_leaf(a.sc, r, st); steps++; }
+            if (can_l) {
+                uint32_t leaf = pend;
+                if (pend != LINK_NONE) pend = LINK_NONE;
+                else { leaf = r.cur; r.cur = stack_pop(r, st); }
+                fast_leaf_tests(a.sc, r, leaf);
+                steps++;
+            }
         } else {
             it_t++;
-            if (in_t) { fast_step_instance(a.sc, r, st); steps++; }
+            if (can_t) {
+                if (r.inst != GDPT_NO_INSTANCE) { r.o = r.wo; r.d = r.wd; r.rd = wrd; r.inst = GDPT_NO_INSTANCE; }
+                fast_enter_instance(a.sc, r, st);
+                steps++;
+            }
         }
     }
     if (prof && lane == 0) {

@@ -13,6 +13,7 @@ src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "c
 rows = list(csv.reader(io.StringIO(src)))
 hdr = None; cur = None; curline = None; seen = set()
 per = collections.defaultdict(lambda: [0, 0, 0])
+noinst = collections.Counter()
 stall = collections.Counter()
 for r in rows:
     if len(r) >= 2 and r[0] == 'File Path': cur = r[1].split('/')[-1]; continue
@@ -28,7 +29,9 @@ for r in rows:
         continue
     for i, h in enumerate(hdr):
         if h.startswith('stall_') and 'Not Issued' not in h:
-            try: stall[h] += int(r[i])
+            try:
+                stall[h] += int(r[i])
+                if h == 'stall_no_inst': noinst[curline] += int(r[i])
             except ValueError: pass
 tot = sum(v[0] for v in per.values()); tt = sum(v[1] for v in per.values()); ts = sum(v[2] for v in per.values())
 print(f"warp instructions {tot}  lanes/instr {tt / max(tot, 1):.1f}  samples {ts}")
@@ -42,3 +45,11 @@ for k, v in sorted(per.items(), key=lambda kv: -kv[1][0])[:int(sys.argv[2]) if l
     print(f"  {k[0]}:{k[1]:4d} inst {v[0] / tot * 100:5.2f}% lanes {v[1] / max(v[0], 1):5.1f} samp {v[2] / max(ts, 1) * 100:5.2f}% | {k[2]}")
 s = sum(stall.values())
 print("stalls:", ", ".join(f"{k[6:]} {v / s * 100:.1f}%" for k, v in stall.most_common(8)))
+
+tn = sum(noinst.values())
+byf = collections.Counter()
+for k, v in noinst.items(): byf[k[0]] += v
+print("no_inst samples by file:", ", ".join(f"{f} {v / max(tn, 1) * 100:.1f}%" for f, v in byf.most_common(6)))
+print("no_inst top lines:")
+for k, v in noinst.most_common(25):
+    print(f"  {k[0]}:{k[1]:4d} {v / max(tn, 1) * 100:5.2f}% | {k[2]}")
