@@ -44,6 +44,11 @@ class ProgressiveParams(Structure):
     _fields_ = [("width", c_int32), ("height", c_int32), ("frame_count", c_uint32)]
 
 
+class TemporalParams(Structure):
+    _fields_ = [("delta_matrix", c_float * 16), ("width", c_int32), ("height", c_int32), ("frame_count", c_uint32),
+                ("blend_factor", c_float), ("near_plane", c_float), ("far_plane", c_float)]
+
+
 class StandardMaterial(Structure):
     _fields_ = [("albedo", c_float * 3), ("metallic", c_float), ("roughness", c_float), ("emission", c_float * 3),
                 ("emission_energy_multiplier", c_float), ("albedo_texture", c_int32), ("is_standard", c_int32)]
@@ -56,6 +61,7 @@ class FrameStats(Structure):
 
 
 assert ctypes.sizeof(RenderParams) == 36 and ctypes.sizeof(Camera) == 160 and ctypes.sizeof(ProgressiveParams) == 12
+assert ctypes.sizeof(TemporalParams) == 88
 
 # numpy dtype of gdpt_trace_record (include/gdpt_wire.h)
 TRACE_DTYPE = [("hit", "<u4"), ("triangle", "<u4"), ("blas", "<u4"), ("front", "<u4"), ("t", "<f4"), ("u", "<f4"),
@@ -90,6 +96,7 @@ CUDA_API = [
     ("gdpt_device_synchronize", c_int, [c_void_p]),
     ("gdpt_render_frame_begin", c_int, [c_void_p, c_void_p, POINTER(Camera), c_int, c_uint32, c_void_p, c_void_p]),
     ("gdpt_render_frame_wait", c_int, [c_void_p, POINTER(FrameStats)]),
+    ("gdpt_shader_stage_params", c_int, [c_void_p, c_void_p, c_uint64]),
     ("gdpt_shader_set_shard", c_int, [c_void_p, c_int, c_int, c_int]),
     ("gdpt_rid_device_pointer", c_int, [c_void_p, c_uint64, POINTER(c_uint64), POINTER(c_uint64)]),
     ("gdpt_host_alloc", c_void_p, [c_uint64]),
@@ -147,6 +154,9 @@ HOST_API = [
     ("gdpt_camera_output_image", c_void_p, [c_void_p]),
     ("gdpt_camera_main_shader", c_void_p, [c_void_p]),
     ("gdpt_camera_progressive_shader", c_void_p, [c_void_p]),
+    ("gdpt_camera_temporal_shader", c_void_p, [c_void_p]),
+    ("gdpt_camera_temporal_rid", c_uint64, [c_void_p, c_int]),
+    ("gdpt_camera_get_temporal_params", c_int, [c_void_p, POINTER(TemporalParams)]),
     ("gdpt_camera_device", c_void_p, [c_void_p]),
     ("gdpt_camera_output_rid", c_uint64, [c_void_p]),
     ("gdpt_camera_depth_rid", c_uint64, [c_void_p]),
@@ -154,6 +164,7 @@ HOST_API = [
     ("gdpt_camera_get_camera_block", None, [c_void_p, POINTER(Camera)]),
     ("gdpt_camera_last_frame_count", c_uint32, [c_void_p]),
     ("gdpt_make_camera_block", None, [c_void_p, c_float, c_int, c_int, c_uint32, POINTER(Camera)]),
+    ("gdpt_make_temporal_delta", None, [c_void_p, c_void_p, c_float, c_int, c_int, c_void_p, c_void_p]),
 ]
 
 

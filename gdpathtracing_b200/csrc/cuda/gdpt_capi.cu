@@ -36,7 +36,7 @@ struct Resource {
     std::vector<uint8_t> shadow; // host copy of storage buffers (used to derive layouts)
 };
 
-enum ShaderKind { SHADER_MAIN, SHADER_PROGRESSIVE };
+enum ShaderKind { SHADER_MAIN, SHADER_PROGRESSIVE, SHADER_TEMPORAL };
 
 } // namespace
 
@@ -93,6 +93,7 @@ struct gdpt_shader {
     bool stage_timing = false;          // record an event between the K1 stage launches
     std::vector<cudaEvent_t> stage_ev;  // 2*max_depth + 1 events when enabled
     int stage_count = 0;
+    std::vector<uint8_t> staged_params; // gdpt_shader_stage_params: bytes the next frame call uploads into set0 b0
 };
 
 namespace {
@@ -363,6 +364,79 @@ int finish_progressive(gdpt_shader *s)
     return GDPT_OK;
 }
 
+int finish_temporal(gdpt_shader *s)
+{
+    gdpt_device *d = s->dev;
+    Resource *params = bound(s, 0, 0), *screen = bound(s, 0, 1), *depth = bound(s, 0, 2), *fb1 = bound(s, 0, 3), *fb2 = bound(s, 0, 4);
+    if (!params || !screen || !depth || !fb1 || !fb2) return fail(d, GDPT_ERR_BAD_BINDING, "temporal_reprojection.glsl needs set0 b0-4 (temporal_reprojection.glsl:4-18)");
+    if (params->kind != RES_BUFFER || params->size < sizeof(gdpt_temporal_params)) return fail(d, GDPT_ERR_BAD_BINDING, "set0 b0 must hold the 88 B Params block");
+    if (screen->kind != RES_IMAGE || screen->format != GDPT_FORMAT_R8G8B8A8_UNORM) return fail(d, GDPT_ERR_BAD_BINDING, "set0 b1 must be the rgba8 screen image");
+    if (depth->kind != RES_IMAGE || depth->format != GDPT_FORMAT_R32_SFLOAT) return fail(d, GDPT_ERR_BAD_BINDING, "set0 b2 must be the r32f depth image");
+    for (Resource *fb : { fb1, fb2 }) {
+        if (fb->kind != RES_IMAGE || fb->format != GDPT_FORMAT_R32G32B32A32_SFLOAT) return fail(d, GDPT_ERR_BAD_BINDING, "set0 b3/b4 must be rgba32f images");
+        if (fb->width != screen->width || fb->height != screen->height) return fail(d, GDPT_ERR_BAD_BINDING, "frame buffers and screen differ in size");
+    }
+    if (fb1 == fb2) return fail(d, GDPT_ERR_BAD_BINDING, "set0 b3 and b4 must be two different images (ping-pong)");
+    if (depth->width != screen->width || depth->height != screen->height) return fail(d, GDPT_ERR_BAD_BINDING, "depth and screen differ in size");
+    init_launch_shapes(d->ordinal);
+    return GDPT_OK;
+}
+
+// K3 with the Params block as last uploaded; the ping-pong roles follow frameCount's parity (temporal_reprojection.glsl:46,62,66).
+int enqueue_k3(gdpt_shader *t)
+{
+    gdpt_device *d = t->dev;
+    Resource *params = bound(t, 0, 0), *screen = bound(t, 0, 1), *depth = bound(t, 0, 2), *fb1 = bound(t, 0, 3), *fb2 = bound(t, 0, 4);
+    gdpt_temporal_params host;
+    memcpy(&host, params->shadow.data(), sizeof(host));
+    if (host.width != screen->width || host.height != screen->height)
+        return fail(d, GDPT_ERR_INVALID_ARG, "temporal Params say %dx%d, the screen image is %dx%d", host.width, host.height, screen->width, screen->height);
+    const bool use_first = (host.frame_count % 2u) == 0u;
+    launch_temporal(static_cast<uint32_t *>(screen->dptr), static_cast<const float *>(depth->dptr),
+                    static_cast<const float *>(use_first ? fb1->dptr : fb2->dptr), static_cast<float *>(use_first ? fb2->dptr : fb1->dptr),
+                    static_cast<const gdpt_temporal_params *>(params->dptr), screen->width, screen->height, d->stream);
+    GDPT_CUDA(d, cudaGetLastError());
+    return GDPT_OK;
+}
+
+// What the frame calls require of the post-process shader for `mode`.
+int check_post(gdpt_shader *m, gdpt_shader *p, gdpt_denoising mode)
+{
+    gdpt_device *d = m->dev;
+    if (mode == GDPT_DENOISE_PROGRESSIVE_RENDERING) {
+        if (!p || p->kind != SHADER_PROGRESSIVE || p->dev != d || !gdpt_shader_check_ready(p)) return fail(d, GDPT_ERR_NOT_READY, "progressive shader missing or not ready");
+        if (bound(p, 0, 1) != bound(m, 0, 0)) return fail(d, GDPT_ERR_BAD_BINDING, "progressive shader must share the main shader's output image (add_existing_buffer)");
+    } else if (mode == GDPT_DENOISE_TEMPORAL_REPROJECTION) {
+        if (!p || p->kind != SHADER_TEMPORAL || p->dev != d || !gdpt_shader_check_ready(p)) return fail(d, GDPT_ERR_NOT_READY, "temporal reprojection shader missing or not ready");
+        if (bound(p, 0, 1) != bound(m, 0, 0) || bound(p, 0, 2) != bound(m, 0, 1))
+            return fail(d, GDPT_ERR_BAD_BINDING, "temporal shader must share the main shader's output and depth images (add_existing_buffer)");
+        if (m->shard_parts > 1) return fail(d, GDPT_ERR_UNSUPPORTED, "temporal reprojection reads other rows' history: not available on a row-sharded frame");
+    } else if (mode != GDPT_DENOISE_NONE) {
+        return fail(d, GDPT_ERR_INVALID_ARG, "unknown denoising mode %d", (int)mode);
+    }
+    return GDPT_OK;
+}
+
+// Stream-ordered upload of the post process's Params block from the pinned block `stage` (>= 256 B free).
+int upload_post_params(gdpt_shader *m, gdpt_shader *p, gdpt_denoising mode, uint32_t frame_count, uint8_t *stage)
+{
+    gdpt_device *d = m->dev;
+    Resource *pp = bound(p, 0, 0);
+    if (mode == GDPT_DENOISE_PROGRESSIVE_RENDERING) {
+        gdpt_progressive_params host_pp = { m->args.width, m->args.height, frame_count };
+        memcpy(stage, &host_pp, sizeof(host_pp));
+        memcpy(pp->shadow.data(), &host_pp, sizeof(host_pp));
+        GDPT_CUDA(d, cudaMemcpyAsync(pp->dptr, stage, sizeof(host_pp), cudaMemcpyHostToDevice, d->stream));
+    } else if (!p->staged_params.empty()) { // temporal: the block the host staged (gdpt_shader_stage_params)
+        const size_t n = p->staged_params.size();
+        memcpy(stage, p->staged_params.data(), n);
+        memcpy(pp->shadow.data(), p->staged_params.data(), n);
+        p->staged_params.clear();
+        GDPT_CUDA(d, cudaMemcpyAsync(pp->dptr, stage, n, cudaMemcpyHostToDevice, d->stream));
+    }
+    return GDPT_OK;
+}
+
 // Enqueue one K1 dispatch on the device stream.
 int enqueue_k1(gdpt_shader *s)
 {
@@ -524,6 +598,7 @@ int gdpt_shader_create(gdpt_device *d, const char *shader_path, const char *cons
     s->dev = d;
     if (base == "main.glsl") s->kind = SHADER_MAIN;
     else if (base == "progressive_rendering.glsl") s->kind = SHADER_PROGRESSIVE;
+    else if (base == "temporal_reprojection.glsl") s->kind = SHADER_TEMPORAL;
     else {
         delete s;
         return fail(d, GDPT_ERR_UNKNOWN_SHADER, "no CUDA kernel set for shader '%s'", shader_path ? shader_path : "(null)");
@@ -615,6 +690,17 @@ int gdpt_shader_update_storage_buffer_uniform(gdpt_shader *s, gdpt_rid rid, cons
     return GDPT_OK;
 }
 
+int gdpt_shader_stage_params(gdpt_shader *s, const void *data, uint64_t size)
+{
+    if (!s || !data) return GDPT_ERR_INVALID_ARG;
+    gdpt_device *d = s->dev;
+    Resource *r = bound(s, 0, 0);
+    if (s->kind == SHADER_MAIN || !r || r->kind != RES_BUFFER) return fail(d, GDPT_ERR_INVALID_ARG, "stage_params: not a post-process shader with a Params block at set0 b0");
+    if (size > r->size || size > 256) return fail(d, GDPT_ERR_INVALID_ARG, "stage_params: %llu B exceed the Params block", (unsigned long long)size);
+    s->staged_params.assign(static_cast<const uint8_t *>(data), static_cast<const uint8_t *>(data) + size);
+    return GDPT_OK;
+}
+
 int gdpt_shader_get_storage_buffer_uniform(gdpt_shader *s, gdpt_rid rid, void *out, uint64_t capacity)
 {
     if (!s || !out) return GDPT_ERR_INVALID_ARG;
@@ -698,7 +784,7 @@ int gdpt_shader_finish_create_uniforms(gdpt_shader *s)
 {
     if (!s || !s->initialized) return GDPT_ERR_INVALID_ARG;
     cudaSetDevice(s->dev->ordinal);
-    const int rc = (s->kind == SHADER_MAIN) ? finish_main(s) : finish_progressive(s);
+    const int rc = (s->kind == SHADER_MAIN) ? finish_main(s) : (s->kind == SHADER_PROGRESSIVE ? finish_progressive(s) : finish_temporal(s));
     s->uniforms_ready = (rc == GDPT_OK);
     return rc;
 }
@@ -735,7 +821,7 @@ int gdpt_shader_compute(gdpt_shader *s, int gx, int gy, int gz)
         GDPT_CUDA(d, cudaEventElapsedTime(&s->stats.k1_ms, d->ev[0], d->ev[1]));
     } else {
         GDPT_CUDA(d, cudaEventRecord(d->ev[2], d->stream));
-        if ((rc = enqueue_k2(s, 0, 1, 4))) return rc;
+        if ((rc = (s->kind == SHADER_PROGRESSIVE ? enqueue_k2(s, 0, 1, 4) : enqueue_k3(s)))) return rc;
         GDPT_CUDA(d, cudaEventRecord(d->ev[3], d->stream));
         GDPT_CUDA(d, cudaStreamSynchronize(d->stream));
         GDPT_CUDA(d, cudaEventElapsedTime(&s->stats.k2_ms, d->ev[2], d->ev[3]));
@@ -748,11 +834,8 @@ static int enqueue_frame(gdpt_shader *m, gdpt_shader *p, const gdpt_camera *came
     if (!m || m->kind != SHADER_MAIN || !camera) return GDPT_ERR_INVALID_ARG;
     gdpt_device *d = m->dev;
     if (!gdpt_shader_check_ready(m)) return fail(d, GDPT_ERR_NOT_READY, "main shader is not ready");
-    if (mode == GDPT_DENOISE_TEMPORAL_REPROJECTION) return fail(d, GDPT_ERR_UNSUPPORTED, "temporal reprojection is not implemented yet");
-    if (mode == GDPT_DENOISE_PROGRESSIVE_RENDERING) {
-        if (!p || p->kind != SHADER_PROGRESSIVE || p->dev != d || !gdpt_shader_check_ready(p)) return fail(d, GDPT_ERR_NOT_READY, "progressive shader missing or not ready");
-        if (bound(p, 0, 1) != bound(m, 0, 0)) return fail(d, GDPT_ERR_BAD_BINDING, "progressive shader must share the main shader's output image (add_existing_buffer)");
-    }
+    int rc;
+    if ((rc = check_post(m, p, mode))) return rc;
     cudaSetDevice(d->ordinal);
     // the previous frame's staging must have been consumed before we overwrite it
     GDPT_CUDA(d, cudaStreamSynchronize(d->stream));
@@ -761,18 +844,13 @@ static int enqueue_frame(gdpt_shader *m, gdpt_shader *p, const gdpt_camera *came
     Resource *cam_r = bound(m, 0, 3);
     memcpy(cam_r->shadow.data(), camera, cam_r->size < sizeof(gdpt_camera) ? cam_r->size : sizeof(gdpt_camera));
     GDPT_CUDA(d, cudaMemcpyAsync(cam_r->dptr, stage, cam_r->size < sizeof(gdpt_camera) ? cam_r->size : sizeof(gdpt_camera), cudaMemcpyHostToDevice, d->stream));
-    int rc;
     GDPT_CUDA(d, cudaEventRecord(d->ev[0], d->stream));
     if ((rc = enqueue_k1(m))) return rc;
     GDPT_CUDA(d, cudaEventRecord(d->ev[1], d->stream));
-    if (mode == GDPT_DENOISE_PROGRESSIVE_RENDERING) {
-        Resource *pp = bound(p, 0, 0);
-        gdpt_progressive_params host_pp = { m->args.width, m->args.height, frame_count };
-        memcpy(stage + 256, &host_pp, sizeof(host_pp));
-        memcpy(pp->shadow.data(), &host_pp, sizeof(host_pp));
-        GDPT_CUDA(d, cudaMemcpyAsync(pp->dptr, stage + 256, sizeof(host_pp), cudaMemcpyHostToDevice, d->stream));
+    if (mode != GDPT_DENOISE_NONE) {
+        if ((rc = upload_post_params(m, p, mode, frame_count, stage + 256))) return rc;
         GDPT_CUDA(d, cudaEventRecord(d->ev[2], d->stream));
-        if ((rc = enqueue_k2(p, m->shard_part, m->shard_parts, m->shard_band))) return rc;
+        if ((rc = (mode == GDPT_DENOISE_PROGRESSIVE_RENDERING ? enqueue_k2(p, m->shard_part, m->shard_parts, m->shard_band) : enqueue_k3(p)))) return rc;
         GDPT_CUDA(d, cudaEventRecord(d->ev[3], d->stream));
     }
     return GDPT_OK;
@@ -942,15 +1020,11 @@ extern "C" int gdpt_render_frame_begin(gdpt_shader *m, gdpt_shader *p, const gdp
     if (!m || m->kind != SHADER_MAIN || !camera || !out_rgba8) return GDPT_ERR_INVALID_ARG;
     gdpt_device *d = m->dev;
     if (!gdpt_shader_check_ready(m)) return fail(d, GDPT_ERR_NOT_READY, "main shader is not ready");
-    if (mode == GDPT_DENOISE_TEMPORAL_REPROJECTION) return fail(d, GDPT_ERR_UNSUPPORTED, "temporal reprojection is not implemented yet");
-    if (mode == GDPT_DENOISE_PROGRESSIVE_RENDERING) {
-        if (!p || p->kind != SHADER_PROGRESSIVE || p->dev != d || !gdpt_shader_check_ready(p)) return fail(d, GDPT_ERR_NOT_READY, "progressive shader missing or not ready");
-        if (bound(p, 0, 1) != bound(m, 0, 0)) return fail(d, GDPT_ERR_BAD_BINDING, "progressive shader must share the main shader's output image (add_existing_buffer)");
-    }
+    int rc;
+    if ((rc = check_post(m, p, mode))) return rc;
     gdpt_shader::FrameSlot &sl = m->slots[m->slot_head & 1u];
     if (sl.pending) return fail(d, GDPT_ERR_NOT_READY, "two frames are already in flight: call gdpt_render_frame_wait first");
     cudaSetDevice(d->ordinal);
-    int rc;
     if ((rc = ensure_slot(m, sl, out_depth != nullptr))) return rc;
 
     // per-frame H2D blocks come from the pinned ring: nothing here waits for the GPU
@@ -961,14 +1035,8 @@ extern "C" int gdpt_render_frame_begin(gdpt_shader *m, gdpt_shader *p, const gdp
     const size_t cam_bytes = cam_r->size < sizeof(gdpt_camera) ? cam_r->size : sizeof(gdpt_camera);
     memcpy(cam_r->shadow.data(), camera, cam_bytes);
     GDPT_CUDA(d, cudaMemcpyAsync(cam_r->dptr, stage, cam_bytes, cudaMemcpyHostToDevice, d->stream));
-    sl.with_k2 = (mode == GDPT_DENOISE_PROGRESSIVE_RENDERING);
-    if (sl.with_k2) {
-        Resource *pp = bound(p, 0, 0);
-        gdpt_progressive_params host_pp = { m->args.width, m->args.height, frame_count };
-        memcpy(stage + 256, &host_pp, sizeof(host_pp));
-        memcpy(pp->shadow.data(), &host_pp, sizeof(host_pp));
-        GDPT_CUDA(d, cudaMemcpyAsync(pp->dptr, stage + 256, sizeof(host_pp), cudaMemcpyHostToDevice, d->stream));
-    }
+    sl.with_k2 = (mode != GDPT_DENOISE_NONE);
+    if (sl.with_k2 && (rc = upload_post_params(m, p, mode, frame_count, stage + 256))) return rc;
     GDPT_CUDA(d, cudaEventRecord(d->ring_ev[ring_slot], d->stream));
     d->ring_used[ring_slot] = true;
 
@@ -982,7 +1050,7 @@ extern "C" int gdpt_render_frame_begin(gdpt_shader *m, gdpt_shader *p, const gdp
     GDPT_CUDA(d, cudaEventRecord(sl.t1, d->stream));
     if (sl.with_k2) {
         GDPT_CUDA(d, cudaEventRecord(sl.t2, d->stream));
-        if ((rc = enqueue_k2(p, m->shard_part, m->shard_parts, m->shard_band))) return rc;
+        if ((rc = (mode == GDPT_DENOISE_PROGRESSIVE_RENDERING ? enqueue_k2(p, m->shard_part, m->shard_parts, m->shard_band) : enqueue_k3(p)))) return rc;
         GDPT_CUDA(d, cudaEventRecord(sl.t3, d->stream));
     }
     const size_t n = (size_t)m->args.width * m->args.height;

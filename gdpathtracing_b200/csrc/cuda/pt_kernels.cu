@@ -22,6 +22,7 @@
 // lanes with a ballot every step to decide when to refill.
 #include "pt_kernels.cuh"
 #include "pt_fast.cuh"
+#include "pt_post.cuh"
 #include "pt_shade.cuh"
 #include "pt_trace.cuh"
 
@@ -1385,6 +1386,24 @@ __global__ void __launch_bounds__(256) k_progressive(uint32_t *__restrict__ scre
     }
 }
 
+// K3 (temporal_reprojection.glsl:31-71): one thread per pixel, rows of 32 x 8 pixel tiles.  Per pixel: 4 B + 4 B of
+// the current frame, a 4 B depth and a 16 B history gather at the reprojected position (the same position while the
+// camera rests), 16 B + 4 B of stores.  `history` / `next` are chosen by the host from frameCount's parity (:46).
+__global__ void __launch_bounds__(256) k_temporal(uint32_t *__restrict__ screen, const float *__restrict__ depth,
+                                                  const float *__restrict__ history, float *__restrict__ next,
+                                                  const gdpt_temporal_params *__restrict__ params)
+{
+    __shared__ gdpt_temporal_params p;
+    if (threadIdx.x < sizeof(gdpt_temporal_params) / 4u)
+        reinterpret_cast<uint32_t *>(&p)[threadIdx.x] = reinterpret_cast<const uint32_t *>(params)[threadIdx.x];
+    __syncthreads();
+    const int tiles_x = (p.width + 31) >> 5, tiles_y = (p.height + 7) >> 3;
+    for (int tile = blockIdx.x; tile < tiles_x * tiles_y; tile += gridDim.x) {
+        const int x = (tile % tiles_x) * 32 + (int)(threadIdx.x & 31u), y = (tile / tiles_x) * 8 + (int)(threadIdx.x >> 5);
+        if (x < p.width && y < p.height) temporal_pixel(p, x, y, screen, depth, history, next);
+    }
+}
+
 struct Shapes {
     bool ready = false;
     int sms = 148;
@@ -1548,6 +1567,15 @@ void launch_progressive(uint32_t *screen_rgba8, float4 *accum, const gdpt_progre
     Shapes &sh = shapes_for_current_device();
     k_progressive<<<sh.prog_blocks, 256, 0, s>>>(screen_rgba8, accum, params_dev, width, height, shard_part, shard_parts,
                                                  shard_band);
+}
+
+void launch_temporal(uint32_t *screen_rgba8, const float *depth, const float *history, float *next,
+                     const gdpt_temporal_params *params_dev, int width, int height, cudaStream_t s)
+{
+    Shapes &sh = shapes_for_current_device();
+    const int tiles = ((width + 31) / 32) * ((height + 7) / 8);
+    const int blocks = tiles < sh.sms * 8 ? tiles : sh.sms * 8; // 8 resident blocks of 256 threads per SM
+    k_temporal<<<blocks, 256, 0, s>>>(screen_rgba8, depth, history, next, params_dev);
 }
 
 static int fast_minb(const FrameArgs &a) { return (a.path_minb == 5 || a.path_minb == 6 || a.path_minb == 8) ? a.path_minb : 4; }

@@ -91,6 +91,9 @@ void launch_trace(const FrameArgs &a, int segment, bool trace, cudaStream_t s);
 // K2: progressive accumulation + ACES (progressive_rendering.glsl:28-46).
 void launch_progressive(uint32_t *screen_rgba8, float4 *accum, const gdpt_progressive_params *params_dev,
                         int width, int height, int shard_part, int shard_parts, int shard_band, cudaStream_t s);
+// K3: temporal reprojection (temporal_reprojection.glsl:31-71); `history` is the frame buffer the previous dispatch wrote.
+void launch_temporal(uint32_t *screen_rgba8, const float *depth, const float *history, float *next,
+                     const gdpt_temporal_params *params_dev, int width, int height, cudaStream_t s);
 // Number of kernels one K1 dispatch launches for a given depth.
 int k1_launch_count(int schedule, int max_depth, bool debug_steps);
 // One-time per device: query SM count / occupancy for the persistent grids.

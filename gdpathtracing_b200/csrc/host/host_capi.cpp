@@ -124,6 +124,17 @@ gdpt_shader *gdpt_camera_progressive_shader(const gdpt_camera_node *c)
 {
     return (c->impl.progressive() && c->impl.progressive()->shader()) ? c->impl.progressive()->shader()->handle() : nullptr;
 }
+gdpt_shader *gdpt_camera_temporal_shader(const gdpt_camera_node *c)
+{
+    return (c->impl.temporal() && c->impl.temporal()->shader()) ? c->impl.temporal()->shader()->handle() : nullptr;
+}
+gdpt_rid gdpt_camera_temporal_rid(const gdpt_camera_node *c, int which) { return c->impl.temporal() ? c->impl.temporal()->frame_buffer_rid(which) : 0; }
+int gdpt_camera_get_temporal_params(const gdpt_camera_node *c, gdpt_temporal_params *out)
+{
+    if (!c->impl.temporal()) return 0;
+    *out = c->impl.temporal()->params();
+    return 1;
+}
 gdpt_device *gdpt_camera_device(const gdpt_camera_node *c) { return c->impl.compute_shader() ? c->impl.compute_shader()->get_rendering_device() : nullptr; }
 gdpt_rid gdpt_camera_output_rid(const gdpt_camera_node *c) { return c->impl.output_texture_rid(); }
 gdpt_rid gdpt_camera_depth_rid(const gdpt_camera_node *c) { return c->impl.depth_texture_rid(); }
@@ -138,6 +149,19 @@ void gdpt_make_camera_block(const float *transform12, float fov_degrees, int wid
     cb.set_camera_transform(gdpt::Xform3::from_rows12(transform12), proj);
     cb.frame_index = frame_index;
     *out = cb;
+}
+
+void gdpt_make_temporal_delta(const float *previous_vp16, const float *transform12, float fov_degrees, int width, int height,
+                              float *out_vp16, float *out_delta16)
+{
+    const gdpt::Mat4 proj = gdpt::Mat4::perspective(fov_degrees, static_cast<float>(width) / height, 0.01f, 1000.0f);
+    const gdpt::Xform3 view = gdpt::Xform3::from_rows12(transform12).affine_inverse(); // path_tracing_camera.cpp:220
+    gdpt::Mat4 prev;
+    for (int c = 0; c < 4; c++)
+        for (int r = 0; r < 4; r++) prev.m[c][r] = previous_vp16[c * 4 + r];
+    const gdpt::Mat4 vp = proj * gdpt::Mat4(view);
+    (prev * vp.inverse()).affine_part().to_float16(out_delta16);
+    vp.to_float16(out_vp16);
 }
 
 } // extern "C"

@@ -56,11 +56,59 @@ void ProgressiveRendering::render(const Xform3 &camera_transform)
     cs_->compute((int)std::ceil(params_.width / 32.0f), (int)std::ceil(params_.height / 32.0f), 1);
 }
 
+// ------------------------------------------------------------ TemporalReprojection
+
+TemporalReprojection::TemporalReprojection()
+{
+    // deltaMatrix is uninitialised upstream until the first render() fills it (temporal_reprojection.h:17); zeros here
+    std::memset(&params_, 0, sizeof(params_));
+    params_.blend_factor = 0.75f; // temporal_reprojection.h:21-23; none of the three is read by the shader
+    params_.near_plane = 0.01f;
+    params_.far_plane = 1000.0f;
+}
+
+TemporalReprojection::~TemporalReprojection() { delete cs_; }
+
+void TemporalReprojection::init(gdpt_device *rd, gdpt_rid original_screen_texture_rid, gdpt_rid original_depth_texture_rid, int width,
+                                int height)
+{
+    screen_rid_ = original_screen_texture_rid;
+    params_.width = width; params_.height = height; params_.frame_count = 1;
+    cs_ = new ComputeShader("res://addons/jar_path_tracing/src/shaders/temporal_reprojection.glsl", rd);
+    params_rid_ = cs_->create_storage_buffer_uniform(&params_, sizeof(params_), 0, 0);
+    cs_->add_existing_buffer(screen_rid_, GDPT_UNIFORM_TYPE_IMAGE, 1, 0);
+    cs_->add_existing_buffer(original_depth_texture_rid, GDPT_UNIFORM_TYPE_IMAGE, 2, 0);
+    // Image::create(..., FORMAT_RGBAF) is zero-filled (temporal_reprojection.cpp:41-46)
+    frame_buffer_rid_1_ = cs_->create_image_uniform(nullptr, width, height, GDPT_FORMAT_R32G32B32A32_SFLOAT, 3, 0);
+    frame_buffer_rid_2_ = cs_->create_image_uniform(nullptr, width, height, GDPT_FORMAT_R32G32B32A32_SFLOAT, 4, 0);
+    cs_->finish_create_uniforms();
+}
+
+const gdpt_temporal_params &TemporalReprojection::advance(const Xform3 &view_matrix, const Mat4 &projection_matrix)
+{
+    const Mat4 vp = projection_matrix * Mat4(view_matrix);
+    // `Transform3D deltaMatrix = previous_vp * vp.inverse();` keeps the affine part only (temporal_reprojection.cpp:58)
+    const Mat4 delta = (previous_vp_ * vp.inverse()).affine_part();
+    previous_vp_ = vp;
+    params_.frame_count++;
+    delta.to_float16(params_.delta_matrix);
+    return params_;
+}
+
+void TemporalReprojection::render(const Xform3 &view_matrix, const Mat4 &projection_matrix)
+{
+    if (cs_ == nullptr || !cs_->check_ready()) return;
+    advance(view_matrix, projection_matrix);
+    cs_->update_storage_buffer_uniform(params_rid_, &params_, sizeof(params_));
+    cs_->compute((int)std::ceil(params_.width / 32.0f), (int)std::ceil(params_.height / 32.0f), 1);
+}
+
 // ------------------------------------------------------------ PathTracingCamera
 
 PathTracingCamera::~PathTracingCamera()
 {
     delete progressive_renderer_;
+    delete temporal_reprojection_;
     delete cs_;
     if (output_image_) gdpt_host_free(output_image_);
     if (pipeline_image_[1]) gdpt_host_free(pipeline_image_[1]); // [0] is output_image_
@@ -149,18 +197,40 @@ void PathTracingCamera::ensure_progressive()
     }
 }
 
+void PathTracingCamera::ensure_temporal()
+{
+    if (temporal_reprojection_ == nullptr) {
+        temporal_reprojection_ = new TemporalReprojection();
+        temporal_reprojection_->init(rd_, output_texture_rid_, depth_texture_rid_, render_parameters_.width, render_parameters_.height);
+    }
+}
+
+gdpt_shader *PathTracingCamera::advance_post(uint32_t *frame_count)
+{
+    *frame_count = 0;
+    if (denoising_mode_ == PROGRESSIVE_RENDERING) {
+        ensure_progressive();
+        *frame_count = progressive_renderer_->advance(global_transform_);
+        return progressive_renderer_->shader()->handle();
+    }
+    if (denoising_mode_ == TEMPORAL_REPROJECTION) {
+        ensure_temporal();
+        const gdpt_temporal_params &tp = temporal_reprojection_->advance(global_transform_.affine_inverse(), projection_matrix_);
+        *frame_count = tp.frame_count;
+        gdpt_shader *h = temporal_reprojection_->shader()->handle();
+        if (gdpt_shader_stage_params(h, &tp, sizeof(tp)) != GDPT_OK) std::fprintf(stderr, "stage_params: %s\n", gdpt_last_error(rd_));
+        return h;
+    }
+    return nullptr;
+}
+
 void PathTracingCamera::render_device_only()
 {
     if (cs_ == nullptr || !cs_->check_ready()) return;
     camera_.set_camera_transform(global_transform_, projection_matrix_);
     camera_.frame_index++;
-    gdpt_shader *prog = nullptr;
     uint32_t frame_count = 0;
-    if (denoising_mode_ == PROGRESSIVE_RENDERING) {
-        ensure_progressive();
-        frame_count = progressive_renderer_->advance(global_transform_);
-        prog = progressive_renderer_->shader()->handle();
-    }
+    gdpt_shader *prog = advance_post(&frame_count);
     last_frame_count_ = frame_count;
     if (gdpt_render_frame_async(cs_->handle(), prog, &camera_, (gdpt_denoising)denoising_mode_, frame_count) != GDPT_OK)
         std::fprintf(stderr, "render_frame_async: %s\n", gdpt_last_error(rd_));
@@ -180,13 +250,8 @@ bool PathTracingCamera::render_begin()
     }
     camera_.set_camera_transform(global_transform_, projection_matrix_);
     camera_.frame_index++;
-    gdpt_shader *prog = nullptr;
     uint32_t frame_count = 0;
-    if (denoising_mode_ == PROGRESSIVE_RENDERING) {
-        ensure_progressive();
-        frame_count = progressive_renderer_->advance(global_transform_);
-        prog = progressive_renderer_->shader()->handle();
-    }
+    gdpt_shader *prog = advance_post(&frame_count);
     last_frame_count_ = frame_count;
     if (gdpt_render_frame_begin(cs_->handle(), prog, &camera_, (gdpt_denoising)denoising_mode_, frame_count,
                                 pipeline_image_[pipe_head_ & 1u], nullptr) != GDPT_OK) {
@@ -215,13 +280,8 @@ void PathTracingCamera::render()
     if (fused_frame_) {
         camera_.set_camera_transform(global_transform_, projection_matrix_);
         camera_.frame_index++;
-        gdpt_shader *prog = nullptr;
         uint32_t frame_count = 0;
-        if (denoising_mode_ == PROGRESSIVE_RENDERING) {
-            ensure_progressive();
-            frame_count = progressive_renderer_->advance(global_transform_);
-            prog = progressive_renderer_->shader()->handle();
-        }
+        gdpt_shader *prog = advance_post(&frame_count);
         last_frame_count_ = frame_count;
         if (gdpt_render_frame(cs_->handle(), prog, &camera_, (gdpt_denoising)denoising_mode_, frame_count, output_image_, nullptr) != GDPT_OK)
             std::fprintf(stderr, "render_frame: %s\n", gdpt_last_error(rd_));
@@ -238,8 +298,10 @@ void PathTracingCamera::render()
         progressive_renderer_->render(global_transform_);
         last_frame_count_ = progressive_renderer_->frame_count();
         break;
-    case TEMPORAL_REPROJECTION:
-        std::fprintf(stderr, "Temporal reprojection is not available in the CUDA backend yet.\n");
+    case TEMPORAL_REPROJECTION: // path_tracing_camera.cpp:215-221
+        ensure_temporal();
+        temporal_reprojection_->render(global_transform_.affine_inverse(), projection_matrix_);
+        last_frame_count_ = temporal_reprojection_->params().frame_count;
         break;
     case NONE:
         break;

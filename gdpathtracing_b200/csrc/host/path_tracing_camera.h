@@ -42,6 +42,26 @@ private:
     gdpt_rid params_rid_ = 0, screen_rid_ = 0, frame_buffer_rid_ = 0;
 };
 
+// post_processing/temporal_reprojection.{h,cpp}
+class TemporalReprojection {
+public:
+    TemporalReprojection();
+    ~TemporalReprojection();
+    void init(gdpt_device *rd, gdpt_rid original_screen_texture_rid, gdpt_rid original_depth_texture_rid, int width, int height);
+    // parameter update of temporal_reprojection.cpp:57-61 (delta matrix, previous_vp, ++frame_count); returns the block dispatched with
+    const gdpt_temporal_params &advance(const Xform3 &view_matrix, const Mat4 &projection_matrix);
+    void render(const Xform3 &view_matrix, const Mat4 &projection_matrix);
+    ComputeShader *shader() const { return cs_; }
+    const gdpt_temporal_params &params() const { return params_; }
+    gdpt_rid frame_buffer_rid(int which) const { return which == 0 ? frame_buffer_rid_1_ : frame_buffer_rid_2_; }
+
+private:
+    ComputeShader *cs_ = nullptr;
+    gdpt_temporal_params params_;
+    Mat4 previous_vp_; // identity, like a default-constructed Projection
+    gdpt_rid params_rid_ = 0, screen_rid_ = 0, frame_buffer_rid_1_ = 0, frame_buffer_rid_2_ = 0;
+};
+
 class PathTracingCamera {
 public:
     enum Denoising { PROGRESSIVE_RENDERING = 0, TEMPORAL_REPROJECTION = 1, NONE = 2 };
@@ -92,6 +112,7 @@ public:
 
     ComputeShader *compute_shader() const { return cs_; }
     ProgressiveRendering *progressive() const { return progressive_renderer_; }
+    TemporalReprojection *temporal() const { return temporal_reprojection_; }
     gdpt_rid output_texture_rid() const { return output_texture_rid_; }
     gdpt_rid depth_texture_rid() const { return depth_texture_rid_; }
     int width() const { return render_parameters_.width; }
@@ -101,9 +122,14 @@ public:
 
 private:
     void ensure_progressive();
+    void ensure_temporal();
+    // post-process bookkeeping of one frame (progressive_rendering.cpp:53-60 / temporal_reprojection.cpp:57-61);
+    // returns the shader to run after K1 (nullptr for NONE) and sets *frame_count
+    gdpt_shader *advance_post(uint32_t *frame_count);
     float fov_ = 90.0f;
     ComputeShader *cs_ = nullptr;
     ProgressiveRendering *progressive_renderer_ = nullptr;
+    TemporalReprojection *temporal_reprojection_ = nullptr;
     GeometryGroup3D *geometry_group_ = nullptr;
     uint8_t *output_image_ = nullptr; // pinned, W*H*4
     uint8_t *pipeline_image_[2] = { nullptr, nullptr }; // pinned targets of the frames in flight

@@ -7,6 +7,7 @@
 //   Basis::invert            godot-cpp/src/variant/basis.cpp:57-72
 //   Transform3D::affine_invert  godot-cpp/src/variant/transform3d.cpp:37-46
 //   Projection(Transform3D)  godot-cpp/src/variant/projection.cpp:916-936
+//   Projection::operator Transform3D  godot-cpp/src/variant/projection.cpp:886-907
 //   Projection::operator*    godot-cpp/src/variant/projection.cpp:709-723
 //   Projection::invert       godot-cpp/src/variant/projection.cpp:601-698
 //   Projection::set_perspective godot-cpp/src/variant/projection.cpp:254-278
@@ -170,6 +171,14 @@ struct Mat4 { // godot::Projection, m[col][row]
                 for (i = 0; i < 4; i++) { float h = a.m[i][k]; a.m[i][k] = -a.m[i][j]; a.m[i][j] = h; }
         }
         return a;
+    }
+    // Projection -> Transform3D -> Projection (godot-cpp/src/variant/projection.cpp:886-907, 916-936): what an
+    // assignment of a Projection to a Transform3D keeps -- the projective row becomes (0, 0, 0, 1).
+    Mat4 affine_part() const
+    {
+        Mat4 r = *this;
+        r.m[0][3] = 0.0f; r.m[1][3] = 0.0f; r.m[2][3] = 0.0f; r.m[3][3] = 1.0f;
+        return r;
     }
     // Utils::projection_to_float (src/utils.h:39-49)
     void to_float16(float *out) const

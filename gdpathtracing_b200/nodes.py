@@ -251,6 +251,15 @@ class PathTracingCamera:
     def progressive_shader(self):
         return host.gdpt_camera_progressive_shader(self._h)
 
+    @property
+    def temporal_shader(self):
+        return host.gdpt_camera_temporal_shader(self._h)
+
+    def temporal_params(self):
+        """The 88 B Params block the last temporal-reprojection dispatch ran with (None before the first one)."""
+        p = _lib.TemporalParams()
+        return p if host.gdpt_camera_get_temporal_params(self._h, ctypes.byref(p)) == 1 else None
+
     def camera_block(self):
         c = _lib.Camera()
         host.gdpt_camera_get_camera_block(self._h, ctypes.byref(c))
@@ -265,8 +274,7 @@ class PathTracingCamera:
         return {k: getattr(st, k) for k, _ in _lib.FrameStats._fields_}
 
     def read_image(self, which="output"):
-        rid = {"output": host.gdpt_camera_output_rid, "depth": host.gdpt_camera_depth_rid,
-               "accum": host.gdpt_camera_accum_rid}[which](self._h)
+        rid = self._rid(which)
         n = self._w * self._h_px
         if which == "output":
             out = np.empty((self._h_px, self._w, 4), np.uint8)
@@ -274,7 +282,8 @@ class PathTracingCamera:
             out = np.empty((self._h_px, self._w), np.float32)
         else:
             out = np.empty((self._h_px, self._w, 4), np.float32)
-        shader = self.main_shader if which != "accum" else self.progressive_shader
+        shader = {"accum": self.progressive_shader, "history1": self.temporal_shader,
+                  "history2": self.temporal_shader}.get(which, self.main_shader)
         _lib.check(cuda.gdpt_shader_get_image_uniform_buffer(shader, rid, 0, _ptr(out), out.nbytes), self.device,
                    "get_image_uniform_buffer")
         return out
@@ -292,9 +301,16 @@ class PathTracingCamera:
                    "read_visits")
         return out
 
+    def _rid(self, which):
+        """output / depth: the main shader's images; accum: progressive accumulation; history1 / history2: the
+        temporal-reprojection ping-pong frame buffers."""
+        if which in ("history1", "history2"):
+            return host.gdpt_camera_temporal_rid(self._h, 0 if which == "history1" else 1)
+        return {"output": host.gdpt_camera_output_rid, "depth": host.gdpt_camera_depth_rid,
+                "accum": host.gdpt_camera_accum_rid}[which](self._h)
+
     def device_pointer(self, which="output"):
-        rid = {"output": host.gdpt_camera_output_rid, "depth": host.gdpt_camera_depth_rid,
-               "accum": host.gdpt_camera_accum_rid}[which](self._h)
+        rid = self._rid(which)
         p, s = ctypes.c_uint64(), ctypes.c_uint64()
         _lib.check(cuda.gdpt_rid_device_pointer(self.device, rid, ctypes.byref(p), ctypes.byref(s)), self.device,
                    "rid_device_pointer")
@@ -306,3 +322,12 @@ def make_camera_block(transform12, fov, width, height, frame_index):
     t = _f32(transform12).reshape(12)
     host.gdpt_make_camera_block(_ptr(t), float(fov), int(width), int(height), int(frame_index), ctypes.byref(c))
     return c
+
+
+def make_temporal_delta(previous_vp16, transform12, fov, width, height):
+    """(vp, delta) of one TemporalReprojection::render parameter update (temporal_reprojection.cpp:57-61)."""
+    prev = _f32(previous_vp16).reshape(16)
+    t = _f32(transform12).reshape(12)
+    vp, delta = np.zeros(16, np.float32), np.zeros(16, np.float32)
+    host.gdpt_make_temporal_delta(_ptr(prev), _ptr(t), float(fov), int(width), int(height), _ptr(vp), _ptr(delta))
+    return vp, delta

@@ -94,6 +94,10 @@ GDPT_API uint32_t gdpt_abi_version(void);
  * The basename of shader_path selects the hand-written kernel set:
  *   "main.glsl"                   -> path-trace kernels (K1)
  *   "progressive_rendering.glsl"  -> accumulate + ACES kernel (K2)
+ *   "temporal_reprojection.glsl"  -> depth-tested reprojection + blend + ACES kernel (K3);
+ *                                    bindings set0 b0 Params 88 B (gdpt_temporal_params), b1 the main
+ *                                    shader's rgba8 image, b2 its r32f depth image, b3/b4 two rgba32f
+ *                                    frame buffers (post_processing/temporal_reprojection.cpp:27-48)
  * `args` are the "#define ..." strings gdcs injects into the GLSL source
  * (gdcs.cpp:277-322).  Recognised defines (all optional):
  *   "#define DEBUG_STEPS"      heat-map mode of main.glsl:4,358-361,423-427
@@ -165,9 +169,11 @@ GDPT_API int  gdpt_shader_compute(gdpt_shader *shader, int groups_x, int groups_
 
 /* One frame of PathTracingCamera::render() (path_tracing_camera.cpp:193-232) in
  * one call: camera upload (:200), K1 (:204), the selected post process
- * (:206-226; `progressive` may be NULL for GDPT_DENOISE_NONE) and the read-back
+ * (:206-226; `progressive` is the post-process shader of `mode`: the progressive
+ * one, the temporal-reprojection one, or NULL for GDPT_DENOISE_NONE) and the read-back
  * (:228-229) into caller memory.  frame_count is the value the host policy of
- * progressive_rendering.cpp:53-60 computed.  out_rgba8 (W*H*4 B) may be pinned
+ * progressive_rendering.cpp:53-60 computed; in temporal mode it is ignored and the
+ * kernel runs with the Params block last uploaded or staged (gdpt_shader_stage_params).  out_rgba8 (W*H*4 B) may be pinned
  * or pageable host memory; out_depth (W*H floats) may be NULL. Blocking. */
 GDPT_API int  gdpt_render_frame(gdpt_shader *main_shader, gdpt_shader *progressive,
                                  const gdpt_camera *camera, gdpt_denoising mode,
@@ -192,6 +198,12 @@ GDPT_API int  gdpt_render_frame_begin(gdpt_shader *main_shader, gdpt_shader *pro
                                  const gdpt_camera *camera, gdpt_denoising mode, uint32_t frame_count,
                                  void *out_rgba8, float *out_depth);
 GDPT_API int  gdpt_render_frame_wait(gdpt_shader *main_shader, struct gdpt_frame_stats *out_stats);
+
+/* Non-blocking form of update_storage_buffer_uniform (gdcs.cpp:108-111) for the Params block
+ * (set0 b0) of a post-process shader: the bytes are kept and uploaded, in stream order, by the
+ * next gdpt_render_frame / _async / _begin call that runs this shader (TemporalReprojection::render
+ * uploads its 88 B block every frame, temporal_reprojection.cpp:61-62).  size <= 256. */
+GDPT_API int  gdpt_shader_stage_params(gdpt_shader *post_shader, const void *data, uint64_t size);
 
 /* Restrict K1/K2 to image rows [row_begin,row_end) interleaved in bands:
  * a pixel row y is rendered iff ((y / band_rows) % n_parts) == part.  Used to

@@ -97,6 +97,11 @@ GDPT_API const uint8_t *gdpt_camera_output_image(const gdpt_camera_node *c);
 /* handles for tests / benchmarks */
 GDPT_API gdpt_shader *gdpt_camera_main_shader(const gdpt_camera_node *c);
 GDPT_API gdpt_shader *gdpt_camera_progressive_shader(const gdpt_camera_node *c);
+/* the TemporalReprojection post process (created by the first frame rendered in that mode): its shader, its two
+ * ping-pong frame buffers (which = 0 / 1 -> frameBuffer1 / frameBuffer2) and the Params block last dispatched with */
+GDPT_API gdpt_shader *gdpt_camera_temporal_shader(const gdpt_camera_node *c);
+GDPT_API gdpt_rid gdpt_camera_temporal_rid(const gdpt_camera_node *c, int which);
+GDPT_API int   gdpt_camera_get_temporal_params(const gdpt_camera_node *c, gdpt_temporal_params *out);
 GDPT_API gdpt_device *gdpt_camera_device(const gdpt_camera_node *c);
 GDPT_API gdpt_rid gdpt_camera_output_rid(const gdpt_camera_node *c);
 GDPT_API gdpt_rid gdpt_camera_depth_rid(const gdpt_camera_node *c);
@@ -108,6 +113,11 @@ GDPT_API uint32_t gdpt_camera_last_frame_count(const gdpt_camera_node *c);
  * (render_parameters.h:23-38, path_tracing_camera.cpp:134): fills vp/ivp/position. */
 GDPT_API void gdpt_make_camera_block(const float *transform12, float fov_degrees, int width, int height,
                                   uint32_t frame_index, gdpt_camera *out);
+/* The parameter update of TemporalReprojection::render, standalone (temporal_reprojection.cpp:57-61 with the
+ * view matrix of path_tracing_camera.cpp:220): vp = projection * Projection(camera_transform.affine_inverse()),
+ * delta = the affine part of previous_vp * vp.inverse().  Matrices are 16 floats, column-major. */
+GDPT_API void gdpt_make_temporal_delta(const float *previous_vp16, const float *transform12, float fov_degrees,
+                                  int width, int height, float *out_vp16, float *out_delta16);
 
 #ifdef __cplusplus
 }

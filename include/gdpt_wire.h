@@ -118,6 +118,22 @@ typedef struct gdpt_progressive_params {
 } gdpt_progressive_params;
 GDPT_STATIC_ASSERT(sizeof(gdpt_progressive_params) == 12, "progressive Params is 12 B");
 
+/* temporal_reprojection.glsl:4-12, host twin TemporalReprojection::RenderParameters
+ * (post_processing/temporal_reprojection.h:15-23).  delta_matrix is column-major
+ * (Utils::projection_to_float, src/utils.h:39-49); blend_factor, near_plane and
+ * far_plane are uploaded but never read by the shader (it blends with a literal 0.75). */
+typedef struct gdpt_temporal_params {
+    float    delta_matrix[16];
+    int32_t  width;
+    int32_t  height;
+    uint32_t frame_count;
+    float    blend_factor;
+    float    near_plane;
+    float    far_plane;
+} gdpt_temporal_params;
+GDPT_STATIC_ASSERT(sizeof(gdpt_temporal_params) == 88, "temporal Params is 88 B");
+GDPT_STATIC_ASSERT(offsetof(gdpt_temporal_params, frame_count) == 72, "frameCount @72");
+
 /* Host-side triangle record handed to the BLAS builder (src/bvh/bvh.h:22-29). */
 typedef struct gdpt_build_triangle {
     float    vertices[3][4];

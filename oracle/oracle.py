@@ -46,6 +46,10 @@ def lib():
                                         c_void_p, c_void_p, c_int, c_void_p, c_uint32, POINTER(OrcStats)]
         _orc.orc_progressive.restype = None
         _orc.orc_progressive.argtypes = [c_void_p, c_void_p, c_int, c_int, c_uint32]
+        _orc.orc_temporal.restype = None
+        _orc.orc_temporal.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+        _orc.orc_mat4_mul.argtypes = [c_void_p, c_void_p, c_void_p]
+        _orc.orc_mat4_inverse.argtypes = [c_void_p, c_void_p]
         _orc.orc_prng_seed.argtypes = [c_uint32, c_uint32, c_uint32, c_void_p]
         _orc.orc_pcg2d.argtypes = [c_void_p, c_void_p]
         _orc.orc_sincosf.argtypes = [c_float, c_void_p]
@@ -126,6 +130,39 @@ def path_trace(scene, width, height, camera_bytes, max_depth=5, debug_steps=Fals
 def progressive(screen_rgba8, accum_rgba32f, frame_count):
     h, w = screen_rgba8.shape[:2]
     lib().orc_progressive(_p(screen_rgba8), _p(accum_rgba32f), w, h, frame_count)
+
+
+def temporal(params_bytes, screen_rgba8, depth, fb1, fb2):
+    """K3 on the CPU (temporal_reprojection.glsl:31-71).  params_bytes: the 88 B Params block; screen (H, W, 4) u8
+    in/out; depth (H, W) f32; fb1 / fb2 (H, W, 4) f32 ping-pong buffers, one read and the other written."""
+    par = np.frombuffer(bytes(params_bytes), np.uint8).copy()
+    assert par.size == 88 and depth.dtype == np.float32 and fb1.dtype == np.float32 and fb2.dtype == np.float32
+    lib().orc_temporal(_p(par), _p(screen_rgba8), _p(depth), _p(fb1), _p(fb2))
+
+
+def mat4_mul(a, b):
+    """Projection::operator* (godot-cpp projection.cpp:709-723) on column-major 16-float matrices."""
+    a, b = np.ascontiguousarray(a, np.float32).reshape(16), np.ascontiguousarray(b, np.float32).reshape(16)
+    out = np.zeros(16, np.float32)
+    lib().orc_mat4_mul(_p(a), _p(b), _p(out))
+    return out
+
+
+def mat4_inverse(a):
+    """Projection::inverse (godot-cpp projection.cpp:601-698)."""
+    a = np.ascontiguousarray(a, np.float32).reshape(16)
+    out = np.zeros(16, np.float32)
+    lib().orc_mat4_inverse(_p(a), _p(out))
+    return out
+
+
+def temporal_delta(previous_vp, vp):
+    """temporal_reprojection.cpp:58-61: `Transform3D deltaMatrix = previous_vp * vp.inverse()` keeps the affine
+    part only (projection.cpp:886-907), then goes back to 16 floats with a (0, 0, 0, 1) bottom row (:916-936)."""
+    d = mat4_mul(previous_vp, mat4_inverse(vp)).copy()
+    d[3] = d[7] = d[11] = 0.0
+    d[15] = 1.0
+    return d
 
 
 def prng_seed(px, py, frame):

@@ -16,6 +16,7 @@
 //   main.glsl  = project/addons/jar_path_tracing/src/shaders/main.glsl
 //   brdfs.glsl = .../shaders/brdfs.glsl
 //   prog.glsl  = .../shaders/progressive_rendering.glsl
+//   temp.glsl  = .../shaders/temporal_reprojection.glsl
 //
 // GLSL leaves built-in precision and NaN behaviour implementation-defined.  The
 // choices made here ARE the parity contract the CUDA kernels implement too
@@ -629,6 +630,124 @@ void orc_progressive(uint8_t *screen, float *accum, int width, int height, uint3
         }
         screen[p * 4 + 3] = 255;
     }
+}
+
+// K3: temp.glsl:31-71.  One dispatch over the whole image, pixel by pixel in row-major order.  No pixel
+// reads what another pixel of the same dispatch writes (screen is read and written at `pos` only; depth
+// and the history buffer are read-only), so the order is immaterial -- as on the GPU.
+//   params     88 B block of temp.glsl:4-12 (delta matrix column-major, width, height, frameCount, ...)
+//   screen     rgba8 in/out;  depth: r32f of the current frame;  fb1/fb2: rgba32f ping-pong buffers
+// ivec2(vec2): truncation toward zero; NaN and values outside the int range become INT_MIN.
+static inline int to_int_trunc(float v)
+{
+    if (v != v) return INT32_MIN;
+    if (v <= -2147483648.0f || v >= 2147483648.0f) return INT32_MIN;
+    return (int)v;
+}
+
+void orc_temporal(const gdpt_temporal_params *params, uint8_t *screen, const float *depth, float *fb1, float *fb2)
+{
+    const float a = 2.51f, b = 0.03f, c = 2.43f, d = 0.59f, e = 0.14f; // temp.glsl:23-29
+    const int W = params->width, H = params->height;
+    const float *M = params->delta_matrix;
+    const float fW = (float)(uint32_t)W, fH = (float)(uint32_t)H;
+    const bool use_first = (params->frame_count % 2u) == 0u;            // temp.glsl:46
+    const float *history = use_first ? fb1 : fb2;                       // temp.glsl:62
+    float *target = use_first ? fb2 : fb1;                              // temp.glsl:66
+    for (int y = 0; y < H; y++) {
+        for (int x = 0; x < W; x++) {
+            const size_t pos = (size_t)y * W + x;
+            float cur[3], rep[3];
+            for (int k = 0; k < 3; k++) { cur[k] = (float)screen[pos * 4 + k] / 255.0f; rep[k] = cur[k]; } // :36, :48
+            const float z = depth[pos];                                                                    // :37
+            float ndc[4];
+            ndc[0] = ((float)x + 0.5f) / fW * 2.0f - 1.0f;   // :40
+            ndc[1] = ((float)y + 0.5f) / fH * -2.0f + 1.0f;  // :41
+            ndc[2] = z; ndc[3] = 1.0f;
+            if (params->frame_count > 0u) {                  // :49
+                float clip[4];
+                for (int r = 0; r < 4; r++)                  // :50, m*v = ((m0*v.x + m1*v.y) + m2*v.z) + m3*v.w
+                    clip[r] = ((M[0 + r] * ndc[0] + M[4 + r] * ndc[1]) + M[8 + r] * ndc[2]) + M[12 + r] * ndc[3];
+                for (int r = 0; r < 3; r++) clip[r] = clip[r] / clip[3]; // :51
+                const float pu = (clip[0] + 1.0f) * 0.5f;    // :54
+                const float pv = (1.0f - clip[1]) * 0.5f;    // :55
+                const int qx = to_int_trunc(pu * fW), qy = to_int_trunc(pv * fH); // :57
+                if (qx >= 0 && qx < W && qy >= 0 && qy < H) { // :59
+                    const size_t q = (size_t)qy * W + qx;
+                    float dz = depth[q] - clip[2];
+                    if (dz < 0.0f) dz = -dz;
+                    if (dz < 0.1f)                           // :59
+                        for (int k = 0; k < 3; k++) rep[k] = history[q * 4 + k]; // :60
+                }
+            }
+            for (int k = 0; k < 3; k++) {
+                const float blended = cur[k] * (1.0f - 0.75f) + rep[k] * 0.75f; // :64 mix(a,b,t) = a*(1-t) + b*t
+                target[pos * 4 + k] = blended;                                  // :66
+                const float tm = (blended * (a * blended + b)) / (blended * (c * blended + d) + e); // :68
+                screen[pos * 4 + k] = to_unorm8(tm);                            // :70
+            }
+            target[pos * 4 + 3] = 1.0f;
+            screen[pos * 4 + 3] = 255;
+        }
+    }
+}
+
+// Host arithmetic the camera and the temporal post process rely on, restated from godot-cpp @56571dc (real_t = float).
+// Matrices are 16 floats, column-major, m[col*4 + row], like godot::Projection::columns.
+// Projection::operator* (godot-cpp/src/variant/projection.cpp:709-723)
+void orc_mat4_mul(const float *A, const float *B, float *out)
+{
+    float r[16];
+    for (int j = 0; j < 4; j++)
+        for (int i = 0; i < 4; i++) {
+            float ab = 0;
+            for (int k = 0; k < 4; k++) ab += A[k * 4 + i] * B[j * 4 + k];
+            r[j * 4 + i] = ab;
+        }
+    memcpy(out, r, sizeof(r));
+}
+
+// Projection::invert (godot-cpp/src/variant/projection.cpp:601-698): Gauss-Jordan with full pivoting.
+void orc_mat4_inverse(const float *in, float *out)
+{
+    float m[4][4];
+    memcpy(m, in, sizeof(m));
+    int pvt_i[4], pvt_j[4];
+    float det = 1.0f;
+    for (int k = 0; k < 4; k++) {
+        float pvt_val = m[k][k];
+        pvt_i[k] = k; pvt_j[k] = k;
+        for (int i = k; i < 4; i++)
+            for (int j = k; j < 4; j++)
+                if (fabsf(m[i][j]) > fabsf(pvt_val)) { pvt_i[k] = i; pvt_j[k] = j; pvt_val = m[i][j]; }
+        det *= pvt_val;
+        if (fabsf(det) < 0.00001f) { memcpy(out, m, sizeof(m)); return; }
+        int i = pvt_i[k];
+        if (i != k)
+            for (int j = 0; j < 4; j++) { const float hold = -m[k][j]; m[k][j] = m[i][j]; m[i][j] = hold; }
+        int j = pvt_j[k];
+        if (j != k)
+            for (i = 0; i < 4; i++) { const float hold = -m[i][k]; m[i][k] = m[i][j]; m[i][j] = hold; }
+        for (i = 0; i < 4; i++)
+            if (i != k) m[i][k] /= (-pvt_val);
+        for (i = 0; i < 4; i++) {
+            const float hold = m[i][k];
+            for (j = 0; j < 4; j++)
+                if (i != k && j != k) m[i][j] += hold * m[k][j];
+        }
+        for (j = 0; j < 4; j++)
+            if (j != k) m[k][j] /= pvt_val;
+        m[k][k] = 1.0f / pvt_val;
+    }
+    for (int k = 4 - 2; k >= 0; k--) {
+        int i = pvt_j[k];
+        if (i != k)
+            for (int j = 0; j < 4; j++) { const float hold = m[k][j]; m[k][j] = -m[i][j]; m[i][j] = hold; }
+        int j = pvt_i[k];
+        if (j != k)
+            for (i = 0; i < 4; i++) { const float hold = m[i][k]; m[i][k] = -m[i][j]; m[i][j] = hold; }
+    }
+    memcpy(out, m, sizeof(m));
 }
 
 // KAT helpers.

@@ -42,6 +42,7 @@ def devcheck(built):
     lib.devcheck_rng.argtypes = [c_uint32, c_uint32, c_uint32, c_void_p, c_void_p, c_void_p]
     lib.devcheck_sincos.argtypes = [c_float, c_void_p]
     lib.devcheck_progressive.argtypes = [c_void_p, c_void_p, c_int, c_int, c_uint32]
+    lib.devcheck_temporal.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     return lib
 
 

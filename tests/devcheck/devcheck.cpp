@@ -12,6 +12,7 @@
 #include "derived_layout.h"
 #include "fast_bvh.h"
 #include "pt_fast.cuh"
+#include "pt_post.cuh"
 #include "pt_shade.cuh"
 #include "pt_trace.cuh"
 
@@ -184,6 +185,19 @@ void devcheck_progressive(uint8_t *screen, float *accum, int width, int height, 
         const uint32_t out = pack_rgba8(mk3(aces_channel(avg.x), aces_channel(avg.y), aces_channel(avg.z)));
         std::memcpy(screen + p * 4, &out, 4);
     }
+}
+
+// K3 with the kernel's per-pixel function (pt_post.cuh); same roles as orc_temporal.
+void devcheck_temporal(const gdpt_temporal_params *params, uint8_t *screen, const float *depth, float *fb1, float *fb2)
+{
+    const bool use_first = (params->frame_count % 2u) == 0u;
+    const float *history = use_first ? fb1 : fb2;
+    float *next = use_first ? fb2 : fb1;
+    std::vector<uint32_t> scr((size_t)params->width * params->height);
+    std::memcpy(scr.data(), screen, scr.size() * 4);
+    for (int y = 0; y < params->height; y++)
+        for (int x = 0; x < params->width; x++) temporal_pixel(*params, x, y, scr.data(), depth, history, next);
+    std::memcpy(screen, scr.data(), scr.size() * 4);
 }
 
 } // extern "C"
