@@ -41,6 +41,26 @@ def measured_peaks():
     return dict(hbm_gbs=6650.0, sm_max_mhz=1965.0, source="fallback")
 
 
+def ncu_traffic(kernel, args):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of `kernel` from the newest committed
+    `ncu --set full` capture under profiles/ (taken on the default workload, so only quoted for it)."""
+    if (args.scene, args.width, args.height, args.depth) != ("demo", 1920, 1080, 8):
+        return None
+    import glob
+    best = None
+    for path in sorted(glob.glob(os.path.join(REPO, "profiles", f"r*_ncu_{kernel}_raw.csv"))):
+        vals = {}
+        for row in open(path):
+            parts = row.strip().split(",")
+            if len(parts) == 3 and parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(parts[1])
+                if scale:
+                    vals[parts[0]] = float(parts[2]) * scale
+        if len(vals) == 2:
+            best = {"bytes": sum(vals.values()), "source": os.path.relpath(path, REPO)}
+    return best
+
+
 class ClockSampler:
     """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -330,14 +350,22 @@ def run_ours(args, rank, local, world):
     k2_bytes = 40.0 * W * H
     roofline = {"kernel": top_label, "bound": "issue", "achieved": achieved / 1e12, "peak": peak_lane_ops / 1e12, "unit": "Tlane-op/s",
                 "frac": achieved / peak_lane_ops, "traffic": None, "launches_per_step": tk["launches"],
+                "algorithmic_bytes": work["algorithmic_bytes"],
                 "avg_launch_ms": tk["ms"] / tk["launches"], "share_of_step": by_kernel[top]["ms"] / max(stage_avg.sum() + k2_avg_ms, 1e-9),
                 "peak_source": f"148 SM x 4 schedulers x 32 lanes x {peaks['sm_max_mhz']:.0f} MHz ({peaks['source']} sm_max_mhz)",
                 "work_model": "22*box_tests + 55*tri_tests + 45*tlas_leaf_visits lane-ops per ray (SURVEY 8d) of the REFERENCE traversal "
                               "(no culling), counted by the instrumented kernels on one frame; the timed kernels skip the part of it "
                               "that tight-box culling proves fruitless"}
+    for rf, kern in ((roofline, "k_path"),):
+        tr = ncu_traffic(kern, args)
+        if tr:
+            rf["traffic"], rf["traffic_unit"], rf["traffic_source"] = tr["bytes"], "bytes of DRAM per launch", tr["source"]
     roofline_k2 = {"kernel": "k_progressive", "bound": "hbm", "achieved": k2_bytes / (k2_avg_ms * 1e-3) / 1e9 if k2_avg_ms > 0 else 0.0,
                    "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": (k2_bytes / (k2_avg_ms * 1e-3) / 1e9) / peaks["hbm_gbs"] if k2_avg_ms > 0 else 0.0,
                    "traffic": None, "avg_launch_ms": k2_avg_ms, "bytes_per_pixel": 40, "peak_source": peaks["source"] + " hbm_gbs"}
+    tr = ncu_traffic("k_progressive", args)
+    if tr:
+        roofline_k2["traffic"], roofline_k2["traffic_source"] = tr["bytes"], tr["source"]
 
     cpu = cpu_baseline(sc, grp, args) if world == 1 else None
     value = rays_total / (dev_ms * 1e-3) / 1e6
@@ -394,7 +422,13 @@ def trace_work(sc, grp, args, local):
                              + LANE_OPS_TLAS_LEAF * t["tlas_leaves"][live].astype(np.float64).sum()))
     totals = {k: int(st[k]) for k in ("rays", "primary_hits", "node_pops", "box_tests", "tri_tests", "tlas_leaves", "max_stack")}
     del cam
-    return {"lane_ops_per_segment": per_seg, "totals": totals}
+    # SURVEY 8d secondary figure: 144 B per internal pop (= per pair of box tests), 48 B per leaf pop, 48 B per triangle test,
+    # 208 B per TLAS leaf, 324 B per shaded hit -- bytes the reference traversal of these rays asks the memory system for
+    internal = totals["box_tests"] // 2
+    leaves = max(totals["node_pops"] - internal, 0)
+    hits = max(totals["rays"] - args.width * args.height, 0)  # every bounce ray was spawned by one shaded hit (lower bound)
+    alg_bytes = 144.0 * internal + 48.0 * leaves + 48.0 * totals["tri_tests"] + 208.0 * totals["tlas_leaves"] + 324.0 * hits
+    return {"lane_ops_per_segment": per_seg, "totals": totals, "algorithmic_bytes": alg_bytes}
 
 
 def cpu_baseline(sc, grp, args):

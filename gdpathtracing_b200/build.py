@@ -14,8 +14,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.normpath(os.path.join(HERE, ".."))
 INCLUDE = os.path.join(REPO, "include")
 CUDA_SRC = [os.path.join(HERE, "csrc", "cuda", f) for f in ("pt_kernels.cu", "gdpt_capi.cu")]
-CUDA_HDR = [os.path.join(HERE, "csrc", "cuda", f) for f in ("pt_math.cuh", "pt_scene.cuh", "pt_trace.cuh", "pt_shade.cuh",
-                                                            "pt_kernels.cuh", "derived_layout.h")]
+CUDA_HDR = sorted(os.path.join(HERE, "csrc", "cuda", f) for f in os.listdir(os.path.join(HERE, "csrc", "cuda"))
+                  if f.endswith((".cuh", ".h")))
 HOST_SRC = [os.path.join(HERE, "csrc", "host", f) for f in ("accel_build.cpp", "geometry_group3d.cpp", "compute_shader.cpp",
                                                             "path_tracing_camera.cpp", "host_capi.cpp")]
 HOST_HDR = [os.path.join(HERE, "csrc", "host", f) for f in ("accel_build.h", "geometry_group3d.h", "compute_shader.h",
