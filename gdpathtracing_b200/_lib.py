@@ -121,6 +121,8 @@ HOST_API = [
     ("gdpt_group_set_default_material", None, [c_void_p, c_int]),
     ("gdpt_group_set_texture_array_resolution", None, [c_void_p, c_int]),
     ("gdpt_group_get_texture_array_resolution", c_int, [c_void_p]),
+    ("gdpt_group_set_build_threads", None, [c_void_p, c_int]),
+    ("gdpt_group_get_build_threads", c_int, [c_void_p]),
     ("gdpt_group_build", None, [c_void_p]),
     ("gdpt_group_last_build_seconds", c_double, [c_void_p]),
     ("gdpt_group_buffer_size", c_uint64, [c_void_p, c_int]),

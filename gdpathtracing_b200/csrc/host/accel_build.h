@@ -39,12 +39,13 @@ public:
     // TLAS::build (src/bvh/bvh.cpp:264-317).
     static void build_tlas(std::vector<gdpt_tlas_node> &tlas, const std::vector<gdpt_blas_instance> &instances);
 
+    // Threads used by build_blas for meshes of 32 k triangles and more: 0 = all hardware threads,
+    // 1 = single-threaded like upstream.  The output bytes do not depend on it.
+    void set_threads(int n) { threads_ = n; }
+    int threads() const { return threads_; }
+
 private:
-    struct Extent { float lo[3], hi[3]; };
-    static Extent seed_extent();
-    static void grow(Extent &e, const float *p);
-    static float half_area(const Extent &e);
-    float binned_sah(const std::vector<gdpt_build_triangle> &tris, const gdpt_bvh_node &node, int axis, float &split) const;
+    int threads_ = 0;
     void subdivide(std::vector<gdpt_bvh_node> &nodes, std::vector<gdpt_build_triangle> &tris, int first, int last) const;
 };
 

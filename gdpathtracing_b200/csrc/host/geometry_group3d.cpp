@@ -157,6 +157,7 @@ void GeometryGroup3D::build()
 
     // one BLAS per unique mesh (:306-313)
     AccelBuilder builder;
+    builder.set_threads(build_threads_);
     std::vector<uint32_t> roots;
     for (int mesh : mesh_refs_) {
         const MeshRes &m = mesh_pool_[mesh];

@@ -46,6 +46,9 @@ public:
     void set_default_material(int material_handle) { default_material_ = material_handle; }
     int get_texture_array_resolution() const { return texture_array_resolution_; }
     void set_texture_array_resolution(int v) { texture_array_resolution_ = v; }
+    // ours (no upstream twin): threads of the BLAS build, 0 = all hardware threads, 1 = upstream's single thread; same bytes
+    int get_build_threads() const { return build_threads_; }
+    void set_build_threads(int v) { build_threads_ = v < 0 ? 0 : v; }
 
     void build();
 
@@ -86,6 +89,7 @@ private:
 
     int default_material_ = -1;
     int texture_array_resolution_;
+    int build_threads_ = 0;
 
     std::vector<int> mesh_refs_;         // initial_geometry_references
     std::vector<int> material_refs_;     // initial_material_references (handle, -2 = built-in default)

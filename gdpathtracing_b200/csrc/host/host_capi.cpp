@@ -56,6 +56,8 @@ void gdpt_group_add_mesh_instance(gdpt_geometry_group *g, int mesh, const float 
 void gdpt_group_set_default_material(gdpt_geometry_group *g, int material) { g->impl.set_default_material(material); }
 void gdpt_group_set_texture_array_resolution(gdpt_geometry_group *g, int r) { g->impl.set_texture_array_resolution(r); }
 int gdpt_group_get_texture_array_resolution(const gdpt_geometry_group *g) { return g->impl.get_texture_array_resolution(); }
+void gdpt_group_set_build_threads(gdpt_geometry_group *g, int n) { g->impl.set_build_threads(n); }
+int gdpt_group_get_build_threads(const gdpt_geometry_group *g) { return g->impl.get_build_threads(); }
 void gdpt_group_build(gdpt_geometry_group *g) { g->impl.build(); }
 double gdpt_group_last_build_seconds(const gdpt_geometry_group *g) { return g->impl.last_build_seconds(); }
 

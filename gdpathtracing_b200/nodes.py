@@ -85,6 +85,15 @@ class GeometryGroup3D:
     def texture_array_resolution(self, v):
         host.gdpt_group_set_texture_array_resolution(self._h, int(v))
 
+    @property
+    def build_threads(self):
+        """Threads of the BLAS build (ours; upstream is single-threaded): 0 = all, 1 = one.  Same bytes either way."""
+        return host.gdpt_group_get_build_threads(self._h)
+
+    @build_threads.setter
+    def build_threads(self, v):
+        host.gdpt_group_set_build_threads(self._h, int(v))
+
     # build + buffers ---------------------------------------------------------------------
     def build(self):
         host.gdpt_group_build(self._h)

@@ -48,6 +48,10 @@ GDPT_API void gdpt_group_add_mesh_instance(gdpt_geometry_group *g, int mesh, con
 GDPT_API void gdpt_group_set_default_material(gdpt_geometry_group *g, int material);
 GDPT_API void gdpt_group_set_texture_array_resolution(gdpt_geometry_group *g, int resolution);
 GDPT_API int  gdpt_group_get_texture_array_resolution(const gdpt_geometry_group *g);
+/* ours: threads used by the BLAS build (bvh.cpp:108-185 is single-threaded); 0 = all hardware threads, 1 = one.
+ * The arrays that come out are byte-identical for every value. */
+GDPT_API void gdpt_group_set_build_threads(gdpt_geometry_group *g, int threads);
+GDPT_API int  gdpt_group_get_build_threads(const gdpt_geometry_group *g);
 /* GeometryGroup3D::build (geometry_group3d.cpp:228-366) */
 GDPT_API void gdpt_group_build(gdpt_geometry_group *g);
 GDPT_API double gdpt_group_last_build_seconds(const gdpt_geometry_group *g);

@@ -97,3 +97,52 @@ def test_builtin_default_material_when_none_set():
     grp.build()
     m = np.frombuffer(grp.buffer("materials"), np.float32).reshape(-1, 16)
     assert np.allclose(m[0, :3], 0.5) and m[0, 9] == 0.5 and m[0, 8] == 0.0   # geometry_group3d.cpp:239-247
+
+
+def _big_degenerate(n=40_000):
+    """Half of the triangles coincide (one centroid), the rest spread along x only: flat axes, one-sided partitions
+    and the nth_element fallback (bvh.cpp:54-55,170-177) at sizes where the builder runs its multi-threaded top."""
+    from gdpathtracing_b200 import scenes
+    sc = scenes.SceneDesc("big_degenerate", camera_transform12=scenes.transform12(None, (0, 0, 6)), fov=60.0)
+    sc.materials = [dict()]
+    sc.default_material = 0
+    rng = np.random.default_rng(11)
+    x = np.where(np.arange(n) < n // 2, 0.0, rng.integers(0, 97, n) * 0.37).astype(np.float32)
+    base = np.array([[-0.5, -0.5, 0.0], [0.5, -0.5, 0.0], [0.0, 0.5, 0.0]], np.float32)
+    p = (base[None, :, :] + np.stack([x, np.zeros_like(x), np.zeros_like(x)], 1)[:, None, :]).reshape(-1, 3).astype(np.float32)
+    nrm = np.tile(np.array([0, 0, -1], np.float32), (len(p), 1))
+    sc.meshes = [[{"positions": p, "normals": nrm, "uvs": np.zeros((len(p), 2), np.float32),
+                   "indices": np.arange(len(p), dtype=np.int32)}]]
+    sc.instances = [dict(mesh=0)]
+    return sc
+
+
+def _buffers_with_threads(sc, threads):
+    from gdpathtracing_b200 import scenes
+    grp = scenes.populate(sc)
+    grp.build_threads = threads
+    assert grp.build_threads == threads
+    grp.build()
+    return {k: bytes(v) for k, v in grp.buffers().items()}
+
+
+@pytest.mark.parametrize("make", [lambda: __import__("gdpathtracing_b200").scenes.triangle_soup(150_000, seed=9), _big_degenerate],
+                         ids=["soup150k", "big_degenerate"])
+def test_multithreaded_build_emits_the_single_thread_bytes(make):
+    """the parallel build (thread-pooled top of the tree + independent subtrees) is byte-identical to the
+    single-threaded one for every thread count."""
+    sc = make()
+    one = _buffers_with_threads(sc, 1)
+    for threads in (2, 3, 8, 0):
+        got = _buffers_with_threads(sc, threads)
+        for key in one:
+            assert got[key] == one[key], f"{key}: {threads} threads differ from 1 thread"
+
+
+@pytest.mark.skipif(not oracle.ref_available(), reason="oracle/_ref/libgdpt_refbvh.so not built")
+def test_multithreaded_build_matches_reference_on_degenerate_input():
+    sc = _big_degenerate()
+    got, _ = product_buffers(sc)   # default: all hardware threads
+    ref = reference_buffers(sc)
+    for key in got:
+        assert np.array_equal(got[key], ref[key]), f"{key}: differs from reference bvh.cpp"
