@@ -367,7 +367,7 @@ def run_ours(args, rank, local, world):
     if tr:
         roofline_k2["traffic"], roofline_k2["traffic_source"] = tr["bytes"], tr["source"]
 
-    cpu = cpu_baseline(sc, grp, args) if world == 1 else None
+    cpu = cpu_baseline(sc, grp, args) if (world == 1 and args.cpu_baseline) else None
     value = rays_total / (dev_ms * 1e-3) / 1e6
     line = {
         "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -472,6 +472,8 @@ def main():
     ap.add_argument("--partition", default="sample", choices=["sample", "rows"])
     ap.add_argument("--band", type=int, default=8)
     ap.add_argument("--no-l2-flush", dest="l2_flush", action="store_false")
+    ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false",
+                    help="A/B runs of kernel variants only: skip the CPU leg (the official line always carries it)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 

@@ -296,15 +296,15 @@ int finish_main(gdpt_shader *s)
     a.queue_cap = (uint32_t)((size_t)rp.width * rp.height);
     if ((rc = dev_alloc(s, &a.queue[0], (size_t)a.queue_cap * 5))) return rc;
     if ((rc = dev_alloc(s, &a.queue[1], (size_t)a.queue_cap * 5))) return rc;
-    a.heavy_cap = a.queue_cap / 8u > 1024u ? a.queue_cap / 8u : 1024u;
+    a.heavy_cap = a.queue_cap / 4u > 1024u ? a.queue_cap / 4u : 1024u;
     if ((rc = dev_alloc(s, &a.hit_list, (size_t)a.queue_cap + (size_t)(kCostClasses - 1) * a.heavy_cap))) return rc;
     if ((rc = dev_alloc(s, &a.cost, (size_t)a.queue_cap))) return rc;
     GDPT_CUDA(d, cudaMemsetAsync(a.cost, 0, (size_t)a.queue_cap * sizeof(uint32_t), d->stream));
     if ((rc = dev_alloc(s, &a.counters, 1))) return rc;
-    a.schedule = s->variant >= 0 ? s->variant : 5;
+    a.schedule = s->variant >= 0 ? s->variant : 6;
     if (const char *e = getenv("GDPT_SCHEDULE")) { if (s->variant < 0) a.schedule = atoi(e); }
-    if (a.schedule < 0 || a.schedule > 5) a.schedule = 5;
-    if (a.schedule == 5 && !a.sc.fast_ok) a.schedule = 3; // closest-hit tables unavailable for these arrays (fast_bvh.h)
+    if (a.schedule < 0 || a.schedule > 6) a.schedule = 6;
+    if (a.schedule >= 5 && !a.sc.fast_ok) a.schedule = 3; // closest-hit tables unavailable for these arrays (fast_bvh.h)
     // culling (pt_scene.cuh) is the default for rendering; parity traces and the DEBUG_STEPS heat map
     // keep the full reference visit order (their output IS the reference's work)
     const bool observes_work = s->trace_segments > 0 || s->debug_steps;
@@ -317,9 +317,9 @@ int finish_main(gdpt_shader *s)
     if (a.mux_k < 1 || a.mux_k > 4) a.mux_k = 2;
     init_launch_shapes(d->ordinal);
     if (a.schedule == 4 && (rc = dev_alloc(s, &a.path_recs, mux_path_record_quads()))) return rc;
-    a.refill_below = a.schedule >= 2 ? 24 : 20;
-    a.burst = a.schedule == 0 ? 8 : (a.schedule == 3 ? 4 : (a.schedule == 5 ? 8 : 16));
-    a.shade_at = a.schedule == 5 ? 16 : 8;
+    a.refill_below = a.schedule == 6 ? 12 : (a.schedule >= 2 ? 24 : 20); // schedule 6: lanes without a walking ray before a pool service
+    a.burst = a.schedule == 0 ? 8 : (a.schedule == 3 ? 4 : (a.schedule >= 5 ? 8 : 16));
+    a.shade_at = a.schedule == 5 ? 16 : (a.schedule == 6 ? 24 : 8);                             // schedule 6: finished rays that justify a partial batch
     if (const char *e = getenv("GDPT_REFILL_BELOW")) a.refill_below = atoi(e);
     if (const char *e = getenv("GDPT_BURST")) a.burst = atoi(e);
     if (const char *e = getenv("GDPT_SHADE_AT")) a.shade_at = atoi(e);
@@ -327,6 +327,10 @@ int finish_main(gdpt_shader *s)
     if (const char *e = getenv("GDPT_BLOCKS_PER_SM")) a.blocks_per_sm = atoi(e);
     a.path_minb = 1; // 1: compact loop (default); 4/5/6/8: the first-generation loop at that occupancy; 2: compact, 6 blocks/SM
     if (const char *e = getenv("GDPT_PATH_MINB")) a.path_minb = atoi(e);
+    a.pool_variant = 0;
+    if (const char *e = getenv("GDPT_POOL_VARIANT")) a.pool_variant = atoi(e);
+    a.pool_wait = 32;
+    if (const char *e = getenv("GDPT_POOL_WAIT")) a.pool_wait = atoi(e);
     a.lead_min = 0;
     if (const char *e = getenv("GDPT_LEAD_MIN")) a.lead_min = atoi(e);
     if (a.refill_below < 1) a.refill_below = 1;
@@ -456,6 +460,7 @@ int enqueue_k1(gdpt_shader *s)
             if (timing) GDPT_CUDA(d, cudaEventRecord(s->stage_ev[ev++], d->stream));
             if (a.schedule == 4) launch_path_mux(a, d->stream);
             else if (a.schedule == 5) launch_path_fast(a, rec, d->stream);
+            else if (a.schedule == 6) launch_path_pool(a, rec, d->stream);
             else launch_path_list(a, trace || rec, d->stream);
         } else {
             launch_path(a, trace, d->stream);

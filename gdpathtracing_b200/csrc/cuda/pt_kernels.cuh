@@ -8,9 +8,12 @@
 namespace gdpt {
 
 enum { kMaxDepth = 32 };
-// Surviving pixels are binned by the cost their path had in the previous frame (longest first):
-// class 0 = light (< 128 iterations or unknown), 1: >=128, 2: >=256, 3: >=512, 4: >=1024.
-enum { kCostClasses = 5 };
+// Surviving pixels are binned by the cost (lane steps) their path had in the previous frame and started
+// longest first: class 0 = < 16 steps or unknown, 1: >= 16, 2: >= 32, ... 7: >= 1024.  Classes from
+// kFirstHeavyClass (>= 128 steps) up are handed out a few pixels at a time so they spread over many warps; the
+// light classes in tile-sized chunks, shortest last, which bounds the drain after the list is exhausted
+// by the latency of a short path.
+enum { kCostClasses = 8, kFirstHeavyClass = 4 };
 
 // Device-resident counters of one frame; zeroed with one memset per dispatch.
 struct FrameCounters {
@@ -48,13 +51,16 @@ struct FrameArgs {
     int lead_min;                            // the path with the most iterations picks the phase once it has this many
     float4 *path_recs;                       // schedule 4: 5 quads per path context
     int mux_k;                               // schedule 4: path contexts per lane (1..4)
+    int pool_variant;                        // schedule 6: compile-time variant of k_path_pool (0 = default), A/B only
+    int pool_wait;                           // schedule 6: lane-iterations finished rays may wait before a pool service (0 = off)
     FrameCounters *counters;
     // scheduling knobs (results do not depend on them)
     int refill_below;  // refill idle lanes when fewer than this many lanes are traversing
     int burst;         // node steps between refill checks
     int schedule;      // 0: wavefront + while-while descent, 1: wavefront + phase voting, 2: single path kernel,
                        // 3: camera-ray classification kernel + path kernel over the surviving pixels,
-                       // 4: classification kernel + lane-multiplexed path kernel
+                       // 4: classification kernel + lane-multiplexed path kernel,
+                       // 5: classification kernel + closest-hit path kernel (pt_fast.cuh), 6: 5 with pooled paths
     int shade_at;      // schedule 2: shade once this many lanes wait with a finished ray
     int cull;          // 1: skip children whose tight box the ray misses (pt_scene.cuh); results identical
     // optional per-warp schedule profile (gdpt_shader_set_warp_profile): 8 x u64 per warp of the path kernel
@@ -80,6 +86,9 @@ void launch_path_list(const FrameArgs &a, bool trace, cudaStream_t s);
 // are answered by the closest-hit search of pt_fast.cuh (+ proof, exact re-trace where it fails).
 // `record` also writes the hit records of the first a.trace_segments segments (no work counters).
 void launch_path_fast(const FrameArgs &a, bool record, cudaStream_t s);
+// Schedule 6: the same search, paths kept in per-warp shared-memory pools (k_path_pool): lanes swap rays
+// instead of waiting for a shading quorum, shading and camera-ray generation run on full warps.
+void launch_path_pool(const FrameArgs &a, bool record, cudaStream_t s);
 // Schedule 4: the same classification kernel, then the lane-multiplexed path kernel (a.mux_k
 // path contexts per lane, kept in shared memory; a.path_recs holds their cold state).
 void launch_path_mux(const FrameArgs &a, cudaStream_t s);

@@ -110,8 +110,9 @@ GDPT_API uint32_t gdpt_abi_version(void);
  *   "#define GDPT_RECORD_HITS n"  the rendering kernels themselves also write the hit records (no work
  *                              counters) of the first n segments; read with gdpt_shader_read_trace
  *   "#define GDPT_VARIANT 3"   keep the reference visiting order (with culling) when rendering; the default
- *                              (variant 5) answers rays with an order-free closest-hit search plus a proof that the
- *                              reference reaches the same triangle, and re-traces the rest; identical results
+ *                              (variant 6; 5 is the same search with one path per lane) answers rays with an
+ *                              order-free closest-hit search plus a proof that the reference reaches the same
+ *                              triangle, and re-traces the rest; identical results
  * Unknown defines are ignored, as a GLSL compiler would ignore an unused macro. */
 GDPT_API int  gdpt_shader_create(gdpt_device *device, const char *shader_path,
                                  const char *const *args, int n_args,
