@@ -1794,6 +1794,9 @@ void init_launch_shapes(int device)
     s.pool_blocks[0][1] = grid_of(k_path_pool<false, 4, 2, kPoolSlotsDefault>, kTraceThreads);
     s.pool_blocks[0][2] = grid_of(k_path_pool<false, 4, kPoolParkDefault, 40>, kTraceThreads);
     s.pool_blocks[0][3] = grid_of(k_path_pool<false, 4, kPoolParkDefault, 96>, kTraceThreads);
+    s.pool_blocks[0][4] = grid_of(k_path_pool<false, 5, kPoolParkDefault, kPoolSlotsDefault>, kTraceThreads);
+    s.pool_blocks[0][5] = grid_of(k_path_pool<false, 6, kPoolParkDefault, kPoolSlotsDefault>, kTraceThreads);
+    s.pool_blocks[0][6] = grid_of(k_path_pool<false, 8, kPoolParkDefault, 40>, kTraceThreads);
     s.pool_blocks[1][0] = grid_of(k_path_pool<true, 4, kPoolParkDefault, kPoolSlotsDefault>, kTraceThreads);
     s.mux_blocks[1] = mux_grid<1, 8>(s.sms);
     s.mux_blocks[2] = mux_grid<2, 8>(s.sms);
@@ -1906,7 +1909,8 @@ void launch_path_fast(const FrameArgs &a, bool record, cudaStream_t s)
 }
 
 // a.pool_variant: 0 default (1 parked leaf, 64 slots), 1: 2 parked leaves, 2: 40 slots, 3: 96 slots -- A/B only
-static int pool_variant(const FrameArgs &a) { return (a.pool_variant >= 0 && a.pool_variant <= 3) ? a.pool_variant : 0; }
+//                 4/5/6: 5, 6, 8 blocks per SM (102, 85, 64 registers; 8 with 40 slots)
+static int pool_variant(const FrameArgs &a) { return (a.pool_variant >= 0 && a.pool_variant <= 6) ? a.pool_variant : 0; }
 
 void launch_path_pool(const FrameArgs &a, bool record, cudaStream_t s)
 {
@@ -1921,6 +1925,9 @@ void launch_path_pool(const FrameArgs &a, bool record, cudaStream_t s)
     case 1: k_path_pool<false, 4, 2, kPoolSlotsDefault><<<grid, kTraceThreads, 0, s>>>(a); break;
     case 2: k_path_pool<false, 4, kPoolParkDefault, 40><<<grid, kTraceThreads, 0, s>>>(a); break;
     case 3: k_path_pool<false, 4, kPoolParkDefault, 96><<<grid, kTraceThreads, 0, s>>>(a); break;
+    case 4: k_path_pool<false, 5, kPoolParkDefault, kPoolSlotsDefault><<<grid, kTraceThreads, 0, s>>>(a); break;
+    case 5: k_path_pool<false, 6, kPoolParkDefault, kPoolSlotsDefault><<<grid, kTraceThreads, 0, s>>>(a); break;
+    case 6: k_path_pool<false, 8, kPoolParkDefault, 40><<<grid, kTraceThreads, 0, s>>>(a); break;
     default: k_path_pool<false, 4, kPoolParkDefault, kPoolSlotsDefault><<<grid, kTraceThreads, 0, s>>>(a); break;
     }
 }
