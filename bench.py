@@ -225,6 +225,15 @@ def run_ours(args, rank, local, world):
 
     out_ptr, out_size = cam.device_pointer("output")
     frame_t = multigpu.as_tensor(out_ptr, (H, W, 4), torch.uint8, dev_t)
+    # row bands: the presented frame assembles itself in every rank's image (K2 writes its rows to the peers over
+    # NVLink, frames separated by a one-element all-reduce) unless --present gather asks for the NCCL all-gather
+    peer_frame = multigpu.PeerFrame(cam, rank, world) if (rows_mode and args.present == "peer") else None
+
+    def present():
+        if peer_frame is not None:
+            peer_frame.barrier()
+        else:
+            multigpu.gather_row_bands(frame_t, args.band, rank, world)
 
     # ---- warm-up
     for w in range(args.warmup):
@@ -232,7 +241,8 @@ def run_ours(args, rank, local, world):
         cam.render_device_only()
         cam.synchronize()
         if rows_mode:
-            multigpu.gather_row_bands(frame_t, args.band, rank, world)
+            present()
+            torch.cuda.synchronize()
     stage_ms = np.zeros(64)
     n_stage = 0
     launches_per_frame = 0
@@ -260,10 +270,11 @@ def run_ours(args, rank, local, world):
         n_stage = n
         launches_per_frame = st["kernel_launches"] + 1  # K1 kernels + K2
         if rows_mode:
+            ts = peer_frame._stream if peer_frame is not None else torch.cuda.current_stream()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            multigpu.gather_row_bands(frame_t, args.band, rank, world)
-            e1.record(); torch.cuda.synchronize()
+            e0.record(ts)
+            present()
+            e1.record(ts); torch.cuda.synchronize(); cam.synchronize()
             gather_ms += e0.elapsed_time(e1)
     if world > 1 and not rows_mode:
         acc_ptr, _ = cam.device_pointer("accum")
@@ -273,6 +284,16 @@ def run_ours(args, rank, local, world):
         multigpu.reduce_accumulations(acc_t, dst=0)
         e1.record(); torch.cuda.synchronize()
         gather_ms += e0.elapsed_time(e1)
+    present_check = None
+    if peer_frame is not None:
+        # the image every rank holds now must be what the NCCL all-gather of the bands assembles
+        whole = frame_t.clone()
+        gathered = multigpu.gather_row_bands(frame_t, args.band, rank, world)
+        same = torch.tensor([1 if torch.equal(whole, gathered) else 0], dtype=torch.int32, device=dev_t)
+        torch.distributed.all_reduce(same, op=torch.distributed.ReduceOp.MIN)
+        present_check = bool(same.item())
+        if not present_check:
+            raise AssertionError("peer-written frame differs from the all-gathered frame")
     barrier()
     wall_ms = (time.perf_counter() - wall0) * 1e3
     clocks = sampler.stop() if rank == 0 else None
@@ -313,6 +334,8 @@ def run_ours(args, rank, local, world):
     e2e_s = time.perf_counter() - t0
     assert touched == 255 * args.steps, "a pipelined frame came back without pixels"
 
+    if peer_frame is not None:
+        peer_frame.close()
     # ---- reduce over ranks: slowest rank's time, everybody's rays
     if world > 1:
         t = torch.tensor([dev_ms, e2e_s, wall_ms, sync_s], dtype=torch.float64, device=dev_t)
@@ -373,7 +396,9 @@ def run_ours(args, rank, local, world):
         "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong" if rows_mode else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args), "partition": ("row bands + all-gather per step" if rows_mode else
+        "config": {"workload": workload_name(args), "partition": (("row bands, bands written to every peer's image by K2 over NVLink + "
+                   "one-element all-reduce per step; equal to the NCCL all-gather of the bands: " + str(present_check)
+                   if peer_frame is not None else "row bands + all-gather per step") if rows_mode else
                    ("sample index, one accumulation sum-reduce at the end" if world > 1 else "single GPU")),
                    "rays_per_step": rays_total / args.steps / world, "frames_per_step": world if not rows_mode else 1,
                    "l2": "256 MiB write between steps (outside the per-step events)" if args.l2_flush else "no flush",
@@ -471,6 +496,8 @@ def main():
     ap.add_argument("--depth", type=int, default=8)
     ap.add_argument("--partition", default="sample", choices=["sample", "rows"])
     ap.add_argument("--band", type=int, default=8)
+    ap.add_argument("--present", default="peer", choices=["peer", "gather"],
+                    help="row bands: how the presented frame is assembled (peer writes fused into K2, or NCCL all-gather)")
     ap.add_argument("--no-l2-flush", dest="l2_flush", action="store_false")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false",
                     help="A/B runs of kernel variants only: skip the CPU leg (the official line always carries it)")

@@ -102,6 +102,10 @@ CUDA_API = [
     ("gdpt_host_alloc", c_void_p, [c_uint64]),
     ("gdpt_host_free", None, [c_void_p]),
     ("gdpt_device_stream", c_uint64, [c_void_p]),
+    ("gdpt_rid_ipc_export", c_int, [c_void_p, c_uint64, c_void_p]),
+    ("gdpt_device_ipc_open", c_int, [c_void_p, c_void_p, POINTER(c_uint64)]),
+    ("gdpt_device_ipc_close", c_int, [c_void_p, c_uint64]),
+    ("gdpt_shader_set_peer_screens", c_int, [c_void_p, POINTER(c_uint64), c_int]),
     ("gdpt_shader_get_stats", c_int, [c_void_p, POINTER(FrameStats)]),
     ("gdpt_shader_set_stage_timing", c_int, [c_void_p, c_int]),
     ("gdpt_shader_get_stage_times", c_int, [c_void_p, c_void_p, c_int]),
@@ -156,6 +160,7 @@ HOST_API = [
     ("gdpt_camera_output_image", c_void_p, [c_void_p]),
     ("gdpt_camera_main_shader", c_void_p, [c_void_p]),
     ("gdpt_camera_progressive_shader", c_void_p, [c_void_p]),
+    ("gdpt_camera_prepare_post", None, [c_void_p]),
     ("gdpt_camera_temporal_shader", c_void_p, [c_void_p]),
     ("gdpt_camera_temporal_rid", c_uint64, [c_void_p, c_int]),
     ("gdpt_camera_get_temporal_params", c_int, [c_void_p, POINTER(TemporalParams)]),

@@ -94,6 +94,7 @@ struct gdpt_shader {
     std::vector<cudaEvent_t> stage_ev;  // 2*max_depth + 1 events when enabled
     int stage_count = 0;
     std::vector<uint8_t> staged_params; // gdpt_shader_stage_params: bytes the next frame call uploads into set0 b0
+    PeerScreens peers = {};             // progressive shader: images of the other GPUs K2 also writes (gdpt_shader_set_peer_screens)
 };
 
 namespace {
@@ -498,7 +499,7 @@ int enqueue_k2(gdpt_shader *p, int part, int parts, int band)
     if (parts > 1 && (screen->width & 3)) return fail(d, GDPT_ERR_UNSUPPORTED, "sharded accumulation needs a width that is a multiple of 4");
     launch_progressive(static_cast<uint32_t *>(screen->dptr), static_cast<float4 *>(accum->dptr),
                        static_cast<const gdpt_progressive_params *>(params->dptr), screen->width, screen->height, part, parts, band,
-                       d->stream);
+                       p->peers, d->stream);
     GDPT_CUDA(d, cudaGetLastError());
     return GDPT_OK;
 }
@@ -886,6 +887,55 @@ int gdpt_rid_device_pointer(gdpt_device *d, gdpt_rid rid, uint64_t *out_ptr, uin
     if (!r) return fail(d, GDPT_ERR_INVALID_ARG, "unknown RID");
     if (out_ptr) *out_ptr = (uint64_t)(uintptr_t)r->dptr;
     if (out_size) *out_size = r->size;
+    return GDPT_OK;
+}
+
+int gdpt_rid_ipc_export(gdpt_device *d, gdpt_rid rid, void *out_handle)
+{
+    if (!d || !out_handle) return GDPT_ERR_INVALID_ARG;
+    Resource *r = find(d, rid);
+    if (!r) return fail(d, GDPT_ERR_INVALID_ARG, "unknown RID");
+    static_assert(sizeof(cudaIpcMemHandle_t) == GDPT_IPC_HANDLE_BYTES, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    GDPT_CUDA(d, cudaSetDevice(d->ordinal));
+    GDPT_CUDA(d, cudaIpcGetMemHandle(&h, r->dptr));
+    memcpy(out_handle, &h, sizeof(h));
+    return GDPT_OK;
+}
+
+int gdpt_device_ipc_open(gdpt_device *d, const void *handle, uint64_t *out_ptr)
+{
+    if (!d || !handle || !out_ptr) return GDPT_ERR_INVALID_ARG;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    void *p = nullptr;
+    GDPT_CUDA(d, cudaSetDevice(d->ordinal));
+    GDPT_CUDA(d, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    *out_ptr = (uint64_t)(uintptr_t)p;
+    return GDPT_OK;
+}
+
+int gdpt_device_ipc_close(gdpt_device *d, uint64_t ptr)
+{
+    if (!d || !ptr) return GDPT_ERR_INVALID_ARG;
+    GDPT_CUDA(d, cudaSetDevice(d->ordinal));
+    GDPT_CUDA(d, cudaStreamSynchronize(d->stream));
+    GDPT_CUDA(d, cudaIpcCloseMemHandle(reinterpret_cast<void *>((uintptr_t)ptr)));
+    return GDPT_OK;
+}
+
+int gdpt_shader_set_peer_screens(gdpt_shader *p, const uint64_t *ptrs, int n)
+{
+    if (!p || p->kind != SHADER_PROGRESSIVE || n < 0 || (n > 0 && !ptrs)) return GDPT_ERR_INVALID_ARG;
+    gdpt_device *d = p->dev;
+    if (n > kMaxPeerScreens) return fail(d, GDPT_ERR_UNSUPPORTED, "at most %d peer images", (int)kMaxPeerScreens);
+    PeerScreens ps = {};
+    for (int i = 0; i < n; i++) {
+        if (!ptrs[i] || (ptrs[i] & 15u)) return fail(d, GDPT_ERR_INVALID_ARG, "peer image %d: null or not 16-byte aligned", i);
+        ps.p[i] = reinterpret_cast<uint32_t *>((uintptr_t)ptrs[i]);
+    }
+    ps.n = n;
+    p->peers = ps;
     return GDPT_OK;
 }
 

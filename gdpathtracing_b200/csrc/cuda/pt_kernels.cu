@@ -1645,9 +1645,14 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade(const FrameArgs a, cons
 // K2 (progressive_rendering.glsl:28-46): acc = (frame_count > 1 ? acc : 0) + screen;
 // screen = rgba8(ACES(acc / frame_count)).  Four pixels per thread: one 128-bit
 // load of the RGBA8 quad, four 128-bit loads/stores of the RGBA32F accumulator.
+// `peers`: RGBA8 images of the other GPUs of a row-band frame (peer memory over NVLink, CUDA IPC).  Every
+// tone-mapped quad this GPU owns is also stored there, so the presented frame assembles itself in every
+// GPU's image while the kernel runs -- the exchange step of the row-band partition fused into its producer
+// instead of an all-gather after it.
 __global__ void __launch_bounds__(256) k_progressive(uint32_t *__restrict__ screen, float4 *__restrict__ accum,
                                                      const gdpt_progressive_params *__restrict__ params, int width,
-                                                     int height, int shard_part, int shard_parts, int shard_band)
+                                                     int height, int shard_part, int shard_parts, int shard_band,
+                                                     const PeerScreens peers)
 {
     const uint32_t frame_count = params->frame_count;
     const float fc = (float)frame_count;
@@ -1674,7 +1679,9 @@ __global__ void __launch_bounds__(256) k_progressive(uint32_t *__restrict__ scre
             const f3 avg = (rad / fc) * 1.0f;
             out[k] = pack_rgba8(mk3(aces_channel(avg.x), aces_channel(avg.y), aces_channel(avg.z)));
         }
-        reinterpret_cast<uint4 *>(screen)[q] = make_uint4(out[0], out[1], out[2], out[3]);
+        const uint4 o4 = make_uint4(out[0], out[1], out[2], out[3]);
+        reinterpret_cast<uint4 *>(screen)[q] = o4;
+        for (int k = 0; k < peers.n; k++) reinterpret_cast<uint4 *>(peers.p[k])[q] = o4;
     }
     // tail pixels when W*H is not a multiple of 4
     if (blockIdx.x == 0 && threadIdx.x < (((size_t)width * height) & 3)) {
@@ -1686,7 +1693,9 @@ __global__ void __launch_bounds__(256) k_progressive(uint32_t *__restrict__ scre
             if (frame_count > 1u) { const float4 acc = accum[p]; rad = rad + mk3(acc.x, acc.y, acc.z); }
             accum[p] = make_float4(rad.x, rad.y, rad.z, 1.0f);
             const f3 avg = (rad / fc) * 1.0f;
-            screen[p] = pack_rgba8(mk3(aces_channel(avg.x), aces_channel(avg.y), aces_channel(avg.z)));
+            const uint32_t o = pack_rgba8(mk3(aces_channel(avg.x), aces_channel(avg.y), aces_channel(avg.z)));
+            screen[p] = o;
+            for (int k = 0; k < peers.n; k++) peers.p[k][p] = o;
         }
     }
 }
@@ -1876,11 +1885,11 @@ void launch_trace(const FrameArgs &a, int segment, bool trace, cudaStream_t s)
 }
 
 void launch_progressive(uint32_t *screen_rgba8, float4 *accum, const gdpt_progressive_params *params_dev, int width,
-                        int height, int shard_part, int shard_parts, int shard_band, cudaStream_t s)
+                        int height, int shard_part, int shard_parts, int shard_band, const PeerScreens &peers, cudaStream_t s)
 {
     Shapes &sh = shapes_for_current_device();
     k_progressive<<<sh.prog_blocks, 256, 0, s>>>(screen_rgba8, accum, params_dev, width, height, shard_part, shard_parts,
-                                                 shard_band);
+                                                 shard_band, peers);
 }
 
 void launch_temporal(uint32_t *screen_rgba8, const float *depth, const float *history, float *next,

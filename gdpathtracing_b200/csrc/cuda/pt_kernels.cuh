@@ -75,6 +75,10 @@ struct FrameArgs {
 
 struct LaunchShape { int blocks; int threads; };
 
+// RGBA8 images of the other GPUs that K2 mirrors its rows into (gdpt_shader_set_peer_screens)
+enum { kMaxPeerScreens = 15 };
+struct PeerScreens { uint32_t *p[kMaxPeerScreens]; int n; };
+
 // K1 stages.  `trace` selects the instrumented instantiation.
 // Single-kernel schedule (a.schedule == 2): whole paths per lane, no stage barriers.
 void launch_path(const FrameArgs &a, bool trace, cudaStream_t s);
@@ -99,7 +103,8 @@ void launch_shade(const FrameArgs &a, int segment, cudaStream_t s);
 void launch_trace(const FrameArgs &a, int segment, bool trace, cudaStream_t s);
 // K2: progressive accumulation + ACES (progressive_rendering.glsl:28-46).
 void launch_progressive(uint32_t *screen_rgba8, float4 *accum, const gdpt_progressive_params *params_dev,
-                        int width, int height, int shard_part, int shard_parts, int shard_band, cudaStream_t s);
+                        int width, int height, int shard_part, int shard_parts, int shard_band, const PeerScreens &peers,
+                        cudaStream_t s);
 // K3: temporal reprojection (temporal_reprojection.glsl:31-71); `history` is the frame buffer the previous dispatch wrote.
 void launch_temporal(uint32_t *screen_rgba8, const float *depth, const float *history, float *next,
                      const gdpt_temporal_params *params_dev, int width, int height, cudaStream_t s);

@@ -126,6 +126,7 @@ gdpt_shader *gdpt_camera_progressive_shader(const gdpt_camera_node *c)
 {
     return (c->impl.progressive() && c->impl.progressive()->shader()) ? c->impl.progressive()->shader()->handle() : nullptr;
 }
+void gdpt_camera_prepare_post(gdpt_camera_node *c) { c->impl.prepare_post(); }
 gdpt_shader *gdpt_camera_temporal_shader(const gdpt_camera_node *c)
 {
     return (c->impl.temporal() && c->impl.temporal()->shader()) ? c->impl.temporal()->shader()->handle() : nullptr;

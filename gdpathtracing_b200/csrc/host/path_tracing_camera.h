@@ -110,6 +110,15 @@ public:
     bool render_begin();
     const uint8_t *render_wait(gdpt_frame_stats *stats = nullptr);
 
+    // upstream creates the post-process object inside the first render() (path_tracing_camera.cpp:207-223); callers that
+    // need its shader before the first frame (peer screens of a row-band frame) create it here, state untouched
+    void prepare_post()
+    {
+        if (cs_ == nullptr) return;
+        if (denoising_mode_ == PROGRESSIVE_RENDERING) ensure_progressive();
+        else if (denoising_mode_ == TEMPORAL_REPROJECTION) ensure_temporal();
+    }
+
     ComputeShader *compute_shader() const { return cs_; }
     ProgressiveRendering *progressive() const { return progressive_renderer_; }
     TemporalReprojection *temporal() const { return temporal_reprojection_; }

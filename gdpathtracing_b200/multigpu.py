@@ -68,6 +68,39 @@ def gather_row_bands(frame, band, rank, world):
     return out
 
 
+class PeerFrame:
+    """Row-band frame whose presentation needs no gather: every rank's accumulate/tone-map kernel also writes its rows
+    into the other ranks' output images over NVLink (CUDA IPC peer memory), so after `barrier()` each rank's image is
+    the whole frame.  One process per GPU; handles travel through torch.distributed."""
+
+    def __init__(self, cam, rank, world):
+        self.cam, self.rank, self.world, self.opened = cam, rank, world, []
+        if world == 1:
+            return
+        handles = [None] * world
+        dist.all_gather_object(handles, cam.export_output_handle())
+        self.opened = [cam.open_peer_image(h) for r, h in enumerate(handles) if r != rank]
+        cam.set_peer_screens(self.opened)
+        self._token = torch.zeros(1, dtype=torch.int32, device=torch.device("cuda", torch.cuda.current_device()))
+        self._stream = torch.cuda.ExternalStream(cam.stream())
+
+    def barrier(self):
+        """All ranks' kernels of the frame enqueued so far have completed once this returns on the device side:
+        a one-element NCCL all-reduce on the backend's own stream (frames are separated by it)."""
+        if self.world > 1:
+            with torch.cuda.stream(self._stream):
+                dist.all_reduce(self._token)
+
+    def close(self):
+        if self.opened:
+            self.cam.set_peer_screens([])
+            self.cam.synchronize()
+            dist.barrier()
+            for p in self.opened:
+                self.cam.close_peer_image(p)
+            self.opened = []
+
+
 def reduce_accumulations(accum, dst=0):
     """Sum the per-rank RGBA32F accumulation buffers onto `dst` (sample-index partition)."""
     if dist.is_initialized() and dist.get_world_size() > 1:

@@ -326,6 +326,41 @@ class PathTracingCamera:
         return p.value, s.value
 
 
+def _camera_ipc_methods():
+    def export_output_handle(self):
+        """CUDA IPC handle (64 bytes) of the RGBA8 output image, for the other per-GPU processes of a row-band frame."""
+        buf = ctypes.create_string_buffer(64)
+        _lib.check(cuda.gdpt_rid_ipc_export(self.device, self._rid("output"), buf), self.device, "rid_ipc_export")
+        return buf.raw
+
+    def open_peer_image(self, handle):
+        p = ctypes.c_uint64()
+        _lib.check(cuda.gdpt_device_ipc_open(self.device, ctypes.create_string_buffer(bytes(handle), 64), ctypes.byref(p)),
+                   self.device, "device_ipc_open")
+        return p.value
+
+    def close_peer_image(self, ptr):
+        _lib.check(cuda.gdpt_device_ipc_close(self.device, int(ptr)), self.device, "device_ipc_close")
+
+    def set_peer_screens(self, ptrs):
+        """Device addresses of the other GPUs' output images: the accumulate/tone-map kernel mirrors the rows this GPU
+        owns into them (include/gdpt.h gdpt_shader_set_peer_screens).  Empty list = off."""
+        host.gdpt_camera_prepare_post(self._h)  # the progressive shader is created lazily, as upstream
+        if not self.progressive_shader:
+            raise _lib.GdptError("set_peer_screens needs denoising_mode PROGRESSIVE_RENDERING and an initialised camera")
+        arr = (ctypes.c_uint64 * max(len(ptrs), 1))(*[int(p) for p in ptrs])
+        _lib.check(cuda.gdpt_shader_set_peer_screens(self.progressive_shader, arr, len(ptrs)), self.device, "set_peer_screens")
+
+    def stream(self):
+        return cuda.gdpt_device_stream(self.device)
+
+    for f in (export_output_handle, open_peer_image, close_peer_image, set_peer_screens, stream):
+        setattr(PathTracingCamera, f.__name__, f)
+
+
+_camera_ipc_methods()
+
+
 def make_camera_block(transform12, fov, width, height, frame_index):
     c = _lib.Camera()
     t = _f32(transform12).reshape(12)

@@ -215,6 +215,19 @@ GDPT_API int  gdpt_shader_set_shard(gdpt_shader *main_shader, int part, int n_pa
  * torch (the caller must not free it). */
 GDPT_API int  gdpt_rid_device_pointer(gdpt_device *device, gdpt_rid rid,
                                  uint64_t *out_ptr, uint64_t *out_size);
+/* Row-band frames without a gather (ours; upstream is single-GPU).  A frame sharded with gdpt_shader_set_shard is
+ * rendered by several GPUs, one process each; the presented image is the union of their bands.  Instead of an
+ * all-gather after the frame, the accumulate/tone-map kernel of `progressive_shader` stores every pixel it owns into
+ * the RGBA8 image of each peer as well (peer memory over NVLink), so every GPU's image holds the whole frame once all
+ * GPUs have finished the dispatch (the caller separates frames with a barrier).  Images cross the process boundary
+ * through CUDA IPC: export the handle of the screen RID (set 0 binding 0 of main.glsl, gdcs.cpp:122-131), open the
+ * peers' handles, hand the addresses to the progressive shader.  n = 0 clears.  Pointers of images on the same
+ * device are accepted too (single-process tests). */
+#define GDPT_IPC_HANDLE_BYTES 64
+GDPT_API int  gdpt_rid_ipc_export(gdpt_device *device, gdpt_rid rid, void *out_handle);
+GDPT_API int  gdpt_device_ipc_open(gdpt_device *device, const void *handle, uint64_t *out_ptr);
+GDPT_API int  gdpt_device_ipc_close(gdpt_device *device, uint64_t ptr);
+GDPT_API int  gdpt_shader_set_peer_screens(gdpt_shader *progressive_shader, const uint64_t *ptrs, int n);
 /* Page-locked host memory for the read-back target (stands in for the
  * PackedByteArray that texture_get_data returns, gdcs.cpp:169-172): D2H copies
  * into it run at full PCIe rate.  Free with gdpt_host_free. */

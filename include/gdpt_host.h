@@ -101,6 +101,9 @@ GDPT_API const uint8_t *gdpt_camera_output_image(const gdpt_camera_node *c);
 /* handles for tests / benchmarks */
 GDPT_API gdpt_shader *gdpt_camera_main_shader(const gdpt_camera_node *c);
 GDPT_API gdpt_shader *gdpt_camera_progressive_shader(const gdpt_camera_node *c);
+/* creates the post-process object of the current denoising_mode now instead of inside the first render()
+ * (path_tracing_camera.cpp:207-223 creates it lazily); frame counters are untouched */
+GDPT_API void gdpt_camera_prepare_post(gdpt_camera_node *c);
 /* the TemporalReprojection post process (created by the first frame rendered in that mode): its shader, its two
  * ping-pong frame buffers (which = 0 / 1 -> frameBuffer1 / frameBuffer2) and the Params block last dispatched with */
 GDPT_API gdpt_shader *gdpt_camera_temporal_shader(const gdpt_camera_node *c);

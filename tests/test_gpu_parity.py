@@ -244,6 +244,34 @@ def test_row_sharding_reassembles_the_unsharded_frame():
     assert rays == total_rays
 
 
+def test_peer_screens_assemble_the_frame_without_a_gather():
+    """Row-band presentation fused into the accumulate/tone-map kernel (gdpt_shader_set_peer_screens): every part also
+    writes its rows into the other parts' images, so each image ends up as the whole, unsharded frame.  Here the parts are
+    three cameras on one GPU (plain device pointers); across processes the same pointers come from CUDA IPC (bench.py
+    --partition rows checks that path against the NCCL all-gather)."""
+    sc = scenes.demo_scene()
+    grp = scenes.populate(sc)
+    W, H, parts, band = 480, 270, 3, 8
+    full_cam = make_camera(sc, grp, W, H, 6, mode=PathTracingCamera.PROGRESSIVE_RENDERING)
+    cams = [make_camera(sc, grp, W, H, 6, mode=PathTracingCamera.PROGRESSIVE_RENDERING, shard=(p, parts, band)) for p in range(parts)]
+    ptrs = [c.device_pointer("output")[0] for c in cams]
+    for p, c in enumerate(cams):
+        c.set_peer_screens([q for i, q in enumerate(ptrs) if i != p])
+    for frame in range(3):
+        full = full_cam.render().copy()
+        for c in cams:
+            c.render_device_only()
+        for c in cams:
+            c.synchronize()
+        for p, c in enumerate(cams):
+            assert np.array_equal(c.read_image("output"), full), f"frame {frame}: image of part {p} is not the whole frame"
+    cams[0].set_peer_screens([])
+    cams[0].render_device_only(); cams[0].synchronize()
+    own = ((np.arange(H) // band) % parts) == 0
+    img0, img1 = cams[0].read_image("output"), cams[1].read_image("output")
+    assert np.array_equal(img1[own], full[own]) and not np.array_equal(img0[own], full[own]), "cleared peers are still written"
+
+
 def test_gdcs_style_error_behaviour():
     """compute() before finish_create_uniforms is refused (gdcs.cpp:239-240,258-273); unknown shaders and bad
     binding tables are reported through the status code + gdpt_last_error, never by crashing."""
