@@ -328,8 +328,8 @@ int finish_main(gdpt_shader *s)
     if (const char *e = getenv("GDPT_BLOCKS_PER_SM")) a.blocks_per_sm = atoi(e);
     a.path_minb = 1; // 1: compact loop (default); 4/5/6/8: the first-generation loop at that occupancy; 2: compact, 6 blocks/SM
     if (const char *e = getenv("GDPT_PATH_MINB")) a.path_minb = atoi(e);
-    a.pool_variant = 0;
-    if (const char *e = getenv("GDPT_POOL_VARIANT")) a.pool_variant = atoi(e);
+    a.pool_alive = 0;
+    if (const char *e = getenv("GDPT_POOL_ALIVE")) a.pool_alive = atoi(e);
     a.pool_wait = 32;
     if (const char *e = getenv("GDPT_POOL_WAIT")) a.pool_wait = atoi(e);
     a.lead_min = 0;

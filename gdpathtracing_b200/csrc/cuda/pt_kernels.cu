@@ -978,6 +978,7 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_pool(const FrameAr
     const int swap_at = min(max(a.refill_below, 1), 32);   // lanes without a walking ray before the pool is serviced ...
     const uint32_t swap_wait = a.pool_wait > 0 ? (uint32_t)a.pool_wait : 0xFFFFFFFFu; // ... or this many lane-iterations spent waiting
     uint32_t waited = 0;
+    const uint32_t min_free = (a.pool_alive >= 32 && a.pool_alive < kPoolSlots) ? (uint32_t)(kPoolSlots - a.pool_alive) : 0u;
     const int shade_low = min(max(a.shade_at, 1), 32);     // finished rays that justify a partial shading batch
     bool heavy_done = false;
     const int last_segment = a.max_depth - 1;
@@ -1011,7 +1012,7 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_pool(const FrameAr
         const int n_i = (int)(census & 63u), n_l = (int)((census >> 6) & 63u), n_t = (int)((census >> 12) & 63u),
                   n_fin = (int)((census >> 18) & 63u), n_idle = (int)(census >> 24);
         const int n_walk = 32 - n_idle - n_fin;
-        const bool can_refill = !exhausted && free_count > 0u;
+        const bool can_refill = !exhausted && free_count > min_free; // alive paths (slots in use) stay below the cap
 
         waited += (uint32_t)n_fin;
         if (done_count >= 32u || n_walk == 0 || n_fin >= swap_at || (n_fin > 0 && waited >= swap_wait) ||
@@ -1125,7 +1126,7 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_pool(const FrameAr
                     chunk_next = base;
                     chunk_end = min(base + len, total);
                 }
-                const uint32_t g = min(min(chunk_end - chunk_next, free_count), 32u);
+                const uint32_t g = min(min(chunk_end - chunk_next, free_count - min_free), 32u);
                 if (lane < g) {
                     const uint32_t sl = (uint32_t)free_list[free_count - 1u - lane];
                     const uint32_t p = lists.pixel(a, chunk_next + lane);
@@ -1800,12 +1801,6 @@ void init_launch_shapes(int device)
     s.fast_blocks[0][8] = grid_of(k_path_fast<false, 8>, kTraceThreads);
     s.fast_blocks[1][4] = grid_of(k_path_fast<true, 4>, kTraceThreads);
     s.pool_blocks[0][0] = grid_of(k_path_pool<false, 4, kPoolParkDefault, kPoolSlotsDefault>, kTraceThreads);
-    s.pool_blocks[0][1] = grid_of(k_path_pool<false, 4, 2, kPoolSlotsDefault>, kTraceThreads);
-    s.pool_blocks[0][2] = grid_of(k_path_pool<false, 4, kPoolParkDefault, 40>, kTraceThreads);
-    s.pool_blocks[0][3] = grid_of(k_path_pool<false, 4, kPoolParkDefault, 96>, kTraceThreads);
-    s.pool_blocks[0][4] = grid_of(k_path_pool<false, 5, kPoolParkDefault, kPoolSlotsDefault>, kTraceThreads);
-    s.pool_blocks[0][5] = grid_of(k_path_pool<false, 6, kPoolParkDefault, kPoolSlotsDefault>, kTraceThreads);
-    s.pool_blocks[0][6] = grid_of(k_path_pool<false, 8, kPoolParkDefault, 40>, kTraceThreads);
     s.pool_blocks[1][0] = grid_of(k_path_pool<true, 4, kPoolParkDefault, kPoolSlotsDefault>, kTraceThreads);
     s.mux_blocks[1] = mux_grid<1, 8>(s.sms);
     s.mux_blocks[2] = mux_grid<2, 8>(s.sms);
@@ -1917,10 +1912,10 @@ void launch_path_fast(const FrameArgs &a, bool record, cudaStream_t s)
     }
 }
 
-// a.pool_variant: 0 default (1 parked leaf, 64 slots), 1: 2 parked leaves, 2: 40 slots, 3: 96 slots -- A/B only
-//                 4/5/6: 5, 6, 8 blocks per SM (102, 85, 64 registers; 8 with 40 slots)
-static int pool_variant(const FrameArgs &a) { return (a.pool_variant >= 0 && a.pool_variant <= 6) ? a.pool_variant : 0; }
-
+// Compile-time shape of k_path_pool, chosen by A/B on the B200 (C2 demo frame / C4 instanced at 1080p, ms):
+//   parked leaves 1 | 2 | 3 | 4          0.859 | 0.892 | 0.908 | 0.918      20.3 | 20.9 | 21.4 | 21.8
+//   slots per warp 40 | 64 | 96          0.961 | 0.878 | 0.896              21.5 | 20.5 | 20.9
+//   blocks per SM 4 | 5 | 6 | 8          0.854 | 0.960 | 1.124 | 1.320      19.0 | 18.6 | 21.8 | 24.8   (registers 128 | 96 | 80 | 64)
 void launch_path_pool(const FrameArgs &a, bool record, cudaStream_t s)
 {
     Shapes &sh = shapes_for_current_device();
@@ -1928,17 +1923,7 @@ void launch_path_pool(const FrameArgs &a, bool record, cudaStream_t s)
         k_path_pool<true, 4, kPoolParkDefault, kPoolSlotsDefault><<<persistent_grid(sh, a, sh.pool_blocks[1][0]), kTraceThreads, 0, s>>>(a);
         return;
     }
-    const int m = pool_variant(a);
-    const int grid = persistent_grid(sh, a, sh.pool_blocks[0][m]);
-    switch (m) {
-    case 1: k_path_pool<false, 4, 2, kPoolSlotsDefault><<<grid, kTraceThreads, 0, s>>>(a); break;
-    case 2: k_path_pool<false, 4, kPoolParkDefault, 40><<<grid, kTraceThreads, 0, s>>>(a); break;
-    case 3: k_path_pool<false, 4, kPoolParkDefault, 96><<<grid, kTraceThreads, 0, s>>>(a); break;
-    case 4: k_path_pool<false, 5, kPoolParkDefault, kPoolSlotsDefault><<<grid, kTraceThreads, 0, s>>>(a); break;
-    case 5: k_path_pool<false, 6, kPoolParkDefault, kPoolSlotsDefault><<<grid, kTraceThreads, 0, s>>>(a); break;
-    case 6: k_path_pool<false, 8, kPoolParkDefault, 40><<<grid, kTraceThreads, 0, s>>>(a); break;
-    default: k_path_pool<false, 4, kPoolParkDefault, kPoolSlotsDefault><<<grid, kTraceThreads, 0, s>>>(a); break;
-    }
+    k_path_pool<false, 4, kPoolParkDefault, kPoolSlotsDefault><<<persistent_grid(sh, a, sh.pool_blocks[0][0]), kTraceThreads, 0, s>>>(a);
 }
 
 void launch_path_mux(const FrameArgs &a, cudaStream_t s)
@@ -1970,7 +1955,7 @@ size_t path_kernel_warps(const FrameArgs &a)
     Shapes &sh = shapes_for_current_device();
     if (a.schedule == 3 && (a.path_minb == 1 || a.path_minb == 2 || a.path_minb == 5 || a.path_minb == 6 || a.path_minb == 8)) return (size_t)sh.path_list_blocks_minb[a.path_minb] * (kTraceThreads / 32);
     if (a.schedule == 5) return (size_t)sh.fast_blocks[0][fast_minb(a)] * (kTraceThreads / 32);
-    if (a.schedule == 6) return (size_t)sh.pool_blocks[0][pool_variant(a)] * (kTraceThreads / 32);
+    if (a.schedule == 6) return (size_t)sh.pool_blocks[0][0] * (kTraceThreads / 32);
     if (a.schedule == 4) return (size_t)sh.mux_blocks[(a.mux_k >= 1 && a.mux_k <= 4) ? a.mux_k : 2] * (kMuxThreads / 32);
     int most = 0;
     for (int t = 0; t < 2; t++) {

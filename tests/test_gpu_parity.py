@@ -147,6 +147,39 @@ def test_rendering_kernels_record_the_reference_hits(name, make, W, H, depth, se
         assert st["retraced"] == 0
 
 
+@pytest.mark.parametrize("variant", [6, 5], ids=["pooled_paths", "path_per_lane"])
+@pytest.mark.parametrize("W,H,depth", [(8, 4, 3), (37, 19, 1), (5, 3, 8), (64, 36, 32)], ids=["one_tile", "ragged_depth1", "sub_tile", "max_depth32"])
+def test_rendering_kernels_on_edge_sizes(W, H, depth, variant):
+    """Fewer pixels than one warp's pool, image sizes that are not multiples of the 8x4 tile, a single segment and the
+    backend's maximum depth: frame, depth image, ray count and every recorded hit equal the oracle's."""
+    sc = scenes.cornell32()
+    grp = scenes.populate(sc)
+    cam = PathTracingCamera()
+    cam.fov = sc.fov
+    cam.geometry_group = grp
+    cam.denoising_mode = PathTracingCamera.NONE
+    cam.set_window_size(W, H)
+    cam.set_global_transform(sc.camera_transform12)
+    cam.set_max_depth(depth)
+    segs = min(depth, 4)
+    cam.set_record_hits(segs)
+    cam.set_variant(variant)
+    cam.init()
+    for _ in range(2):  # the second frame runs with cost classes from the first
+        frame = cam.render().copy()
+        st = cam.stats()
+        ref = oracle.path_trace(oracle_scene(grp), W, H, bytes(cam.camera_block()), max_depth=depth, trace_segments=segs)
+        assert st["rays"] == ref["stats"]["rays"]
+        for s in range(segs):
+            a, b = cam.read_trace(s), ref["trace"][s]
+            assert np.array_equal(a["hit"], b["hit"])
+            live = b["hit"] != 0xFFFFFFFF
+            for f in ("triangle", "blas", "front", "t", "u", "v"):
+                assert np.array_equal(a[f][live].view(np.uint32), b[f][live].view(np.uint32)), f"segment {s} field {f}"
+        assert np.array_equal(frame, ref["rgba8"])
+        assert np.array_equal(cam.read_image("depth").view(np.uint32), ref["depth"].view(np.uint32))
+
+
 def test_fast_kernels_equal_traced_kernels():
     """The un-instrumented instantiation (the one that is timed) produces the same frame."""
     sc = scenes.demo_scene()
