@@ -1089,9 +1089,29 @@ extern "C" int gdpt_render_frame_begin(gdpt_shader *m, gdpt_shader *p, const gdp
     Resource *cam_r = bound(m, 0, 3);
     const size_t cam_bytes = cam_r->size < sizeof(gdpt_camera) ? cam_r->size : sizeof(gdpt_camera);
     memcpy(cam_r->shadow.data(), camera, cam_bytes);
-    GDPT_CUDA(d, cudaMemcpyAsync(cam_r->dptr, stage, cam_bytes, cudaMemcpyHostToDevice, d->stream));
+    SmallCopies up = {};
+    up.c[0].dst = static_cast<uint32_t *>(cam_r->dptr); up.c[0].src = reinterpret_cast<const uint32_t *>(stage);
+    up.c[0].words = (uint32_t)(cam_bytes / 4u);
     sl.with_k2 = (mode != GDPT_DENOISE_NONE);
-    if (sl.with_k2 && (rc = upload_post_params(m, p, mode, frame_count, stage + 256))) return rc;
+    if (sl.with_k2) { // post-process parameter block (upload_post_params), staged behind the camera block
+        Resource *pp = bound(p, 0, 0);
+        size_t n = 0;
+        if (mode == GDPT_DENOISE_PROGRESSIVE_RENDERING) {
+            gdpt_progressive_params host_pp = { m->args.width, m->args.height, frame_count };
+            n = sizeof(host_pp);
+            memcpy(stage + 256, &host_pp, n);
+        } else if (!p->staged_params.empty()) {
+            n = p->staged_params.size();
+            memcpy(stage + 256, p->staged_params.data(), n);
+            p->staged_params.clear();
+        }
+        if (n) {
+            memcpy(pp->shadow.data(), stage + 256, n);
+            up.c[1].dst = static_cast<uint32_t *>(pp->dptr); up.c[1].src = reinterpret_cast<const uint32_t *>(stage + 256);
+            up.c[1].words = (uint32_t)(n / 4u);
+        }
+    }
+    launch_small_copies(up, d->stream); // reads the page-locked ring directly: no copy-engine operation in the frame
     GDPT_CUDA(d, cudaEventRecord(d->ring_ev[ring_slot], d->stream));
     d->ring_used[ring_slot] = true;
 
@@ -1103,15 +1123,32 @@ extern "C" int gdpt_render_frame_begin(gdpt_shader *m, gdpt_shader *p, const gdp
     if (rc) return rc;
     sl.launches = m->stats.kernel_launches;
     GDPT_CUDA(d, cudaEventRecord(sl.t1, d->stream));
+    // the read-back streams from a staging copy so the next K1 may overwrite the image.  An unsharded progressive
+    // frame gets that copy for free: K2 stores every quad into the staging image as well (the peer-screen store)
+    bool staged_by_k2 = false;
     if (sl.with_k2) {
         GDPT_CUDA(d, cudaEventRecord(sl.t2, d->stream));
-        if ((rc = (mode == GDPT_DENOISE_PROGRESSIVE_RENDERING ? enqueue_k2(p, m->shard_part, m->shard_parts, m->shard_band) : enqueue_k3(p)))) return rc;
+        if (mode == GDPT_DENOISE_PROGRESSIVE_RENDERING) {
+            const PeerScreens keep = p->peers;
+            if (m->shard_parts <= 1 && p->peers.n < kMaxPeerScreens && (((size_t)m->args.width * m->args.height) & 3u) == 0u) {
+                p->peers.p[p->peers.n++] = static_cast<uint32_t *>(sl.stage_rgba8);
+                staged_by_k2 = true;
+            }
+            rc = enqueue_k2(p, m->shard_part, m->shard_parts, m->shard_band);
+            p->peers = keep;
+        } else {
+            rc = enqueue_k3(p);
+        }
+        if (rc) return rc;
         GDPT_CUDA(d, cudaEventRecord(sl.t3, d->stream));
     }
     const size_t n = (size_t)m->args.width * m->args.height;
-    GDPT_CUDA(d, cudaMemcpyAsync(sl.stage_rgba8, m->args.out_rgba8, n * 4, cudaMemcpyDeviceToDevice, d->stream));
+    if (!staged_by_k2) GDPT_CUDA(d, cudaMemcpyAsync(sl.stage_rgba8, m->args.out_rgba8, n * 4, cudaMemcpyDeviceToDevice, d->stream));
     if (out_depth) GDPT_CUDA(d, cudaMemcpyAsync(sl.stage_depth, m->args.out_depth, n * 4, cudaMemcpyDeviceToDevice, d->stream));
-    GDPT_CUDA(d, cudaMemcpyAsync(sl.hcnt, sl.dcnt, sizeof(FrameCounters), cudaMemcpyDeviceToHost, d->stream));
+    SmallCopies down = {};
+    down.c[0].dst = reinterpret_cast<uint32_t *>(sl.hcnt); down.c[0].src = reinterpret_cast<const uint32_t *>(sl.dcnt);
+    down.c[0].words = (uint32_t)(sizeof(FrameCounters) / 4u);
+    launch_small_copies(down, d->stream); // counters into the page-locked block the host reads after `done`
     GDPT_CUDA(d, cudaEventRecord(sl.k_done, d->stream));
     // the read-back leaves on the copy stream while the compute stream starts the next frame
     GDPT_CUDA(d, cudaStreamWaitEvent(d->copy_stream, sl.k_done, 0));

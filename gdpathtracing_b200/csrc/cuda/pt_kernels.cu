@@ -1887,6 +1887,14 @@ void launch_progressive(uint32_t *screen_rgba8, float4 *accum, const gdpt_progre
                                                  shard_band, peers);
 }
 
+__global__ void __launch_bounds__(128) k_small_copies(const SmallCopies sc)
+{
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+        for (uint32_t i = threadIdx.x; i < sc.c[k].words; i += blockDim.x) sc.c[k].dst[i] = sc.c[k].src[i];
+}
+void launch_small_copies(const SmallCopies &sc, cudaStream_t s) { k_small_copies<<<1, 128, 0, s>>>(sc); }
+
 void launch_temporal(uint32_t *screen_rgba8, const float *depth, const float *history, float *next,
                      const gdpt_temporal_params *params_dev, int width, int height, cudaStream_t s)
 {

@@ -108,6 +108,11 @@ void launch_progressive(uint32_t *screen_rgba8, float4 *accum, const gdpt_progre
 // K3: temporal reprojection (temporal_reprojection.glsl:31-71); `history` is the frame buffer the previous dispatch wrote.
 void launch_temporal(uint32_t *screen_rgba8, const float *depth, const float *history, float *next,
                      const gdpt_temporal_params *params_dev, int width, int height, cudaStream_t s);
+// Up to three word copies in one launch: the per-frame blocks (camera, post-process params) read straight from
+// page-locked host memory, counters written straight into it -- keeps copy-engine operations (and the engine
+// switches around them) out of the frame's stream.
+struct SmallCopies { struct { uint32_t *dst; const uint32_t *src; uint32_t words; } c[3]; };
+void launch_small_copies(const SmallCopies &sc, cudaStream_t s);
 // Number of kernels one K1 dispatch launches for a given depth.
 int k1_launch_count(int schedule, int max_depth, bool debug_steps);
 // One-time per device: query SM count / occupancy for the persistent grids.
