@@ -209,7 +209,8 @@ def run_ours(args, rank, local, world):
         cam.set_shard(rank, world, args.band)
     cam.init()
     build_s = None  # GeometryGroup3D.build ran inside init(); timed separately below on rank 0
-    _lib.check(cuda.gdpt_shader_set_stage_timing(cam.main_shader, 1), cam.device, "set_stage_timing")
+    # per-kernel split: measured on a few untimed frames after the timed region (the events it records between the K1
+    # kernels cost ~60 us per frame, so they stay out of every timed leg)
 
     def set_index(step):
         # frame_index is incremented by render(); make step s use index s*world + rank + 1 (sample partition)
@@ -254,7 +255,7 @@ def run_ours(args, rank, local, world):
         sampler.start()
     barrier()
     wall0 = time.perf_counter()
-    dev_ms, rays_total, k2_ms_total, gather_ms = 0.0, 0, 0.0, 0.0
+    dev_ms, rays_total, k2_ms_total, gather_ms, k1_ms_total = 0.0, 0, 0.0, 0.0, 0.0
     for s in range(args.steps):
         if flush is not None:
             flush.fill_(s & 0xFF)
@@ -264,10 +265,8 @@ def run_ours(args, rank, local, world):
         st = cam.stats()  # blocks until the frame is done; k1_ms/k2_ms are CUDA-event times on the launching stream
         dev_ms += st["k1_ms"] + st["k2_ms"]
         k2_ms_total += st["k2_ms"]
+        k1_ms_total += st["k1_ms"]
         rays_total += st["rays"]
-        n = cuda.gdpt_shader_get_stage_times(cam.main_shader, buf, 64)
-        stage_ms[:n] += np.array(buf[:n])
-        n_stage = n
         launches_per_frame = st["kernel_launches"] + 1  # K1 kernels + K2
         if rows_mode:
             ts = peer_frame._stream if peer_frame is not None else torch.cuda.current_stream()
@@ -284,6 +283,20 @@ def run_ours(args, rank, local, world):
         multigpu.reduce_accumulations(acc_t, dst=0)
         e1.record(); torch.cuda.synchronize()
         gather_ms += e0.elapsed_time(e1)
+    # ---- per-kernel split of K1 (untimed frames, stage events on)
+    _lib.check(cuda.gdpt_shader_set_stage_timing(cam.main_shader, 1), cam.device, "set_stage_timing")
+    split_frames = min(args.steps, 8)
+    for s in range(split_frames):
+        set_index(args.warmup + s)
+        cam.render_device_only()
+        cam.stats()
+        n = cuda.gdpt_shader_get_stage_times(cam.main_shader, buf, 64)
+        stage_ms[:n] += np.array(buf[:n])
+        n_stage = n
+        if rows_mode:
+            present()
+            torch.cuda.synchronize(); cam.synchronize()
+    _lib.check(cuda.gdpt_shader_set_stage_timing(cam.main_shader, 0), cam.device, "set_stage_timing")
     present_check = None
     if peer_frame is not None:
         # the image every rank holds now must be what the NCCL all-gather of the bands assembles
@@ -349,7 +362,7 @@ def run_ours(args, rank, local, world):
 
     # ---- algorithmic work of one representative frame (instrumented kernels, untimed)
     work = trace_work(sc, grp, args, local)
-    stage_avg = stage_ms[:n_stage] / args.steps
+    stage_avg = stage_ms[:n_stage] / min(args.steps, 8)
     kinds = stage_kinds(n_stage, D)
     by_kernel = {}
     for i in range(n_stage):
@@ -361,7 +374,8 @@ def run_ours(args, rank, local, world):
         # the traversal of every segment runs inside k_path; k_primary_cull (if any) does the TLAS walk of the camera
         # rays that hit nothing.  The frame's algorithmic work is charged to the pair and timed over both.
         top = "k_path"
-        tk = {"ms": float(stage_avg.sum()), "launches": 1, "lane_ops": float(sum(work["lane_ops_per_segment"]))}
+        # duration: CUDA events around K1 in the timed region (the split above only apportions it)
+        tk = {"ms": k1_ms_total / args.steps, "launches": 1, "lane_ops": float(sum(work["lane_ops_per_segment"]))}
         top_label = "k_path" if n_stage == 1 else "k_path (+ k_primary_cull, timed together)"
     else:
         top = max((k for k in by_kernel if by_kernel[k]["lane_ops"] > 0), key=lambda k: by_kernel[k]["ms"])
@@ -374,7 +388,8 @@ def run_ours(args, rank, local, world):
     roofline = {"kernel": top_label, "bound": "issue", "achieved": achieved / 1e12, "peak": peak_lane_ops / 1e12, "unit": "Tlane-op/s",
                 "frac": achieved / peak_lane_ops, "traffic": None, "launches_per_step": tk["launches"],
                 "algorithmic_bytes": work["algorithmic_bytes"],
-                "avg_launch_ms": tk["ms"] / tk["launches"], "share_of_step": by_kernel[top]["ms"] / max(stage_avg.sum() + k2_avg_ms, 1e-9),
+                "avg_launch_ms": tk["ms"] / tk["launches"], "share_of_step": (by_kernel[top]["ms"] / max(stage_avg.sum(), 1e-9)) * tk["ms"] / max(tk["ms"] + k2_avg_ms, 1e-9)
+                if n_stage <= 2 else by_kernel[top]["ms"] / max(stage_avg.sum() + k2_avg_ms, 1e-9),
                 "peak_source": f"148 SM x 4 schedulers x 32 lanes x {peaks['sm_max_mhz']:.0f} MHz ({peaks['source']} sm_max_mhz)",
                 "work_model": "22*box_tests + 55*tri_tests + 45*tlas_leaf_visits lane-ops per ray (SURVEY 8d) of the REFERENCE traversal "
                               "(no culling), counted by the instrumented kernels on one frame; the timed kernels skip the part of it "
@@ -404,6 +419,7 @@ def run_ours(args, rank, local, world):
                    "l2": "256 MiB write between steps (outside the per-step events)" if args.l2_flush else "no flush",
                    "timing": "CUDA events around K1 and K2 on the launching stream, summed over steps, max over ranks",
                    "wall_ms_per_step_incl_flush_and_sync": wall_ms / args.steps,
+                   "stage_ms_note": "split measured on untimed frames with an event between the K1 kernels",
                    "stage_ms": {f"{i}:{kinds[i]}": round(float(stage_avg[i]), 5) for i in range(n_stage)},
                    "kernels": {k: {"ms_per_step": v["ms"], "launches": v["launches"]} for k, v in by_kernel.items()},
                    "work_per_frame": work["totals"]},

@@ -32,7 +32,9 @@ namespace gdpt {
 struct FastLayout {
     std::vector<FastNode> nodes;     // internal nodes of every BLAS
     std::vector<FastTri> tris;       // triangle copies in leaf order
-    std::vector<FastNode> tlas;      // TLAS internal nodes: reference topology, true world boxes
+    std::vector<FastNode> tlas;      // TLAS internal nodes: reference topology, true world boxes (appended to `nodes`
+                                     // at `tlas_base` when the layout is complete: one table for both levels)
+    uint32_t tlas_base = 0;
     std::vector<uint32_t> tri_leaf;  // per reference triangle index: reference node index of the leaf that holds it
     std::vector<uint32_t> inst_root; // per instance: link of the root of its BLAS in `nodes`/`tris`
     uint32_t tlas_root_link = LINK_NONE;
@@ -267,6 +269,8 @@ inline void build_fast_layout(const gdpt_bvh_node *bvh, uint32_t n_nodes, const 
     out.tlas_root_link = lay.tlas_root_link;
     out.max_depth += tlas_depth + 2u;
     if (out.max_depth >= GDPT_FAST_MAX_DEPTH) { out.why_not = "closest-hit tree deeper than the traversal stack"; return; }
+    out.tlas_base = (uint32_t)out.nodes.size();
+    out.nodes.insert(out.nodes.end(), out.tlas.begin(), out.tlas.end());
     out.ok = true;
 }
 

@@ -205,7 +205,7 @@ int build_derived_layout(gdpt_shader *s, const Resource &bvh_r, const Resource &
     if (fast.ok) {
         for (size_t b = 0; b < lay.inst_recs.size(); b++) lay.inst_recs[b].fast_root = fast.inst_root[b];
         if ((rc = dev_upload(s, &s->args.sc.fast_nodes, fast.nodes))) return rc;
-        if ((rc = dev_upload(s, &s->args.sc.fast_tlas, fast.tlas))) return rc;
+        s->args.sc.fast_tlas_base = fast.tlas_base;
         if ((rc = dev_upload(s, &s->args.sc.fast_tris, fast.tris))) return rc;
         if ((rc = dev_upload(s, &s->args.sc.tri_leaf, fast.tri_leaf))) return rc;
     }

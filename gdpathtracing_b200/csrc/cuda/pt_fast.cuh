@@ -46,8 +46,8 @@ GDPT_HD bool fast_slab(const RayState &r, float nx, float ny, float nz, float xx
 // One internal node of either level: nearer child next, farther child pushed.
 template <class Stack> GDPT_HD void fast_step_node(const SceneView &sc, RayState &r, Stack &st)
 {
-    const void *table = (r.cur & LINK_TLAS) ? static_cast<const void *>(sc.fast_tlas) : static_cast<const void *>(sc.fast_nodes);
-    const uint32_t idx = r.cur & LINK_INDEX_MASK;
+    const void *table = sc.fast_nodes; // both levels in one table, TLAS nodes behind the BLAS nodes
+    const uint32_t idx = (r.cur & LINK_INDEX_MASK) + ((r.cur & LINK_TLAS) ? sc.fast_tlas_base : 0u);
     const q4f q0 = ldq(table, idx * 4u + 0u);
     const q4f q1 = ldq(table, idx * 4u + 1u);
     const q4f q2 = ldq(table, idx * 4u + 2u);

@@ -945,6 +945,17 @@ enum PoolField {
     PF_COUNT
 };
 
+// Phases of k_path_pool.  The node step never changes space: a TLAS link that comes up while the lane is inside an
+// instance is a crossing (phase T), like an instance entry, so the node-step code carries no space restore.
+__device__ __forceinline__ bool pool_can_node(uint32_t cur, uint32_t inst)
+{
+    return cur != LINK_NONE && (cur & LINK_LEAF) == 0u && ((cur & LINK_TLAS) == 0u || inst == GDPT_NO_INSTANCE);
+}
+__device__ __forceinline__ bool pool_can_cross(uint32_t cur, uint32_t pend, uint32_t inst)
+{
+    return cur != LINK_NONE && (cur & LINK_TLAS) != 0u && pend == LINK_NONE && ((cur & LINK_LEAF) != 0u || inst != GDPT_NO_INSTANCE);
+}
+
 template <bool REC, int MINB, int kPoolPark, int kPoolSlots>
 __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_pool(const FrameArgs a)
 {
@@ -1003,9 +1014,9 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_pool(const FrameAr
 
     for (;;) {
         const uint32_t pend = n_park ? park[0] : LINK_NONE;
-        const bool can_i = has && lane_can_node(r.cur, pend);
+        const bool can_i = has && pool_can_node(r.cur, r.inst);
         const bool can_l = has && lane_can_leaf(r.cur, pend);
-        const bool can_t = has && lane_can_enter(r.cur, pend);
+        const bool can_t = has && pool_can_cross(r.cur, pend, r.inst);
         const bool fin = has && r.cur == LINK_NONE && pend == LINK_NONE;
         const uint32_t census = __reduce_add_sync(kFull, (can_i ? 1u : 0u) | (can_l ? 1u << 6 : 0u) | (can_t ? 1u << 12 : 0u) |
                                                              (fin ? 1u << 18 : 0u) | (has ? 0u : 1u << 24));
@@ -1172,9 +1183,6 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_pool(const FrameAr
 #pragma unroll 1
             for (int b = 0; b < a.burst; b++) { // node burst: no census while at least half of the starters stay on internal nodes
                 if (go) {
-                    if ((r.cur & LINK_TLAS) != 0u && r.inst != GDPT_NO_INSTANCE) { // back to world space (main.glsl:316-327)
-                        r.o = r.wo; r.d = r.wd; r.rd = wrd; r.inst = GDPT_NO_INSTANCE;
-                    }
                     fast_step_node(a.sc, r, st);
                     steps++;
                     if (n_park < (uint32_t)kPoolPark && fast_link_is_leaf(r.cur)) { // park the leaf, keep descending
@@ -1184,7 +1192,7 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_pool(const FrameAr
                         n_park++;
                         r.cur = stack_pop(r, st);
                     }
-                    go = lane_can_node(r.cur, n_park ? park[0] : LINK_NONE);
+                    go = pool_can_node(r.cur, r.inst);
                 }
                 if (__popc(__ballot_sync(kFull, go)) < need) break;
             }
@@ -1202,9 +1210,9 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_pool(const FrameAr
             }
         } else {
             it_t++;
-            if (can_t) {
+            if (can_t) { // back to world space (main.glsl:316-327) and/or into the instance the link names
                 if (r.inst != GDPT_NO_INSTANCE) { r.o = r.wo; r.d = r.wd; r.rd = wrd; r.inst = GDPT_NO_INSTANCE; }
-                fast_enter_instance(a.sc, r, st);
+                if (r.cur & LINK_LEAF) fast_enter_instance(a.sc, r, st);
                 steps++;
             }
         }

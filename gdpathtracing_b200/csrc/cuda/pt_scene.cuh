@@ -80,7 +80,7 @@ static_assert(sizeof(InstRec) == 112, "InstRec is seven 128-bit loads");
 //   q0 = Lmin.x Lmin.y Lmin.z Lmax.x   q1 = Lmax.y Lmax.z Rmin.x Rmin.y
 //   q2 = Rmin.z Rmax.x Rmax.y Rmax.z   q3 = left right - -
 // Links: [31] TLAS level, [30] leaf.  BLAS leaf = LINK_LEAF | (count-1) << 27 | first FastTri;
-// TLAS leaf = LINK_TLAS | LINK_LEAF | instance; internal = index into fast_nodes / fast_tlas.
+// TLAS leaf = LINK_TLAS | LINK_LEAF | instance; internal = index into fast_nodes (TLAS nodes at fast_tlas_base + index).
 struct __attribute__((aligned(64))) FastNode {
     float lmin[3]; float lmax[3];
     float rmin[3]; float rmax[3];
@@ -117,7 +117,7 @@ struct SceneView {
     uint32_t tlas_root_link;
     // closest-hit tables; fast_ok == 0 means "use the reference-order traversal only"
     const FastNode *fast_nodes;
-    const FastNode *fast_tlas;
+    uint32_t fast_tlas_base;      // TLAS internal node i is fast_nodes[fast_tlas_base + i]
     const FastTri *fast_tris;
     const uint32_t *tri_leaf;
     uint32_t fast_ok;

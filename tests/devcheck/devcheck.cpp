@@ -72,7 +72,7 @@ static void make_view(const devcheck_scene *in, DerivedLayout &lay, FastLayout &
         build_fast_layout(sc.bvh, (uint32_t)in->n_nodes, sc.blas, (uint32_t)in->n_blas, sc.tlas, (uint32_t)in->n_tlas, sc.tri_geom,
                           (uint32_t)in->n_tris, lay, fast);
         for (size_t b = 0; b < lay.inst_recs.size(); b++) lay.inst_recs[b].fast_root = fast.inst_root[b];
-        sc.fast_nodes = fast.nodes.data(); sc.fast_tlas = fast.tlas.data(); sc.fast_tris = fast.tris.data();
+        sc.fast_nodes = fast.nodes.data(); sc.fast_tlas_base = fast.tlas_base; sc.fast_tris = fast.tris.data();
         sc.tri_leaf = fast.tri_leaf.data(); sc.fast_ok = fast.ok ? 1u : 0u;
         if (!fast.ok) std::fprintf(stderr, "devcheck: closest-hit tables unavailable: %s\n", fast.why_not.c_str());
     }

@@ -54,5 +54,32 @@ while inflight:
 out["pipelined_ms"] = (time.perf_counter() - t0) / N * 1e3
 out["pipelined_host_begin_ms"] = host_begin / N * 1e3
 out["pipelined_host_wait_ms"] = host_wait / N * 1e3
-st = cam.stats()
+
+
+def pipelined(tag, set_index=False, touch=False):
+    t0 = time.perf_counter()
+    inflight = 0
+    acc = 0
+    for i in range(N):
+        if set_index:
+            cam.set_frame_index(1000 + i)
+        cam.render_begin()
+        inflight += 1
+        if inflight == 2:
+            img, fst = cam.render_wait()
+            if touch:
+                acc += int(img[0, 0, 3])
+            inflight -= 1
+    while inflight:
+        cam.render_wait(); inflight -= 1
+    out[tag] = (time.perf_counter() - t0) / N * 1e3
+
+
+pipelined("pipe_plain_ms")
+pipelined("pipe_set_index_ms", set_index=True)
+pipelined("pipe_touch_ms", touch=True)
+from gdpathtracing_b200 import _lib
+_lib.cuda.gdpt_shader_set_stage_timing(cam.main_shader, 1)
+pipelined("pipe_stage_timing_ms")
+pipelined("pipe_all_ms", set_index=True, touch=True)
 print(json.dumps(out))
