@@ -50,6 +50,8 @@ struct gdpt_device {
     cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
     // pipelined frames: read-backs run on their own stream; per-frame H2D blocks come from a ring
     cudaStream_t copy_stream = nullptr;
+    cudaStream_t stream2 = nullptr;     // second frame stream of overlapped pipelined frames (created on first use)
+    bool frame_overlap = true;          // GDPT_FRAME_OVERLAP=0: pipelined frames share one stream
     uint8_t *ring = nullptr;            // kRingSlots x 512 B of pinned memory
     cudaEvent_t ring_ev[8] = {};        // slot i may be rewritten once ring_ev[i] has completed
     bool ring_used[8] = {};
@@ -85,6 +87,10 @@ struct gdpt_shader {
         float *stage_depth = nullptr;
         cudaEvent_t k_done = nullptr, done = nullptr, t0 = nullptr, t1 = nullptr, t2 = nullptr, t3 = nullptr;
         bool pending = false, with_k2 = false;
+        // overlapped frames: what K1 of this frame reads and writes (the other frame in flight has its own)
+        gdpt_camera *cam_dev = nullptr; gdpt_progressive_params *pp_dev = nullptr;
+        uint32_t *raw_rgba8 = nullptr; float *raw_depth = nullptr; uint32_t *hit_list = nullptr;
+        bool finished_once = false;      // k_done has been recorded at least once
         uint32_t launches = 0;
     } slots[2];
     unsigned slot_head = 0, slot_tail = 0; // begin fills slots[head % 2], wait drains slots[tail % 2]
@@ -492,14 +498,16 @@ int enqueue_k1(gdpt_shader *s)
     return GDPT_OK;
 }
 
-int enqueue_k2(gdpt_shader *p, int part, int parts, int band)
+int enqueue_k2(gdpt_shader *p, int part, int parts, int band, const uint32_t *raw_in = nullptr,
+               const gdpt_progressive_params *params_in = nullptr)
 {
     gdpt_device *d = p->dev;
     Resource *params = bound(p, 0, 0), *screen = bound(p, 0, 1), *accum = bound(p, 0, 2);
     if (parts > 1 && (screen->width & 3)) return fail(d, GDPT_ERR_UNSUPPORTED, "sharded accumulation needs a width that is a multiple of 4");
-    launch_progressive(static_cast<uint32_t *>(screen->dptr), static_cast<float4 *>(accum->dptr),
-                       static_cast<const gdpt_progressive_params *>(params->dptr), screen->width, screen->height, part, parts, band,
-                       p->peers, d->stream);
+    launch_progressive(raw_in ? raw_in : static_cast<const uint32_t *>(screen->dptr), static_cast<uint32_t *>(screen->dptr),
+                       static_cast<float4 *>(accum->dptr),
+                       params_in ? params_in : static_cast<const gdpt_progressive_params *>(params->dptr), screen->width, screen->height,
+                       part, parts, band, p->peers, d->stream);
     GDPT_CUDA(d, cudaGetLastError());
     return GDPT_OK;
 }
@@ -544,6 +552,7 @@ int gdpt_device_create(int cuda_ordinal, gdpt_device **out_device)
     if (cuda_ordinal < 0 || cuda_ordinal >= count) return fail(nullptr, GDPT_ERR_NO_DEVICE, "CUDA ordinal %d out of range (0..%d)", cuda_ordinal, count - 1);
     gdpt_device *d = new gdpt_device();
     d->ordinal = cuda_ordinal;
+    if (const char *e = getenv("GDPT_FRAME_OVERLAP")) d->frame_overlap = atoi(e) != 0;
     if (cudaSetDevice(cuda_ordinal) != cudaSuccess || cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaHostAlloc(&d->pinned_staging, 4096, cudaHostAllocDefault) != cudaSuccess) {
         fail(nullptr, GDPT_ERR_CUDA, "device %d: stream/staging setup failed: %s", cuda_ordinal, cudaGetErrorString(cudaGetLastError()));
@@ -572,6 +581,7 @@ void gdpt_device_destroy(gdpt_device *d)
     for (int i = 0; i < 4; i++) if (d->ev[i]) cudaEventDestroy(d->ev[i]);
     if (d->pinned_staging) cudaFreeHost(d->pinned_staging);
     if (d->copy_stream) { cudaStreamSynchronize(d->copy_stream); cudaStreamDestroy(d->copy_stream); }
+    if (d->stream2) { cudaStreamSynchronize(d->stream2); cudaStreamDestroy(d->stream2); }
     if (d->ring) cudaFreeHost(d->ring);
     for (int i = 0; i < 8; i++) if (d->ring_ev[i]) cudaEventDestroy(d->ring_ev[i]);
     cudaStreamDestroy(d->stream);
@@ -582,6 +592,7 @@ int gdpt_device_synchronize(gdpt_device *d)
 {
     if (!d) return GDPT_ERR_INVALID_ARG;
     GDPT_CUDA(d, cudaStreamSynchronize(d->stream));
+    if (d->stream2) GDPT_CUDA(d, cudaStreamSynchronize(d->stream2));
     return GDPT_OK;
 }
 
@@ -639,6 +650,7 @@ void gdpt_shader_destroy(gdpt_shader *s)
     gdpt_device *d = s->dev;
     cudaSetDevice(d->ordinal);
     cudaStreamSynchronize(d->stream);
+    if (d->stream2) cudaStreamSynchronize(d->stream2);
     if (d->copy_stream) cudaStreamSynchronize(d->copy_stream);
     for (void *p : s->derived) cudaFree(p);
     for (cudaEvent_t e : s->stage_ev) cudaEventDestroy(e);
@@ -819,6 +831,7 @@ int gdpt_shader_compute(gdpt_shader *s, int gx, int gy, int gz)
     if (gx != (w + 31) / 32 || gy != (h + 31) / 32 || gz != 1)
         return fail(d, GDPT_ERR_INVALID_ARG, "compute(%d,%d,%d): expected ceil(W/32) x ceil(H/32) x 1 = (%d,%d,1)", gx, gy, gz, (w + 31) / 32, (h + 31) / 32);
     int rc;
+    if (d->stream2) GDPT_CUDA(d, cudaStreamSynchronize(d->stream2)); // overlapped pipelined frames still in flight
     if (s->kind == SHADER_MAIN) {
         GDPT_CUDA(d, cudaEventRecord(d->ev[0], d->stream));
         if ((rc = enqueue_k1(s))) return rc;
@@ -845,6 +858,7 @@ static int enqueue_frame(gdpt_shader *m, gdpt_shader *p, const gdpt_camera *came
     cudaSetDevice(d->ordinal);
     // the previous frame's staging must have been consumed before we overwrite it
     GDPT_CUDA(d, cudaStreamSynchronize(d->stream));
+    if (d->stream2) GDPT_CUDA(d, cudaStreamSynchronize(d->stream2));
     uint8_t *stage = static_cast<uint8_t *>(d->pinned_staging);
     memcpy(stage, camera, sizeof(gdpt_camera));
     Resource *cam_r = bound(m, 0, 3);
@@ -1082,6 +1096,100 @@ extern "C" int gdpt_render_frame_begin(gdpt_shader *m, gdpt_shader *p, const gdp
     cudaSetDevice(d->ordinal);
     if ((rc = ensure_slot(m, sl, out_depth != nullptr))) return rc;
 
+    // Overlapped frames: the two frames in flight run on two streams with their own camera block, K1 images, survivor
+    // lists and counters, so frame N+1's kernels fill the SMs that frame N's last paths leave idle (a whole path is
+    // more than half a 1080p frame long).  What orders them: the accumulate/tone-map step (one
+    // accumulation image, one presented image) waits for the other frame's.  `cost` (the scheduling hint of
+    // k_primary_cull) is shared and read while the other frame writes it: any value is a valid hint.
+    if (d->frame_overlap && mode != GDPT_DENOISE_TEMPORAL_REPROJECTION && m->args.trace == nullptr && !m->debug_steps &&
+        !m->warp_profile && m->args.schedule >= 3) {
+        const unsigned idx = m->slot_head & 1u;
+        gdpt_shader::FrameSlot &other = m->slots[idx ^ 1u];
+        const size_t n = (size_t)m->args.width * m->args.height;
+        if (!sl.cam_dev) {
+            if ((rc = dev_alloc(m, &sl.cam_dev, 2))) return rc;
+            if ((rc = dev_alloc(m, &sl.pp_dev, 16))) return rc;
+            if ((rc = dev_alloc(m, &sl.raw_rgba8, n))) return rc;
+            if ((rc = dev_alloc(m, &sl.raw_depth, n))) return rc;
+            if ((rc = dev_alloc(m, &sl.hit_list, (size_t)m->args.queue_cap + (size_t)(kCostClasses - 1) * m->args.heavy_cap))) return rc;
+        }
+        if (!d->stream2) GDPT_CUDA(d, cudaStreamCreateWithFlags(&d->stream2, cudaStreamNonBlocking));
+        cudaStream_t const main_stream = d->stream;
+        cudaStream_t const S = idx == 0 ? d->stream : d->stream2;
+        uint8_t *stage = nullptr; unsigned ring_slot = 0;
+        if ((rc = ring_take(d, &stage, &ring_slot))) return rc;
+        memcpy(stage, camera, sizeof(gdpt_camera));
+        Resource *cam_r = bound(m, 0, 3);
+        memcpy(cam_r->shadow.data(), camera, cam_r->size < sizeof(gdpt_camera) ? cam_r->size : sizeof(gdpt_camera));
+        SmallCopies up = {};
+        up.c[0].dst = reinterpret_cast<uint32_t *>(sl.cam_dev); up.c[0].src = reinterpret_cast<const uint32_t *>(stage);
+        up.c[0].words = (uint32_t)(sizeof(gdpt_camera) / 4u);
+        sl.with_k2 = (mode == GDPT_DENOISE_PROGRESSIVE_RENDERING);
+        if (sl.with_k2) {
+            gdpt_progressive_params host_pp = { m->args.width, m->args.height, frame_count };
+            memcpy(stage + 256, &host_pp, sizeof(host_pp));
+            memcpy(bound(p, 0, 0)->shadow.data(), &host_pp, sizeof(host_pp));
+            up.c[1].dst = reinterpret_cast<uint32_t *>(sl.pp_dev); up.c[1].src = reinterpret_cast<const uint32_t *>(stage + 256);
+            up.c[1].words = (uint32_t)(sizeof(host_pp) / 4u);
+        }
+        launch_small_copies(up, S);
+        GDPT_CUDA(d, cudaEventRecord(d->ring_ev[ring_slot], S));
+        d->ring_used[ring_slot] = true;
+
+        const FrameArgs saved = m->args;
+        m->args.counters = sl.dcnt; m->args.camera = sl.cam_dev; m->args.out_rgba8 = sl.raw_rgba8; m->args.out_depth = sl.raw_depth;
+        m->args.hit_list = sl.hit_list;
+        d->stream = S; // enqueue_k1 / enqueue_k2 launch on the device's current stream
+        cudaEventRecord(sl.t0, S);
+        rc = enqueue_k1(m);
+        cudaEventRecord(sl.t1, S);
+        m->args = saved;
+        sl.launches = m->stats.kernel_launches;
+        if (rc == GDPT_OK && other.finished_once) rc = cudaStreamWaitEvent(S, other.k_done, 0) == cudaSuccess ? GDPT_OK : GDPT_ERR_CUDA;
+        const void *readback_rgba8 = sl.raw_rgba8;
+        if (rc == GDPT_OK) {
+            if (sl.with_k2) {
+                cudaEventRecord(sl.t2, S);
+                const PeerScreens keep = p->peers;
+                if (m->shard_parts <= 1 && p->peers.n < kMaxPeerScreens) {
+                    p->peers.p[p->peers.n++] = static_cast<uint32_t *>(sl.stage_rgba8);
+                    readback_rgba8 = sl.stage_rgba8;
+                }
+                rc = enqueue_k2(p, m->shard_part, m->shard_parts, m->shard_band, sl.raw_rgba8, sl.pp_dev);
+                p->peers = keep;
+                cudaEventRecord(sl.t3, S);
+                if (rc == GDPT_OK && readback_rgba8 == sl.raw_rgba8) { // sharded: the presented image is the bound one
+                    cudaMemcpyAsync(sl.stage_rgba8, saved.out_rgba8, n * 4, cudaMemcpyDeviceToDevice, S);
+                    readback_rgba8 = sl.stage_rgba8;
+                }
+            } else { // GDPT_DENOISE_NONE: K1's image is the frame
+                cudaMemcpyAsync(saved.out_rgba8, sl.raw_rgba8, n * 4, cudaMemcpyDeviceToDevice, S);
+            }
+            cudaMemcpyAsync(saved.out_depth, sl.raw_depth, n * 4, cudaMemcpyDeviceToDevice, S);
+            SmallCopies down = {};
+            down.c[0].dst = reinterpret_cast<uint32_t *>(sl.hcnt); down.c[0].src = reinterpret_cast<const uint32_t *>(sl.dcnt);
+            down.c[0].words = (uint32_t)(sizeof(FrameCounters) / 4u);
+            launch_small_copies(down, S);
+            cudaEventRecord(sl.k_done, S);
+            sl.finished_once = true;
+        }
+        d->stream = main_stream;
+        if (rc) return rc;
+        GDPT_CUDA(d, cudaGetLastError());
+        GDPT_CUDA(d, cudaStreamWaitEvent(d->copy_stream, sl.k_done, 0));
+        GDPT_CUDA(d, cudaMemcpyAsync(out_rgba8, readback_rgba8, n * 4, cudaMemcpyDeviceToHost, d->copy_stream));
+        if (out_depth) GDPT_CUDA(d, cudaMemcpyAsync(out_depth, sl.raw_depth, n * 4, cudaMemcpyDeviceToHost, d->copy_stream));
+        GDPT_CUDA(d, cudaEventRecord(sl.done, d->copy_stream));
+        sl.pending = true;
+        m->slot_head++;
+        m->stats_valid = false;
+        return GDPT_OK;
+    }
+
+    {   // single-stream form; an overlapped frame of the other slot may still be running on the second stream
+        gdpt_shader::FrameSlot &other = m->slots[(m->slot_head & 1u) ^ 1u];
+        if (d->stream2 && other.finished_once) GDPT_CUDA(d, cudaStreamWaitEvent(d->stream, other.k_done, 0));
+    }
     // per-frame H2D blocks come from the pinned ring: nothing here waits for the GPU
     uint8_t *stage = nullptr; unsigned ring_slot = 0;
     if ((rc = ring_take(d, &stage, &ring_slot))) return rc;

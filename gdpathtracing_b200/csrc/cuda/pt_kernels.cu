@@ -1658,7 +1658,9 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade(const FrameArgs a, cons
 // tone-mapped quad this GPU owns is also stored there, so the presented frame assembles itself in every
 // GPU's image while the kernel runs -- the exchange step of the row-band partition fused into its producer
 // instead of an all-gather after it.
-__global__ void __launch_bounds__(256) k_progressive(uint32_t *__restrict__ screen, float4 *__restrict__ accum,
+// `raw` is the image K1 wrote (the bound screen image itself in the reference's call sequence; a frame-private image
+// when two pipelined frames overlap), `screen` receives the tone-mapped result.
+__global__ void __launch_bounds__(256) k_progressive(const uint32_t *raw, uint32_t *screen, float4 *__restrict__ accum,
                                                      const gdpt_progressive_params *__restrict__ params, int width,
                                                      int height, int shard_part, int shard_parts, int shard_band,
                                                      const PeerScreens peers)
@@ -1673,7 +1675,7 @@ __global__ void __launch_bounds__(256) k_progressive(uint32_t *__restrict__ scre
             const int y = (int)(p / (size_t)width);
             if ((y / shard_band) % shard_parts != shard_part) continue;
         }
-        const uint4 s4 = reinterpret_cast<const uint4 *>(screen)[q];
+        const uint4 s4 = reinterpret_cast<const uint4 *>(raw)[q];
         const uint32_t in[4] = { s4.x, s4.y, s4.z, s4.w };
         uint32_t out[4];
 #pragma unroll
@@ -1697,7 +1699,7 @@ __global__ void __launch_bounds__(256) k_progressive(uint32_t *__restrict__ scre
         const size_t p = (n_quads << 2) + threadIdx.x;
         const int y = (int)(p / (size_t)width);
         if (shard_parts <= 1 || (y / shard_band) % shard_parts == shard_part) {
-            const uint32_t in = screen[p];
+            const uint32_t in = raw[p];
             f3 rad = mk3((float)(in & 0xffu) / 255.0f, (float)((in >> 8) & 0xffu) / 255.0f, (float)((in >> 16) & 0xffu) / 255.0f);
             if (frame_count > 1u) { const float4 acc = accum[p]; rad = rad + mk3(acc.x, acc.y, acc.z); }
             accum[p] = make_float4(rad.x, rad.y, rad.z, 1.0f);
@@ -1887,11 +1889,11 @@ void launch_trace(const FrameArgs &a, int segment, bool trace, cudaStream_t s)
     launch_trace_kernel<1>(shapes_for_current_device(), a, trace, segment, segment & 1, s);
 }
 
-void launch_progressive(uint32_t *screen_rgba8, float4 *accum, const gdpt_progressive_params *params_dev, int width,
-                        int height, int shard_part, int shard_parts, int shard_band, const PeerScreens &peers, cudaStream_t s)
+void launch_progressive(const uint32_t *raw_rgba8, uint32_t *screen_rgba8, float4 *accum, const gdpt_progressive_params *params_dev,
+                        int width, int height, int shard_part, int shard_parts, int shard_band, const PeerScreens &peers, cudaStream_t s)
 {
     Shapes &sh = shapes_for_current_device();
-    k_progressive<<<sh.prog_blocks, 256, 0, s>>>(screen_rgba8, accum, params_dev, width, height, shard_part, shard_parts,
+    k_progressive<<<sh.prog_blocks, 256, 0, s>>>(raw_rgba8, screen_rgba8, accum, params_dev, width, height, shard_part, shard_parts,
                                                  shard_band, peers);
 }
 

@@ -102,7 +102,7 @@ void launch_primary(const FrameArgs &a, bool trace, cudaStream_t s);
 void launch_shade(const FrameArgs &a, int segment, cudaStream_t s);
 void launch_trace(const FrameArgs &a, int segment, bool trace, cudaStream_t s);
 // K2: progressive accumulation + ACES (progressive_rendering.glsl:28-46).
-void launch_progressive(uint32_t *screen_rgba8, float4 *accum, const gdpt_progressive_params *params_dev,
+void launch_progressive(const uint32_t *raw_rgba8, uint32_t *screen_rgba8, float4 *accum, const gdpt_progressive_params *params_dev,
                         int width, int height, int shard_part, int shard_parts, int shard_band, const PeerScreens &peers,
                         cudaStream_t s);
 // K3: temporal reprojection (temporal_reprojection.glsl:31-71); `history` is the frame buffer the previous dispatch wrote.
