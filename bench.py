@@ -314,7 +314,7 @@ def run_ours(args, rank, local, world):
 
     # ---- end-to-end leg: host camera block in, RGBA8 frame back in (pinned) host memory, every step.
     # (a) the reference's blocking render(): one frame at a time; (b) the pipelined form of the same call
-    # (render_begin / render_wait, two frames in flight: frame N's read-back overlaps frame N+1's kernels).
+    # (render_begin / render_wait, up to three frames in flight: read-back and the next frame's kernels overlap the tail of a frame).
     # Every step of both does its own H2D camera upload and its own full-frame D2H.
     barrier()
     sync_rays = 0
@@ -337,7 +337,7 @@ def run_ours(args, rank, local, world):
         set_index(args.warmup + 2 * args.steps + s)
         cam.render_begin()
         in_flight += 1
-        if in_flight == 2:
+        if in_flight == 3:
             img, fst = cam.render_wait()
             e2e_rays += fst["rays"]; touched += int(img[own_row, 0, 3]); in_flight -= 1
     while in_flight:
@@ -427,7 +427,7 @@ def run_ours(args, rank, local, world):
         "e2e": {"value": e2e_rays / e2e_s / 1e6, "unit": "Mrays/s", "ms_per_step": e2e_s / args.steps * 1e3,
                 "h2d_bytes_per_step": 160 + 12, "d2h_bytes_per_step": W * H * 4,
                 "api": "PathTracingCamera.render_begin()/render_wait() -> gdpt_render_frame_begin/_wait: host camera block in, "
-                       "pinned host RGBA8 frame out, every step; two frames in flight",
+                       "pinned host RGBA8 frame out, every step; three frames in flight on two streams",
                 "blocking_render": {"value": sync_rays / sync_s / 1e6, "ms_per_step": sync_s / args.steps * 1e3,
                                     "api": "PathTracingCamera.render() -> gdpt_render_frame, one frame at a time"}},
         "gpu_launches": int(launches_per_frame * args.steps * 3),  # device-timed leg + the two end-to-end legs

@@ -50,7 +50,8 @@ struct gdpt_device {
     cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
     // pipelined frames: read-backs run on their own stream; per-frame H2D blocks come from a ring
     cudaStream_t copy_stream = nullptr;
-    cudaStream_t stream2 = nullptr;     // second frame stream of overlapped pipelined frames (created on first use)
+    cudaStream_t extra_streams[GDPT_MAX_FRAMES_IN_FLIGHT - 1] = {}; // frame streams of overlapped pipelined frames besides `stream`
+    bool extra_streams_made = false;
     bool frame_overlap = true;          // GDPT_FRAME_OVERLAP=0: pipelined frames share one stream
     uint8_t *ring = nullptr;            // kRingSlots x 512 B of pinned memory
     cudaEvent_t ring_ev[8] = {};        // slot i may be rewritten once ring_ev[i] has completed
@@ -92,8 +93,8 @@ struct gdpt_shader {
         uint32_t *raw_rgba8 = nullptr; float *raw_depth = nullptr; uint32_t *hit_list = nullptr;
         bool finished_once = false;      // k_done has been recorded at least once
         uint32_t launches = 0;
-    } slots[2];
-    unsigned slot_head = 0, slot_tail = 0; // begin fills slots[head % 2], wait drains slots[tail % 2]
+    } slots[GDPT_MAX_FRAMES_IN_FLIGHT];
+    unsigned slot_head = 0, slot_tail = 0; // begin fills slots[head % N], wait drains slots[tail % N]
     bool warp_profile = false;          // per-warp schedule profile of the path kernel
     size_t warp_prof_warps = 0;
     bool stage_timing = false;          // record an event between the K1 stage launches
@@ -581,7 +582,7 @@ void gdpt_device_destroy(gdpt_device *d)
     for (int i = 0; i < 4; i++) if (d->ev[i]) cudaEventDestroy(d->ev[i]);
     if (d->pinned_staging) cudaFreeHost(d->pinned_staging);
     if (d->copy_stream) { cudaStreamSynchronize(d->copy_stream); cudaStreamDestroy(d->copy_stream); }
-    if (d->stream2) { cudaStreamSynchronize(d->stream2); cudaStreamDestroy(d->stream2); }
+    for (cudaStream_t &x : d->extra_streams) if (x) { cudaStreamSynchronize(x); cudaStreamDestroy(x); }
     if (d->ring) cudaFreeHost(d->ring);
     for (int i = 0; i < 8; i++) if (d->ring_ev[i]) cudaEventDestroy(d->ring_ev[i]);
     cudaStreamDestroy(d->stream);
@@ -592,7 +593,7 @@ int gdpt_device_synchronize(gdpt_device *d)
 {
     if (!d) return GDPT_ERR_INVALID_ARG;
     GDPT_CUDA(d, cudaStreamSynchronize(d->stream));
-    if (d->stream2) GDPT_CUDA(d, cudaStreamSynchronize(d->stream2));
+    for (cudaStream_t x : d->extra_streams) if (x) GDPT_CUDA(d, cudaStreamSynchronize(x));
     return GDPT_OK;
 }
 
@@ -650,7 +651,7 @@ void gdpt_shader_destroy(gdpt_shader *s)
     gdpt_device *d = s->dev;
     cudaSetDevice(d->ordinal);
     cudaStreamSynchronize(d->stream);
-    if (d->stream2) cudaStreamSynchronize(d->stream2);
+    for (cudaStream_t x : d->extra_streams) if (x) cudaStreamSynchronize(x);
     if (d->copy_stream) cudaStreamSynchronize(d->copy_stream);
     for (void *p : s->derived) cudaFree(p);
     for (cudaEvent_t e : s->stage_ev) cudaEventDestroy(e);
@@ -831,7 +832,7 @@ int gdpt_shader_compute(gdpt_shader *s, int gx, int gy, int gz)
     if (gx != (w + 31) / 32 || gy != (h + 31) / 32 || gz != 1)
         return fail(d, GDPT_ERR_INVALID_ARG, "compute(%d,%d,%d): expected ceil(W/32) x ceil(H/32) x 1 = (%d,%d,1)", gx, gy, gz, (w + 31) / 32, (h + 31) / 32);
     int rc;
-    if (d->stream2) GDPT_CUDA(d, cudaStreamSynchronize(d->stream2)); // overlapped pipelined frames still in flight
+    for (cudaStream_t x : d->extra_streams) if (x) GDPT_CUDA(d, cudaStreamSynchronize(x)); // overlapped pipelined frames still in flight
     if (s->kind == SHADER_MAIN) {
         GDPT_CUDA(d, cudaEventRecord(d->ev[0], d->stream));
         if ((rc = enqueue_k1(s))) return rc;
@@ -858,7 +859,7 @@ static int enqueue_frame(gdpt_shader *m, gdpt_shader *p, const gdpt_camera *came
     cudaSetDevice(d->ordinal);
     // the previous frame's staging must have been consumed before we overwrite it
     GDPT_CUDA(d, cudaStreamSynchronize(d->stream));
-    if (d->stream2) GDPT_CUDA(d, cudaStreamSynchronize(d->stream2));
+    for (cudaStream_t x : d->extra_streams) if (x) GDPT_CUDA(d, cudaStreamSynchronize(x));
     uint8_t *stage = static_cast<uint8_t *>(d->pinned_staging);
     memcpy(stage, camera, sizeof(gdpt_camera));
     Resource *cam_r = bound(m, 0, 3);
@@ -1091,8 +1092,8 @@ extern "C" int gdpt_render_frame_begin(gdpt_shader *m, gdpt_shader *p, const gdp
     if (!gdpt_shader_check_ready(m)) return fail(d, GDPT_ERR_NOT_READY, "main shader is not ready");
     int rc;
     if ((rc = check_post(m, p, mode))) return rc;
-    gdpt_shader::FrameSlot &sl = m->slots[m->slot_head & 1u];
-    if (sl.pending) return fail(d, GDPT_ERR_NOT_READY, "two frames are already in flight: call gdpt_render_frame_wait first");
+    gdpt_shader::FrameSlot &sl = m->slots[m->slot_head % GDPT_MAX_FRAMES_IN_FLIGHT];
+    if (sl.pending) return fail(d, GDPT_ERR_NOT_READY, "%d frames are already in flight: call gdpt_render_frame_wait first", GDPT_MAX_FRAMES_IN_FLIGHT);
     cudaSetDevice(d->ordinal);
     if ((rc = ensure_slot(m, sl, out_depth != nullptr))) return rc;
 
@@ -1103,8 +1104,8 @@ extern "C" int gdpt_render_frame_begin(gdpt_shader *m, gdpt_shader *p, const gdp
     // k_primary_cull) is shared and read while the other frame writes it: any value is a valid hint.
     if (d->frame_overlap && mode != GDPT_DENOISE_TEMPORAL_REPROJECTION && m->args.trace == nullptr && !m->debug_steps &&
         !m->warp_profile && m->args.schedule >= 3) {
-        const unsigned idx = m->slot_head & 1u;
-        gdpt_shader::FrameSlot &other = m->slots[idx ^ 1u];
+        const unsigned idx = m->slot_head % GDPT_MAX_FRAMES_IN_FLIGHT; // every frame in flight has its own stream
+        gdpt_shader::FrameSlot &other = m->slots[(m->slot_head + GDPT_MAX_FRAMES_IN_FLIGHT - 1u) % GDPT_MAX_FRAMES_IN_FLIGHT]; // previous frame
         const size_t n = (size_t)m->args.width * m->args.height;
         if (!sl.cam_dev) {
             if ((rc = dev_alloc(m, &sl.cam_dev, 2))) return rc;
@@ -1113,9 +1114,12 @@ extern "C" int gdpt_render_frame_begin(gdpt_shader *m, gdpt_shader *p, const gdp
             if ((rc = dev_alloc(m, &sl.raw_depth, n))) return rc;
             if ((rc = dev_alloc(m, &sl.hit_list, (size_t)m->args.queue_cap + (size_t)(kCostClasses - 1) * m->args.heavy_cap))) return rc;
         }
-        if (!d->stream2) GDPT_CUDA(d, cudaStreamCreateWithFlags(&d->stream2, cudaStreamNonBlocking));
+        if (!d->extra_streams_made) {
+            for (cudaStream_t &x : d->extra_streams) GDPT_CUDA(d, cudaStreamCreateWithFlags(&x, cudaStreamNonBlocking));
+            d->extra_streams_made = true;
+        }
         cudaStream_t const main_stream = d->stream;
-        cudaStream_t const S = idx == 0 ? d->stream : d->stream2;
+        cudaStream_t const S = idx == 0 ? d->stream : d->extra_streams[idx - 1u];
         uint8_t *stage = nullptr; unsigned ring_slot = 0;
         if ((rc = ring_take(d, &stage, &ring_slot))) return rc;
         memcpy(stage, camera, sizeof(gdpt_camera));
@@ -1187,8 +1191,8 @@ extern "C" int gdpt_render_frame_begin(gdpt_shader *m, gdpt_shader *p, const gdp
     }
 
     {   // single-stream form; an overlapped frame of the other slot may still be running on the second stream
-        gdpt_shader::FrameSlot &other = m->slots[(m->slot_head & 1u) ^ 1u];
-        if (d->stream2 && other.finished_once) GDPT_CUDA(d, cudaStreamWaitEvent(d->stream, other.k_done, 0));
+        gdpt_shader::FrameSlot &other = m->slots[(m->slot_head + GDPT_MAX_FRAMES_IN_FLIGHT - 1u) % GDPT_MAX_FRAMES_IN_FLIGHT];
+        if (d->extra_streams_made && other.finished_once) GDPT_CUDA(d, cudaStreamWaitEvent(d->stream, other.k_done, 0));
     }
     // per-frame H2D blocks come from the pinned ring: nothing here waits for the GPU
     uint8_t *stage = nullptr; unsigned ring_slot = 0;
@@ -1273,7 +1277,7 @@ extern "C" int gdpt_render_frame_wait(gdpt_shader *m, gdpt_frame_stats *out_stat
 {
     if (!m || m->kind != SHADER_MAIN) return GDPT_ERR_INVALID_ARG;
     gdpt_device *d = m->dev;
-    gdpt_shader::FrameSlot &sl = m->slots[m->slot_tail & 1u];
+    gdpt_shader::FrameSlot &sl = m->slots[m->slot_tail % GDPT_MAX_FRAMES_IN_FLIGHT];
     if (!sl.pending) return fail(d, GDPT_ERR_NOT_READY, "no frame in flight");
     cudaSetDevice(d->ordinal);
     GDPT_CUDA(d, cudaEventSynchronize(sl.done));

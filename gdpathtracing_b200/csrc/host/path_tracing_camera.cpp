@@ -111,7 +111,8 @@ PathTracingCamera::~PathTracingCamera()
     delete temporal_reprojection_;
     delete cs_;
     if (output_image_) gdpt_host_free(output_image_);
-    if (pipeline_image_[1]) gdpt_host_free(pipeline_image_[1]); // [0] is output_image_
+    for (int i = 1; i < GDPT_MAX_FRAMES_IN_FLIGHT; i++) // [0] is output_image_
+        if (pipeline_image_[i]) gdpt_host_free(pipeline_image_[i]);
     if (rd_) gdpt_device_destroy(rd_);
 }
 
@@ -239,14 +240,16 @@ void PathTracingCamera::render_device_only()
 bool PathTracingCamera::render_begin()
 {
     if (cs_ == nullptr || !cs_->check_ready()) return false;
-    if (pipe_head_ - pipe_tail_ >= 2) {
-        std::fprintf(stderr, "render_begin: two frames are already in flight\n");
+    if (pipe_head_ - pipe_tail_ >= GDPT_MAX_FRAMES_IN_FLIGHT) {
+        std::fprintf(stderr, "render_begin: %d frames are already in flight\n", GDPT_MAX_FRAMES_IN_FLIGHT);
         return false;
     }
     if (!pipeline_image_[1]) {
         pipeline_image_[0] = output_image_;
-        pipeline_image_[1] = static_cast<uint8_t *>(gdpt_host_alloc((size_t)window_w_ * window_h_ * 4));
-        if (!pipeline_image_[1]) return false;
+        for (int i = 1; i < GDPT_MAX_FRAMES_IN_FLIGHT; i++) {
+            pipeline_image_[i] = static_cast<uint8_t *>(gdpt_host_alloc((size_t)window_w_ * window_h_ * 4));
+            if (!pipeline_image_[i]) return false;
+        }
     }
     camera_.set_camera_transform(global_transform_, projection_matrix_);
     camera_.frame_index++;
@@ -254,7 +257,7 @@ bool PathTracingCamera::render_begin()
     gdpt_shader *prog = advance_post(&frame_count);
     last_frame_count_ = frame_count;
     if (gdpt_render_frame_begin(cs_->handle(), prog, &camera_, (gdpt_denoising)denoising_mode_, frame_count,
-                                pipeline_image_[pipe_head_ & 1u], nullptr) != GDPT_OK) {
+                                pipeline_image_[pipe_head_ % GDPT_MAX_FRAMES_IN_FLIGHT], nullptr) != GDPT_OK) {
         std::fprintf(stderr, "render_frame_begin: %s\n", gdpt_last_error(rd_));
         return false;
     }
@@ -270,7 +273,7 @@ const uint8_t *PathTracingCamera::render_wait(gdpt_frame_stats *stats)
         pipe_tail_++;
         return nullptr;
     }
-    return pipeline_image_[pipe_tail_++ & 1u];
+    return pipeline_image_[pipe_tail_++ % GDPT_MAX_FRAMES_IN_FLIGHT];
 }
 
 void PathTracingCamera::render()

@@ -141,7 +141,7 @@ private:
     TemporalReprojection *temporal_reprojection_ = nullptr;
     GeometryGroup3D *geometry_group_ = nullptr;
     uint8_t *output_image_ = nullptr; // pinned, W*H*4
-    uint8_t *pipeline_image_[2] = { nullptr, nullptr }; // pinned targets of the frames in flight
+    uint8_t *pipeline_image_[GDPT_MAX_FRAMES_IN_FLIGHT] = {}; // pinned targets of the frames in flight
     unsigned pipe_head_ = 0, pipe_tail_ = 0;
     gdpt_render_params render_parameters_ = {};
     CameraBlock camera_;

@@ -219,13 +219,14 @@ class PathTracingCamera:
         host.gdpt_camera_render_device_only(self._h)
 
     def render_begin(self):
-        """Pipelined render(): enqueue one frame including its read-back; at most two may be in flight."""
+        """Pipelined render(): enqueue one frame including its read-back; at most MAX_FRAMES_IN_FLIGHT (3) may be
+        in flight."""
         if host.gdpt_camera_render_begin(self._h) != 1:
             raise _lib.GdptError("render_begin failed: " + (cuda.gdpt_last_error(self.device) or b"").decode())
 
     def render_wait(self):
         """Block for the oldest frame in flight.  Returns (image, stats): the image is a zero-copy view of the
-        page-locked buffer the frame was read back into, valid until two more frames have been begun."""
+        page-locked buffer the frame was read back into, valid until three more frames have been begun."""
         st = _lib.FrameStats()
         p = host.gdpt_camera_render_wait(self._h, ctypes.byref(st))
         if not p:

@@ -191,9 +191,13 @@ GDPT_API int  gdpt_device_synchronize(gdpt_device *device);
 /* Pipelined form of gdpt_render_frame: `begin` enqueues the camera upload, K1, the post process AND the
  * read-back of the finished frame into out_rgba8 / out_depth (page-locked memory from gdpt_host_alloc
  * keeps the copy asynchronous), then returns without waiting.  The read-back runs on a second stream from
- * a device-side copy of the images, so the next frame's kernels overlap it.  At most two frames may be in
- * flight; `wait` blocks until the OLDEST of them is complete in its caller buffers and reports its stats
- * (out_stats may be NULL).  Results are byte-identical to gdpt_render_frame called frame by frame. */
+ * a device-side copy of the images, so the next frame's kernels overlap it; consecutive progressive / un-denoised
+ * frames also overlap each other (two compute streams, frame-private K1 images, lists and counters; only the
+ * accumulate/tone-map steps are ordered), which fills the SMs a frame's last long paths leave idle.  At most
+ * GDPT_MAX_FRAMES_IN_FLIGHT frames may be in flight; `wait` blocks until the OLDEST of them is complete in its
+ * caller buffers and reports its stats (out_stats may be NULL).  Results are byte-identical to gdpt_render_frame
+ * called frame by frame. */
+#define GDPT_MAX_FRAMES_IN_FLIGHT 3
 struct gdpt_frame_stats;
 GDPT_API int  gdpt_render_frame_begin(gdpt_shader *main_shader, gdpt_shader *progressive,
                                  const gdpt_camera *camera, gdpt_denoising mode, uint32_t frame_count,

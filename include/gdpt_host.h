@@ -94,7 +94,7 @@ GDPT_API int   gdpt_camera_init(gdpt_camera_node *c);
 GDPT_API void  gdpt_camera_render(gdpt_camera_node *c);
 GDPT_API void  gdpt_camera_render_device_only(gdpt_camera_node *c);
 /* pipelined render(): begin returns 1 once a frame (incl. its read-back) is enqueued; wait blocks for the oldest
- * frame in flight (at most two) and returns its RGBA8 pixels in page-locked host memory (NULL: none / error). */
+ * frame in flight (at most GDPT_MAX_FRAMES_IN_FLIGHT) and returns its RGBA8 pixels in page-locked host memory (NULL: none / error). */
 GDPT_API int   gdpt_camera_render_begin(gdpt_camera_node *c);
 GDPT_API const uint8_t *gdpt_camera_render_wait(gdpt_camera_node *c, gdpt_frame_stats *stats);
 GDPT_API const uint8_t *gdpt_camera_output_image(const gdpt_camera_node *c);

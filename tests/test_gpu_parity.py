@@ -341,27 +341,27 @@ def test_storage_buffer_round_trip():
 
 @pytest.mark.gpu
 def test_pipelined_frames_equal_blocking_frames():
-    """gdpt_render_frame_begin/_wait (two frames in flight, read-back overlapped with the next frame's kernels)
-    returns the very bytes and ray counts of the blocking render(), frame after frame."""
+    """gdpt_render_frame_begin/_wait (three frames in flight on two streams, consecutive frames overlapping each other and
+    the read-back) returns the very bytes and ray counts of the blocking render(), frame after frame."""
     sc = scenes.demo_scene()
     grp = scenes.populate(sc)
     a = make_camera(sc, grp, 320, 180, 5, mode=PathTracingCamera.PROGRESSIVE_RENDERING)
     b = make_camera(sc, grp, 320, 180, 5, mode=PathTracingCamera.PROGRESSIVE_RENDERING)
     want, want_rays = [], []
-    for _ in range(5):
+    for _ in range(8):
         want.append(a.render().copy()); want_rays.append(a.stats()["rays"])
     got, got_rays = [], []
-    b.render_begin(); b.render_begin()
+    b.render_begin(); b.render_begin(); b.render_begin()
     with pytest.raises(_lib.GdptError):
-        b.render_begin()  # a third frame in flight is refused, loudly
-    for i in range(5):
+        b.render_begin()  # a fourth frame in flight is refused, loudly
+    for i in range(8):
         img, st = b.render_wait()
         got.append(img.copy()); got_rays.append(st["rays"])
-        if i + 2 < 5:
+        if i + 3 < 8:
             b.render_begin()
     with pytest.raises(_lib.GdptError):
         b.render_wait()
     assert got_rays == want_rays
-    for i in range(5):
+    for i in range(8):
         assert np.array_equal(got[i], want[i]), f"pipelined frame {i} differs"
     assert np.array_equal(b.read_image("accum").view(np.uint32), a.read_image("accum").view(np.uint32))

@@ -11,6 +11,7 @@ sys.path.insert(0, os.path.normpath(os.path.join(os.path.dirname(os.path.abspath
 from gdpathtracing_b200 import PathTracingCamera, scenes  # noqa: E402
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 300
+DEPTH = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 sc = scenes.demo_scene()
 grp = scenes.populate(sc)
 cam = PathTracingCamera()
@@ -34,7 +35,7 @@ t0 = time.perf_counter()
 for _ in range(N):
     cam.render()
 out["blocking_ms"] = (time.perf_counter() - t0) / N * 1e3
-for _ in range(2):
+for _ in range(3):
     cam.render_begin(); cam.render_wait()
 t0 = time.perf_counter()
 inflight = 0
@@ -44,7 +45,7 @@ for _ in range(N):
     cam.render_begin()
     host_begin += time.perf_counter() - a
     inflight += 1
-    if inflight == 2:
+    if inflight == DEPTH:
         a = time.perf_counter()
         cam.render_wait()
         host_wait += time.perf_counter() - a
@@ -65,7 +66,7 @@ def pipelined(tag, set_index=False, touch=False):
             cam.set_frame_index(1000 + i)
         cam.render_begin()
         inflight += 1
-        if inflight == 2:
+        if inflight == DEPTH:
             img, fst = cam.render_wait()
             if touch:
                 acc += int(img[0, 0, 3])
