@@ -326,9 +326,12 @@ def run_ours(args, rank, local, world):
     barrier()
     sync_s = time.perf_counter() - t0
 
-    for s in range(2):  # untimed: first use of the pipelined path
-        set_index(s)
-        cam.render_begin(); cam.render_wait()
+    for rep in range(2):  # untimed: first use of the pipelined path (every frame slot allocates its buffers and stream once)
+        for s in range(3):
+            set_index(3 * rep + s)
+            cam.render_begin()
+        for s in range(3):
+            cam.render_wait()
     barrier()
     e2e_rays, in_flight, touched = 0, 0, 0
     own_row = rank * args.band if rows_mode else 0  # a row this rank renders (row bands: rank r owns rows r*band ..)

@@ -335,6 +335,8 @@ int finish_main(gdpt_shader *s)
     if (const char *e = getenv("GDPT_BLOCKS_PER_SM")) a.blocks_per_sm = atoi(e);
     a.path_minb = 1; // 1: compact loop (default); 4/5/6/8: the first-generation loop at that occupancy; 2: compact, 6 blocks/SM
     if (const char *e = getenv("GDPT_PATH_MINB")) a.path_minb = atoi(e);
+    a.cost_ema = 1;
+    if (const char *e = getenv("GDPT_COST_EMA")) a.cost_ema = atoi(e);
     a.pool_alive = 0;
     if (const char *e = getenv("GDPT_POOL_ALIVE")) a.pool_alive = atoi(e);
     a.pool_wait = 32;

@@ -1103,7 +1103,14 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_pool(const FrameAr
                     }
                     if (!alive) {
                         a.out_rgba8[pixel] = pack_rgba8(radiance);
-                        a.cost[pixel] = PF(PF_STEPS, sl);
+                        // scheduling hint for the next frame: running mean of the path's cost at this pixel (a single
+                        // frame's cost is one random walk; the mean says what the pixel usually sees)
+                        if (a.cost_ema) {
+                            const uint32_t old = a.cost[pixel];
+                            a.cost[pixel] = old ? (old * 3u + PF(PF_STEPS, sl) + 2u) >> 2 : PF(PF_STEPS, sl);
+                        } else {
+                            a.cost[pixel] = PF(PF_STEPS, sl);
+                        }
                         dead = true;
                     }
                 }
