@@ -255,6 +255,29 @@ def test_full_size_demo_frame_sampled_against_oracle():
     assert np.array_equal(cam.render(), a), "same frame_index must reproduce the same bytes"
 
 
+@pytest.mark.parametrize("name,make,W,H,depth,row_step", [
+    ("C3_soup_1M", lambda: scenes.triangle_soup(1_000_000), 1920, 1080, 2, 120),
+    ("C4_instanced_10M_4K", lambda: scenes.instanced_grid(), 3840, 2160, 8, 240),
+], ids=["C3_soup_1M", "C4_instanced_10M_4K"])
+def test_full_size_stress_configs_sampled_against_oracle(name, make, W, H, depth, row_step):
+    """BASELINE configs C3 (1 M-triangle soup, 1080p) and C4 (10 M instanced triangles, 4K, depth 8) at full size: the rows
+    the oracle renders (every row_step-th) are bit-identical in the GPU frame and depth image, two frames in a row
+    (the second one scheduled by the cost classes of the first)."""
+    sc = make()
+    grp = scenes.populate(sc)
+    cam = make_camera(sc, grp, W, H, depth)
+    osc = oracle_scene(grp)
+    for frame in range(2):
+        img = cam.render().copy()
+        dep = cam.read_image("depth")
+        ref = oracle.path_trace(osc, W, H, bytes(cam.camera_block()), max_depth=depth, row_step=row_step)
+        rows = np.arange(0, H, row_step)
+        assert np.array_equal(img[rows], ref["rgba8"][rows]), f"{name} frame {frame}: sampled rows differ"
+        assert np.array_equal(dep[rows].view(np.uint32), ref["depth"][rows].view(np.uint32)), f"{name} frame {frame}: depth differs"
+        assert ref["rgba8"][rows].any()
+    assert cam.stats()["rays"] >= W * H
+
+
 def test_row_sharding_reassembles_the_unsharded_frame():
     """Tile/row-band sharding (multi-GPU partition) is exact: the union of the parts' rows is the full frame,
     rows outside a part are untouched, ray counts add up."""
