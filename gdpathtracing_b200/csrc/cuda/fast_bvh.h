@@ -39,6 +39,12 @@ struct FastLayout {
     std::vector<uint32_t> inst_root; // per instance: link of the root of its BLAS in `nodes`/`tris`
     uint32_t tlas_root_link = LINK_NONE;
     uint32_t max_depth = 0;          // deepest root-to-leaf chain of our trees (stack bound)
+    // four-wide form (collapse of the trees above): one table for both levels
+    std::vector<FastNode4> nodes4;
+    std::vector<uint32_t> inst_root4; // per instance: link of its BLAS root in nodes4
+    uint32_t root4 = LINK_NONE;       // TLAS root link in nodes4
+    uint32_t need4 = 0;               // stack entries the four-wide search can need
+    bool ok4 = false;
     bool ok = false;
     std::string why_not;
 };
@@ -151,6 +157,64 @@ struct Builder {
         for (int k = 0; k < 3; k++) { nd.lmin[k] = li.lo[k]; nd.lmax[k] = li.hi[k]; nd.rmin[k] = ri.lo[k]; nd.rmax[k] = ri.hi[k]; }
         nd.left = l; nd.right = r;
         return idx;
+    }
+};
+
+// Four-wide collapse: a node takes its two children and, while it has fewer than four, replaces the internal child
+// with the largest box by that child's two children.  Boxes and leaves are the two-wide tree's, so the search visits
+// the same triangles; only the number of steps (and dependent loads) per ray drops.
+struct Collapse {
+    FastLayout *o;
+    std::vector<uint32_t> done_blas; // two-wide BLAS node index -> four-wide link (0xFFFFFFFE = not yet)
+    struct Child { uint32_t link; float lo[3], hi[3]; };
+    const FastNode &node2(uint32_t link) const { return (link & LINK_TLAS) ? o->tlas[link & LINK_INDEX_MASK] : o->nodes[link & LINK_INDEX_MASK]; }
+    static bool internal(uint32_t link) { return link != LINK_NONE && (link & LINK_LEAF) == 0u; }
+    static void push2(Child *c, int &n, const FastNode &f)
+    {
+        if (f.left != LINK_NONE) { c[n].link = f.left; for (int k = 0; k < 3; k++) { c[n].lo[k] = f.lmin[k]; c[n].hi[k] = f.lmax[k]; } n++; }
+        if (f.right != LINK_NONE) { c[n].link = f.right; for (int k = 0; k < 3; k++) { c[n].lo[k] = f.rmin[k]; c[n].hi[k] = f.rmax[k]; } n++; }
+    }
+    uint32_t run(uint32_t link2, uint32_t *need)
+    {
+        *need = 0;
+        if (!internal(link2)) return link2;
+        Child c[5];
+        int n = 0;
+        push2(c, n, node2(link2));
+        while (n > 0 && n < 4) {
+            int best = -1;
+            float best_area = -1.0f;
+            for (int i = 0; i < n; i++) {
+                if (!internal(c[i].link)) continue;
+                const float x = c[i].hi[0] - c[i].lo[0], y = c[i].hi[1] - c[i].lo[1], z = c[i].hi[2] - c[i].lo[2];
+                const float area = x * y + y * z + z * x;
+                if (best < 0 || area > best_area) { best = i; best_area = area; }
+            }
+            if (best < 0) break;
+            const FastNode &f = node2(c[best].link);
+            Child pair[2];
+            int m = 0;
+            push2(pair, m, f);
+            if (m == 0) { c[best] = c[--n]; continue; }
+            c[best] = pair[0];
+            if (m == 2) c[n++] = pair[1];
+        }
+        const uint32_t idx = (uint32_t)o->nodes4.size();
+        o->nodes4.push_back(FastNode4());
+        uint32_t links[4] = { LINK_NONE, LINK_NONE, LINK_NONE, LINK_NONE }, worst = 0;
+        for (int i = 0; i < n; i++) {
+            uint32_t below = 0;
+            links[i] = run(c[i].link, &below);
+            if (below > worst) worst = below;
+        }
+        FastNode4 &nd = o->nodes4[idx];
+        std::memset(&nd, 0, sizeof(nd));
+        for (int i = 0; i < 4; i++) {
+            nd.link[i] = links[i];
+            if (i < n) { nd.lox[i] = c[i].lo[0]; nd.loy[i] = c[i].lo[1]; nd.loz[i] = c[i].lo[2]; nd.hix[i] = c[i].hi[0]; nd.hiy[i] = c[i].hi[1]; nd.hiz[i] = c[i].hi[2]; }
+        }
+        *need = (n > 0 ? (uint32_t)(n - 1) : 0u) + worst;
+        return idx | (link2 & LINK_TLAS);
     }
 };
 
@@ -269,6 +333,27 @@ inline void build_fast_layout(const gdpt_bvh_node *bvh, uint32_t n_nodes, const 
     out.tlas_root_link = lay.tlas_root_link;
     out.max_depth += tlas_depth + 2u;
     if (out.max_depth >= GDPT_FAST_MAX_DEPTH) { out.why_not = "closest-hit tree deeper than the traversal stack"; return; }
+    {   // four-wide form of every tree (before the TLAS nodes join the two-wide table: Collapse reads both)
+        fastbvh::Collapse col;
+        col.o = &out;
+        out.inst_root4.assign(n_blas, LINK_NONE);
+        std::vector<uint32_t> done(out.nodes.size(), 0xFFFFFFFEu);
+        uint32_t need_blas = 0;
+        for (uint32_t b = 0; b < n_blas; b++) {
+            const uint32_t l2 = out.inst_root[b];
+            if (!fastbvh::Collapse::internal(l2)) { out.inst_root4[b] = l2; continue; }
+            if (done[l2 & LINK_INDEX_MASK] == 0xFFFFFFFEu) {
+                uint32_t need = 0;
+                done[l2 & LINK_INDEX_MASK] = col.run(l2, &need);
+                if (need > need_blas) need_blas = need;
+            }
+            out.inst_root4[b] = done[l2 & LINK_INDEX_MASK];
+        }
+        uint32_t need_tlas = 0;
+        out.root4 = col.run(out.tlas_root_link, &need_tlas);
+        out.need4 = need_tlas + need_blas + 2u;
+        out.ok4 = out.need4 < GDPT_FAST_MAX_DEPTH && out.nodes4.size() < (size_t)LINK_INDEX_MASK;
+    }
     out.tlas_base = (uint32_t)out.nodes.size();
     out.nodes.insert(out.nodes.end(), out.tlas.begin(), out.tlas.end());
     out.ok = true;

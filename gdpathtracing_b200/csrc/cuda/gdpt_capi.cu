@@ -210,7 +210,13 @@ int build_derived_layout(gdpt_shader *s, const Resource &bvh_r, const Resource &
     s->args.sc.fast_ok = fast.ok ? 1u : 0u;
     s->fast_why_not = fast.why_not;
     if (fast.ok) {
-        for (size_t b = 0; b < lay.inst_recs.size(); b++) lay.inst_recs[b].fast_root = fast.inst_root[b];
+        for (size_t b = 0; b < lay.inst_recs.size(); b++) {
+            lay.inst_recs[b].fast_root = fast.inst_root[b];
+            std::memcpy(&lay.inst_recs[b].tight_min[3], &fast.inst_root4[b], 4); // root in the four-wide table
+        }
+        s->args.sc.fast4_ok = fast.ok4 ? 1u : 0u;
+        s->args.sc.fast4_root = fast.root4;
+        if (fast.ok4 && (rc = dev_upload(s, &s->args.sc.fast4, fast.nodes4))) return rc;
         if ((rc = dev_upload(s, &s->args.sc.fast_nodes, fast.nodes))) return rc;
         s->args.sc.fast_tlas_base = fast.tlas_base;
         if ((rc = dev_upload(s, &s->args.sc.fast_tris, fast.tris))) return rc;
@@ -335,6 +341,8 @@ int finish_main(gdpt_shader *s)
     if (const char *e = getenv("GDPT_BLOCKS_PER_SM")) a.blocks_per_sm = atoi(e);
     a.path_minb = 1; // 1: compact loop (default); 4/5/6/8: the first-generation loop at that occupancy; 2: compact, 6 blocks/SM
     if (const char *e = getenv("GDPT_PATH_MINB")) a.path_minb = atoi(e);
+    a.wide_bvh = 1;
+    if (const char *e = getenv("GDPT_WIDE_BVH")) a.wide_bvh = atoi(e);
     a.cost_ema = 1;
     if (const char *e = getenv("GDPT_COST_EMA")) a.cost_ema = atoi(e);
     a.pool_alive = 0;

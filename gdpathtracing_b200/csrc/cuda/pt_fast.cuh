@@ -68,6 +68,45 @@ template <class Stack> GDPT_HD void fast_step_node(const SceneView &sc, RayState
     }
 }
 
+GDPT_HD uint32_t fast_bits(float x)
+{
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(x);
+#else
+    uint32_t u; memcpy(&u, &x, 4); return u;
+#endif
+}
+// One internal node of the four-wide tables: four true-box tests, children visited nearest first.
+// Sort key = entry distance clamped at 0 (the origin may be inside a box) as ordered bits; misses sort last.
+template <class Stack> GDPT_HD void fast_step_node4(const SceneView &sc, RayState &r, Stack &st)
+{
+    const uint32_t idx = r.cur & LINK_INDEX_MASK;
+    const q4f lx = ldq(sc.fast4, idx * 8u + 0u), ly = ldq(sc.fast4, idx * 8u + 1u), lz = ldq(sc.fast4, idx * 8u + 2u);
+    const q4f hx = ldq(sc.fast4, idx * 8u + 3u), hy = ldq(sc.fast4, idx * 8u + 4u), hz = ldq(sc.fast4, idx * 8u + 5u);
+    const q4u lk = ldqu(sc.fast4, idx * 8u + 6u);
+    float e0, e1, e2, e3;
+    const bool h0 = fast_slab(r, lx.x, ly.x, lz.x, hx.x, hy.x, hz.x, &e0) && lk.x != LINK_NONE;
+    const bool h1 = fast_slab(r, lx.y, ly.y, lz.y, hx.y, hy.y, hz.y, &e1) && lk.y != LINK_NONE;
+    const bool h2 = fast_slab(r, lx.z, ly.z, lz.z, hx.z, hy.z, hz.z, &e2) && lk.z != LINK_NONE;
+    const bool h3 = fast_slab(r, lx.w, ly.w, lz.w, hx.w, hy.w, hz.w, &e3) && lk.w != LINK_NONE;
+    const uint32_t kMiss = 0xFFFFFFFFu;
+    uint32_t k0 = h0 ? fast_bits(max_num(e0, 0.0f)) : kMiss, k1 = h1 ? fast_bits(max_num(e1, 0.0f)) : kMiss;
+    uint32_t k2 = h2 ? fast_bits(max_num(e2, 0.0f)) : kMiss, k3 = h3 ? fast_bits(max_num(e3, 0.0f)) : kMiss;
+    uint32_t l0 = lk.x, l1 = lk.y, l2 = lk.z, l3 = lk.w;
+#define GDPT_CSWAP(ka, la, kb, lb)                                                        \
+    {                                                                                     \
+        const bool sw = kb < ka;                                                          \
+        const uint32_t tk = sw ? kb : ka, tl = sw ? lb : la;                              \
+        kb = sw ? ka : kb; lb = sw ? la : lb; ka = tk; la = tl;                           \
+    }
+    GDPT_CSWAP(k0, l0, k1, l1) GDPT_CSWAP(k2, l2, k3, l3) GDPT_CSWAP(k0, l0, k2, l2) GDPT_CSWAP(k1, l1, k3, l3) GDPT_CSWAP(k1, l1, k2, l2)
+#undef GDPT_CSWAP
+    if (k3 != kMiss) stack_push(r, st, l3); // farthest first: the nearest pushed child is popped first
+    if (k2 != kMiss) stack_push(r, st, l2);
+    if (k1 != kMiss) stack_push(r, st, l1);
+    r.cur = (k0 != kMiss) ? l0 : stack_pop(r, st);
+}
+
 // intersectTriangle (main.glsl:224-257), same operations as triangle_test_loaded; the running minimum
 // replaces hit.t, and a pair that reaches the minimum exactly is recorded instead of accepted.
 GDPT_HD void fast_triangle_test(RayState &r, const q4f a, const q4f b, const q4f c)
@@ -148,7 +187,7 @@ GDPT_HD void fast_local_ray(const q4f c0, const q4f c1, const q4f c2, const q4f 
              ((c0.z * wd.x + c1.z * wd.y) + c2.z * wd.z) + c3.z * 0.0f);
 }
 
-template <class Stack> GDPT_HD void fast_enter_instance(const SceneView &sc, RayState &r, Stack &st);
+template <bool WIDE = false, class Stack> GDPT_HD void fast_enter_instance(const SceneView &sc, RayState &r, Stack &st);
 // Space changes: back to world space after an instance and/or into the instance `cur` names.
 template <class Stack> GDPT_HD void fast_step_instance(const SceneView &sc, RayState &r, Stack &st)
 {
@@ -160,7 +199,7 @@ template <class Stack> GDPT_HD void fast_step_instance(const SceneView &sc, RayS
     fast_enter_instance(sc, r, st);
 }
 // r is in world space and r.cur names an instance: into its space (main.glsl:316-321), or past it if its true box is missed
-template <class Stack> GDPT_HD void fast_enter_instance(const SceneView &sc, RayState &r, Stack &st)
+template <bool WIDE, class Stack> GDPT_HD void fast_enter_instance(const SceneView &sc, RayState &r, Stack &st)
 {
     const uint32_t idx = r.cur & LINK_INDEX_MASK;
     const q4f c0 = ldq(sc.inst_recs, idx * 7u + 0u);
@@ -175,7 +214,8 @@ template <class Stack> GDPT_HD void fast_enter_instance(const SceneView &sc, Ray
     r.inst = idx;
     float entry;
     const bool touches = fast_slab(r, tmin4.x, tmin4.y, tmin4.z, tmax4.x, tmax4.y, tmax4.z, &entry);
-    r.cur = (touches && tail.w != LINK_NONE) ? tail.w : stack_pop(r, st);
+    const uint32_t root = WIDE ? fast_bits(tmin4.w) : tail.w; // the BLAS root in the table being searched
+    r.cur = (touches && root != LINK_NONE) ? root : stack_pop(r, st);
 }
 
 GDPT_HD bool fast_link_is_leaf(uint32_t l) { return (l & (LINK_TLAS | LINK_LEAF)) == LINK_LEAF; }
@@ -191,6 +231,20 @@ template <class Stack> GDPT_HD void fast_trace_ray(const SceneView &sc, RayState
         if (fast_link_is_leaf(r.cur)) fast_step_leaf(sc, r, st);
         else if (fast_link_is_node(r.cur, r.inst)) fast_step_node(sc, r, st);
         else fast_step_instance(sc, r, st);
+    }
+}
+
+// The same search over the four-wide tables (sc.fast4_ok).
+template <class Stack> GDPT_HD void fast_trace_ray4(const SceneView &sc, RayState &r, Stack &st)
+{
+    r.cur = sc.fast4_root;
+    while (r.cur != LINK_NONE) {
+        if (fast_link_is_leaf(r.cur)) fast_step_leaf(sc, r, st);
+        else if (fast_link_is_node(r.cur, r.inst)) fast_step_node4(sc, r, st);
+        else {
+            if (r.inst != GDPT_NO_INSTANCE) { r.o = r.wo; r.d = r.wd; r.rd = rcp3(r.wd); r.inst = GDPT_NO_INSTANCE; }
+            if (r.cur & LINK_LEAF) fast_enter_instance<true>(sc, r, st);
+        }
     }
 }
 

@@ -956,7 +956,7 @@ __device__ __forceinline__ bool pool_can_cross(uint32_t cur, uint32_t pend, uint
     return cur != LINK_NONE && (cur & LINK_TLAS) != 0u && pend == LINK_NONE && ((cur & LINK_LEAF) != 0u || inst != GDPT_NO_INSTANCE);
 }
 
-template <bool REC, int MINB, int kPoolPark, int kPoolSlots>
+template <bool REC, int MINB, int kPoolPark, int kPoolSlots, bool WIDE>
 __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_pool(const FrameArgs a)
 {
     __shared__ uint32_t s_stack[kSmemStack * kTraceThreads];
@@ -1170,6 +1170,7 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_pool(const FrameAr
                     slot = (uint32_t)ready_list[ready_count - 1u - rank];
                     fast_ray_begin(r, a.sc, mk3(PFF(PF_WOX, slot), PFF(PF_WOY, slot), PFF(PF_WOZ, slot)),
                                    mk3(PFF(PF_WDX, slot), PFF(PF_WDY, slot), PFF(PF_WDZ, slot)));
+                    if (WIDE) r.cur = a.sc.fast4_root; // the four-wide tables have their own root link
                     wrd = r.rd;
                     n_park = 0;
                     steps = 0;
@@ -1190,7 +1191,7 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_pool(const FrameAr
 #pragma unroll 1
             for (int b = 0; b < a.burst; b++) { // node burst: no census while at least half of the starters stay on internal nodes
                 if (go) {
-                    fast_step_node(a.sc, r, st);
+                    if (WIDE) fast_step_node4(a.sc, r, st); else fast_step_node(a.sc, r, st);
                     steps++;
                     if (n_park < (uint32_t)kPoolPark && fast_link_is_leaf(r.cur)) { // park the leaf, keep descending
 #pragma unroll
@@ -1219,7 +1220,7 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_pool(const FrameAr
             it_t++;
             if (can_t) { // back to world space (main.glsl:316-327) and/or into the instance the link names
                 if (r.inst != GDPT_NO_INSTANCE) { r.o = r.wo; r.d = r.wd; r.rd = wrd; r.inst = GDPT_NO_INSTANCE; }
-                if (r.cur & LINK_LEAF) fast_enter_instance(a.sc, r, st);
+                if (r.cur & LINK_LEAF) fast_enter_instance<WIDE>(a.sc, r, st);
                 steps++;
             }
         }
@@ -1817,8 +1818,10 @@ void init_launch_shapes(int device)
     s.fast_blocks[0][6] = grid_of(k_path_fast<false, 6>, kTraceThreads);
     s.fast_blocks[0][8] = grid_of(k_path_fast<false, 8>, kTraceThreads);
     s.fast_blocks[1][4] = grid_of(k_path_fast<true, 4>, kTraceThreads);
-    s.pool_blocks[0][0] = grid_of(k_path_pool<false, 4, kPoolParkDefault, kPoolSlotsDefault>, kTraceThreads);
-    s.pool_blocks[1][0] = grid_of(k_path_pool<true, 4, kPoolParkDefault, kPoolSlotsDefault>, kTraceThreads);
+    s.pool_blocks[0][0] = grid_of(k_path_pool<false, 4, kPoolParkDefault, kPoolSlotsDefault, false>, kTraceThreads);
+    s.pool_blocks[0][1] = grid_of(k_path_pool<false, 4, kPoolParkDefault, kPoolSlotsDefault, true>, kTraceThreads);
+    s.pool_blocks[1][1] = grid_of(k_path_pool<true, 4, kPoolParkDefault, kPoolSlotsDefault, true>, kTraceThreads);
+    s.pool_blocks[1][0] = grid_of(k_path_pool<true, 4, kPoolParkDefault, kPoolSlotsDefault, false>, kTraceThreads);
     s.mux_blocks[1] = mux_grid<1, 8>(s.sms);
     s.mux_blocks[2] = mux_grid<2, 8>(s.sms);
     s.mux_blocks[3] = mux_grid<3, 5>(s.sms);
@@ -1944,11 +1947,14 @@ void launch_path_fast(const FrameArgs &a, bool record, cudaStream_t s)
 void launch_path_pool(const FrameArgs &a, bool record, cudaStream_t s)
 {
     Shapes &sh = shapes_for_current_device();
+    const bool wide = a.wide_bvh != 0 && a.sc.fast4_ok != 0; // four-wide tables (fast_bvh.h Collapse)
     if (record) {
-        k_path_pool<true, 4, kPoolParkDefault, kPoolSlotsDefault><<<persistent_grid(sh, a, sh.pool_blocks[1][0]), kTraceThreads, 0, s>>>(a);
+        if (wide) k_path_pool<true, 4, kPoolParkDefault, kPoolSlotsDefault, true><<<persistent_grid(sh, a, sh.pool_blocks[1][1]), kTraceThreads, 0, s>>>(a);
+        else k_path_pool<true, 4, kPoolParkDefault, kPoolSlotsDefault, false><<<persistent_grid(sh, a, sh.pool_blocks[1][0]), kTraceThreads, 0, s>>>(a);
         return;
     }
-    k_path_pool<false, 4, kPoolParkDefault, kPoolSlotsDefault><<<persistent_grid(sh, a, sh.pool_blocks[0][0]), kTraceThreads, 0, s>>>(a);
+    if (wide) k_path_pool<false, 4, kPoolParkDefault, kPoolSlotsDefault, true><<<persistent_grid(sh, a, sh.pool_blocks[0][1]), kTraceThreads, 0, s>>>(a);
+    else k_path_pool<false, 4, kPoolParkDefault, kPoolSlotsDefault, false><<<persistent_grid(sh, a, sh.pool_blocks[0][0]), kTraceThreads, 0, s>>>(a);
 }
 
 void launch_path_mux(const FrameArgs &a, cudaStream_t s)
@@ -1980,7 +1986,7 @@ size_t path_kernel_warps(const FrameArgs &a)
     Shapes &sh = shapes_for_current_device();
     if (a.schedule == 3 && (a.path_minb == 1 || a.path_minb == 2 || a.path_minb == 5 || a.path_minb == 6 || a.path_minb == 8)) return (size_t)sh.path_list_blocks_minb[a.path_minb] * (kTraceThreads / 32);
     if (a.schedule == 5) return (size_t)sh.fast_blocks[0][fast_minb(a)] * (kTraceThreads / 32);
-    if (a.schedule == 6) return (size_t)sh.pool_blocks[0][0] * (kTraceThreads / 32);
+    if (a.schedule == 6) return (size_t)sh.pool_blocks[0][(a.wide_bvh != 0 && a.sc.fast4_ok != 0) ? 1 : 0] * (kTraceThreads / 32);
     if (a.schedule == 4) return (size_t)sh.mux_blocks[(a.mux_k >= 1 && a.mux_k <= 4) ? a.mux_k : 2] * (kMuxThreads / 32);
     int most = 0;
     for (int t = 0; t < 2; t++) {

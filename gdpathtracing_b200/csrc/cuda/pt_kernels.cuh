@@ -51,6 +51,7 @@ struct FrameArgs {
     int lead_min;                            // the path with the most iterations picks the phase once it has this many
     float4 *path_recs;                       // schedule 4: 5 quads per path context
     int mux_k;                               // schedule 4: path contexts per lane (1..4)
+    int wide_bvh;                            // schedule 6: search the four-wide tables when they exist (1) or the two-wide ones (0)
     int cost_ema;                            // schedule 6: per-pixel cost hint is a running mean over frames (1) or the last frame's (0)
     int pool_alive;                          // schedule 6: cap on the paths a warp keeps alive (32..slots; 0 = all slots)
     int pool_wait;                           // schedule 6: lane-iterations finished rays may wait before a pool service (0 = off)

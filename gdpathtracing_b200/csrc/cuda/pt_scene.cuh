@@ -70,7 +70,7 @@ struct __attribute__((aligned(16))) InstRec {
     uint32_t tlas_orig;     // reference TLAS node index of this leaf
     uint32_t root_orig;     // reference BVH node index of the root
     uint32_t fast_root;     // link of this BLAS's root in the closest-hit tables (fast_bvh.h)
-    float tight_min[4];     // tight box of the whole BLAS, object space (w unused)
+    float tight_min[4];     // tight box of the whole BLAS, object space; w = bits of this BLAS's root link in the four-wide table
     float tight_max[4];
 };
 static_assert(sizeof(InstRec) == 112, "InstRec is seven 128-bit loads");
@@ -94,6 +94,14 @@ struct __attribute__((aligned(16))) FastTri {
     float v2[3]; uint32_t pad2;
 };
 static_assert(sizeof(FastTri) == 48, "FastTri is three 128-bit loads");
+// 128 B, one cache line, eight 128-bit quads: FOUR children (the two-wide tree collapsed by one level where that
+// pays, fast_bvh.h).  q0..q5 = lo.x[4] lo.y[4] lo.z[4] hi.x[4] hi.y[4] hi.z[4] (true boxes, inflated), q6 = links
+// (LINK_NONE = no child), q7 unused.  Same link encoding; TLAS-level nodes live in the same table and keep LINK_TLAS.
+struct __attribute__((aligned(128))) FastNode4 {
+    float lox[4], loy[4], loz[4], hix[4], hiy[4], hiz[4];
+    uint32_t link[4], pad[4];
+};
+static_assert(sizeof(FastNode4) == 128, "FastNode4 is one cache line");
 #define FAST_LEAF_COUNT_SHIFT 27
 #define FAST_LEAF_FIRST_MASK 0x07FFFFFFu
 #define GDPT_FAST_MAX_DEPTH 120u
@@ -121,6 +129,10 @@ struct SceneView {
     const FastTri *fast_tris;
     const uint32_t *tri_leaf;
     uint32_t fast_ok;
+    // four-wide form of the same trees (fast4_ok == 0: not built / too deep for the stack bound)
+    const FastNode4 *fast4;
+    uint32_t fast4_root;          // link the search starts from (TLAS root)
+    uint32_t fast4_ok;
 };
 
 } // namespace gdpt

@@ -40,7 +40,8 @@ template <bool CULL> static void run_ray(const SceneView &sc, RayState &r, HostS
     if (g_fast && sc.fast_ok) {
         // closest-hit search + proof; rays that fail it are re-traced in reference order (what the kernels do)
         RayState f = r;
-        fast_trace_ray(sc, f, st);
+        if (g_fast == 2 && sc.fast4_ok) fast_trace_ray4(sc, f, st); // four-wide tables
+        else fast_trace_ray(sc, f, st);
         __atomic_add_fetch(&g_fast_rays, 1, __ATOMIC_RELAXED);
         if (fast_result_is_reference(sc, f)) { r = f; return; }
         __atomic_add_fetch(&g_fast_retraced, 1, __ATOMIC_RELAXED);
@@ -71,7 +72,11 @@ static void make_view(const devcheck_scene *in, DerivedLayout &lay, FastLayout &
     if (g_fast) {
         build_fast_layout(sc.bvh, (uint32_t)in->n_nodes, sc.blas, (uint32_t)in->n_blas, sc.tlas, (uint32_t)in->n_tlas, sc.tri_geom,
                           (uint32_t)in->n_tris, lay, fast);
-        for (size_t b = 0; b < lay.inst_recs.size(); b++) lay.inst_recs[b].fast_root = fast.inst_root[b];
+        for (size_t b = 0; b < lay.inst_recs.size(); b++) {
+            lay.inst_recs[b].fast_root = fast.inst_root[b];
+            std::memcpy(&lay.inst_recs[b].tight_min[3], &fast.inst_root4[b], 4);
+        }
+        sc.fast4 = fast.nodes4.data(); sc.fast4_root = fast.root4; sc.fast4_ok = fast.ok4 ? 1u : 0u;
         sc.fast_nodes = fast.nodes.data(); sc.fast_tlas_base = fast.tlas_base; sc.fast_tris = fast.tris.data();
         sc.tri_leaf = fast.tri_leaf.data(); sc.fast_ok = fast.ok ? 1u : 0u;
         if (!fast.ok) std::fprintf(stderr, "devcheck: closest-hit tables unavailable: %s\n", fast.why_not.c_str());

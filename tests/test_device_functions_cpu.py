@@ -158,11 +158,13 @@ FAST_CASES = CASES + [
 ]
 
 
+@pytest.mark.parametrize("tables", [1, 2], ids=["two_wide", "four_wide"])
 @pytest.mark.parametrize("name,make,W,H,depth,segs,frame", FAST_CASES, ids=[c[0] for c in FAST_CASES])
-def test_closest_hit_search_with_proof_equals_reference_traversal(devcheck, name, make, W, H, depth, segs, frame):
-    """pt_fast.cuh: an order-free closest-hit search over our own BVH plus the proof that the reference
-    reaches that triangle (exact re-trace where the proof fails) returns the reference's hit records, bit for bit."""
-    devcheck.devcheck_set_fast(1)
+def test_closest_hit_search_with_proof_equals_reference_traversal(devcheck, name, make, W, H, depth, segs, frame, tables):
+    """pt_fast.cuh: an order-free closest-hit search over our own BVH (two-wide, or its four-wide collapse) plus the proof
+    that the reference reaches that triangle (exact re-trace where the proof fails) returns the reference's hit records,
+    bit for bit."""
+    devcheck.devcheck_set_fast(tables)
     try:
         sc = make()
         grp = scenes.populate(sc)
