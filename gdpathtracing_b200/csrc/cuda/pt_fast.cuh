@@ -157,6 +157,16 @@ GDPT_HD void fast_leaf_tests(const SceneView &sc, RayState &r, uint32_t leaf_lin
 #pragma unroll
     for (uint32_t i = 0; i < 4u; i++)
         if (i < count) fast_triangle_test(r, va[i], vb[i], vc[i]);
+#elif GDPT_FAST_LEAF_UNROLL == 2
+    // two triangles per trip: six loads in flight, one copy of the test in the instruction stream (called twice)
+#pragma unroll 1
+    for (uint32_t i = 0; i < count; i += 2u) {
+        const uint32_t t0 = first + i, t1 = first + (i + 1u < count ? i + 1u : i);
+        const q4f a0 = ldq(sc.fast_tris, t0 * 3u + 0u), b0 = ldq(sc.fast_tris, t0 * 3u + 1u), c0 = ldq(sc.fast_tris, t0 * 3u + 2u);
+        const q4f a1 = ldq(sc.fast_tris, t1 * 3u + 0u), b1 = ldq(sc.fast_tris, t1 * 3u + 1u), c1 = ldq(sc.fast_tris, t1 * 3u + 2u);
+        fast_triangle_test(r, a0, b0, c0);
+        if (i + 1u < count) fast_triangle_test(r, a1, b1, c1);
+    }
 #else
     // software-pipelined by one triangle: the next triangle's vertices are in flight during the current test
     q4f a = ldq(sc.fast_tris, first * 3u + 0u), b = ldq(sc.fast_tris, first * 3u + 1u), c = ldq(sc.fast_tris, first * 3u + 2u);
