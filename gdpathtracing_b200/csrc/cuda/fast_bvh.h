@@ -26,6 +26,11 @@
 #include "derived_layout.h"
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <thread>
 
 namespace gdpt {
 
@@ -39,6 +44,7 @@ struct FastLayout {
     std::vector<uint32_t> inst_root; // per instance: link of the root of its BLAS in `nodes`/`tris`
     uint32_t tlas_root_link = LINK_NONE;
     uint32_t max_depth = 0;          // deepest root-to-leaf chain of our trees (stack bound)
+    int build_threads = 0;           // input: threads of the tree build, 0 = all hardware threads (same tables for any value)
     // four-wide form (collapse of the trees above): one table for both levels
     std::vector<FastNode4> nodes4;
     std::vector<uint32_t> inst_root4; // per instance: link of its BLAS root in nodes4
@@ -68,19 +74,68 @@ inline float half_area(const TightBox &b)
     return x * y + y * z + z * x;
 }
 
+// run fn(0..parts-1) on `threads` threads (the caller is one of them); parts are claimed dynamically
+template <class Fn> inline void parallel_parts(int threads, int parts, const Fn &fn)
+{
+    if (threads <= 1 || parts <= 1) { for (int p = 0; p < parts; p++) fn(p); return; }
+    std::atomic<int> next(0);
+    auto work = [&] { for (;;) { const int p = next.fetch_add(1); if (p >= parts) break; fn(p); } };
+    std::vector<std::thread> pool;
+    const int extra = std::min(threads, parts) - 1;
+    for (int i = 0; i < extra; i++) pool.emplace_back(work);
+    work();
+    for (std::thread &t : pool) t.join();
+}
+
 struct Builder {
     const gdpt_triangle_geometry *tris;
     std::vector<Prim> prims;
     FastLayout *out;
     float owner_extent = 0.0f;
     uint32_t depth_seen = 0;
+    // multi-threaded form: ranges of at most `cut_at` primitives become tasks built into private tables, which are
+    // placed behind one another in the depth-first order the single-threaded recursion would have produced
+    enum : uint32_t { kTaskMark = 0x3F000000u }; // internal-link value space above any real node index
+    struct Task { uint32_t b, e, depth, link = 0, depth_seen = 0, node_base = 0, tri_base = 0; FastLayout part; };
+    std::vector<Task> tasks;
+    uint32_t cut_at = 0; // 0 = single-threaded
+    int threads = 1;
+    enum : uint32_t { kChunk = 16384u, kParallelFrom = 65536u };
+    // folds over a large range run in fixed chunks merged in chunk order: the same bits for any thread count
+    template <class Fn> void for_chunks(uint32_t b, uint32_t e, const Fn &fn) const
+    {
+        const int parts = (int)((e - b + kChunk - 1u) / kChunk);
+        parallel_parts(threads, parts, [&](int p) { fn(b + (uint32_t)p * kChunk, std::min(e, b + (uint32_t)(p + 1) * kChunk), p); });
+    }
+    TightBox bounds_parallel(uint32_t b, uint32_t e, bool centroids) const
+    {
+        const int parts = (int)((e - b + kChunk - 1u) / kChunk);
+        std::vector<TightBox> part((size_t)parts);
+        for_chunks(b, e, [&](uint32_t cb, uint32_t ce, int p) {
+            TightBox t = tight_empty();
+            for (uint32_t i = cb; i < ce; i++) {
+                if (centroids) tight_grow(t, prims[i].c);
+                else { tight_grow(t, prims[i].lo); tight_grow(t, prims[i].hi); }
+            }
+            part[(size_t)p] = t;
+        });
+        TightBox all = tight_empty();
+        for (const TightBox &t : part) tight_merge(all, t);
+        return all;
+    }
 
     // builds [b, e) and returns its link; *box receives the true bounds
     uint32_t build(uint32_t b, uint32_t e, uint32_t depth, TightBox *box)
     {
         if (depth > depth_seen) depth_seen = depth;
-        *box = bounds_of(prims, b, e);
         const uint32_t n = e - b;
+        const bool wide_range = threads > 1 && n >= kParallelFrom;
+        *box = wide_range ? bounds_parallel(b, e, false) : bounds_of(prims, b, e);
+        if (cut_at && n <= cut_at) { // hand the whole range to a task; its tables are placed later (place_tasks)
+            tasks.emplace_back();
+            tasks.back().b = b; tasks.back().e = e; tasks.back().depth = depth;
+            return kTaskMark | (uint32_t)(tasks.size() - 1);
+        }
         if (n <= kLeafMax) {
             const uint32_t first = (uint32_t)out->tris.size();
             for (uint32_t i = b; i < e; i++) {
@@ -95,7 +150,8 @@ struct Builder {
         }
         // binned SAH over the centroid bounds, three axes
         TightBox cb = tight_empty();
-        for (uint32_t i = b; i < e; i++) tight_grow(cb, prims[i].c);
+        if (wide_range) cb = bounds_parallel(b, e, true);
+        else for (uint32_t i = b; i < e; i++) tight_grow(cb, prims[i].c);
         int best_axis = -1, best_bin = -1;
         float best_cost = FLT_MAX;
         for (int axis = 0; axis < 3; axis++) {
@@ -105,10 +161,25 @@ struct Builder {
             uint32_t cnt[kBins];
             for (int k = 0; k < kBins; k++) { bb[k] = tight_empty(); cnt[k] = 0; }
             const float scale = (float)kBins / ext;
-            for (uint32_t i = b; i < e; i++) {
-                int k = (int)((prims[i].c[axis] - lo) * scale);
-                k = k < 0 ? 0 : (k >= kBins ? kBins - 1 : k);
-                cnt[k]++; tight_grow(bb[k], prims[i].lo); tight_grow(bb[k], prims[i].hi);
+            auto bin_range = [&](uint32_t rb, uint32_t re, TightBox *obb, uint32_t *ocnt) {
+                for (uint32_t i = rb; i < re; i++) {
+                    int k = (int)((prims[i].c[axis] - lo) * scale);
+                    k = k < 0 ? 0 : (k >= kBins ? kBins - 1 : k);
+                    ocnt[k]++; tight_grow(obb[k], prims[i].lo); tight_grow(obb[k], prims[i].hi);
+                }
+            };
+            if (wide_range) {
+                const int parts = (int)((n + kChunk - 1u) / kChunk);
+                std::vector<TightBox> pbb((size_t)parts * kBins, tight_empty());
+                std::vector<uint32_t> pcnt((size_t)parts * kBins, 0u);
+                for_chunks(b, e, [&](uint32_t rb, uint32_t re, int p) { bin_range(rb, re, &pbb[(size_t)p * kBins], &pcnt[(size_t)p * kBins]); });
+                for (int p = 0; p < parts; p++)
+                    for (int k = 0; k < kBins; k++) {
+                        if (pcnt[(size_t)p * kBins + k]) tight_merge(bb[k], pbb[(size_t)p * kBins + k]);
+                        cnt[k] += pcnt[(size_t)p * kBins + k];
+                    }
+            } else {
+                bin_range(b, e, bb, cnt);
             }
             float right_area[kBins];
             uint32_t right_cnt[kBins];
@@ -157,6 +228,73 @@ struct Builder {
         for (int k = 0; k < 3; k++) { nd.lmin[k] = li.lo[k]; nd.lmax[k] = li.hi[k]; nd.rmin[k] = ri.lo[k]; nd.rmax[k] = ri.hi[k]; }
         nd.left = l; nd.right = r;
         return idx;
+    }
+
+    // Builds the tasks on `threads` threads and splices their tables into out->nodes / out->tris.  `first_node` /
+    // `first_tri`: sizes of the shared tables when this tree's top was started.  Returns the final root link.
+    uint32_t finish_tasks(uint32_t root_link, int threads, uint32_t first_node)
+    {
+        if (tasks.empty()) return root_link;
+        parallel_parts(threads, (int)tasks.size(), [&](int k) {
+            Task &t = tasks[(size_t)k];
+            Builder sub;
+            sub.tris = tris; sub.out = &t.part; sub.owner_extent = owner_extent;
+            sub.prims.assign(prims.begin() + t.b, prims.begin() + t.e);
+            TightBox box;
+            t.link = sub.build(0, t.e - t.b, t.depth, &box);
+            t.depth_seen = sub.depth_seen;
+        });
+        // depth-first order: a top node comes before everything below it, children left to right.  Top nodes were
+        // appended to out->nodes in exactly that order, with the task blocks missing: walk the top and assign bases.
+        const std::vector<FastNode> top(out->nodes.begin() + first_node, out->nodes.end());
+        std::vector<uint32_t> top_final(top.size(), 0u);
+        uint32_t next_node = first_node, next_tri = (uint32_t)out->tris.size();
+        struct Visit { uint32_t link; };
+        std::vector<uint32_t> stack;
+        auto is_task = [](uint32_t l) { return (l & LINK_LEAF) == 0u && (l & 0x3F000000u) == 0x3F000000u && l != LINK_NONE; };
+        stack.push_back(root_link);
+        while (!stack.empty()) {
+            const uint32_t l = stack.back();
+            stack.pop_back();
+            if (is_task(l)) {
+                Task &t = tasks[l & 0x00FFFFFFu];
+                t.node_base = next_node; t.tri_base = next_tri;
+                next_node += (uint32_t)t.part.nodes.size(); next_tri += (uint32_t)t.part.tris.size();
+                if (t.depth_seen > depth_seen) depth_seen = t.depth_seen;
+            } else if ((l & LINK_LEAF) == 0u) {
+                const uint32_t ti = l - first_node;
+                top_final[ti] = next_node++;
+                stack.push_back(top[ti].right); // right below left: left is popped (numbered) first
+                stack.push_back(top[ti].left);
+            }
+        }
+        auto resolve = [&](uint32_t l) -> uint32_t {
+            if (is_task(l)) {
+                const Task &t = tasks[l & 0x00FFFFFFu];
+                return (t.link & LINK_LEAF) ? t.link + t.tri_base : t.link + t.node_base;
+            }
+            return (l & LINK_LEAF) ? l : top_final[l - first_node];
+        };
+        out->nodes.resize(next_node);
+        out->tris.resize(next_tri);
+        for (size_t i = 0; i < top.size(); i++) {
+            FastNode nd = top[i];
+            nd.left = resolve(top[i].left); nd.right = resolve(top[i].right);
+            out->nodes[top_final[i]] = nd;
+        }
+        parallel_parts(threads, (int)tasks.size(), [&](int k) {
+            const Task &t = tasks[(size_t)k];
+            for (size_t i = 0; i < t.part.nodes.size(); i++) {
+                FastNode nd = t.part.nodes[i];
+                nd.left += (nd.left & LINK_LEAF) ? t.tri_base : t.node_base;
+                nd.right += (nd.right & LINK_LEAF) ? t.tri_base : t.node_base;
+                out->nodes[t.node_base + i] = nd;
+            }
+            std::copy(t.part.tris.begin(), t.part.tris.end(), out->tris.begin() + t.tri_base);
+        });
+        const uint32_t final_root = resolve(root_link);
+        tasks.clear();
+        return final_root;
     }
 };
 
@@ -232,7 +370,16 @@ inline void build_fast_layout(const gdpt_bvh_node *bvh, uint32_t n_nodes, const 
                               const gdpt_tlas_node *tlas, uint32_t n_tlas, const gdpt_triangle_geometry *tris, uint32_t n_tris,
                               const DerivedLayout &lay, FastLayout &out)
 {
+    const bool timing = std::getenv("GDPT_BUILD_TIMING") != nullptr;
+    auto t_lap = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        const auto now = std::chrono::steady_clock::now();
+        if (timing) std::fprintf(stderr, "[fast_bvh] %-10s %.3f s\n", what, std::chrono::duration<double>(now - t_lap).count());
+        t_lap = now;
+    };
+    const int want_threads = out.build_threads;
     out = FastLayout();
+    out.build_threads = want_threads;
     out.tri_leaf.assign(n_tris, 0xFFFFFFFFu);
     out.inst_root.assign(n_blas, LINK_NONE);
     if (n_tris >= (1u << FAST_LEAF_COUNT_SHIFT)) { out.why_not = "too many triangles for the leaf link encoding"; return; }
@@ -284,12 +431,21 @@ inline void build_fast_layout(const gdpt_bvh_node *bvh, uint32_t n_nodes, const 
         }
         // the reference keeps 64 stack entries per level without a check (main.glsl:272); a tree this shallow cannot exceed them
         if (ref_depth >= 60u) { out.why_not = "reference BVH too deep to bound its stack use"; return; }
+        lap("walk");
         uint32_t link = LINK_NONE;
         if (!bld.prims.empty()) {
             const TightBox all = fastbvh::bounds_of(bld.prims, 0, (uint32_t)bld.prims.size());
             bld.owner_extent = tight_extent(all);
             TightBox box;
-            link = bld.build(0, (uint32_t)bld.prims.size(), 0, &box);
+            const int threads = out.build_threads > 0 ? out.build_threads : (int)std::min(32u, std::max(1u, std::thread::hardware_concurrency()));
+            const uint32_t count = (uint32_t)bld.prims.size();
+            bld.threads = threads;
+            if (threads > 1 && count >= 65536u) bld.cut_at = std::max(4096u, count / (uint32_t)(threads * 8));
+            const uint32_t first_node = (uint32_t)out.nodes.size();
+            link = bld.build(0, count, 0, &box);
+            lap("top");
+            link = bld.finish_tasks(link, threads, first_node);
+            lap("tasks");
             if (bld.depth_seen > out.max_depth) out.max_depth = bld.depth_seen;
         }
         root_link[root] = link;
@@ -333,6 +489,7 @@ inline void build_fast_layout(const gdpt_bvh_node *bvh, uint32_t n_nodes, const 
     out.tlas_root_link = lay.tlas_root_link;
     out.max_depth += tlas_depth + 2u;
     if (out.max_depth >= GDPT_FAST_MAX_DEPTH) { out.why_not = "closest-hit tree deeper than the traversal stack"; return; }
+    lap("tlas");
     {   // four-wide form of every tree (before the TLAS nodes join the two-wide table: Collapse reads both)
         fastbvh::Collapse col;
         col.o = &out;
@@ -354,6 +511,7 @@ inline void build_fast_layout(const gdpt_bvh_node *bvh, uint32_t n_nodes, const 
         out.need4 = need_tlas + need_blas + 2u;
         out.ok4 = out.need4 < GDPT_FAST_MAX_DEPTH && out.nodes4.size() < (size_t)LINK_INDEX_MASK;
     }
+    lap("collapse");
     out.tlas_base = (uint32_t)out.nodes.size();
     out.nodes.insert(out.nodes.end(), out.tlas.begin(), out.tlas.end());
     out.ok = true;

@@ -94,6 +94,34 @@ void devcheck_set_stepwise(int on) { g_stepwise = on; }
 // 0: reference visit order, 1: tight-box culling (hit records must not change)
 void devcheck_set_cull(int on) { g_cull = on; }
 // 1: closest-hit search + proof, exact re-trace where the proof fails (pt_fast.cuh); hit records must not change
+// FNV-1a digests of the closest-hit tables built with `threads` threads (0 = all): [0] two-wide nodes, [1] triangle
+// copies, [2] four-wide nodes, [3] roots / depths.  Returns 0 when the tables could be built.
+int devcheck_fast_layout_digest(const devcheck_scene *in, int threads, uint64_t *out4)
+{
+    DerivedLayout lay;
+    const std::string err = derive_layout((const gdpt_bvh_node *)in->bvh, (uint32_t)in->n_nodes, (const gdpt_blas_instance *)in->blas,
+                                          (uint32_t)in->n_blas, (const gdpt_tlas_node *)in->tlas, (uint32_t)in->n_tlas,
+                                          (const gdpt_triangle_geometry *)in->tri_geom, (uint32_t)in->n_tris, lay);
+    if (!err.empty()) return 1;
+    FastLayout fast;
+    fast.build_threads = threads;
+    build_fast_layout((const gdpt_bvh_node *)in->bvh, (uint32_t)in->n_nodes, (const gdpt_blas_instance *)in->blas, (uint32_t)in->n_blas,
+                      (const gdpt_tlas_node *)in->tlas, (uint32_t)in->n_tlas, (const gdpt_triangle_geometry *)in->tri_geom,
+                      (uint32_t)in->n_tris, lay, fast);
+    if (!fast.ok || !fast.ok4) return 2;
+    auto fnv = [](const void *p, size_t n) {
+        uint64_t h = 1469598103934665603ull;
+        const uint8_t *b = static_cast<const uint8_t *>(p);
+        for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 1099511628211ull; }
+        return h;
+    };
+    out4[0] = fnv(fast.nodes.data(), fast.nodes.size() * sizeof(FastNode));
+    out4[1] = fnv(fast.tris.data(), fast.tris.size() * sizeof(FastTri));
+    out4[2] = fnv(fast.nodes4.data(), fast.nodes4.size() * sizeof(FastNode4));
+    const uint64_t tail[4] = { fast.inst_root.empty() ? 0u : fast.inst_root[0], fast.root4, fast.max_depth, fast.need4 };
+    out4[3] = fnv(tail, sizeof(tail));
+    return 0;
+}
 void devcheck_set_fast(int on) { g_fast = on; g_fast_rays = g_fast_retraced = g_fast_ties = 0; }
 void devcheck_fast_counts(uint64_t *out3) { out3[0] = g_fast_rays; out3[1] = g_fast_retraced; out3[2] = g_fast_ties; }
 

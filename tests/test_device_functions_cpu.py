@@ -217,3 +217,19 @@ def test_closest_hit_search_sends_ties_to_the_exact_traversal(devcheck):
     assert counts["ties"] == int(hits.sum()) > 0
     for f in HIT_FIELDS:
         assert np.array_equal(tr[0][f][hits].view(np.uint32), ref["trace"][0][f][hits].view(np.uint32)), f
+
+
+def test_closest_hit_tables_do_not_depend_on_the_thread_count(devcheck):
+    """fast_bvh.h builds large trees with a thread-pooled top and independent subtrees placed in depth-first order:
+    one, three and all threads give byte-identical two-wide, triangle and four-wide tables."""
+    sc = scenes.triangle_soup(150_000, seed=4)
+    grp = scenes.populate(sc)
+    grp.build()
+    osc = oracle.Scene(grp.buffers(), grp.texture_layers())
+    devcheck.devcheck_fast_layout_digest.restype = ctypes.c_int
+    digests = []
+    for threads in (1, 3, 0):
+        d = np.zeros(4, np.uint64)
+        assert devcheck.devcheck_fast_layout_digest(ctypes.byref(osc.c), threads, ptr(d)) == 0
+        digests.append(d.tolist())
+    assert digests[0] == digests[1] == digests[2]
