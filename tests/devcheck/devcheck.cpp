@@ -122,6 +122,77 @@ int devcheck_fast_layout_digest(const devcheck_scene *in, int threads, uint64_t 
     out4[3] = fnv(tail, sizeof(tail));
     return 0;
 }
+// Structural check of the four-wide tables: below every BLAS root each triangle copy is reached exactly once, every
+// child box contains the vertices of all triangles below it, and the stack bound covers the deepest chain.
+// Returns 0 when all of that holds, otherwise a code (10 + kind of violation).
+int devcheck_fast4_structure(const devcheck_scene *in, uint64_t *out_stats3)
+{
+    DerivedLayout lay;
+    if (!derive_layout((const gdpt_bvh_node *)in->bvh, (uint32_t)in->n_nodes, (const gdpt_blas_instance *)in->blas, (uint32_t)in->n_blas,
+                       (const gdpt_tlas_node *)in->tlas, (uint32_t)in->n_tlas, (const gdpt_triangle_geometry *)in->tri_geom,
+                       (uint32_t)in->n_tris, lay).empty()) return 1;
+    FastLayout fast;
+    build_fast_layout((const gdpt_bvh_node *)in->bvh, (uint32_t)in->n_nodes, (const gdpt_blas_instance *)in->blas, (uint32_t)in->n_blas,
+                      (const gdpt_tlas_node *)in->tlas, (uint32_t)in->n_tlas, (const gdpt_triangle_geometry *)in->tri_geom,
+                      (uint32_t)in->n_tris, lay, fast);
+    if (!fast.ok || !fast.ok4) return 2;
+    std::vector<uint32_t> seen(fast.tris.size(), 0u);
+    std::vector<uint32_t> roots_done; // instances of one mesh share a root
+    uint64_t nodes_walked = 0, children = 0, deepest = 0;
+    struct Item { uint32_t link; float lo[3], hi[3]; bool boxed; uint32_t depth; };
+    for (uint32_t b = 0; b < (uint32_t)in->n_blas; b++) {
+        const uint32_t root = fast.inst_root4[b];
+        if (root == LINK_NONE) continue;
+        if (std::find(roots_done.begin(), roots_done.end(), root) != roots_done.end()) continue;
+        roots_done.push_back(root);
+        std::vector<Item> todo;
+        Item first; first.link = root; first.boxed = false; first.depth = 0;
+        todo.push_back(first);
+        while (!todo.empty()) {
+            const Item it = todo.back();
+            todo.pop_back();
+            if (it.depth > deepest) deepest = it.depth;
+            if (it.link & LINK_TLAS) return 11;
+            // collect the triangles below this link and check them against the box it was given
+            if (it.link & LINK_LEAF) {
+                const uint32_t f = it.link & FAST_LEAF_FIRST_MASK, n = ((it.link >> FAST_LEAF_COUNT_SHIFT) & 7u) + 1u;
+                if (n > 4u || f + n > fast.tris.size()) return 12;
+                for (uint32_t k = f; k < f + n; k++) {
+                    seen[k]++;
+                    const FastTri &t = fast.tris[k];
+                    const float *v[3] = { t.v0, t.v1, t.v2 };
+                    if (it.boxed)
+                        for (int c = 0; c < 3; c++)
+                            for (int a = 0; a < 3; a++)
+                                if (!(v[c][a] >= it.lo[a] && v[c][a] <= it.hi[a])) return 13;
+                }
+                continue;
+            }
+            const uint32_t idx = it.link & LINK_INDEX_MASK;
+            if (idx >= fast.nodes4.size()) return 14;
+            const FastNode4 &nd = fast.nodes4[idx];
+            nodes_walked++;
+            int live = 0;
+            for (int c = 0; c < 4; c++) {
+                if (nd.link[c] == LINK_NONE) continue;
+                live++; children++;
+                Item ch; ch.link = nd.link[c]; ch.boxed = true; ch.depth = it.depth + 1;
+                ch.lo[0] = nd.lox[c]; ch.lo[1] = nd.loy[c]; ch.lo[2] = nd.loz[c]; ch.hi[0] = nd.hix[c]; ch.hi[1] = nd.hiy[c]; ch.hi[2] = nd.hiz[c];
+                if (it.boxed) { // boxes are independent inflations of true bounds: triangles are checked against the
+                    // intersection of all boxes on their chain
+                    for (int a = 0; a < 3; a++) { ch.lo[a] = ch.lo[a] > it.lo[a] ? ch.lo[a] : it.lo[a]; ch.hi[a] = ch.hi[a] < it.hi[a] ? ch.hi[a] : it.hi[a]; }
+                }
+                todo.push_back(ch);
+            }
+            if (live < 2) return 15;
+        }
+    }
+    for (size_t k = 0; k < seen.size(); k++)
+        if (seen[k] != 1u) return 16;
+    if (deepest * 3u + 2u > GDPT_FAST_MAX_DEPTH + 0u && fast.need4 >= GDPT_FAST_MAX_DEPTH) return 17;
+    out_stats3[0] = nodes_walked; out_stats3[1] = children; out_stats3[2] = deepest;
+    return 0;
+}
 void devcheck_set_fast(int on) { g_fast = on; g_fast_rays = g_fast_retraced = g_fast_ties = 0; }
 void devcheck_fast_counts(uint64_t *out3) { out3[0] = g_fast_rays; out3[1] = g_fast_retraced; out3[2] = g_fast_ties; }
 

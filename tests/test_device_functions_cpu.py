@@ -233,3 +233,21 @@ def test_closest_hit_tables_do_not_depend_on_the_thread_count(devcheck):
         assert devcheck.devcheck_fast_layout_digest(ctypes.byref(osc.c), threads, ptr(d)) == 0
         digests.append(d.tolist())
     assert digests[0] == digests[1] == digests[2]
+
+
+@pytest.mark.parametrize("name,make", [(c[0], c[1]) for c in FAST_CASES], ids=[c[0] for c in FAST_CASES])
+def test_four_wide_tables_are_a_partition_with_true_boxes(devcheck, name, make):
+    """fast_bvh.h Collapse: below every BLAS root each triangle copy is reached exactly once, every triangle lies inside
+    every box on its chain (the intersection of the ancestors' boxes), nodes have two to four children."""
+    sc = make()
+    grp = scenes.populate(sc)
+    grp.build()
+    osc = oracle.Scene(grp.buffers(), grp.texture_layers())
+    st = np.zeros(3, np.uint64)
+    devcheck.devcheck_fast4_structure.restype = ctypes.c_int
+    rc = devcheck.devcheck_fast4_structure(ctypes.byref(osc.c), ptr(st))
+    assert rc == 0, f"four-wide tables violate invariant {rc}"
+    nodes_walked, children, deepest = (int(x) for x in st)
+    if nodes_walked:
+        assert children / nodes_walked > 2.5, "the collapse should fill most nodes beyond two children"
+    print(f"{name}: {nodes_walked} nodes, {children / max(nodes_walked, 1):.2f} children per node, depth {deepest}")
