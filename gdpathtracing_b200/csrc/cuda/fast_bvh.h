@@ -58,7 +58,17 @@ struct FastLayout {
 namespace fastbvh {
 
 constexpr int kBins = 16;
-constexpr uint32_t kLeafMax = 4;
+constexpr uint32_t kLeafMaxDefault = 3; // A/B on the B200 (C2 path kernel ms): 2: 0.799, 3: 0.788, 4: 0.807, 6: 0.825, 8: 0.813
+// triangles per leaf of our trees (1..8, the leaf link holds count-1 in 3 bits); GDPT_FAST_LEAF_MAX overrides for A/B runs
+inline uint32_t leaf_max()
+{
+    static const uint32_t v = [] {
+        const char *e = std::getenv("GDPT_FAST_LEAF_MAX");
+        const int n = e ? std::atoi(e) : (int)kLeafMaxDefault;
+        return (uint32_t)(n < 1 ? 1 : (n > 8 ? 8 : n));
+    }();
+    return v;
+}
 
 struct Prim { float lo[3], hi[3], c[3]; uint32_t orig; };
 
@@ -136,7 +146,7 @@ struct Builder {
             tasks.back().b = b; tasks.back().e = e; tasks.back().depth = depth;
             return kTaskMark | (uint32_t)(tasks.size() - 1);
         }
-        if (n <= kLeafMax) {
+        if (n <= leaf_max()) {
             const uint32_t first = (uint32_t)out->tris.size();
             for (uint32_t i = b; i < e; i++) {
                 FastTri t;

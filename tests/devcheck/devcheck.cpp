@@ -156,7 +156,7 @@ int devcheck_fast4_structure(const devcheck_scene *in, uint64_t *out_stats3)
             // collect the triangles below this link and check them against the box it was given
             if (it.link & LINK_LEAF) {
                 const uint32_t f = it.link & FAST_LEAF_FIRST_MASK, n = ((it.link >> FAST_LEAF_COUNT_SHIFT) & 7u) + 1u;
-                if (n > 4u || f + n > fast.tris.size()) return 12;
+                if (n > 8u || f + n > fast.tris.size()) return 12;
                 for (uint32_t k = f; k < f + n; k++) {
                     seen[k]++;
                     const FastTri &t = fast.tris[k];
