@@ -388,3 +388,51 @@ def test_pipelined_frames_equal_blocking_frames():
     for i in range(8):
         assert np.array_equal(got[i], want[i]), f"pipelined frame {i} differs"
     assert np.array_equal(b.read_image("accum").view(np.uint32), a.read_image("accum").view(np.uint32))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [PathTracingCamera.NONE, PathTracingCamera.PROGRESSIVE_RENDERING], ids=["none", "progressive"])
+def test_frames_in_flight_through_the_c_abi_with_depth_read_back(mode):
+    """gdpt_render_frame_begin / _wait called directly (the host twin never asks for depth): three overlapped frames
+    with colour AND depth read back equal the blocking frames bit for bit, and the bound images hold the last frame."""
+    from gdpathtracing_b200._lib import cuda
+    sc = scenes.demo_scene()
+    grp = scenes.populate(sc)
+    W, H, depth, frames = 320, 180, 5, 7
+    a = make_camera(sc, grp, W, H, depth, mode=mode)
+    b = make_camera(sc, grp, W, H, depth, mode=mode)
+    want = []
+    for f in range(frames):
+        img = a.render().copy()
+        want.append((img, a.read_image("depth").copy(), bytes(a.camera_block()), a.last_frame_count()))
+    b.render()  # creates the post-process shader exactly like the first frame of `a` did
+    assert np.array_equal(b.output_image(), want[0][0])
+    n = W * H
+    slots = [(cuda.gdpt_host_alloc(n * 4), cuda.gdpt_host_alloc(n * 4)) for _ in range(3)]
+    prog = b.progressive_shader if mode == PathTracingCamera.PROGRESSIVE_RENDERING else None
+    try:
+        got = []
+        def begin(f):
+            cam = _lib.Camera.from_buffer_copy(want[f][2])
+            rgba, dep = slots[f % 3]
+            _lib.check(cuda.gdpt_render_frame_begin(b.main_shader, prog, ctypes.byref(cam), mode, want[f][3], rgba, dep), b.device, "begin")
+        def wait(f):
+            st = _lib.FrameStats()
+            _lib.check(cuda.gdpt_render_frame_wait(b.main_shader, ctypes.byref(st)), b.device, "wait")
+            rgba, dep = slots[f % 3]
+            got.append((np.ctypeslib.as_array(ctypes.cast(rgba, ctypes.POINTER(ctypes.c_uint8)), (H, W, 4)).copy(),
+                        np.ctypeslib.as_array(ctypes.cast(dep, ctypes.POINTER(ctypes.c_float)), (H, W)).copy()))
+        begin(1); begin(2); begin(3)
+        for f in range(1, frames):
+            wait(f)
+            if f + 3 < frames:
+                begin(f + 3)
+        for f in range(1, frames):
+            assert np.array_equal(got[f - 1][0], want[f][0]), f"frame {f}: colour differs"
+            assert np.array_equal(got[f - 1][1].view(np.uint32), want[f][1].view(np.uint32)), f"frame {f}: depth differs"
+        assert np.array_equal(b.read_image("output"), want[-1][0])
+        assert np.array_equal(b.read_image("depth").view(np.uint32), want[-1][1].view(np.uint32))
+    finally:
+        b.synchronize()
+        for rgba, dep in slots:
+            cuda.gdpt_host_free(rgba); cuda.gdpt_host_free(dep)
