@@ -1272,6 +1272,7 @@ extern "C" int gdpt_render_frame_begin(gdpt_shader *m, gdpt_shader *p, const gdp
     down.c[0].words = (uint32_t)(sizeof(FrameCounters) / 4u);
     launch_small_copies(down, d->stream); // counters into the page-locked block the host reads after `done`
     GDPT_CUDA(d, cudaEventRecord(sl.k_done, d->stream));
+    sl.finished_once = true; // an overlapped frame that follows orders its post-process step after this one
     // the read-back leaves on the copy stream while the compute stream starts the next frame
     GDPT_CUDA(d, cudaStreamWaitEvent(d->copy_stream, sl.k_done, 0));
     GDPT_CUDA(d, cudaMemcpyAsync(out_rgba8, sl.stage_rgba8, n * 4, cudaMemcpyDeviceToHost, d->copy_stream));
