@@ -1821,6 +1821,7 @@ void init_launch_shapes(int device)
     s.pool_blocks[0][0] = grid_of(k_path_pool<false, 4, kPoolParkDefault, kPoolSlotsDefault, false>, kTraceThreads);
     s.pool_blocks[0][1] = grid_of(k_path_pool<false, 4, kPoolParkDefault, kPoolSlotsDefault, true>, kTraceThreads);
     s.pool_blocks[1][1] = grid_of(k_path_pool<true, 4, kPoolParkDefault, kPoolSlotsDefault, true>, kTraceThreads);
+    s.pool_blocks[0][2] = grid_of(k_path_pool<false, 3, kPoolParkDefault, kPoolSlotsDefault, true>, kTraceThreads);
     s.pool_blocks[1][0] = grid_of(k_path_pool<true, 4, kPoolParkDefault, kPoolSlotsDefault, false>, kTraceThreads);
     s.mux_blocks[1] = mux_grid<1, 8>(s.sms);
     s.mux_blocks[2] = mux_grid<2, 8>(s.sms);
@@ -1953,7 +1954,9 @@ void launch_path_pool(const FrameArgs &a, bool record, cudaStream_t s)
         else k_path_pool<true, 4, kPoolParkDefault, kPoolSlotsDefault, false><<<persistent_grid(sh, a, sh.pool_blocks[1][0]), kTraceThreads, 0, s>>>(a);
         return;
     }
-    if (wide) k_path_pool<false, 4, kPoolParkDefault, kPoolSlotsDefault, true><<<persistent_grid(sh, a, sh.pool_blocks[0][1]), kTraceThreads, 0, s>>>(a);
+    if (wide && a.path_minb == 3) // A/B: 3 blocks per SM, no register cap (GDPT_PATH_MINB=3)
+        k_path_pool<false, 3, kPoolParkDefault, kPoolSlotsDefault, true><<<persistent_grid(sh, a, sh.pool_blocks[0][2]), kTraceThreads, 0, s>>>(a);
+    else if (wide) k_path_pool<false, 4, kPoolParkDefault, kPoolSlotsDefault, true><<<persistent_grid(sh, a, sh.pool_blocks[0][1]), kTraceThreads, 0, s>>>(a);
     else k_path_pool<false, 4, kPoolParkDefault, kPoolSlotsDefault, false><<<persistent_grid(sh, a, sh.pool_blocks[0][0]), kTraceThreads, 0, s>>>(a);
 }
 
