@@ -1673,6 +1673,11 @@ __global__ void __launch_bounds__(256) k_progressive(const uint32_t *raw, uint32
                                                      int height, int shard_part, int shard_parts, int shard_band,
                                                      const PeerScreens peers)
 {
+    // imageLoad of an rgba8 texel = byte / 255.0f (progressive_rendering.glsl:33): every block divides each of the 256
+    // byte values once and looks the quotients up afterwards -- the same IEEE quotients, three divisions per pixel fewer
+    __shared__ float s_unorm[256];
+    s_unorm[threadIdx.x] = (float)threadIdx.x / 255.0f;
+    __syncthreads();
     const uint32_t frame_count = params->frame_count;
     const float fc = (float)frame_count;
     const size_t n_quads = ((size_t)width * height) >> 2;
@@ -1688,8 +1693,7 @@ __global__ void __launch_bounds__(256) k_progressive(const uint32_t *raw, uint32
         uint32_t out[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            f3 rad = mk3((float)(in[k] & 0xffu) / 255.0f, (float)((in[k] >> 8) & 0xffu) / 255.0f,
-                         (float)((in[k] >> 16) & 0xffu) / 255.0f);
+            f3 rad = mk3(s_unorm[in[k] & 0xffu], s_unorm[(in[k] >> 8) & 0xffu], s_unorm[(in[k] >> 16) & 0xffu]);
             if (frame_count > 1u) {
                 const float4 acc = accum[p + k];
                 rad = rad + mk3(acc.x, acc.y, acc.z);
@@ -1708,7 +1712,7 @@ __global__ void __launch_bounds__(256) k_progressive(const uint32_t *raw, uint32
         const int y = (int)(p / (size_t)width);
         if (shard_parts <= 1 || (y / shard_band) % shard_parts == shard_part) {
             const uint32_t in = raw[p];
-            f3 rad = mk3((float)(in & 0xffu) / 255.0f, (float)((in >> 8) & 0xffu) / 255.0f, (float)((in >> 16) & 0xffu) / 255.0f);
+            f3 rad = mk3(s_unorm[in & 0xffu], s_unorm[(in >> 8) & 0xffu], s_unorm[(in >> 16) & 0xffu]);
             if (frame_count > 1u) { const float4 acc = accum[p]; rad = rad + mk3(acc.x, acc.y, acc.z); }
             accum[p] = make_float4(rad.x, rad.y, rad.z, 1.0f);
             const f3 avg = (rad / fc) * 1.0f;
