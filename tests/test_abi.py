@@ -80,3 +80,21 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(root, f), errors="ignore").read()
                 assert "oracle" not in text.replace("the oracle", "").replace("an oracle", "") or f in ("pt_math.cuh",), \
                     f"{f} mentions the oracle package"
+
+
+def test_reference_arm_of_bench_runs_without_a_gpu():
+    """`bench.py --impl reference` (the oracle on host threads) is what the driver times beside our arm: it must run on
+    a machine without a GPU and print exactly one JSON line with the contract's keys."""
+    import json
+    import subprocess
+    import sys
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(repo, "bench.py"), "--impl", "reference", "--scene", "cornell32", "--width", "64",
+                          "--height", "64", "--depth", "4", "--steps", "2", "--warmup", "1"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, out.stdout
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["metric"] == "Mrays/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
