@@ -334,7 +334,19 @@ extern "C" int devcheck_path_costs(const devcheck_scene *in, const gdpt_render_p
                 TraceCounters tc;
                 counters_init(tc, nullptr, 0);
                 uint32_t tri_next = 0, tri_end = 0;
-                if (g_fast && sc.fast_ok) { // step counts of the closest-hit search (c[5] = exact re-traces)
+                if (g_fast == 2 && sc.fast4_ok) { // the same over the four-wide tables
+                    r.cur = sc.fast4_root;
+                    while (r.cur != LINK_NONE) {
+                        if (fast_link_is_leaf(r.cur)) { c[1]++; c[2] += ((r.cur >> FAST_LEAF_COUNT_SHIFT) & 7u) + 1u; fast_step_leaf(sc, r, st); }
+                        else if (fast_link_is_node(r.cur, r.inst)) { c[0]++; fast_step_node4(sc, r, st); }
+                        else {
+                            c[3]++;
+                            if (r.inst != GDPT_NO_INSTANCE) { r.o = r.wo; r.d = r.wd; r.rd = rcp3(r.wd); r.inst = GDPT_NO_INSTANCE; }
+                            if (r.cur & LINK_LEAF) fast_enter_instance<true>(sc, r, st);
+                        }
+                    }
+                    if (!fast_result_is_reference(sc, r)) { c[5]++; ray_begin(r, sc, o, d); trace_ray_compact<true, true>(sc, r, st, &tc); }
+                } else if (g_fast && sc.fast_ok) { // step counts of the closest-hit search (c[5] = exact re-traces)
                     while (r.cur != LINK_NONE) {
                         if (fast_link_is_leaf(r.cur)) { c[1]++; c[2] += ((r.cur >> FAST_LEAF_COUNT_SHIFT) & 7u) + 1u; fast_step_leaf(sc, r, st); }
                         else if (fast_link_is_node(r.cur, r.inst)) { c[0]++; fast_step_node(sc, r, st); }
