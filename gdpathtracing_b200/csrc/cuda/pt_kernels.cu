@@ -657,7 +657,7 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path(const FrameArgs a)
 // ------------------------------------------------------------------------------------------------
 // Path kernel of schedule 5: k_path's scheduler (whole paths per lane, phase census, longest path
 // first) over the closest-hit tables.  A ray is answered by the order-free search of pt_fast.cuh --
-// I: one internal node (two true-box tests, four LDG.128), L: one leaf (<= 4 triangles), T: instance
+// I: one internal node (two true-box tests, four LDG.128), L: one leaf (a few triangles), T: instance
 // entry/exit -- and, when the search ends, by the proof that the reference traversal returns the same
 // record.  The few rays without a proof (ties, hits that sit on a reference box face) are re-traced in
 // reference order by an out-of-line call, so every record equals the reference's bit for bit.
