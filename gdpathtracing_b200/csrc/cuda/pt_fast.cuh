@@ -25,6 +25,21 @@ namespace gdpt {
 #define RAY_OVERFLOW 1u /* RayState.overflow bit 0: traversal stack exceeded */
 #define RAY_TIE 2u      /* RayState.overflow bit 1: a second pair reached the current minimum t (or t was NaN) */
 
+// Stack of the search.  The trees' stack need is bounded at upload (fast_bvh.h: max_depth / need4 < GDPT_FAST_MAX_DEPTH
+// < GDPT_MAX_STACK), so no overflow test is needed here -- unlike the reference-order traversal, whose 64+64 entries
+// (main.glsl:272,307) are a property of the caller's arrays.
+template <class Stack> GDPT_HD void fast_push(RayState &r, Stack &st, uint32_t link)
+{
+    st.store(r.sp, link);
+    r.sp++;
+}
+template <class Stack> GDPT_HD uint32_t fast_pop(RayState &r, Stack &st)
+{
+    if (r.sp == 0u) return LINK_NONE;
+    r.sp--;
+    return st.load(r.sp);
+}
+
 GDPT_HD void fast_ray_begin(RayState &r, const SceneView &sc, f3 o, f3 d)
 {
     ray_begin(r, sc, o, d);
@@ -59,12 +74,12 @@ template <class Stack> GDPT_HD void fast_step_node(const SceneView &sc, RayState
     const uint32_t first = left_first ? q3.x : q3.y, second = left_first ? q3.y : q3.x;
     const bool fv = left_first ? hl : hr, sv = left_first ? hr : hl;
     if (fv) {
-        if (sv) stack_push(r, st, second);
+        if (sv) fast_push(r, st, second);
         r.cur = first;
     } else if (sv) {
         r.cur = second;
     } else {
-        r.cur = stack_pop(r, st);
+        r.cur = fast_pop(r, st);
     }
 }
 
@@ -101,10 +116,10 @@ template <class Stack> GDPT_HD void fast_step_node4(const SceneView &sc, RayStat
     }
     GDPT_CSWAP(k0, l0, k1, l1) GDPT_CSWAP(k2, l2, k3, l3) GDPT_CSWAP(k0, l0, k2, l2) GDPT_CSWAP(k1, l1, k3, l3) GDPT_CSWAP(k1, l1, k2, l2)
 #undef GDPT_CSWAP
-    if (k3 != kMiss) stack_push(r, st, l3); // farthest first: the nearest pushed child is popped first
-    if (k2 != kMiss) stack_push(r, st, l2);
-    if (k1 != kMiss) stack_push(r, st, l1);
-    r.cur = (k0 != kMiss) ? l0 : stack_pop(r, st);
+    if (k3 != kMiss) fast_push(r, st, l3); // farthest first: the nearest pushed child is popped first
+    if (k2 != kMiss) fast_push(r, st, l2);
+    if (k1 != kMiss) fast_push(r, st, l1);
+    r.cur = (k0 != kMiss) ? l0 : fast_pop(r, st);
 }
 
 // intersectTriangle (main.glsl:224-257), same operations as triangle_test_loaded; the running minimum
@@ -182,7 +197,7 @@ GDPT_HD void fast_leaf_tests(const SceneView &sc, RayState &r, uint32_t leaf_lin
 template <class Stack> GDPT_HD void fast_step_leaf(const SceneView &sc, RayState &r, Stack &st)
 {
     const uint32_t leaf = r.cur;
-    r.cur = stack_pop(r, st);
+    r.cur = fast_pop(r, st);
     fast_leaf_tests(sc, r, leaf);
 }
 
@@ -225,7 +240,7 @@ template <bool WIDE, class Stack> GDPT_HD void fast_enter_instance(const SceneVi
     float entry;
     const bool touches = fast_slab(r, tmin4.x, tmin4.y, tmin4.z, tmax4.x, tmax4.y, tmax4.z, &entry);
     const uint32_t root = WIDE ? fast_bits(tmin4.w) : tail.w; // the BLAS root in the table being searched
-    r.cur = (touches && root != LINK_NONE) ? root : stack_pop(r, st);
+    r.cur = (touches && root != LINK_NONE) ? root : fast_pop(r, st);
 }
 
 GDPT_HD bool fast_link_is_leaf(uint32_t l) { return (l & (LINK_TLAS | LINK_LEAF)) == LINK_LEAF; }

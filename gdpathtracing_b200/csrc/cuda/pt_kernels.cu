@@ -1198,7 +1198,7 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_pool(const FrameAr
                         for (int k = 0; k < kPoolPark; k++)
                             if (n_park == (uint32_t)k) park[k] = r.cur;
                         n_park++;
-                        r.cur = stack_pop(r, st);
+                        r.cur = fast_pop(r, st);
                     }
                     go = pool_can_node(r.cur, r.inst);
                 }
@@ -1212,7 +1212,7 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_pool(const FrameAr
 #pragma unroll
                     for (int k = 0; k + 1 < kPoolPark; k++) park[k] = park[k + 1];
                     n_park--;
-                } else { leaf = r.cur; r.cur = stack_pop(r, st); }
+                } else { leaf = r.cur; r.cur = fast_pop(r, st); }
                 fast_leaf_tests(a.sc, r, leaf);
                 steps++;
             }
