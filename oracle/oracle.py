@@ -3,6 +3,8 @@
   libgdpt_oracle.so        our restatement of main.glsl / brdfs.glsl / progressive_rendering.glsl
                            (oracle/pt_oracle.cpp)
   _ref/libgdpt_refbvh.so   the REFERENCE's own src/bvh/bvh.cpp compiled in place (oracle/ref_bridge.cpp)
+  _ref/libgdpt_refshader.so  the REFERENCE's own shader text compiled as C++ (oracle/ref_shader_bridge.cpp,
+                           oracle/glsl_shim/): what pins the restatement to the reference
 
 Never imported by the product package; used by tests/, smoke() and bench.py's CPU-baseline legs.
 """
@@ -15,6 +17,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_LIB = os.path.join(_HERE, "libgdpt_oracle.so")
 REF_LIB = os.path.join(_HERE, "_ref", "libgdpt_refbvh.so")
+REF_SHADER_LIB = os.path.join(_HERE, "_ref", "libgdpt_refshader.so")
 
 TRACE_DTYPE = [("hit", "<u4"), ("triangle", "<u4"), ("blas", "<u4"), ("front", "<u4"), ("t", "<f4"), ("u", "<f4"),
                ("v", "<f4"), ("node_pops", "<u4"), ("box_tests", "<u4"), ("tri_tests", "<u4"), ("tlas_leaves", "<u4"),
@@ -43,7 +46,9 @@ def lib():
         _orc = ctypes.CDLL(ORACLE_LIB)
         _orc.orc_path_trace.restype = c_int
         _orc.orc_path_trace.argtypes = [POINTER(OrcScene), c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
-                                        c_void_p, c_void_p, c_int, c_void_p, c_uint32, POINTER(OrcStats)]
+                                        c_void_p, c_void_p, c_int, c_void_p, c_uint32, POINTER(OrcStats), c_void_p]
+        _orc.orc_trace_rays.restype = None
+        _orc.orc_trace_rays.argtypes = [POINTER(OrcScene), c_uint64, c_void_p, c_void_p, c_void_p]
         _orc.orc_progressive.restype = None
         _orc.orc_progressive.argtypes = [c_void_p, c_void_p, c_int, c_int, c_uint32]
         _orc.orc_temporal.restype = None
@@ -59,6 +64,32 @@ def lib():
 
 def ref_available():
     return os.path.exists(REF_LIB)
+
+
+def ref_shader_available():
+    return os.path.exists(REF_SHADER_LIB)
+
+
+_refsh = None
+
+
+def ref_shader():
+    """The reference's shader text compiled as C++ (same entry-point shapes as the restatement's)."""
+    global _refsh
+    if _refsh is None:
+        _refsh = ctypes.CDLL(REF_SHADER_LIB)
+        _refsh.refsh_path_trace.restype = c_int
+        _refsh.refsh_path_trace.argtypes = [POINTER(OrcScene), c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                            c_void_p, c_void_p, c_int, c_void_p, c_uint32, POINTER(OrcStats), c_void_p]
+        _refsh.refsh_trace_rays.restype = None
+        _refsh.refsh_trace_rays.argtypes = [POINTER(OrcScene), c_uint64, c_void_p, c_void_p, c_void_p]
+        _refsh.refsh_progressive.restype = None
+        _refsh.refsh_progressive.argtypes = [c_void_p, c_void_p, c_int, c_int, c_uint32]
+        _refsh.refsh_temporal.restype = None
+        _refsh.refsh_temporal.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+        _refsh.refsh_prng_seed.argtypes = [c_uint32, c_uint32, c_uint32, c_void_p]
+        _refsh.refsh_pcg2d.argtypes = [c_void_p, c_void_p]
+    return _refsh
 
 
 def ref():
@@ -108,8 +139,12 @@ class Scene:
 
 
 def path_trace(scene, width, height, camera_bytes, max_depth=5, debug_steps=False, threads=None, rows=None,
-               trace_segments=0, visits_per_ray=0, row_step=1):
-    """K1 on the CPU.  Returns dict(rgba8, depth, stats, trace, visits)."""
+               trace_segments=0, visits_per_ray=0, row_step=1, radiance=False, impl="restatement"):
+    """K1 on the CPU.  Returns dict(rgba8, depth, stats, trace, visits[, radiance]).
+
+    impl="restatement": oracle/pt_oracle.cpp.  impl="reference": the reference's own main.glsl (+ brdfs.glsl)
+    compiled as C++ (oracle/_ref/libgdpt_refshader.so); its trace records leave t / u / v / front / max_stack
+    zero (use trace_rays for those)."""
     threads = threads or hardware_threads()
     params = np.zeros(9, np.uint32)
     params[4], params[5] = width, height
@@ -118,26 +153,40 @@ def path_trace(scene, width, height, camera_bytes, max_depth=5, debug_steps=Fals
     depth = np.zeros((height, width), np.float32)
     trace = np.zeros((trace_segments, height * width), dtype=TRACE_DTYPE) if trace_segments else None
     visits = np.full((height * width, visits_per_ray), 0xFFFFFFFF, np.uint32) if visits_per_ray else None
+    raw = np.zeros((height, width, 4), np.float32) if radiance else None
     st = OrcStats()
     y0, y1 = rows if rows else (0, height)
-    lib().orc_path_trace(ctypes.byref(scene.c), _p(params), _p(cam), max_depth, 1 if debug_steps else 0, threads, y0, y1, row_step,
-                         _p(out), _p(depth), _p(trace) if trace is not None else None, trace_segments,
-                         _p(visits) if visits is not None else None, visits_per_ray, ctypes.byref(st))
+    fn = lib().orc_path_trace if impl == "restatement" else ref_shader().refsh_path_trace
+    fn(ctypes.byref(scene.c), _p(params), _p(cam), max_depth, 1 if debug_steps else 0, threads, y0, y1, row_step,
+       _p(out), _p(depth), _p(trace) if trace is not None else None, trace_segments,
+       _p(visits) if visits is not None else None, visits_per_ray, ctypes.byref(st), _p(raw) if raw is not None else None)
     stats = {k: getattr(st, k) for k, _ in OrcStats._fields_}
-    return dict(rgba8=out, depth=depth, stats=stats, trace=trace, visits=visits)
+    return dict(rgba8=out, depth=depth, stats=stats, trace=trace, visits=visits, radiance=raw)
 
 
-def progressive(screen_rgba8, accum_rgba32f, frame_count):
+def trace_rays(scene, origins, directions, impl="restatement"):
+    """ray_trace_tlas (main.glsl:305-350) on the given rays; one TRACE_DTYPE record per ray."""
+    o = np.ascontiguousarray(origins, np.float32).reshape(-1, 3)
+    d = np.ascontiguousarray(directions, np.float32).reshape(-1, 3)
+    out = np.zeros(len(o), dtype=TRACE_DTYPE)
+    fn = lib().orc_trace_rays if impl == "restatement" else ref_shader().refsh_trace_rays
+    fn(ctypes.byref(scene.c), len(o), _p(o), _p(d), _p(out))
+    return out
+
+
+def progressive(screen_rgba8, accum_rgba32f, frame_count, impl="restatement"):
     h, w = screen_rgba8.shape[:2]
-    lib().orc_progressive(_p(screen_rgba8), _p(accum_rgba32f), w, h, frame_count)
+    fn = lib().orc_progressive if impl == "restatement" else ref_shader().refsh_progressive
+    fn(_p(screen_rgba8), _p(accum_rgba32f), w, h, frame_count)
 
 
-def temporal(params_bytes, screen_rgba8, depth, fb1, fb2):
+def temporal(params_bytes, screen_rgba8, depth, fb1, fb2, impl="restatement"):
     """K3 on the CPU (temporal_reprojection.glsl:31-71).  params_bytes: the 88 B Params block; screen (H, W, 4) u8
     in/out; depth (H, W) f32; fb1 / fb2 (H, W, 4) f32 ping-pong buffers, one read and the other written."""
     par = np.frombuffer(bytes(params_bytes), np.uint8).copy()
     assert par.size == 88 and depth.dtype == np.float32 and fb1.dtype == np.float32 and fb2.dtype == np.float32
-    lib().orc_temporal(_p(par), _p(screen_rgba8), _p(depth), _p(fb1), _p(fb2))
+    fn = lib().orc_temporal if impl == "restatement" else ref_shader().refsh_temporal
+    fn(_p(par), _p(screen_rgba8), _p(depth), _p(fb1), _p(fb2))
 
 
 def mat4_mul(a, b):

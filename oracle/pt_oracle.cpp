@@ -442,7 +442,7 @@ struct RenderJob {
     const gdpt_camera *cam;
     int max_depth, debug_steps;
     int y_begin, y_end, y_step;
-    uint8_t *out_rgba8; float *out_depth;
+    uint8_t *out_rgba8; float *out_depth; float *out_radiance;
     gdpt_trace_record *trace; int trace_segments;
     uint32_t *visits; uint32_t visits_per_ray;
     std::atomic<int> next_row;
@@ -539,6 +539,7 @@ static void render_rows(RenderJob *job)
             uint8_t *px = job->out_rgba8 + pix * 4;
             px[0] = to_unorm8(radiance.x); px[1] = to_unorm8(radiance.y); px[2] = to_unorm8(radiance.z); px[3] = 255;
             if (job->out_depth) job->out_depth[pix] = depth;
+            if (job->out_radiance) { float *r = job->out_radiance + pix * 4; r[0] = radiance.x; r[1] = radiance.y; r[2] = radiance.z; r[3] = 1.0f; }
         }
     }
     job->rays += rays; job->primary_hits += phits; job->node_pops += pops; job->box_tests += boxes;
@@ -568,11 +569,12 @@ typedef struct orc_stats {
 } orc_stats;
 
 // K1 on rows y_begin, y_begin + y_step, ... < y_end of the frame (y_step <= 1: every row).  trace: [trace_segments][W*H] or NULL.
-// visits: [W*H][visits_per_ray] (primary rays) or NULL.
+// visits: [W*H][visits_per_ray] (primary rays) or NULL.  out_radiance: [W*H][4] or NULL, the vec4 of main.glsl:434 before
+// the rgba8 conversion.
 int orc_path_trace(const orc_scene *scene, const gdpt_render_params *params, const gdpt_camera *camera,
                    int max_depth, int debug_steps, int n_threads, int y_begin, int y_end, int y_step,
                    uint8_t *out_rgba8, float *out_depth, gdpt_trace_record *trace, int trace_segments,
-                   uint32_t *visits, uint32_t visits_per_ray, orc_stats *stats)
+                   uint32_t *visits, uint32_t visits_per_ray, orc_stats *stats, float *out_radiance)
 {
     RenderJob job;
     job.sc.tri_geom = (const gdpt_triangle_geometry *)scene->tri_geom; job.sc.n_tris = scene->n_tris;
@@ -587,7 +589,7 @@ int orc_path_trace(const orc_scene *scene, const gdpt_render_params *params, con
     if (y_begin < 0) y_begin = 0;
     if (y_end > params->height) y_end = params->height;
     job.y_begin = y_begin; job.y_end = y_end; job.y_step = y_step < 1 ? 1 : y_step;
-    job.out_rgba8 = out_rgba8; job.out_depth = out_depth;
+    job.out_rgba8 = out_rgba8; job.out_depth = out_depth; job.out_radiance = out_radiance;
     job.trace = trace; job.trace_segments = trace_segments;
     job.visits = visits; job.visits_per_ray = visits_per_ray;
     job.next_row = y_begin;
@@ -608,6 +610,41 @@ int orc_path_trace(const orc_scene *scene, const gdpt_render_params *params, con
         stats->max_stack = job.max_stack; stats->stack_overflow = job.overflow;
     }
     return 0;
+}
+
+// ray_trace_tlas (main.glsl:305-350) on caller-given rays: HitInfo initialised as in ray_trace (main.glsl:354-356),
+// rD = 1.0 / d (main.glsl:421).  One trace record per ray.
+void orc_trace_rays(const orc_scene *scene, uint64_t n, const float *origins, const float *directions, gdpt_trace_record *out)
+{
+    Scene sc;
+    sc.tri_geom = (const gdpt_triangle_geometry *)scene->tri_geom; sc.n_tris = scene->n_tris;
+    sc.tri_data = (const gdpt_triangle_data *)scene->tri_data;
+    sc.materials = (const gdpt_material *)scene->materials; sc.n_materials = scene->n_materials;
+    sc.bvh = (const gdpt_bvh_node *)scene->bvh; sc.n_nodes = scene->n_nodes;
+    sc.blas = (const gdpt_blas_instance *)scene->blas; sc.n_blas = scene->n_blas;
+    sc.tlas = (const gdpt_tlas_node *)scene->tlas; sc.n_tlas = scene->n_tlas;
+    sc.textures = scene->textures; sc.tex_w = scene->tex_w; sc.tex_h = scene->tex_h; sc.tex_layers = scene->tex_layers;
+    for (uint64_t i = 0; i < n; i++) {
+        Ray ray;
+        ray.o = mk(origins[3 * i], origins[3 * i + 1], origins[3 * i + 2]);
+        ray.d = mk(directions[3 * i], directions[3 * i + 1], directions[3 * i + 2]);
+        ray.rD = mk(1.0f / ray.d.x, 1.0f / ray.d.y, 1.0f / ray.d.z);
+        Hit h;
+        memset(&h, 0, sizeof(h));
+        h.t = 1e9f; h.steps = 0;
+        Counters c;
+        memset(&c, 0, sizeof(c));
+        c.hash = GDPT_FNV64_OFFSET;
+        const bool hit = trace_tlas(sc, ray, h, &c);
+        gdpt_trace_record &tr = out[i];
+        memset(&tr, 0, sizeof(tr));
+        tr.hit = hit ? 1u : 0u; tr.triangle = hit ? h.triangle : 0u; tr.blas = hit ? h.blas : 0u;
+        tr.front = hit ? (h.front ? 1u : 0u) : 0u;
+        tr.t = h.t; tr.u = hit ? h.bu : 0.0f; tr.v = hit ? h.bv : 0.0f;
+        tr.node_pops = c.node_pops; tr.box_tests = c.box_tests; tr.tri_tests = h.steps;
+        tr.tlas_leaves = c.tlas_leaves; tr.max_stack = c.max_stack;
+        tr.visit_hash_lo = (uint32_t)c.hash; tr.visit_hash_hi = (uint32_t)(c.hash >> 32);
+    }
 }
 
 // K2: prog.glsl:19-46.  screen is RGBA8 in/out, accum is RGBA32F in/out.
