@@ -151,6 +151,7 @@ HOST_API = [
     ("gdpt_camera_set_cull", None, [c_void_p, c_int]),
     ("gdpt_camera_set_record_hits", None, [c_void_p, c_int]),
     ("gdpt_camera_set_variant", None, [c_void_p, c_int]),
+    ("gdpt_camera_set_tuning", None, [c_void_p, c_char_p, c_int]),
     ("gdpt_camera_set_fused_frame", None, [c_void_p, c_int]),
     ("gdpt_camera_init", c_int, [c_void_p]),
     ("gdpt_camera_render", None, [c_void_p]),

@@ -52,7 +52,7 @@ struct gdpt_device {
     cudaStream_t copy_stream = nullptr;
     cudaStream_t extra_streams[GDPT_MAX_FRAMES_IN_FLIGHT - 1] = {}; // frame streams of overlapped pipelined frames besides `stream`
     bool extra_streams_made = false;
-    bool frame_overlap = true;          // GDPT_FRAME_OVERLAP=0: pipelined frames share one stream
+    bool frame_overlap = true;          // pipelined frames run on their own streams (false: they share one)
     uint8_t *ring = nullptr;            // kRingSlots x 512 B of pinned memory
     cudaEvent_t ring_ev[8] = {};        // slot i may be rewritten once ring_ev[i] has completed
     bool ring_used[8] = {};
@@ -73,6 +73,7 @@ struct gdpt_shader {
     int variant = -1; // "#define GDPT_VARIANT n": traversal schedule, -1 = default
     int cull = -1;    // "#define GDPT_CULL n" / "#define GDPT_REFERENCE_ORDER": -1 = default
     int record_hits = 0; // "#define GDPT_RECORD_HITS n": hit records of the first n segments from the rendering kernels
+    std::map<std::string, int> tuning; // "#define GDPT_TUNE_<NAME> n": scheduling knobs of the path kernels (A/B runs)
     std::string fast_why_not; // why the closest-hit tables are not in use ("" = in use)
     // main-shader state built by finish_create_uniforms
     FrameArgs args;
@@ -123,6 +124,12 @@ int fail(gdpt_device *d, int code, const char *fmt, ...)
         if (e__ != cudaSuccess)                                                                                      \
             return fail((dev), GDPT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
     } while (0)
+
+int tune(const gdpt_shader *s, const char *name, int fallback)
+{
+    auto it = s->tuning.find(name);
+    return it == s->tuning.end() ? fallback : it->second;
+}
 
 Resource *find(gdpt_device *d, gdpt_rid rid)
 {
@@ -250,7 +257,7 @@ int ensure_slot(gdpt_shader *m, gdpt_shader::FrameSlot &sl, bool want_depth);
 int alloc_warp_profile(gdpt_shader *s)
 {
     FrameArgs &a = s->args;
-    if (a.warp_prof || a.schedule < 2) return GDPT_OK;
+    if (a.warp_prof) return GDPT_OK;
     s->warp_prof_warps = path_kernel_warps(a);
     int rc = dev_alloc(s, &a.warp_prof, s->warp_prof_warps * 8);
     if (rc) return rc;
@@ -308,49 +315,32 @@ int finish_main(gdpt_shader *s)
     a.out_rgba8 = static_cast<uint32_t *>(out->dptr);
     a.out_depth = static_cast<float *>(depth->dptr);
     a.queue_cap = (uint32_t)((size_t)rp.width * rp.height);
-    if ((rc = dev_alloc(s, &a.queue[0], (size_t)a.queue_cap * 5))) return rc;
-    if ((rc = dev_alloc(s, &a.queue[1], (size_t)a.queue_cap * 5))) return rc;
     a.heavy_cap = a.queue_cap / 4u > 1024u ? a.queue_cap / 4u : 1024u;
     if ((rc = dev_alloc(s, &a.hit_list, (size_t)a.queue_cap + (size_t)(kCostClasses - 1) * a.heavy_cap))) return rc;
     if ((rc = dev_alloc(s, &a.cost, (size_t)a.queue_cap))) return rc;
     GDPT_CUDA(d, cudaMemsetAsync(a.cost, 0, (size_t)a.queue_cap * sizeof(uint32_t), d->stream));
     if ((rc = dev_alloc(s, &a.counters, 1))) return rc;
-    a.schedule = s->variant >= 0 ? s->variant : 6;
-    if (const char *e = getenv("GDPT_SCHEDULE")) { if (s->variant < 0) a.schedule = atoi(e); }
-    if (a.schedule < 0 || a.schedule > 6) a.schedule = 6;
-    if (a.schedule >= 5 && !a.sc.fast_ok) a.schedule = 3; // closest-hit tables unavailable for these arrays (fast_bvh.h)
+    // Which kernels run is decided by the shader's own "#define" list (gdpt_shader_create) and by what the arrays
+    // allow -- never by the process environment.
+    a.schedule = (s->variant == 2 || s->variant == 3 || s->variant == 6) ? s->variant : 6;
+    if (a.schedule == 6 && !a.sc.fast_ok) a.schedule = 3; // closest-hit tables unavailable for these arrays (fast_bvh.h)
     // culling (pt_scene.cuh) is the default for rendering; parity traces and the DEBUG_STEPS heat map
     // keep the full reference visit order (their output IS the reference's work)
     const bool observes_work = s->trace_segments > 0 || s->debug_steps;
     a.cull = s->cull >= 0 ? s->cull : (observes_work ? 0 : 1);
-    if (const char *e = getenv("GDPT_CULL")) { if (s->cull < 0 && !observes_work) a.cull = atoi(e) != 0; }
     // the classification kernel is a tight-box test and writes no parity records
     if (a.schedule >= 3 && (!a.cull || observes_work)) a.schedule = 2;
-    a.mux_k = 2;
-    if (const char *e = getenv("GDPT_MUX_K")) a.mux_k = atoi(e);
-    if (a.mux_k < 1 || a.mux_k > 4) a.mux_k = 2;
     init_launch_shapes(d->ordinal);
-    if (a.schedule == 4 && (rc = dev_alloc(s, &a.path_recs, mux_path_record_quads()))) return rc;
-    a.refill_below = a.schedule == 6 ? 12 : (a.schedule >= 2 ? 24 : 20); // schedule 6: lanes without a walking ray before a pool service
-    a.burst = a.schedule == 0 ? 8 : (a.schedule == 3 ? 4 : (a.schedule >= 5 ? 8 : 16));
-    a.shade_at = a.schedule == 5 ? 16 : (a.schedule == 6 ? 24 : 8);                             // schedule 6: finished rays that justify a partial batch
-    if (const char *e = getenv("GDPT_REFILL_BELOW")) a.refill_below = atoi(e);
-    if (const char *e = getenv("GDPT_BURST")) a.burst = atoi(e);
-    if (const char *e = getenv("GDPT_SHADE_AT")) a.shade_at = atoi(e);
-    a.blocks_per_sm = 0;
-    if (const char *e = getenv("GDPT_BLOCKS_PER_SM")) a.blocks_per_sm = atoi(e);
-    a.path_minb = 1; // 1: compact loop (default); 4/5/6/8: the first-generation loop at that occupancy; 2: compact, 6 blocks/SM
-    if (const char *e = getenv("GDPT_PATH_MINB")) a.path_minb = atoi(e);
-    a.wide_bvh = 1;
-    if (const char *e = getenv("GDPT_WIDE_BVH")) a.wide_bvh = atoi(e);
-    a.cost_ema = 1;
-    if (const char *e = getenv("GDPT_COST_EMA")) a.cost_ema = atoi(e);
-    a.pool_alive = 0;
-    if (const char *e = getenv("GDPT_POOL_ALIVE")) a.pool_alive = atoi(e);
-    a.pool_wait = 32;
-    if (const char *e = getenv("GDPT_POOL_WAIT")) a.pool_wait = atoi(e);
-    a.lead_min = 0;
-    if (const char *e = getenv("GDPT_LEAD_MIN")) a.lead_min = atoi(e);
+    // scheduling knobs ("#define GDPT_TUNE_<NAME> n"; results do not depend on them)
+    a.refill_below = tune(s, "REFILL_BELOW", a.schedule == 6 ? 12 : 24); // schedule 6: lanes without a walking ray before a pool service
+    a.burst = tune(s, "BURST", a.schedule == 3 ? 4 : (a.schedule == 6 ? 8 : 16));
+    a.shade_at = tune(s, "SHADE_AT", a.schedule == 6 ? 24 : 8);          // schedule 6: finished rays that justify a partial batch
+    a.blocks_per_sm = tune(s, "BLOCKS_PER_SM", 0);
+    a.wide_bvh = tune(s, "WIDE_BVH", 1);
+    a.cost_ema = tune(s, "COST_EMA", 1);
+    a.pool_alive = tune(s, "POOL_ALIVE", 0);
+    a.pool_wait = tune(s, "POOL_WAIT", 32);
+    a.lead_min = tune(s, "LEAD_MIN", 0);
     if (a.refill_below < 1) a.refill_below = 1;
     if (a.refill_below > 32) a.refill_below = 32;
     if (a.burst < 1) a.burst = 1;
@@ -472,40 +462,19 @@ int enqueue_k1(gdpt_shader *s)
     const bool timing = s->stage_timing && !s->stage_ev.empty();
     int ev = 0;
     if (timing) GDPT_CUDA(d, cudaEventRecord(s->stage_ev[ev++], d->stream));
-    if (a.schedule >= 2) {
-        if (a.schedule >= 3) {
-            launch_primary_cull(a, d->stream);
-            if (timing) GDPT_CUDA(d, cudaEventRecord(s->stage_ev[ev++], d->stream));
-            if (a.schedule == 4) launch_path_mux(a, d->stream);
-            else if (a.schedule == 5) launch_path_fast(a, rec, d->stream);
-            else if (a.schedule == 6) launch_path_pool(a, rec, d->stream);
-            else launch_path_list(a, trace || rec, d->stream);
-        } else {
-            launch_path(a, trace, d->stream);
-        }
+    if (a.schedule >= 3) {
+        launch_primary_cull(a, d->stream);
         if (timing) GDPT_CUDA(d, cudaEventRecord(s->stage_ev[ev++], d->stream));
-        s->stage_count = timing ? ev - 1 : 0;
-        GDPT_CUDA(d, cudaGetLastError());
-        s->stats_valid = false;
-        s->stats.kernel_launches = (uint32_t)k1_launch_count(a.schedule, a.max_depth, s->debug_steps);
-        return GDPT_OK;
+        if (a.schedule == 6) launch_path_pool(a, rec, d->stream);
+        else launch_path_list(a, rec, d->stream);
+    } else {
+        launch_path(a, trace, d->stream);
     }
-    launch_primary(a, trace, d->stream);
     if (timing) GDPT_CUDA(d, cudaEventRecord(s->stage_ev[ev++], d->stream));
-    if (!s->debug_steps) {
-        for (int i = 0; i < a.max_depth; i++) {
-            launch_shade(a, i, d->stream);
-            if (timing) GDPT_CUDA(d, cudaEventRecord(s->stage_ev[ev++], d->stream));
-            if (i + 1 < a.max_depth) {
-                launch_trace(a, i + 1, trace, d->stream);
-                if (timing) GDPT_CUDA(d, cudaEventRecord(s->stage_ev[ev++], d->stream));
-            }
-        }
-    }
     s->stage_count = timing ? ev - 1 : 0;
     GDPT_CUDA(d, cudaGetLastError());
     s->stats_valid = false;
-    s->stats.kernel_launches = (uint32_t)k1_launch_count(a.schedule, a.max_depth, s->debug_steps);
+    s->stats.kernel_launches = (uint32_t)k1_launch_count(a.schedule);
     return GDPT_OK;
 }
 
@@ -530,11 +499,7 @@ int collect_stats(gdpt_shader *s)
     GDPT_CUDA(d, cudaMemcpyAsync(&c, s->args.counters, sizeof(c), cudaMemcpyDeviceToHost, d->stream));
     GDPT_CUDA(d, cudaStreamSynchronize(d->stream));
     gdpt_frame_stats &st = s->stats;
-    uint64_t rays = (uint64_t)s->args.width * s->args.local_rows;
-    if (s->args.schedule >= 2) rays = c.rays;
-    else if (!s->debug_steps)
-        for (int i = 1; i < s->args.max_depth; i++) rays += c.qcount[i];
-    st.rays = rays;
+    st.rays = c.rays;
     st.primary_hits = c.primary_hits;
     st.retraced = c.retraced;
     st.node_pops = c.node_pops; st.box_tests = c.box_tests; st.tri_tests = c.tri_tests; st.tlas_leaves = c.tlas_leaves;
@@ -563,7 +528,6 @@ int gdpt_device_create(int cuda_ordinal, gdpt_device **out_device)
     if (cuda_ordinal < 0 || cuda_ordinal >= count) return fail(nullptr, GDPT_ERR_NO_DEVICE, "CUDA ordinal %d out of range (0..%d)", cuda_ordinal, count - 1);
     gdpt_device *d = new gdpt_device();
     d->ordinal = cuda_ordinal;
-    if (const char *e = getenv("GDPT_FRAME_OVERLAP")) d->frame_overlap = atoi(e) != 0;
     if (cudaSetDevice(cuda_ordinal) != cudaSuccess || cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaHostAlloc(&d->pinned_staging, 4096, cudaHostAllocDefault) != cudaSuccess) {
         fail(nullptr, GDPT_ERR_CUDA, "device %d: stream/staging setup failed: %s", cuda_ordinal, cudaGetErrorString(cudaGetLastError()));
@@ -642,6 +606,7 @@ int gdpt_shader_create(gdpt_device *d, const char *shader_path, const char *cons
         else if (name == "GDPT_CULL" && has_value) s->cull = value != 0 ? 1 : 0;
         else if (name == "GDPT_REFERENCE_ORDER") s->cull = 0;
         else if (name == "GDPT_RECORD_HITS" && has_value) s->record_hits = (int)value;
+        else if (name.rfind("GDPT_TUNE_", 0) == 0 && has_value) s->tuning[name.substr(10)] = (int)value;
     }
     if (s->max_depth < 1 || s->max_depth > kMaxDepth) {
         delete s;
@@ -1298,11 +1263,7 @@ extern "C" int gdpt_render_frame_wait(gdpt_shader *m, gdpt_frame_stats *out_stat
     if (c.overflow) return fail(d, GDPT_ERR_UNSUPPORTED, "a ray exceeded the reference's 64+64 traversal stack entries");
     if (out_stats) {
         memset(out_stats, 0, sizeof(*out_stats));
-        uint64_t rays = (uint64_t)m->args.width * m->args.local_rows;
-        if (m->args.schedule >= 2) rays = c.rays;
-        else if (!m->debug_steps)
-            for (int i = 1; i < m->args.max_depth; i++) rays += c.qcount[i];
-        out_stats->rays = rays;
+        out_stats->rays = c.rays;
         out_stats->primary_hits = c.primary_hits;
         out_stats->retraced = c.retraced;
         out_stats->node_pops = c.node_pops; out_stats->box_tests = c.box_tests; out_stats->tri_tests = c.tri_tests;

@@ -1,0 +1,325 @@
+// k_path_pool.cuh -- path kernel of schedule 6 (part of pt_kernels.cu's translation unit): closest-hit search +
+// proof (pt_fast.cuh), paths pooled per warp in shared memory.
+#ifndef GDPT_K_PATH_POOL_CUH
+#define GDPT_K_PATH_POOL_CUH
+// (included inside namespace gdpt { namespace { ... } } of pt_kernels.cu)
+
+// ------------------------------------------------------------------------------------------------
+// Path kernel of schedule 6: k_path_fast's search (phases I / L / T over the closest-hit tables, proof,
+// exact re-trace) with the PATHS taken out of the lanes.  A warp owns a pool of kPoolSlots path slots in
+// shared memory (world ray, hit, throughput, radiance, seed, pixel, segment); a lane only ever holds the
+// traversal state of one RAY and the number of its slot.  A lane whose search ends writes the hit into
+// the slot, queues the slot for shading and takes the next ready ray, so lanes do not wait for a shading
+// quorum; shading (verdict, material, BRDF sample, continuation ray) runs when 32 finished rays wait --
+// a full warp per instruction instead of the 10-16 lanes of the quorum scheme -- and camera-ray generation
+// refills free slots up to 32 at a time.  Every number a path produces is the one k_path_fast produces:
+// the per-ray and per-path arithmetic is shared, only the lane that executes it differs.
+constexpr int kPoolSlotsDefault = 64; // path slots per warp (template argument kPoolSlots)
+constexpr int kPoolParkDefault = 1; // leaves a lane may park while it keeps descending (template argument kPoolPark)
+enum PoolField {
+    PF_WOX, PF_WOY, PF_WOZ, PF_WDX, PF_WDY, PF_WDZ,   // ray.o, ray.d (world)
+    PF_T, PF_U, PF_V, PF_TRI, PF_BF, PF_FLAGS,        // finished search
+    PF_THR, PF_THG, PF_THB, PF_RAR, PF_RAG, PF_RAB,   // throughput, radiance
+    PF_SEEDX, PF_SEEDY, PF_PIXEL, PF_SEGMENT, PF_STEPS,
+    PF_COUNT
+};
+
+// Phases of k_path_pool.  The node step never changes space: a TLAS link that comes up while the lane is inside an
+// instance is a crossing (phase T), like an instance entry, so the node-step code carries no space restore.
+__device__ __forceinline__ bool pool_can_node(uint32_t cur, uint32_t inst)
+{
+    return cur != LINK_NONE && (cur & LINK_LEAF) == 0u && ((cur & LINK_TLAS) == 0u || inst == GDPT_NO_INSTANCE);
+}
+__device__ __forceinline__ bool pool_can_cross(uint32_t cur, uint32_t pend, uint32_t inst)
+{
+    return cur != LINK_NONE && (cur & LINK_TLAS) != 0u && pend == LINK_NONE && ((cur & LINK_LEAF) != 0u || inst != GDPT_NO_INSTANCE);
+}
+
+template <bool REC, int MINB, int kPoolPark, int kPoolSlots, bool WIDE>
+__global__ void __launch_bounds__(kTraceThreads, MINB) k_path_pool(const FrameArgs a)
+{
+    __shared__ uint32_t s_stack[kSmemStack * kTraceThreads];
+    __shared__ uint32_t s_pool[kTraceThreads / 32][PF_COUNT * kPoolSlots];
+    __shared__ uint8_t s_lists[kTraceThreads / 32][3 * kPoolSlots];
+    __shared__ gdpt_camera s_cam;
+    uint32_t spill[GDPT_MAX_STACK - kSmemStack];
+    SmemStack st;
+    st.col = s_stack + threadIdx.x;
+    st.spill = spill;
+    if (threadIdx.x < sizeof(gdpt_camera) / 4u)
+        reinterpret_cast<uint32_t *>(&s_cam)[threadIdx.x] = reinterpret_cast<const uint32_t *>(a.camera)[threadIdx.x];
+    static_assert(kPoolSlots >= 32 && kPoolSlots <= 255 && kPoolSlots % 8 == 0, "pool: 32..248 slots");
+    const unsigned lane = threadIdx.x & 31u;
+    uint32_t *const pool = s_pool[threadIdx.x >> 5];
+    uint8_t *const ready_list = s_lists[threadIdx.x >> 5];
+    uint8_t *const done_list = ready_list + kPoolSlots;
+    uint8_t *const free_list = done_list + kPoolSlots;
+    for (unsigned i = lane; i < (unsigned)kPoolSlots; i += 32u) free_list[i] = (uint8_t)(kPoolSlots - 1 - i);
+    __syncthreads();
+    const gdpt_camera &cam = s_cam;
+#define PF(f, sl) pool[(f) * kPoolSlots + (sl)]
+#define PFF(f, sl) __uint_as_float(pool[(f) * kPoolSlots + (sl)])
+
+    const unsigned lanemask_lt = (1u << lane) - 1u;
+    FrameCounters *cnt = a.counters;
+    SurvivorLists lists;
+    lists.load(a);
+    const uint32_t total = lists.total;
+    const int swap_at = min(max(a.refill_below, 1), 32);   // lanes without a walking ray before the pool is serviced ...
+    const uint32_t swap_wait = a.pool_wait > 0 ? (uint32_t)a.pool_wait : 0xFFFFFFFFu; // ... or this many lane-iterations spent waiting
+    uint32_t waited = 0;
+    const uint32_t min_free = (a.pool_alive >= 32 && a.pool_alive < kPoolSlots) ? (uint32_t)(kPoolSlots - a.pool_alive) : 0u;
+    const int shade_low = min(max(a.shade_at, 1), 32);     // finished rays that justify a partial shading batch
+    bool heavy_done = false;
+    const int last_segment = a.max_depth - 1;
+
+    RayState r;
+    r.cur = LINK_NONE; r.sp = 0; r.overflow = 0; r.t = 1e9f; r.inst = GDPT_NO_INSTANCE;
+    f3 wrd = mk3(0.0f, 0.0f, 0.0f);
+    uint32_t park[kPoolPark];  // parked leaves, oldest first (instance-local: flushed before the space changes)
+    uint32_t n_park = 0;
+#pragma unroll
+    for (int k = 0; k < kPoolPark; k++) park[k] = LINK_NONE;
+    uint32_t slot = 0, steps = 0;
+    bool has = false;
+    uint32_t ready_count = 0, done_count = 0, free_count = (uint32_t)kPoolSlots; // warp-uniform
+    uint32_t chunk_next = 0, chunk_end = 0;
+    bool exhausted = (total == 0u);
+    unsigned long long my_rays = 0, my_phits = 0, my_retraced = 0;
+    uint32_t my_overflow = 0;
+    const bool prof = a.warp_prof != nullptr;
+    const unsigned long long t_start = prof ? global_ns() : 0ull;
+    uint32_t it_i = 0, it_l = 0, it_t = 0, it_f = 0, it_e = 0, n_started = 0;
+
+    for (;;) {
+        const uint32_t pend = n_park ? park[0] : LINK_NONE;
+        const bool can_i = has && pool_can_node(r.cur, r.inst);
+        const bool can_l = has && lane_can_leaf(r.cur, pend);
+        const bool can_t = has && pool_can_cross(r.cur, pend, r.inst);
+        const bool fin = has && r.cur == LINK_NONE && pend == LINK_NONE;
+        const uint32_t census = __reduce_add_sync(kFull, (can_i ? 1u : 0u) | (can_l ? 1u << 6 : 0u) | (can_t ? 1u << 12 : 0u) |
+                                                             (fin ? 1u << 18 : 0u) | (has ? 0u : 1u << 24));
+        const int n_i = (int)(census & 63u), n_l = (int)((census >> 6) & 63u), n_t = (int)((census >> 12) & 63u),
+                  n_fin = (int)((census >> 18) & 63u), n_idle = (int)(census >> 24);
+        const int n_walk = 32 - n_idle - n_fin;
+        const bool can_refill = !exhausted && free_count > min_free; // alive paths (slots in use) stay below the cap
+
+        waited += (uint32_t)n_fin;
+        if (done_count >= 32u || n_walk == 0 || n_fin >= swap_at || (n_fin > 0 && waited >= swap_wait) ||
+            (n_idle >= swap_at && (ready_count > 0u || can_refill || done_count >= (uint32_t)shade_low))) {
+            waited = 0;
+            // ---------------- pool service ----------------
+            // 1. retire: finished searches go to their slots, the slots to the shading queue
+            if (n_fin > 0) {
+                const unsigned m = __ballot_sync(kFull, fin);
+                if (fin) {
+                    PF(PF_T, slot) = __float_as_uint(r.t); PF(PF_U, slot) = __float_as_uint(r.u); PF(PF_V, slot) = __float_as_uint(r.v);
+                    PF(PF_TRI, slot) = r.tri; PF(PF_BF, slot) = r.blas_front; PF(PF_FLAGS, slot) = r.overflow;
+                    PF(PF_STEPS, slot) += steps;
+                    done_list[done_count + (uint32_t)__popc(m & lanemask_lt)] = (uint8_t)slot;
+                    has = false;
+                }
+                done_count += (uint32_t)__popc(m);
+                __syncwarp();
+            }
+            const uint32_t n_out = (uint32_t)(n_fin + n_idle); // lanes that hold no walking ray now
+            const bool shade = done_count >= 32u ||
+                               (done_count > 0u && n_out > ready_count && !can_refill && (done_count >= (uint32_t)shade_low || n_walk == 0));
+            if (shade) {
+                // 2. S: prove and shade up to 32 finished rays, oldest first
+                it_f++;
+                const uint32_t n = min(done_count, 32u);
+                const bool mine = lane < n;
+                const uint32_t sl = mine ? (uint32_t)done_list[lane] : 0u;
+                const uint32_t rest = done_count - n; // < 32
+                const uint32_t moved = lane < rest ? (uint32_t)done_list[n + lane] : 0u;
+                __syncwarp();
+                if (lane < rest) done_list[lane] = (uint8_t)moved;
+                done_count = rest;
+                bool alive = false, dead = false;
+                if (mine) {
+                    const f3 wo = mk3(PFF(PF_WOX, sl), PFF(PF_WOY, sl), PFF(PF_WOZ, sl));
+                    const f3 wd = mk3(PFF(PF_WDX, sl), PFF(PF_WDY, sl), PFF(PF_WDZ, sl));
+                    float ht = PFF(PF_T, sl), hu = PFF(PF_U, sl), hv = PFF(PF_V, sl);
+                    uint32_t htri = PF(PF_TRI, sl), hbf = PF(PF_BF, sl), hflags = PF(PF_FLAGS, sl);
+                    const uint32_t pixel = PF(PF_PIXEL, sl);
+                    const int segment = (int)PF(PF_SEGMENT, sl);
+                    if (!fast_verdict_ool(&a.sc, wo, wd, ht, htri, hbf, hflags)) {
+                        ExactHit eh; // rare: exact reference-order traversal of this ray
+                        exact_retrace(&a.sc, wo, wd, &eh);
+                        ht = eh.t; hu = eh.u; hv = eh.v; htri = eh.tri; hbf = eh.blas_front; hflags = eh.overflow & RAY_OVERFLOW;
+                        my_retraced++;
+                    }
+                    const bool hit = ht < 1e9f;
+                    my_rays++;
+                    if (segment == 0 && hit) my_phits++;
+                    if (REC) write_hit_record(a, segment, pixel, ht, hu, hv, htri, hbf);
+                    my_overflow |= hflags & RAY_OVERFLOW;
+                    f3 radiance = mk3(PFF(PF_RAR, sl), PFF(PF_RAG, sl), PFF(PF_RAB, sl));
+                    const f3 throughput = mk3(PFF(PF_THR, sl), PFF(PF_THG, sl), PFF(PF_THB, sl));
+                    if (!hit) {
+                        radiance = radiance + throughput * sample_sky(wd);
+                        if (segment == 0) a.out_depth[pixel] = encode_depth(cam, cam.z_far);
+                    } else {
+                        BounceResult br;
+                        u2 sd; sd.x = PF(PF_SEEDX, sl); sd.y = PF(PF_SEEDY, sl);
+                        shade_and_bounce_ool(&a.sc, wo, wd, ht, hu, hv, htri, hbf, radiance, throughput, &sd, &br);
+                        radiance = br.radiance;
+                        if (segment == 0) a.out_depth[pixel] = encode_depth(cam, br.first_hit_distance);
+                        alive = br.alive && segment < last_segment;
+                        if (alive) {
+                            PF(PF_SEEDX, sl) = sd.x; PF(PF_SEEDY, sl) = sd.y;
+                            PF(PF_THR, sl) = __float_as_uint(br.throughput.x); PF(PF_THG, sl) = __float_as_uint(br.throughput.y);
+                            PF(PF_THB, sl) = __float_as_uint(br.throughput.z);
+                            PF(PF_RAR, sl) = __float_as_uint(radiance.x); PF(PF_RAG, sl) = __float_as_uint(radiance.y);
+                            PF(PF_RAB, sl) = __float_as_uint(radiance.z);
+                            PF(PF_WOX, sl) = __float_as_uint(br.next_o.x); PF(PF_WOY, sl) = __float_as_uint(br.next_o.y);
+                            PF(PF_WOZ, sl) = __float_as_uint(br.next_o.z);
+                            PF(PF_WDX, sl) = __float_as_uint(br.next_d.x); PF(PF_WDY, sl) = __float_as_uint(br.next_d.y);
+                            PF(PF_WDZ, sl) = __float_as_uint(br.next_d.z);
+                            PF(PF_SEGMENT, sl) = (uint32_t)(segment + 1);
+                        }
+                    }
+                    if (!alive) {
+                        a.out_rgba8[pixel] = pack_rgba8(radiance);
+                        // scheduling hint for the next frame: running mean of the path's cost at this pixel (a single
+                        // frame's cost is one random walk; the mean says what the pixel usually sees)
+                        if (a.cost_ema) {
+                            const uint32_t old = a.cost[pixel];
+                            a.cost[pixel] = old ? (old * 3u + PF(PF_STEPS, sl) + 2u) >> 2 : PF(PF_STEPS, sl);
+                        } else {
+                            a.cost[pixel] = PF(PF_STEPS, sl);
+                        }
+                        dead = true;
+                    }
+                }
+                const unsigned m_alive = __ballot_sync(kFull, alive), m_dead = __ballot_sync(kFull, dead);
+                if (alive) ready_list[ready_count + (uint32_t)__popc(m_alive & lanemask_lt)] = (uint8_t)sl;
+                if (dead) free_list[free_count + (uint32_t)__popc(m_dead & lanemask_lt)] = (uint8_t)sl;
+                ready_count += (uint32_t)__popc(m_alive);
+                free_count += (uint32_t)__popc(m_dead);
+                __syncwarp();
+            } else if (n_out > ready_count && can_refill) {
+                // 3. R: camera rays into free slots
+                it_e++;
+                if (chunk_next == chunk_end) {
+                    uint32_t base = 0, len = kChunkPrimary;
+                    if (lane == 0) {
+                        if (!heavy_done) {
+                            base = atomicAdd(&cnt->cursor[0], kChunkHeavy);
+                            len = kChunkHeavy;
+                            if (base >= lists.heavy_total) base = 0xFFFFFFFFu;
+                            else if (base + len > lists.heavy_total) len = lists.heavy_total - base;
+                        }
+                        if (heavy_done || base == 0xFFFFFFFFu) {
+                            base = lists.heavy_total + atomicAdd(&cnt->cursor[1], kChunkPrimary);
+                            len = kChunkPrimary | 0x80000000u;
+                        }
+                    }
+                    base = __shfl_sync(kFull, base, 0);
+                    len = __shfl_sync(kFull, len, 0);
+                    if (len & 0x80000000u) { heavy_done = true; len &= 0x7FFFFFFFu; }
+                    if (base >= total) { exhausted = true; continue; }
+                    chunk_next = base;
+                    chunk_end = min(base + len, total);
+                }
+                const uint32_t g = min(min(chunk_end - chunk_next, free_count - min_free), 32u);
+                if (lane < g) {
+                    const uint32_t sl = (uint32_t)free_list[free_count - 1u - lane];
+                    const uint32_t p = lists.pixel(a, chunk_next + lane);
+                    const int py = (int)(p / (uint32_t)a.width), px = (int)(p - (uint32_t)py * (uint32_t)a.width);
+                    PrimaryRay pr;
+                    generate_primary_ray_ool(&cam, a.width, a.height, px, py, &pr);
+                    PF(PF_WOX, sl) = __float_as_uint(pr.o.x); PF(PF_WOY, sl) = __float_as_uint(pr.o.y); PF(PF_WOZ, sl) = __float_as_uint(pr.o.z);
+                    PF(PF_WDX, sl) = __float_as_uint(pr.d.x); PF(PF_WDY, sl) = __float_as_uint(pr.d.y); PF(PF_WDZ, sl) = __float_as_uint(pr.d.z);
+                    PF(PF_THR, sl) = __float_as_uint(1.0f); PF(PF_THG, sl) = __float_as_uint(1.0f); PF(PF_THB, sl) = __float_as_uint(1.0f);
+                    PF(PF_RAR, sl) = 0u; PF(PF_RAG, sl) = 0u; PF(PF_RAB, sl) = 0u;
+                    PF(PF_SEEDX, sl) = pr.seed.x; PF(PF_SEEDY, sl) = pr.seed.y;
+                    PF(PF_PIXEL, sl) = p; PF(PF_SEGMENT, sl) = 0u; PF(PF_STEPS, sl) = 0u;
+                    ready_list[ready_count + lane] = (uint8_t)sl;
+                }
+                free_count -= g; ready_count += g; chunk_next += g; n_started += g;
+                __syncwarp();
+            }
+            // 4. feed: lanes without a ray take ready slots
+            if (ready_count > 0u) {
+                const unsigned idle = __ballot_sync(kFull, !has);
+                const uint32_t rank = (uint32_t)__popc(idle & lanemask_lt);
+                if (!has && rank < ready_count) {
+                    slot = (uint32_t)ready_list[ready_count - 1u - rank];
+                    fast_ray_begin(r, a.sc, mk3(PFF(PF_WOX, slot), PFF(PF_WOY, slot), PFF(PF_WOZ, slot)),
+                                   mk3(PFF(PF_WDX, slot), PFF(PF_WDY, slot), PFF(PF_WDZ, slot)));
+                    if (WIDE) r.cur = a.sc.fast4_root; // the four-wide tables have their own root link
+                    wrd = r.rd;
+                    n_park = 0;
+                    steps = 0;
+                    has = true;
+                }
+                ready_count -= min((uint32_t)__popc(idle), ready_count);
+                __syncwarp();
+            }
+            if (exhausted && ready_count == 0u && done_count == 0u && __ballot_sync(kFull, has) == 0u) break;
+            continue;
+        }
+        // ---------------- I / L / T: the phase that advances most lanes per instruction ----------------
+        const int run = (n_i * 3 >= n_l && n_i * 3 >= n_t * 2) ? 1 : (n_l >= n_t * 2 ? 0 : 2);
+        if (run == 1) {
+            it_i++;
+            bool go = can_i;
+            const int need = (n_i + 1) >> 1;
+#pragma unroll 1
+            for (int b = 0; b < a.burst; b++) { // node burst: no census while at least half of the starters stay on internal nodes
+                if (go) {
+                    if (WIDE) fast_step_node4(a.sc, r, st); else fast_step_node(a.sc, r, st);
+                    steps++;
+                    if (n_park < (uint32_t)kPoolPark && fast_link_is_leaf(r.cur)) { // park the leaf, keep descending
+#pragma unroll
+                        for (int k = 0; k < kPoolPark; k++)
+                            if (n_park == (uint32_t)k) park[k] = r.cur;
+                        n_park++;
+                        r.cur = fast_pop(r, st);
+                    }
+                    go = pool_can_node(r.cur, r.inst);
+                }
+                if (__popc(__ballot_sync(kFull, go)) < need) break;
+            }
+        } else if (run == 0) {
+            it_l++;
+            if (can_l) {
+                uint32_t leaf = park[0];
+                if (n_park) {
+#pragma unroll
+                    for (int k = 0; k + 1 < kPoolPark; k++) park[k] = park[k + 1];
+                    n_park--;
+                } else { leaf = r.cur; r.cur = fast_pop(r, st); }
+                fast_leaf_tests(a.sc, r, leaf);
+                steps++;
+            }
+        } else {
+            it_t++;
+            if (can_t) { // back to world space (main.glsl:316-327) and/or into the instance the link names
+                if (r.inst != GDPT_NO_INSTANCE) { r.o = r.wo; r.d = r.wd; r.rd = wrd; r.inst = GDPT_NO_INSTANCE; }
+                if (r.cur & LINK_LEAF) fast_enter_instance<WIDE>(a.sc, r, st);
+                steps++;
+            }
+        }
+    }
+#undef PF
+#undef PFF
+    if (prof && lane == 0) {
+        unsigned long long *w = a.warp_prof + (size_t)((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 8u;
+        w[0] = t_start; w[1] = global_ns(); w[2] = it_i; w[3] = it_l; w[4] = it_t; w[5] = it_f; w[6] = it_e; w[7] = n_started;
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        my_rays += __shfl_down_sync(kFull, my_rays, off);
+        my_phits += __shfl_down_sync(kFull, my_phits, off);
+        my_retraced += __shfl_down_sync(kFull, my_retraced, off);
+    }
+    if (lane == 0) {
+        atomicAdd(&cnt->rays, my_rays); atomicAdd(&cnt->primary_hits, my_phits);
+        if (my_retraced) atomicAdd(&cnt->retraced, my_retraced);
+    }
+    if (my_overflow) atomicOr(&cnt->overflow, 1u);
+}
+
+#endif

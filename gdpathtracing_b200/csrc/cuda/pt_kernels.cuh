@@ -28,10 +28,6 @@ struct FrameCounters {
     unsigned long long retraced;        // schedule 5: rays re-traced in reference order (proof failed or tie)
 };
 
-// Path queue: structure-of-arrays of five 16 B planes per entry.
-//   plane 0: ray.o.xyz, pixel          plane 1: ray.d.xyz, hit t
-//   plane 2: throughput.rgb, hit u     plane 3: radiance.rgb, hit v
-//   plane 4: seed.x, seed.y, hit triangle, hit blas|front<<31
 struct FrameArgs {
     SceneView sc;
     const gdpt_camera *camera; // bound Camera storage buffer (device)
@@ -41,16 +37,12 @@ struct FrameArgs {
     uint32_t n_work;                         // primary work items (8x4-pixel tiles x 32)
     uint32_t *out_rgba8;                     // bound RGBA8 image
     float *out_depth;                        // bound R32F image
-    float4 *queue[2];
-    uint32_t queue_cap;
-    uint32_t *hit_list;                      // schedules 3/4: surviving pixels, kCostClasses lists (see class_base)
+    uint32_t queue_cap;                      // pixels of the frame = capacity of the light survivor list
+    uint32_t *hit_list;                      // surviving pixels of k_primary_cull, kCostClasses lists (see class_base)
     uint32_t heavy_cap;                      // capacity of each of the heavy-class lists behind the light list
     uint32_t *cost;                          // per pixel: scheduler iterations its path took in the previous frame
-    int blocks_per_sm;                       // schedules 3/4: cap on resident path-kernel blocks per SM (0 = occupancy limit)
-    int path_minb;                           // schedule 3: min-blocks-per-SM variant of the path kernel (register cap)
-    int lead_min;                            // the path with the most iterations picks the phase once it has this many
-    float4 *path_recs;                       // schedule 4: 5 quads per path context
-    int mux_k;                               // schedule 4: path contexts per lane (1..4)
+    int blocks_per_sm;                       // cap on resident path-kernel blocks per SM (0 = occupancy limit)
+    int lead_min;                            // schedule 3: the path with the most iterations picks the phase once it has this many
     int wide_bvh;                            // schedule 6: search the four-wide tables when they exist (1) or the two-wide ones (0)
     int cost_ema;                            // schedule 6: per-pixel cost hint is a running mean over frames (1) or the last frame's (0)
     int pool_alive;                          // schedule 6: cap on the paths a warp keeps alive (32..slots; 0 = all slots)
@@ -59,10 +51,9 @@ struct FrameArgs {
     // scheduling knobs (results do not depend on them)
     int refill_below;  // refill idle lanes when fewer than this many lanes are traversing
     int burst;         // node steps between refill checks
-    int schedule;      // 0: wavefront + while-while descent, 1: wavefront + phase voting, 2: single path kernel,
-                       // 3: camera-ray classification kernel + path kernel over the surviving pixels,
-                       // 4: classification kernel + lane-multiplexed path kernel,
-                       // 5: classification kernel + closest-hit path kernel (pt_fast.cuh), 6: 5 with pooled paths
+    int schedule;      // 2: single path kernel over all pixels in reference order (trace mode, DEBUG_STEPS, no culling),
+                       // 3: camera-ray classification kernel + reference-order path kernel over the surviving pixels,
+                       // 6: classification kernel + closest-hit path kernel with pooled paths (pt_fast.cuh, k_path_pool.cuh)
     int shade_at;      // schedule 2: shade once this many lanes wait with a finished ray
     int cull;          // 1: skip children whose tight box the ray misses (pt_scene.cuh); results identical
     // optional per-warp schedule profile (gdpt_shader_set_warp_profile): 8 x u64 per warp of the path kernel
@@ -81,28 +72,19 @@ struct LaunchShape { int blocks; int threads; };
 enum { kMaxPeerScreens = 15 };
 struct PeerScreens { uint32_t *p[kMaxPeerScreens]; int n; };
 
-// K1 stages.  `trace` selects the instrumented instantiation.
-// Single-kernel schedule (a.schedule == 2): whole paths per lane, no stage barriers.
+// K1.  `trace` selects the instrumented instantiation.
+// Schedule 2: whole paths per lane over all pixels, reference visiting order, no stage barriers.
 void launch_path(const FrameArgs &a, bool trace, cudaStream_t s);
-// Two-kernel schedule (a.schedule == 3, needs a.cull): camera-ray classification against the tight
-// boxes, then whole paths per lane for the pixels that can hit something.
+// Schedules 3 and 6 start with the camera-ray classification against the tight boxes ...
 void launch_primary_cull(const FrameArgs &a, cudaStream_t s);
-void launch_path_list(const FrameArgs &a, bool trace, cudaStream_t s);
-// Schedule 5 (default when rendering): the same classification kernel, then whole paths per lane whose rays
-// are answered by the closest-hit search of pt_fast.cuh (+ proof, exact re-trace where it fails).
-// `record` also writes the hit records of the first a.trace_segments segments (no work counters).
-void launch_path_fast(const FrameArgs &a, bool record, cudaStream_t s);
-// Schedule 6: the same search, paths kept in per-warp shared-memory pools (k_path_pool): lanes swap rays
-// instead of waiting for a shading quorum, shading and camera-ray generation run on full warps.
+// ... then schedule 3 runs whole paths per lane, in reference order with culling, for the pixels that can hit something
+// (`record` also writes the hit records of the first a.trace_segments segments) ...
+void launch_path_list(const FrameArgs &a, bool record, cudaStream_t s);
+// ... and schedule 6 (default when rendering) answers every ray by the closest-hit search of pt_fast.cuh (+ proof, exact
+// re-trace where it fails), paths kept in per-warp shared-memory pools (k_path_pool): lanes swap rays instead of
+// waiting for a shading quorum, shading and camera-ray generation run on full warps.
 void launch_path_pool(const FrameArgs &a, bool record, cudaStream_t s);
-// Schedule 4: the same classification kernel, then the lane-multiplexed path kernel (a.mux_k
-// path contexts per lane, kept in shared memory; a.path_recs holds their cold state).
-void launch_path_mux(const FrameArgs &a, cudaStream_t s);
-size_t mux_path_record_quads(); // float4 elements a.path_recs must provide on the current device
 size_t path_kernel_warps(const FrameArgs &a); // warps of the path kernel enqueue_k1 would launch for `a`
-void launch_primary(const FrameArgs &a, bool trace, cudaStream_t s);
-void launch_shade(const FrameArgs &a, int segment, cudaStream_t s);
-void launch_trace(const FrameArgs &a, int segment, bool trace, cudaStream_t s);
 // K2: progressive accumulation + ACES (progressive_rendering.glsl:28-46).
 void launch_progressive(const uint32_t *raw_rgba8, uint32_t *screen_rgba8, float4 *accum, const gdpt_progressive_params *params_dev,
                         int width, int height, int shard_part, int shard_parts, int shard_band, const PeerScreens &peers,
@@ -115,8 +97,8 @@ void launch_temporal(uint32_t *screen_rgba8, const float *depth, const float *hi
 // switches around them) out of the frame's stream.
 struct SmallCopies { struct { uint32_t *dst; const uint32_t *src; uint32_t words; } c[3]; };
 void launch_small_copies(const SmallCopies &sc, cudaStream_t s);
-// Number of kernels one K1 dispatch launches for a given depth.
-int k1_launch_count(int schedule, int max_depth, bool debug_steps);
+// Number of kernels one K1 dispatch launches.
+int k1_launch_count(int schedule);
 // One-time per device: query SM count / occupancy for the persistent grids.
 void init_launch_shapes(int device);
 

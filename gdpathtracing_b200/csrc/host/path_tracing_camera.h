@@ -13,6 +13,8 @@
 #include "xform_math.h"
 
 #include <cstdint>
+#include <map>
+#include <string>
 #include <vector>
 
 namespace gdpt {
@@ -96,6 +98,8 @@ public:
     void set_record_hits(int segments) { record_hits_ = segments; }
     // kernel schedule ("#define GDPT_VARIANT n", include/gdpt.h); -1 = backend default.  Results do not depend on it.
     void set_variant(int variant) { variant_ = variant; }
+    // scheduling knob of the path kernels ("#define GDPT_TUNE_<NAME> n", include/gdpt.h), for A/B measurements only
+    void set_tuning(const std::string &name, int value) { tuning_[name] = value; }
     // true: one gdpt_render_frame call per frame; false: the reference's dispatch-by-dispatch sequence
     void set_fused_frame(bool on) { fused_frame_ = on; }
 
@@ -160,6 +164,7 @@ private:
     int cull_ = -1;
     int record_hits_ = 0;
     int variant_ = -1;
+    std::map<std::string, int> tuning_;
     uint32_t last_frame_count_ = 0;
 };
 

@@ -191,6 +191,10 @@ class PathTracingCamera:
         """Kernel schedule (include/gdpt.h GDPT_VARIANT); -1 backend default.  Results are identical for every value."""
         host.gdpt_camera_set_variant(self._h, int(variant))
 
+    def set_tuning(self, name, value):
+        """Scheduling knob of the path kernels ("#define GDPT_TUNE_<NAME> n"); A/B measurements only, results identical."""
+        host.gdpt_camera_set_tuning(self._h, str(name).upper().encode(), int(value))
+
     def set_record_hits(self, segments):
         """Hit records of the first n segments from the rendering kernels (no work counters)."""
         host.gdpt_camera_set_record_hits(self._h, int(segments))

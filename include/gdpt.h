@@ -103,16 +103,18 @@ GDPT_API uint32_t gdpt_abi_version(void);
  *   "#define DEBUG_STEPS"      heat-map mode of main.glsl:4,358-361,423-427
  *   "#define MAX_DEPTH n"      path segments; default 5 = main.glsl:377
  *   "#define GDPT_TRACE"       also emit per-ray parity records (gdpt_shader_read_trace)
- *   "#define GDPT_VARIANT n"   kernel schedule variant; results identical
  *   "#define GDPT_REFERENCE_ORDER"  visit every node the reference visits (no tight-box culling);
  *                              results are identical either way, only the work differs.  Implied
  *                              by GDPT_TRACE unless "#define GDPT_CULL 1" is also given
  *   "#define GDPT_RECORD_HITS n"  the rendering kernels themselves also write the hit records (no work
  *                              counters) of the first n segments; read with gdpt_shader_read_trace
  *   "#define GDPT_VARIANT 3"   keep the reference visiting order (with culling) when rendering; the default
- *                              (variant 6; 5 is the same search with one path per lane) answers rays with an
- *                              order-free closest-hit search plus a proof that the reference reaches the same
- *                              triangle, and re-traces the rest; identical results
+ *                              (variant 6) answers rays with an order-free closest-hit search plus a proof that
+ *                              the reference reaches the same triangle, and re-traces the rest;
+ *                              variant 2 is one kernel over all pixels in reference order.  Identical results
+ *   "#define GDPT_TUNE_<NAME> n"  scheduling knob of the path kernels (BURST, SHADE_AT, REFILL_BELOW, POOL_WAIT,
+ *                              ...; A/B measurements).  Results do not depend on them.  The process environment
+ *                              is never consulted: what runs is decided by this list alone
  * Unknown defines are ignored, as a GLSL compiler would ignore an unused macro. */
 GDPT_API int  gdpt_shader_create(gdpt_device *device, const char *shader_path,
                                  const char *const *args, int n_args,

@@ -209,17 +209,17 @@ inline vec3 reflect(const vec3 &I, const vec3 &N) { return I - 2.0f * dot(N, I) 
 inline vec3 clamp(const vec3 &v, float lo, float hi) { return vec3(clamp(v.x, lo, hi), clamp(v.y, lo, hi), clamp(v.z, lo, hi)); }
 
 // ---- resources
-struct access_log { std::vector<uint32_t> *sink = nullptr; };
-
 // std430 runtime array in a storage buffer.  `tag` marks which buffer a logged read came from.
 template <class T> struct ssbo {
     const uint8_t *base = nullptr;
     size_t stride = 0, count = 0;
     std::vector<uint64_t> *log = nullptr;
     uint64_t tag = 0;
+    uint64_t *reads_of_record_0 = nullptr; // optional cheap observer (ray count = reads of TLAS node 0)
     T operator[](uint i) const
     {
         if (log) log->push_back(tag | i);
+        if (reads_of_record_0 && i == 0u) ++*reads_of_record_0;
         T t;
         std::memcpy(&t, base + stride * (size_t)i, sizeof(T));
         return t;

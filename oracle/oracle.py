@@ -139,12 +139,12 @@ class Scene:
 
 
 def path_trace(scene, width, height, camera_bytes, max_depth=5, debug_steps=False, threads=None, rows=None,
-               trace_segments=0, visits_per_ray=0, row_step=1, radiance=False, impl="restatement"):
+               trace_segments=0, visits_per_ray=0, row_step=1, radiance=False, impl="restatement", counters=True):
     """K1 on the CPU.  Returns dict(rgba8, depth, stats, trace, visits[, radiance]).
 
     impl="restatement": oracle/pt_oracle.cpp.  impl="reference": the reference's own main.glsl (+ brdfs.glsl)
     compiled as C++ (oracle/_ref/libgdpt_refshader.so); its trace records leave t / u / v / front / max_stack
-    zero (use trace_rays for those)."""
+    zero (use trace_rays for those); counters=False (timing runs) keeps only the ray count of its stats."""
     threads = threads or hardware_threads()
     params = np.zeros(9, np.uint32)
     params[4], params[5] = width, height
@@ -157,7 +157,8 @@ def path_trace(scene, width, height, camera_bytes, max_depth=5, debug_steps=Fals
     st = OrcStats()
     y0, y1 = rows if rows else (0, height)
     fn = lib().orc_path_trace if impl == "restatement" else ref_shader().refsh_path_trace
-    fn(ctypes.byref(scene.c), _p(params), _p(cam), max_depth, 1 if debug_steps else 0, threads, y0, y1, row_step,
+    flags = (1 if debug_steps else 0) | (2 if (counters and impl != "restatement") else 0)
+    fn(ctypes.byref(scene.c), _p(params), _p(cam), max_depth, flags, threads, y0, y1, row_step,
        _p(out), _p(depth), _p(trace) if trace is not None else None, trace_segments,
        _p(visits) if visits is not None else None, visits_per_ray, ctypes.byref(st), _p(raw) if raw is not None else None)
     stats = {k: getattr(st, k) for k, _ in OrcStats._fields_}

@@ -159,7 +159,7 @@ struct LogDecoder {
 struct Job {
     SceneView sc;
     const void *params36, *camera160;
-    int width, height, max_depth, debug_steps, y_begin, y_end, y_step;
+    int width, height, max_depth, debug_steps, y_begin, y_end, y_step, want_counters;
     uint8_t *out_rgba8; float *out_depth, *out_radiance;
     gdpt_trace_record *trace; int trace_segments;
     uint32_t *visits; uint32_t visits_per_ray;
@@ -171,8 +171,12 @@ template <class S> void render_rows(Job *job)
 {
     S sh;
     std::vector<uint64_t> log;
-    const bool observe = job->trace != nullptr || job->visits != nullptr;
-    bind_scene(sh, job->sc, &log); // the log also yields the ray count, so it is always on
+    // The read log feeds the per-segment observables; when nobody asked for them (timing runs) only the ray count is
+    // kept: TLAS node 0 is read exactly once per ray_trace_tlas call (main.glsl:309-313; child reads never name it).
+    const bool observe = job->trace != nullptr || job->visits != nullptr || job->want_counters;
+    uint64_t tlas_root_reads = 0;
+    bind_scene(sh, job->sc, observe ? &log : nullptr);
+    if (!observe) sh.tlas_nodes.reads_of_record_0 = &tlas_root_reads;
     memcpy(&sh.params, job->params36, sizeof(sh.params));
     memcpy(&sh.camera, job->camera160, sizeof(sh.camera));
     sh.gdpt_segments = job->max_depth;
@@ -189,6 +193,7 @@ template <class S> void render_rows(Job *job)
             log.clear();
             sh.gl_GlobalInvocationID = glsl::uvec3((uint32_t)x, (uint32_t)y, 0u);
             sh.main();
+            if (!observe) continue;
             dec.decode(log);
             const size_t pix = (size_t)y * job->width + x;
             rays += dec.segs.size();
@@ -196,7 +201,7 @@ template <class S> void render_rows(Job *job)
                 const Segment &g = dec.segs[i];
                 pops += g.node_pops; boxes += g.box_tests; tris += g.tri_tests; leaves += g.tlas_leaves;
                 if (i == 0 && g.hit) phits++;
-                if (observe && job->trace && (int)i < job->trace_segments) {
+                if (job->trace && (int)i < job->trace_segments) {
                     gdpt_trace_record &tr = job->trace[i * n_pix + pix];
                     memset(&tr, 0, sizeof(tr));
                     tr.hit = g.hit; tr.triangle = g.triangle; tr.blas = g.blas;
@@ -209,6 +214,7 @@ template <class S> void render_rows(Job *job)
                     job->visits[pix * job->visits_per_ray + k] = dec.first_visits[k];
         }
     }
+    if (!observe) rays = tlas_root_reads;
     job->rays += rays; job->primary_hits += phits; job->node_pops += pops; job->box_tests += boxes;
     job->tri_tests += tris; job->tlas_leaves += leaves;
 }
@@ -245,6 +251,8 @@ static SceneView view_of(const refsh_scene *s)
 // main.glsl `main()` for every pixel of rows y_begin, y_begin + y_step, ... < y_end.  Same arguments as
 // orc_path_trace; out_radiance (optional) receives the vec4 handed to imageStore(outputImage, ..) unconverted.
 // trace records carry hit / triangle / blas / counters / visit hash (t, u, v, front: see refsh_trace_rays).
+// stats: rays always; the other totals only when trace or visits are requested or debug_steps & 2 is set (they come
+// from the read log, which costs about a quarter of the run time).
 int refsh_path_trace(const refsh_scene *scene, const void *params36, const void *camera160, int max_depth, int debug_steps,
                      int n_threads, int y_begin, int y_end, int y_step, uint8_t *out_rgba8, float *out_depth,
                      gdpt_trace_record *trace, int trace_segments, uint32_t *visits, uint32_t visits_per_ray,
@@ -255,7 +263,7 @@ int refsh_path_trace(const refsh_scene *scene, const void *params36, const void 
     job.params36 = params36; job.camera160 = camera160;
     const gdpt_render_params *p = (const gdpt_render_params *)params36;
     job.width = p->width; job.height = p->height;
-    job.max_depth = max_depth; job.debug_steps = debug_steps;
+    job.max_depth = max_depth; job.debug_steps = debug_steps & 1; job.want_counters = (debug_steps & 2) ? 1 : 0;
     job.y_begin = y_begin < 0 ? 0 : y_begin; job.y_end = y_end > p->height ? p->height : y_end; job.y_step = y_step < 1 ? 1 : y_step;
     job.out_rgba8 = out_rgba8; job.out_depth = out_depth; job.out_radiance = out_radiance;
     job.trace = trace; job.trace_segments = trace_segments; job.visits = visits; job.visits_per_ray = visits_per_ray;
@@ -266,7 +274,7 @@ int refsh_path_trace(const refsh_scene *scene, const void *params36, const void 
         for (size_t i = 0; i < n; i++) { memset(&trace[i], 0, sizeof(trace[i])); trace[i].hit = 0xFFFFFFFFu; }
     }
     if (n_threads < 1) n_threads = 1;
-    void (*worker)(Job *) = debug_steps ? render_rows<glsl::ref_main_debug::Shader> : render_rows<glsl::ref_main::Shader>;
+    void (*worker)(Job *) = job.debug_steps ? render_rows<glsl::ref_main_debug::Shader> : render_rows<glsl::ref_main::Shader>;
     std::vector<std::thread> pool;
     for (int i = 1; i < n_threads; i++) pool.emplace_back(worker, &job);
     worker(&job);
