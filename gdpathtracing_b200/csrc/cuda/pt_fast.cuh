@@ -40,9 +40,37 @@ template <class Stack> GDPT_HD uint32_t fast_pop(RayState &r, Stack &st)
     return st.load(r.sp);
 }
 
+// Arithmetic of the SEARCH's box tests only.  The boxes are our own, true bounds inflated by a margin (fast_bvh.h,
+// derived_layout.h tight_inflate), so their slab tests need not reproduce any reference number: a fused multiply-add and
+// the hardware reciprocal move a plane by a few ulp of the coordinates, the margin is 1/512 of the mesh.  (Rays whose
+// origin is so far out that a few ulp reach the margin are sent to the exact traversal: fast_far_origin.)  Everything the
+// reference computes -- Moller-Trumbore, the instance-local ray, the proof's slab tests -- keeps the exact operations.
+GDPT_HD float fast_fma(float a, float b, float c)
+{
+#if defined(__CUDA_ARCH__)
+    return __fmaf_rn(a, b, c);
+#else
+    return fmaf(a, b, c);
+#endif
+}
+GDPT_HD float fast_rcp(float x)
+{
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); // MUFU.RCP; a denormal direction component counts as zero
+    return r;
+#else
+    return 1.0f / x;
+#endif
+}
+GDPT_HD f3 fast_rcp3(f3 a) { return mk3(fast_rcp(a.x), fast_rcp(a.y), fast_rcp(a.z)); }
+// true when an origin coordinate is beyond `reach`: the search's culling margins are not trusted there
+GDPT_HD bool fast_far_origin(f3 o, float reach) { return !(max_num(max_num(fabsf(o.x), fabsf(o.y)), fabsf(o.z)) <= reach); }
+
 GDPT_HD void fast_ray_begin(RayState &r, const SceneView &sc, f3 o, f3 d)
 {
     ray_begin(r, sc, o, d);
+    r.rd = fast_rcp3(d); // the search's own reciprocal; the proof recomputes the exact one
 }
 
 // true box of a child: entry distance and whether the subtree can still hold a hit with t <= r.t
@@ -92,34 +120,50 @@ GDPT_HD uint32_t fast_bits(float x)
 #endif
 }
 // One internal node of the four-wide tables: four true-box tests, children visited nearest first.
-// Sort key = entry distance clamped at 0 (the origin may be inside a box) as ordered bits; misses sort last.
-template <class Stack> GDPT_HD void fast_step_node4(const SceneView &sc, RayState &r, Stack &st)
+// The near and the far plane of every axis are picked by the sign of the ray direction (which quad is loaded), so a
+// child costs six FFMA, two FMNMX3 + two FMNMX and one compare:  entry = max(near planes, 0), exit = min(far planes, r.t),
+// touched iff entry <= exit.  NaNs (0 * inf, inf - inf on axis-parallel rays) are dropped by fmaxf / fminf, which ignores
+// that axis: more children visited, never fewer.
+// SORT: all touched children in order of entry distance (key = distance bits with the child number in the two low bits,
+// five min/max comparators); otherwise the nearest child next and the others pushed in table order.
+template <bool SORT = true, class Stack> GDPT_HD void fast_step_node4(const SceneView &sc, RayState &r, Stack &st)
 {
-    const uint32_t idx = r.cur & LINK_INDEX_MASK;
-    const q4f lx = ldq(sc.fast4, idx * 8u + 0u), ly = ldq(sc.fast4, idx * 8u + 1u), lz = ldq(sc.fast4, idx * 8u + 2u);
-    const q4f hx = ldq(sc.fast4, idx * 8u + 3u), hy = ldq(sc.fast4, idx * 8u + 4u), hz = ldq(sc.fast4, idx * 8u + 5u);
-    const q4u lk = ldqu(sc.fast4, idx * 8u + 6u);
-    float e0, e1, e2, e3;
-    const bool h0 = fast_slab(r, lx.x, ly.x, lz.x, hx.x, hy.x, hz.x, &e0) && lk.x != LINK_NONE;
-    const bool h1 = fast_slab(r, lx.y, ly.y, lz.y, hx.y, hy.y, hz.y, &e1) && lk.y != LINK_NONE;
-    const bool h2 = fast_slab(r, lx.z, ly.z, lz.z, hx.z, hy.z, hz.z, &e2) && lk.z != LINK_NONE;
-    const bool h3 = fast_slab(r, lx.w, ly.w, lz.w, hx.w, hy.w, hz.w, &e3) && lk.w != LINK_NONE;
+    const uint32_t base = (r.cur & LINK_INDEX_MASK) * 8u;
+    const bool sx = r.rd.x < 0.0f, sy = r.rd.y < 0.0f, sz = r.rd.z < 0.0f;
+    const q4f nx = ldq(sc.fast4, base + (sx ? 3u : 0u)), ny = ldq(sc.fast4, base + (sy ? 4u : 1u)), nz = ldq(sc.fast4, base + (sz ? 5u : 2u));
+    const q4f fx = ldq(sc.fast4, base + (sx ? 0u : 3u)), fy = ldq(sc.fast4, base + (sy ? 1u : 4u)), fz = ldq(sc.fast4, base + (sz ? 2u : 5u));
+    const q4u lk = ldqu(sc.fast4, base + 6u);
+    const float ox = -(r.o.x * r.rd.x), oy = -(r.o.y * r.rd.y), oz = -(r.o.z * r.rd.z);
     const uint32_t kMiss = 0xFFFFFFFFu;
-    uint32_t k0 = h0 ? fast_bits(max_num(e0, 0.0f)) : kMiss, k1 = h1 ? fast_bits(max_num(e1, 0.0f)) : kMiss;
-    uint32_t k2 = h2 ? fast_bits(max_num(e2, 0.0f)) : kMiss, k3 = h3 ? fast_bits(max_num(e3, 0.0f)) : kMiss;
-    uint32_t l0 = lk.x, l1 = lk.y, l2 = lk.z, l3 = lk.w;
-#define GDPT_CSWAP(ka, la, kb, lb)                                                        \
-    {                                                                                     \
-        const bool sw = kb < ka;                                                          \
-        const uint32_t tk = sw ? kb : ka, tl = sw ? lb : la;                              \
-        kb = sw ? ka : kb; lb = sw ? la : lb; ka = tk; la = tl;                           \
+#define GDPT_CHILD(c, n)                                                                                              \
+    uint32_t k##n;                                                                                                    \
+    {                                                                                                                 \
+        const float e = max_num(max_num(fast_fma(nx.c, r.rd.x, ox), fast_fma(ny.c, r.rd.y, oy)),                      \
+                                max_num(fast_fma(nz.c, r.rd.z, oz), 0.0f));                                           \
+        const float x = min_num(min_num(fast_fma(fx.c, r.rd.x, ox), fast_fma(fy.c, r.rd.y, oy)),                      \
+                                min_num(fast_fma(fz.c, r.rd.z, oz), r.t));                                            \
+        k##n = (e <= x && lk.c != LINK_NONE) ? ((fast_bits(e) & ~3u) | (uint32_t)n) : kMiss;                          \
     }
-    GDPT_CSWAP(k0, l0, k1, l1) GDPT_CSWAP(k2, l2, k3, l3) GDPT_CSWAP(k0, l0, k2, l2) GDPT_CSWAP(k1, l1, k3, l3) GDPT_CSWAP(k1, l1, k2, l2)
+    GDPT_CHILD(x, 0) GDPT_CHILD(y, 1) GDPT_CHILD(z, 2) GDPT_CHILD(w, 3)
+#undef GDPT_CHILD
+#define GDPT_LINK_OF(k) (((k) & 2u) ? (((k) & 1u) ? lk.w : lk.z) : (((k) & 1u) ? lk.y : lk.x))
+    if (SORT) {
+#define GDPT_CSWAP(a, b) { const uint32_t lo = a < b ? a : b; b = a < b ? b : a; a = lo; }
+        GDPT_CSWAP(k0, k1) GDPT_CSWAP(k2, k3) GDPT_CSWAP(k0, k2) GDPT_CSWAP(k1, k3) GDPT_CSWAP(k1, k2)
 #undef GDPT_CSWAP
-    if (k3 != kMiss) fast_push(r, st, l3); // farthest first: the nearest pushed child is popped first
-    if (k2 != kMiss) fast_push(r, st, l2);
-    if (k1 != kMiss) fast_push(r, st, l1);
-    r.cur = (k0 != kMiss) ? l0 : fast_pop(r, st);
+        if (k3 != kMiss) fast_push(r, st, GDPT_LINK_OF(k3)); // farthest first: the nearest pushed child is popped first
+        if (k2 != kMiss) fast_push(r, st, GDPT_LINK_OF(k2));
+        if (k1 != kMiss) fast_push(r, st, GDPT_LINK_OF(k1));
+        r.cur = (k0 != kMiss) ? GDPT_LINK_OF(k0) : fast_pop(r, st);
+    } else {
+        const uint32_t a = k0 < k1 ? k0 : k1, b = k2 < k3 ? k2 : k3, best = a < b ? a : b;
+        if (k3 != kMiss && k3 != best) fast_push(r, st, lk.w);
+        if (k2 != kMiss && k2 != best) fast_push(r, st, lk.z);
+        if (k1 != kMiss && k1 != best) fast_push(r, st, lk.y);
+        if (k0 != kMiss && k0 != best) fast_push(r, st, lk.x);
+        r.cur = (best != kMiss) ? GDPT_LINK_OF(best) : fast_pop(r, st);
+    }
+#undef GDPT_LINK_OF
 }
 
 // intersectTriangle (main.glsl:224-257), same operations as triangle_test_loaded; the running minimum
@@ -217,7 +261,7 @@ template <bool WIDE = false, class Stack> GDPT_HD void fast_enter_instance(const
 template <class Stack> GDPT_HD void fast_step_instance(const SceneView &sc, RayState &r, Stack &st)
 {
     if (r.inst != GDPT_NO_INSTANCE) {
-        r.o = r.wo; r.d = r.wd; r.rd = rcp3(r.wd);
+        r.o = r.wo; r.d = r.wd; r.rd = fast_rcp3(r.wd);
         r.inst = GDPT_NO_INSTANCE;
     }
     if ((r.cur & LINK_LEAF) == 0u) return;
@@ -235,7 +279,7 @@ template <bool WIDE, class Stack> GDPT_HD void fast_enter_instance(const SceneVi
     const q4f tmin4 = ldq(sc.inst_recs, idx * 7u + 5u);
     const q4f tmax4 = ldq(sc.inst_recs, idx * 7u + 6u);
     fast_local_ray(c0, c1, c2, c3, r.wo, r.wd, &r.o, &r.d);
-    r.rd = rcp3(r.d);
+    r.rd = fast_rcp3(r.d);
     r.inst = idx;
     float entry;
     const bool touches = fast_slab(r, tmin4.x, tmin4.y, tmin4.z, tmax4.x, tmax4.y, tmax4.z, &entry);
@@ -267,7 +311,7 @@ template <class Stack> GDPT_HD void fast_trace_ray4(const SceneView &sc, RayStat
         if (fast_link_is_leaf(r.cur)) fast_step_leaf(sc, r, st);
         else if (fast_link_is_node(r.cur, r.inst)) fast_step_node4(sc, r, st);
         else {
-            if (r.inst != GDPT_NO_INSTANCE) { r.o = r.wo; r.d = r.wd; r.rd = rcp3(r.wd); r.inst = GDPT_NO_INSTANCE; }
+            if (r.inst != GDPT_NO_INSTANCE) { r.o = r.wo; r.d = r.wd; r.rd = fast_rcp3(r.wd); r.inst = GDPT_NO_INSTANCE; }
             if (r.cur & LINK_LEAF) fast_enter_instance<true>(sc, r, st);
         }
     }
