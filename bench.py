@@ -207,6 +207,11 @@ def run_ours(args, rank, local, world):
     cam.set_cuda_device(local)
     if rows_mode:
         cam.set_shard(rank, world, args.band)
+    if args.variant >= 0:
+        cam.set_variant(args.variant)
+    for kv in args.tune:
+        k, v = kv.split("=")
+        cam.set_tuning(k, int(v))
     cam.init()
     build_s = None  # GeometryGroup3D.build ran inside init(); timed separately below on rank 0
     # per-kernel split: measured on a few untimed frames after the timed region (the events it records between the K1
@@ -517,6 +522,8 @@ def main():
     ap.add_argument("--band", type=int, default=8)
     ap.add_argument("--present", default="peer", choices=["peer", "gather"],
                     help="row bands: how the presented frame is assembled (peer writes fused into K2, or NCCL all-gather)")
+    ap.add_argument("--variant", type=int, default=-1, help="A/B: kernel schedule (include/gdpt.h GDPT_VARIANT); -1 = backend default")
+    ap.add_argument("--tune", action="append", default=[], metavar="NAME=N", help="A/B: scheduling knob (GDPT_TUNE_<NAME>)")
     ap.add_argument("--no-l2-flush", dest="l2_flush", action="store_false")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false",
                     help="A/B runs of kernel variants only: skip the CPU leg (the official line always carries it)")

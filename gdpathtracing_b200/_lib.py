@@ -57,7 +57,9 @@ class StandardMaterial(Structure):
 class FrameStats(Structure):
     _fields_ = [("rays", c_uint64), ("primary_hits", c_uint64), ("node_pops", c_uint64), ("box_tests", c_uint64),
                 ("tri_tests", c_uint64), ("tlas_leaves", c_uint64), ("kernel_launches", c_uint32),
-                ("max_stack", c_uint32), ("k1_ms", c_float), ("k2_ms", c_float), ("retraced", c_uint64)]
+                ("max_stack", c_uint32), ("k1_ms", c_float), ("k2_ms", c_float), ("retraced", c_uint64),
+                ("own_node_steps", c_uint64), ("own_box_tests", c_uint64), ("own_tri_tests", c_uint64),
+                ("own_inst_entries", c_uint64), ("own_proofs", c_uint64)]
 
 
 assert ctypes.sizeof(RenderParams) == 36 and ctypes.sizeof(Camera) == 160 and ctypes.sizeof(ProgressiveParams) == 12
@@ -152,6 +154,7 @@ HOST_API = [
     ("gdpt_camera_set_record_hits", None, [c_void_p, c_int]),
     ("gdpt_camera_set_variant", None, [c_void_p, c_int]),
     ("gdpt_camera_set_tuning", None, [c_void_p, c_char_p, c_int]),
+    ("gdpt_camera_set_count_work", None, [c_void_p, c_int]),
     ("gdpt_camera_set_fused_frame", None, [c_void_p, c_int]),
     ("gdpt_camera_init", c_int, [c_void_p]),
     ("gdpt_camera_render", None, [c_void_p]),

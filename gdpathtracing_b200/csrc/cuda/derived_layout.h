@@ -21,6 +21,7 @@ struct DerivedLayout {
     std::vector<WideNode> wide_tlas;
     std::vector<InstRec> inst_recs;
     uint32_t tlas_root_link = LINK_NONE;
+    float world_reach = 0.0f; // SceneView::fast_world_reach
 };
 
 struct TightBox { float lo[3], hi[3]; };
@@ -61,6 +62,21 @@ inline TightBox tight_inflate(const TightBox &b, float owner_extent)
     if (!finite)
         for (int k = 0; k < 3; k++) { r.lo[k] = -FLT_MAX; r.hi[k] = FLT_MAX; }
     return r;
+}
+
+// How far out a ray may start for a box's culling margin to be trusted (pt_fast.cuh fast_far_origin).  Two errors grow
+// with the size of the coordinates the search works with and must stay inside the margin (>= extent / 512):
+//   * Moller-Trumbore accepts hits up to ~1e-6 x (distance to the origin) outside the triangle it tests;
+//   * the search's own slab tests (FFMA + hardware reciprocal) move a plane by a few ulp (~2.4e-7) of the larger
+//     of |origin| and |plane|.
+// With coordinates below 256 x extent both stay under a quarter of the margin.  A box that itself lies farther than
+// half of that from its space's origin gets reach 0: every ray that enters it is answered by the exact traversal.
+inline float fast_reach(const TightBox &b, float extent)
+{
+    float far_corner = 0.0f;
+    for (int k = 0; k < 3; k++) { far_corner = std::fmax(far_corner, std::fabs(b.lo[k])); far_corner = std::fmax(far_corner, std::fabs(b.hi[k])); }
+    const float reach = 256.0f * extent;
+    return (std::isfinite(reach) && far_corner <= 0.5f * reach) ? reach : 0.0f;
 }
 
 // Returns "" on success, otherwise what is wrong with the input arrays.
@@ -190,6 +206,7 @@ inline std::string derive_layout(const gdpt_bvh_node *bvh, uint32_t n_nodes, con
         r.fast_root = LINK_NONE; // filled by the closest-hit builder (fast_bvh.h)
         const TightBox obj = tight_inflate(raw[blas[b].root], owner_extent[blas[b].root]);
         for (int k = 0; k < 3; k++) { r.tight_min[k] = obj.lo[k]; r.tight_max[k] = obj.hi[k]; }
+        r.tight_max[3] = fast_reach(raw[blas[b].root], owner_extent[blas[b].root]);
         // world-space culling box: the eight transformed corners of the object-space one, inflated again
         TightBox w = tight_empty();
         const float *m = blas[b].transform;
@@ -200,6 +217,8 @@ inline std::string derive_layout(const gdpt_bvh_node *bvh, uint32_t n_nodes, con
             tight_grow(w, p);
         }
         world[b] = tight_inflate(w, tight_extent(w));
+        const float wr = fast_reach(w, tight_extent(w)); // world level: the smallest instance decides
+        out.world_reach = (b == 0 || wr < out.world_reach) ? wr : out.world_reach;
     }
     // tight boxes of TLAS nodes, bottom-up (TLAS nodes are few: plain recursion-free fixpoint by depth)
     std::vector<TightBox> traw(n_tlas, tight_empty());

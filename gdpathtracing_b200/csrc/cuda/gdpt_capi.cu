@@ -75,6 +75,8 @@ struct gdpt_shader {
     int record_hits = 0; // "#define GDPT_RECORD_HITS n": hit records of the first n segments from the rendering kernels
     std::map<std::string, int> tuning; // "#define GDPT_TUNE_<NAME> n": scheduling knobs of the path kernels (A/B runs)
     std::string fast_why_not; // why the closest-hit tables are not in use ("" = in use)
+    uint32_t fast_need4 = 0;  // stack entries the four-wide search can need (fast_bvh.h)
+    bool count_work = false;  // "#define GDPT_COUNT_WORK": the path kernel also counts its own work (gdpt_frame_stats own_*)
     // main-shader state built by finish_create_uniforms
     FrameArgs args;
     std::vector<void *> derived; // device allocations owned by this shader
@@ -91,7 +93,7 @@ struct gdpt_shader {
         bool pending = false, with_k2 = false;
         // overlapped frames: what K1 of this frame reads and writes (the other frame in flight has its own)
         gdpt_camera *cam_dev = nullptr; gdpt_progressive_params *pp_dev = nullptr;
-        uint32_t *raw_rgba8 = nullptr; float *raw_depth = nullptr; uint32_t *hit_list = nullptr;
+        uint32_t *raw_rgba8 = nullptr; float *raw_depth = nullptr; uint32_t *hit_list = nullptr; uint32_t *spill = nullptr;
         bool finished_once = false;      // k_done has been recorded at least once
         uint32_t launches = 0;
     } slots[GDPT_MAX_FRAMES_IN_FLIGHT];
@@ -222,6 +224,7 @@ int build_derived_layout(gdpt_shader *s, const Resource &bvh_r, const Resource &
             std::memcpy(&lay.inst_recs[b].tight_min[3], &fast.inst_root4[b], 4); // root in the four-wide table
         }
         s->args.sc.fast4_ok = fast.ok4 ? 1u : 0u;
+        s->fast_need4 = fast.need4;
         s->args.sc.fast4_root = fast.root4;
         if (fast.ok4 && (rc = dev_upload(s, &s->args.sc.fast4, fast.nodes4))) return rc;
         if ((rc = dev_upload(s, &s->args.sc.fast_nodes, fast.nodes))) return rc;
@@ -234,6 +237,7 @@ int build_derived_layout(gdpt_shader *s, const Resource &bvh_r, const Resource &
     if ((rc = dev_upload(s, &s->args.sc.wide_tlas, lay.wide_tlas))) return rc;
     if ((rc = dev_upload(s, &s->args.sc.inst_recs, lay.inst_recs))) return rc;
     s->args.sc.tlas_root_link = lay.tlas_root_link;
+    s->args.sc.fast_world_reach = lay.world_reach;
     GDPT_CUDA(d, cudaStreamSynchronize(d->stream)); // host vectors die at return
     return GDPT_OK;
 }
@@ -290,6 +294,15 @@ int finish_main(gdpt_shader *s)
         depth->height != out->height)
         return fail(d, GDPT_ERR_BAD_BINDING, "Params width/height (%d x %d) must match the bound images", rp.width, rp.height);
 
+    // A second finish (scene rebuild: add_existing_buffer / create_*_uniform cleared uniforms_ready) frees every derived
+    // buffer, so nothing may still be using them: refuse while pipelined frames are pending, drain every stream a frame
+    // may have run on, and forget the frame slots' pointers into the freed set.
+    for (const auto &sl : s->slots)
+        if (sl.pending) return fail(d, GDPT_ERR_NOT_READY, "finish_create_uniforms while pipelined frames are in flight: call gdpt_render_frame_wait first");
+    GDPT_CUDA(d, cudaStreamSynchronize(d->stream));
+    if (d->extra_streams_made)
+        for (cudaStream_t x : d->extra_streams) GDPT_CUDA(d, cudaStreamSynchronize(x));
+    if (d->copy_stream) GDPT_CUDA(d, cudaStreamSynchronize(d->copy_stream));
     for (void *p : s->derived) cudaFree(p);
     s->derived.clear();
     FrameArgs &a = s->args;
@@ -322,7 +335,8 @@ int finish_main(gdpt_shader *s)
     if ((rc = dev_alloc(s, &a.counters, 1))) return rc;
     // Which kernels run is decided by the shader's own "#define" list (gdpt_shader_create) and by what the arrays
     // allow -- never by the process environment.
-    a.schedule = (s->variant == 2 || s->variant == 3 || s->variant == 6) ? s->variant : 6;
+    a.schedule = (s->variant == 2 || s->variant == 3 || s->variant == 6 || s->variant == 7) ? s->variant : 6;
+    if (a.schedule == 7 && !a.sc.fast4_ok) a.schedule = 6; // the phase-sorted kernel searches the four-wide tables only
     if (a.schedule == 6 && !a.sc.fast_ok) a.schedule = 3; // closest-hit tables unavailable for these arrays (fast_bvh.h)
     // culling (pt_scene.cuh) is the default for rendering; parity traces and the DEBUG_STEPS heat map
     // keep the full reference visit order (their output IS the reference's work)
@@ -341,6 +355,16 @@ int finish_main(gdpt_shader *s)
     a.pool_alive = tune(s, "POOL_ALIVE", 0);
     a.pool_wait = tune(s, "POOL_WAIT", 32);
     a.lead_min = tune(s, "LEAD_MIN", 0);
+    a.sort4 = tune(s, "SORT4", 1);
+    a.count_work = s->count_work ? 1 : 0;
+    if (a.schedule == 7) {
+        a.burst = tune(s, "BURST", 2);
+        a.shade_at = tune(s, "SHADE_AT", 16);
+        a.refill_below = tune(s, "REFILL_BELOW", 32);
+        a.lead_min = tune(s, "AFFINITY", 12); // rays of a warp's own phase that keep it on that phase (0 = no phase affinity)
+        a.sorted_spill_depth = s->fast_need4 > (uint32_t)14 ? s->fast_need4 - 14u : 1u; // kSortStack entries live in shared memory
+        if ((rc = dev_alloc(s, &a.sorted_spill, sorted_spill_words(a)))) return rc;
+    }
     if (a.refill_below < 1) a.refill_below = 1;
     if (a.refill_below > 32) a.refill_below = 32;
     if (a.burst < 1) a.burst = 1;
@@ -357,6 +381,8 @@ int finish_main(gdpt_shader *s)
     // the two frame slots of gdpt_render_frame_begin are set up here, not on the first pipelined frame
     for (auto &sl : s->slots) {
         sl.dcnt = nullptr; sl.stage_rgba8 = nullptr; sl.stage_depth = nullptr; // (re)allocated with the derived buffers
+        sl.cam_dev = nullptr; sl.pp_dev = nullptr; sl.raw_rgba8 = nullptr; sl.raw_depth = nullptr; sl.hit_list = nullptr;
+        sl.spill = nullptr; sl.finished_once = false;
         if ((rc = ensure_slot(s, sl, false))) return rc;
     }
     if (s->warp_profile) return alloc_warp_profile(s);
@@ -465,7 +491,8 @@ int enqueue_k1(gdpt_shader *s)
     if (a.schedule >= 3) {
         launch_primary_cull(a, d->stream);
         if (timing) GDPT_CUDA(d, cudaEventRecord(s->stage_ev[ev++], d->stream));
-        if (a.schedule == 6) launch_path_pool(a, rec, d->stream);
+        if (a.schedule == 7) launch_path_sorted(a, rec, d->stream);
+        else if (a.schedule == 6) launch_path_pool(a, rec, d->stream);
         else launch_path_list(a, rec, d->stream);
     } else {
         launch_path(a, trace, d->stream);
@@ -502,6 +529,8 @@ int collect_stats(gdpt_shader *s)
     st.rays = c.rays;
     st.primary_hits = c.primary_hits;
     st.retraced = c.retraced;
+    st.own_node_steps = c.own_node_steps; st.own_box_tests = c.own_box_tests; st.own_tri_tests = c.own_tri_tests;
+    st.own_inst_entries = c.own_inst_entries; st.own_proofs = c.own_proofs;
     st.node_pops = c.node_pops; st.box_tests = c.box_tests; st.tri_tests = c.tri_tests; st.tlas_leaves = c.tlas_leaves;
     st.max_stack = c.max_stack;
     if (c.overflow) return fail(d, GDPT_ERR_UNSUPPORTED, "a ray exceeded the reference's 64+64 traversal stack entries");
@@ -513,7 +542,7 @@ int collect_stats(gdpt_shader *s)
 
 extern "C" {
 
-uint32_t gdpt_abi_version(void) { return 1u; }
+uint32_t gdpt_abi_version(void) { return 2u; }
 
 const char *gdpt_last_error(const gdpt_device *device) { return device ? device->last_error.c_str() : g_create_error.c_str(); }
 
@@ -606,6 +635,7 @@ int gdpt_shader_create(gdpt_device *d, const char *shader_path, const char *cons
         else if (name == "GDPT_CULL" && has_value) s->cull = value != 0 ? 1 : 0;
         else if (name == "GDPT_REFERENCE_ORDER") s->cull = 0;
         else if (name == "GDPT_RECORD_HITS" && has_value) s->record_hits = (int)value;
+        else if (name == "GDPT_COUNT_WORK") s->count_work = true;
         else if (name.rfind("GDPT_TUNE_", 0) == 0 && has_value) s->tuning[name.substr(10)] = (int)value;
     }
     if (s->max_depth < 1 || s->max_depth > kMaxDepth) {
@@ -1088,6 +1118,7 @@ extern "C" int gdpt_render_frame_begin(gdpt_shader *m, gdpt_shader *p, const gdp
             if ((rc = dev_alloc(m, &sl.raw_rgba8, n))) return rc;
             if ((rc = dev_alloc(m, &sl.raw_depth, n))) return rc;
             if ((rc = dev_alloc(m, &sl.hit_list, (size_t)m->args.queue_cap + (size_t)(kCostClasses - 1) * m->args.heavy_cap))) return rc;
+            if (m->args.schedule == 7 && (rc = dev_alloc(m, &sl.spill, sorted_spill_words(m->args)))) return rc;
         }
         if (!d->extra_streams_made) {
             for (cudaStream_t &x : d->extra_streams) GDPT_CUDA(d, cudaStreamCreateWithFlags(&x, cudaStreamNonBlocking));
@@ -1118,6 +1149,7 @@ extern "C" int gdpt_render_frame_begin(gdpt_shader *m, gdpt_shader *p, const gdp
         const FrameArgs saved = m->args;
         m->args.counters = sl.dcnt; m->args.camera = sl.cam_dev; m->args.out_rgba8 = sl.raw_rgba8; m->args.out_depth = sl.raw_depth;
         m->args.hit_list = sl.hit_list;
+        if (sl.spill) m->args.sorted_spill = sl.spill;
         d->stream = S; // enqueue_k1 / enqueue_k2 launch on the device's current stream
         cudaEventRecord(sl.t0, S);
         rc = enqueue_k1(m);
@@ -1266,6 +1298,8 @@ extern "C" int gdpt_render_frame_wait(gdpt_shader *m, gdpt_frame_stats *out_stat
         out_stats->rays = c.rays;
         out_stats->primary_hits = c.primary_hits;
         out_stats->retraced = c.retraced;
+        out_stats->own_node_steps = c.own_node_steps; out_stats->own_box_tests = c.own_box_tests; out_stats->own_tri_tests = c.own_tri_tests;
+        out_stats->own_inst_entries = c.own_inst_entries; out_stats->own_proofs = c.own_proofs;
         out_stats->node_pops = c.node_pops; out_stats->box_tests = c.box_tests; out_stats->tri_tests = c.tri_tests;
         out_stats->tlas_leaves = c.tlas_leaves; out_stats->max_stack = c.max_stack;
         out_stats->kernel_launches = sl.launches;

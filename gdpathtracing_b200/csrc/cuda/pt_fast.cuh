@@ -24,6 +24,7 @@ namespace gdpt {
 
 #define RAY_OVERFLOW 1u /* RayState.overflow bit 0: traversal stack exceeded */
 #define RAY_TIE 2u      /* RayState.overflow bit 1: a second pair reached the current minimum t (or t was NaN) */
+#define RAY_FAR 4u      /* RayState.overflow bit 2: the ray starts beyond the reach of the search's culling margins */
 
 // Stack of the search.  The trees' stack need is bounded at upload (fast_bvh.h: max_depth / need4 < GDPT_FAST_MAX_DEPTH
 // < GDPT_MAX_STACK), so no overflow test is needed here -- unlike the reference-order traversal, whose 64+64 entries
@@ -71,6 +72,7 @@ GDPT_HD void fast_ray_begin(RayState &r, const SceneView &sc, f3 o, f3 d)
 {
     ray_begin(r, sc, o, d);
     r.rd = fast_rcp3(d); // the search's own reciprocal; the proof recomputes the exact one
+    if (fast_far_origin(o, sc.fast_world_reach)) r.overflow |= RAY_FAR;
 }
 
 // true box of a child: entry distance and whether the subtree can still hold a hit with t <= r.t
@@ -281,6 +283,7 @@ template <bool WIDE, class Stack> GDPT_HD void fast_enter_instance(const SceneVi
     fast_local_ray(c0, c1, c2, c3, r.wo, r.wd, &r.o, &r.d);
     r.rd = fast_rcp3(r.d);
     r.inst = idx;
+    if (fast_far_origin(r.o, tmax4.w)) r.overflow |= RAY_FAR; // too far out for this BLAS's margins (derived_layout.h fast_reach)
     float entry;
     const bool touches = fast_slab(r, tmin4.x, tmin4.y, tmin4.z, tmax4.x, tmax4.y, tmax4.z, &entry);
     const uint32_t root = WIDE ? fast_bits(tmin4.w) : tail.w; // the BLAS root in the table being searched
@@ -317,11 +320,51 @@ template <class Stack> GDPT_HD void fast_trace_ray4(const SceneView &sc, RayStat
     }
 }
 
-// The search ended with a hit (r.t < 1e9) and no tie.  Does the reference traversal test this pair?
-// Sufficient condition: with the reference's own box arithmetic (slab_test == intersectAABB,
-// main.glsl:259-268), the TLAS leaf of the instance (world ray) and the BLAS leaf of the triangle
-// (instance-local ray) are entered strictly before r.t.  Rays with a zero direction component are
-// sent to the exact traversal: 0 * inf in a slab would void the monotonicity argument.
+// Is there a pair other than (skip_inst, skip_tri) that the ray hits at t <= bound?  The same complete search, with the
+// running minimum started at `bound` and the one pair left out.  Cold path: a few rays per frame get here.
+struct FastLocalStack {
+    uint32_t slots[GDPT_FAST_MAX_DEPTH + 4u];
+    GDPT_HD void store(uint32_t i, uint32_t v) { slots[i] = v; }
+    GDPT_HD uint32_t load(uint32_t i) const { return slots[i]; }
+};
+GDPT_HD bool fast_other_pair_within(const SceneView &sc, f3 wo, f3 wd, float bound, uint32_t skip_inst, uint32_t skip_tri)
+{
+    FastLocalStack st;
+    RayState r;
+    fast_ray_begin(r, sc, wo, wd);
+    r.t = bound;
+    const bool wide = sc.fast4_ok != 0u;
+    if (wide) r.cur = sc.fast4_root;
+    while (r.cur != LINK_NONE) {
+        if (fast_link_is_leaf(r.cur)) {
+            const uint32_t leaf = r.cur;
+            r.cur = fast_pop(r, st);
+            const uint32_t first = leaf & FAST_LEAF_FIRST_MASK, count = ((leaf >> FAST_LEAF_COUNT_SHIFT) & 7u) + 1u;
+            for (uint32_t i = 0; i < count; i++) {
+                const q4f a = ldq(sc.fast_tris, (first + i) * 3u + 0u), b = ldq(sc.fast_tris, (first + i) * 3u + 1u), c = ldq(sc.fast_tris, (first + i) * 3u + 2u);
+                if (fast_bits(a.w) == skip_tri && r.inst == skip_inst) continue;
+                fast_triangle_test(r, a, b, c);
+            }
+        } else if (fast_link_is_node(r.cur, r.inst)) {
+            if (wide) fast_step_node4(sc, r, st); else fast_step_node(sc, r, st);
+        } else {
+            if (r.inst != GDPT_NO_INSTANCE) { r.o = r.wo; r.d = r.wd; r.rd = fast_rcp3(r.wd); r.inst = GDPT_NO_INSTANCE; }
+            if (r.cur & LINK_LEAF) { if (wide) fast_enter_instance<true>(sc, r, st); else fast_enter_instance<false>(sc, r, st); }
+        }
+    }
+    return r.t < bound || (r.overflow & (RAY_TIE | RAY_FAR)) != 0u; // a closer pair, one exactly at the bound, or margins not trusted
+}
+
+// The search ended with a hit at the unique minimum t_w = r.t (no tie).  Does the reference traversal test this pair?
+// It does iff every box on the way to it passes the reference's push test  d < hit.t  at the time its parent is
+// visited (main.glsl:290-299, 336-345).  Until the pair is tested, hit.t is the smallest t of the OTHER pairs tested so far,
+// hence >= t2 := the smallest t over all other pairs.  So it is enough that, with the reference's own box arithmetic
+// (slab_test == intersectAABB, main.glsl:259-268), the TLAS leaf of the instance (world ray) and the BLAS leaf of the
+// triangle (instance-local ray) are entered at  d < t_w  (then d < t_w < hit.t whatever was tested before) -- or,
+// when rounding puts an entry distance at or a few ulp beyond t_w (a hit on the face of its own leaf box), at  d < t2,
+// which one more search with the pair left out decides (fast_other_pair_within).  Reference boxes are nested and the
+// slab arithmetic is monotone in the box, so the ancestors of those two boxes are entered no later.  Rays with a zero
+// direction component are sent to the exact traversal: 0 * inf in a slab would void the monotonicity argument.
 GDPT_HD bool fast_proves_reference_hit(const SceneView &sc, const RayState &r)
 {
     const uint32_t inst = r.blas_front & ~GDPT_FRONT_BIT;
@@ -332,16 +375,17 @@ GDPT_HD bool fast_proves_reference_hit(const SceneView &sc, const RayState &r)
     const q4u tail = ldqu(sc.inst_recs, inst * 7u + 4u);
     RayState w;
     w.o = r.wo; w.rd = rcp3(r.wd);
-    bool ok = r.wd.x != 0.0f && r.wd.y != 0.0f && r.wd.z != 0.0f;
+    if (!(r.wd.x != 0.0f && r.wd.y != 0.0f && r.wd.z != 0.0f)) return false;
+    float entered = 0.0f; // the later of the two entry distances
     if ((sc.tlas_root_link & LINK_LEAF) == 0u) {
         const q4f n0 = ldq(sc.tlas, tail.y * 2u + 0u);
         const q4f n1 = ldq(sc.tlas, tail.y * 2u + 1u);
-        ok = ok && slab_test(w, n0.x, n0.y, n0.z, n1.x, n1.y, n1.z) < r.t;
+        entered = slab_test(w, n0.x, n0.y, n0.z, n1.x, n1.y, n1.z);
     }
     f3 ld;
     fast_local_ray(c0, c1, c2, c3, r.wo, r.wd, &w.o, &ld);
     w.rd = rcp3(ld);
-    ok = ok && ld.x != 0.0f && ld.y != 0.0f && ld.z != 0.0f;
+    if (!(ld.x != 0.0f && ld.y != 0.0f && ld.z != 0.0f)) return false;
 #if defined(__CUDA_ARCH__)
     const uint32_t leaf = __ldg(sc.tri_leaf + r.tri);
 #else
@@ -350,15 +394,18 @@ GDPT_HD bool fast_proves_reference_hit(const SceneView &sc, const RayState &r)
     if (leaf != tail.z) { // a root that is itself the leaf is never box-tested (main.glsl:274)
         const q4f b0 = ldq(sc.bvh, leaf * 3u + 0u);
         const q4f b1 = ldq(sc.bvh, leaf * 3u + 1u);
-        ok = ok && slab_test(w, b0.x, b0.y, b0.z, b1.x, b1.y, b1.z) < r.t;
+        const float d = slab_test(w, b0.x, b0.y, b0.z, b1.x, b1.y, b1.z);
+        entered = d > entered ? d : entered;
     }
-    return ok;
+    if (entered < r.t) return true;
+    if (!(entered < 1e29f)) return false; // the reference's arithmetic misses one of the boxes outright
+    return !fast_other_pair_within(sc, r.wo, r.wd, entered, inst, r.tri);
 }
 
 // Verdict on a finished search: true = the record in `r` is the reference's record.
 GDPT_HD bool fast_result_is_reference(const SceneView &sc, const RayState &r)
 {
-    if (r.overflow & RAY_TIE) return false;
+    if (r.overflow & (RAY_TIE | RAY_FAR)) return false;
     if (!(r.t < 1e9f)) return true;
     return fast_proves_reference_hit(sc, r);
 }

@@ -25,7 +25,9 @@ struct FrameCounters {
     unsigned long long primary_hits;
     unsigned long long rays;            // ray_trace() calls, counted by the single-kernel schedule
     unsigned long long node_pops, box_tests, tri_tests, tlas_leaves; // TRACE builds only
-    unsigned long long retraced;        // schedule 5: rays re-traced in reference order (proof failed or tie)
+    unsigned long long retraced;        // closest-hit schedules: rays re-traced in reference order (proof failed, tie, far origin)
+    // own work of the closest-hit search (COUNT instantiations only): what the timed kernel itself executes
+    unsigned long long own_node_steps, own_box_tests, own_tri_tests, own_inst_entries, own_proofs;
 };
 
 struct FrameArgs {
@@ -47,6 +49,10 @@ struct FrameArgs {
     int cost_ema;                            // schedule 6: per-pixel cost hint is a running mean over frames (1) or the last frame's (0)
     int pool_alive;                          // schedule 6: cap on the paths a warp keeps alive (32..slots; 0 = all slots)
     int pool_wait;                           // schedule 6: lane-iterations finished rays may wait before a pool service (0 = off)
+    uint32_t *sorted_spill;                  // schedule 7: stack entries beyond the shared-memory part, per block and slot
+    uint32_t sorted_spill_depth;             //   entries per slot (>= 1)
+    int sort4;                               // schedules 6/7: children of a four-wide node in full distance order (1) or nearest first (0)
+    int count_work;                          // schedule 7: run the instantiation that counts its own work (untimed frames of bench.py)
     FrameCounters *counters;
     // scheduling knobs (results do not depend on them)
     int refill_below;  // refill idle lanes when fewer than this many lanes are traversing
@@ -54,6 +60,7 @@ struct FrameArgs {
     int schedule;      // 2: single path kernel over all pixels in reference order (trace mode, DEBUG_STEPS, no culling),
                        // 3: camera-ray classification kernel + reference-order path kernel over the surviving pixels,
                        // 6: classification kernel + closest-hit path kernel with pooled paths (pt_fast.cuh, k_path_pool.cuh)
+                       // 7: classification kernel + closest-hit path kernel with phase-sorted rays (k_path_sorted.cuh)
     int shade_at;      // schedule 2: shade once this many lanes wait with a finished ray
     int cull;          // 1: skip children whose tight box the ray misses (pt_scene.cuh); results identical
     // optional per-warp schedule profile (gdpt_shader_set_warp_profile): 8 x u64 per warp of the path kernel
@@ -84,6 +91,9 @@ void launch_path_list(const FrameArgs &a, bool record, cudaStream_t s);
 // re-trace where it fails), paths kept in per-warp shared-memory pools (k_path_pool): lanes swap rays instead of
 // waiting for a shading quorum, shading and camera-ray generation run on full warps.
 void launch_path_pool(const FrameArgs &a, bool record, cudaStream_t s);
+// ... schedule 7 keeps the rays themselves in shared memory and runs every phase of the search on the rays that are in it.
+void launch_path_sorted(const FrameArgs &a, bool record, cudaStream_t s);
+size_t sorted_spill_words(const FrameArgs &a); // uint32 elements a.sorted_spill must provide on the current device
 size_t path_kernel_warps(const FrameArgs &a); // warps of the path kernel enqueue_k1 would launch for `a`
 // K2: progressive accumulation + ACES (progressive_rendering.glsl:28-46).
 void launch_progressive(const uint32_t *raw_rgba8, uint32_t *screen_rgba8, float4 *accum, const gdpt_progressive_params *params_dev,

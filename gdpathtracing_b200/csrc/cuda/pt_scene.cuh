@@ -71,7 +71,7 @@ struct __attribute__((aligned(16))) InstRec {
     uint32_t root_orig;     // reference BVH node index of the root
     uint32_t fast_root;     // link of this BLAS's root in the closest-hit tables (fast_bvh.h)
     float tight_min[4];     // tight box of the whole BLAS, object space; w = bits of this BLAS's root link in the four-wide table
-    float tight_max[4];
+    float tight_max[4];     // w = largest |local origin coordinate| for which the search's margins are trusted in this BLAS
 };
 static_assert(sizeof(InstRec) == 112, "InstRec is seven 128-bit loads");
 
@@ -133,6 +133,9 @@ struct SceneView {
     const FastNode4 *fast4;
     uint32_t fast4_root;          // link the search starts from (TLAS root)
     uint32_t fast4_ok;
+    // largest |origin coordinate| (world space) for which the search's culling margins are trusted; rays from farther
+    // out are answered by the exact traversal (derived_layout.h fast_reach)
+    float fast_world_reach;
 };
 
 } // namespace gdpt

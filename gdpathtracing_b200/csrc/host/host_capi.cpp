@@ -113,6 +113,7 @@ void gdpt_camera_set_trace(gdpt_camera_node *c, int segments, uint32_t visits) {
 void gdpt_camera_set_debug_steps(gdpt_camera_node *c, int on) { c->impl.set_debug_steps(on != 0); }
 void gdpt_camera_set_cull(gdpt_camera_node *c, int mode) { c->impl.set_cull(mode); }
 void gdpt_camera_set_variant(gdpt_camera_node *c, int variant) { c->impl.set_variant(variant); }
+void gdpt_camera_set_count_work(gdpt_camera_node *c, int on) { c->impl.set_count_work(on != 0); }
 void gdpt_camera_set_tuning(gdpt_camera_node *c, const char *name, int value) { if (name) c->impl.set_tuning(name, value); }
 void gdpt_camera_set_record_hits(gdpt_camera_node *c, int segments) { c->impl.set_record_hits(segments); }
 void gdpt_camera_set_fused_frame(gdpt_camera_node *c, int on) { c->impl.set_fused_frame(on != 0); }

@@ -150,6 +150,7 @@ bool PathTracingCamera::init()
     if (cull_ >= 0) defines.push_back("#define GDPT_CULL " + std::to_string(cull_));
     if (variant_ >= 0) defines.push_back("#define GDPT_VARIANT " + std::to_string(variant_));
     if (record_hits_ > 0) defines.push_back("#define GDPT_RECORD_HITS " + std::to_string(record_hits_));
+    if (count_work_) defines.push_back("#define GDPT_COUNT_WORK");
     for (const auto &kv : tuning_) defines.push_back("#define GDPT_TUNE_" + kv.first + " " + std::to_string(kv.second));
     cs_ = new ComputeShader("res://addons/jar_path_tracing/src/shaders/main.glsl", rd_, defines);
 

@@ -100,6 +100,8 @@ public:
     void set_variant(int variant) { variant_ = variant; }
     // scheduling knob of the path kernels ("#define GDPT_TUNE_<NAME> n", include/gdpt.h), for A/B measurements only
     void set_tuning(const std::string &name, int value) { tuning_[name] = value; }
+    // "#define GDPT_COUNT_WORK": the path kernel also counts its own work (gdpt_frame_stats own_*); measurement aid
+    void set_count_work(bool on) { count_work_ = on; }
     // true: one gdpt_render_frame call per frame; false: the reference's dispatch-by-dispatch sequence
     void set_fused_frame(bool on) { fused_frame_ = on; }
 
@@ -165,6 +167,7 @@ private:
     int record_hits_ = 0;
     int variant_ = -1;
     std::map<std::string, int> tuning_;
+    bool count_work_ = false;
     uint32_t last_frame_count_ = 0;
 };
 

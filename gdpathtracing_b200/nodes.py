@@ -195,6 +195,10 @@ class PathTracingCamera:
         """Scheduling knob of the path kernels ("#define GDPT_TUNE_<NAME> n"); A/B measurements only, results identical."""
         host.gdpt_camera_set_tuning(self._h, str(name).upper().encode(), int(value))
 
+    def set_count_work(self, on):
+        """The closest-hit path kernel also counts the work it executes itself (stats own_*); measurement aid."""
+        host.gdpt_camera_set_count_work(self._h, 1 if on else 0)
+
     def set_record_hits(self, segments):
         """Hit records of the first n segments from the rendering kernels (no work counters)."""
         host.gdpt_camera_set_record_hits(self._h, int(segments))

@@ -112,6 +112,8 @@ GDPT_API uint32_t gdpt_abi_version(void);
  *                              (variant 6) answers rays with an order-free closest-hit search plus a proof that
  *                              the reference reaches the same triangle, and re-traces the rest;
  *                              variant 2 is one kernel over all pixels in reference order.  Identical results
+ *   "#define GDPT_COUNT_WORK"  the closest-hit path kernel also counts the work it executes itself
+ *                              (gdpt_frame_stats own_*); slower, for the roofline numerator of bench.py
  *   "#define GDPT_TUNE_<NAME> n"  scheduling knob of the path kernels (BURST, SHADE_AT, REFILL_BELOW, POOL_WAIT,
  *                              ...; A/B measurements).  Results do not depend on them.  The process environment
  *                              is never consulted: what runs is decided by this list alone
@@ -254,6 +256,9 @@ typedef struct gdpt_frame_stats {
     float    k1_ms;         /* CUDA-event time of the last K1 dispatch */
     float    k2_ms;
     uint64_t retraced;      /* rays the closest-hit search handed to the exact reference-order traversal */
+    /* own work of the closest-hit search, filled only under "#define GDPT_COUNT_WORK": what the rendering kernel itself
+     * executed (four-wide node steps, slab tests = 4 per step, triangle tests, instance entries, proofs) */
+    uint64_t own_node_steps, own_box_tests, own_tri_tests, own_inst_entries, own_proofs;
 } gdpt_frame_stats;
 GDPT_API int  gdpt_shader_get_stats(gdpt_shader *main_shader, gdpt_frame_stats *out);
 

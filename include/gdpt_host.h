@@ -89,6 +89,7 @@ GDPT_API void  gdpt_camera_set_record_hits(gdpt_camera_node *c, int segments);
 /* kernel schedule ("#define GDPT_VARIANT n", gdpt.h); -1 = backend default; results are identical for every value */
 GDPT_API void  gdpt_camera_set_variant(gdpt_camera_node *c, int variant);
 /* scheduling knob of the path kernels ("#define GDPT_TUNE_<NAME> n", gdpt.h): A/B measurements; results are identical */
+GDPT_API void  gdpt_camera_set_count_work(gdpt_camera_node *c, int on);
 GDPT_API void  gdpt_camera_set_tuning(gdpt_camera_node *c, const char *name, int value);
 GDPT_API void  gdpt_camera_set_fused_frame(gdpt_camera_node *c, int on);
 /* init() / render() (path_tracing_camera.cpp:111-232); init returns 1 when check_ready() */

@@ -45,7 +45,7 @@ template <bool CULL> static void run_ray(const SceneView &sc, RayState &r, HostS
         __atomic_add_fetch(&g_fast_rays, 1, __ATOMIC_RELAXED);
         if (fast_result_is_reference(sc, f)) { r = f; return; }
         __atomic_add_fetch(&g_fast_retraced, 1, __ATOMIC_RELAXED);
-        if (f.overflow & RAY_TIE) __atomic_add_fetch(&g_fast_ties, 1, __ATOMIC_RELAXED);
+        if (f.overflow & (RAY_TIE | RAY_FAR)) __atomic_add_fetch(&g_fast_ties, 1, __ATOMIC_RELAXED);
     }
     if (g_stepwise == 2) trace_ray_compact<true, CULL>(sc, r, st, tc);
     else if (g_stepwise) trace_ray_stepwise<true, CULL>(sc, r, st, tc);
@@ -84,6 +84,7 @@ static void make_view(const devcheck_scene *in, DerivedLayout &lay, FastLayout &
     sc.wide_nodes = lay.wide_nodes.data(); sc.leaf_recs = lay.leaf_recs.data();
     sc.wide_tlas = lay.wide_tlas.data(); sc.inst_recs = lay.inst_recs.data();
     sc.tlas_root_link = lay.tlas_root_link;
+    sc.fast_world_reach = lay.world_reach;
 }
 
 extern "C" {

@@ -19,6 +19,8 @@ ap.add_argument("--height", type=int, default=1080)
 ap.add_argument("--depth", type=int, default=8)
 ap.add_argument("--frames", type=int, default=4)
 ap.add_argument("--soup-tris", type=int, default=1_000_000)
+ap.add_argument("--variant", type=int, default=-1)
+ap.add_argument("--tune", action="append", default=[], metavar="NAME=N")
 ap.add_argument("--mode", type=int, default=0, help="0 progressive, 2 none")
 args = ap.parse_args()
 
@@ -32,6 +34,10 @@ cam.denoising_mode = args.mode
 cam.set_window_size(args.width, args.height)
 cam.set_global_transform(sc.camera_transform12)
 cam.set_max_depth(args.depth)
+if args.variant >= 0:
+    cam.set_variant(args.variant)
+for kv in args.tune:
+    cam.set_tuning(kv.split("=")[0], int(kv.split("=")[1]))
 cam.init()
 _lib.cuda.gdpt_shader_set_stage_timing(cam.main_shader, 1)
 buf = (ctypes.c_float * 64)()

@@ -20,6 +20,8 @@ ap.add_argument("--height", type=int, default=1080)
 ap.add_argument("--depth", type=int, default=8)
 ap.add_argument("--frames", type=int, default=3)
 ap.add_argument("--soup-tris", type=int, default=1_000_000)
+ap.add_argument("--variant", type=int, default=-1)
+ap.add_argument("--tune", action="append", default=[], metavar="NAME=N")
 ap.add_argument("--out", default="")
 args = ap.parse_args()
 
@@ -33,6 +35,10 @@ cam.denoising_mode = 2
 cam.set_window_size(args.width, args.height)
 cam.set_global_transform(sc.camera_transform12)
 cam.set_max_depth(args.depth)
+if args.variant >= 0:
+    cam.set_variant(args.variant)
+for kv in args.tune:
+    cam.set_tuning(kv.split("=")[0], int(kv.split("=")[1]))
 cam.init()
 _lib.check(_lib.cuda.gdpt_shader_set_warp_profile(cam.main_shader, 1), cam.device, "set_warp_profile")
 for f in range(args.frames):
@@ -43,6 +49,9 @@ n = _lib.cuda.gdpt_shader_read_warp_profile(cam.main_shader, buf.ctypes.data_as(
 assert n > 0, n
 t = buf[:8 * n].reshape(n, 8).astype(np.int64)
 t = t[t[:, 1] > 0]
+lanes = t[:, 2:7] >> 32          # schedule 7 packs the lanes that held a ray into the high words
+idle_iters = t[:, 7] >> 32
+t[:, 2:8] &= 0xFFFFFFFF
 t0 = t[:, 0].min()
 start, end = (t[:, 0] - t0) / 1e3, (t[:, 1] - t0) / 1e3
 iters = t[:, 2:7]
@@ -58,6 +67,8 @@ print(json.dumps({
     "ns_per_iter_slowest_warps": round(float(np.mean((dur * 1e3 / np.maximum(tot, 1))[np.argsort(end)[-32:]])), 1),
     "paths_started_pcts(10,50,90,100)": [int(x) for x in np.percentile(t[:, 7], [10, 50, 90, 100])],
     "busy_fraction": round(float(dur.sum() / (len(t) * end.max())), 3),
+    "lanes_per_iteration_I_L_T_F_E": [round(float(lanes[:, k].sum() / max(iters[:, k].sum(), 1)), 1) for k in range(5)],
+    "idle_iterations": int(idle_iters.sum()),
 }))
 if args.out:
     np.save(args.out, t)
