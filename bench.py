@@ -8,12 +8,15 @@ reference (main.glsl:352): a primary ray or one bounce segment; counted exactly 
 
   python bench.py [--gpus N] [--steps K] [--warmup W]            our arm
   python bench.py --impl reference ...                           the reference arm: the CPU
-        restatement of the reference's shader loop (oracle/, kind "port") on all host threads
+        reference's own shader text compiled as C++ (oracle/_ref, kind "reference"; our restatement of it,
+        kind "port", where that library is absent) on all host threads
 
 Prints ONE JSON line (rank 0).  Multi-GPU (torchrun): sample-index partition, each rank renders
-frame_index = step*N + rank + 1 of the same scene, one NCCL sum-reduce of the accumulations at
-the end of the timed region (weak scaling; `--partition rows` = row-band strong scaling with a
-per-step all-gather).
+frame_index = step*N + rank + 1 of the same scene; the row blocks of those frames are exchanged (NCCL
+over NVLink) and accumulated in frame order by their owners inside the timed region (weak scaling;
+`--partition rows` = row-band strong scaling, presentation fused into K2 as peer writes).  The line also
+carries `extra.c5`: BASELINE config C5 (4K instanced scene accumulated to 256 spp, presented every 64)
+in both partitions.
 """
 import argparse
 import ctypes
@@ -122,6 +125,14 @@ def workload_name(args):
 
 
 # ------------------------------------------------------------------------------------------ reference arm
+def reference_impl():
+    """What plays the reference on the host: its own shader text compiled as C++ (oracle/_ref/libgdpt_refshader.so,
+    built by oracle/Makefile where /root/reference exists and shipped with the snapshot) -> kind "reference";
+    our C++ restatement of it (oracle/pt_oracle.cpp) where that library is missing -> kind "port"."""
+    from oracle import oracle
+    return ("reference", "reference") if oracle.ref_shader_available() else ("restatement", "port")
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -132,14 +143,15 @@ def run_reference(args, rank, world):
     osc = oracle.Scene(grp.buffers(), grp.texture_layers())
     W, H = args.width, args.height
     threads = oracle.hardware_threads()
+    impl, kind = reference_impl()
 
-    def frame(idx, row_step):
+    def frame(idx, row_step, which=impl):
         cam = bytes(nodes.make_camera_block(sc.camera_transform12, sc.fov, W, H, idx))
         t0 = time.perf_counter()
-        r = oracle.path_trace(osc, W, H, cam, max_depth=args.depth, threads=threads, row_step=row_step)
+        r = oracle.path_trace(osc, W, H, cam, max_depth=args.depth, threads=threads, row_step=row_step, impl=which, counters=False)
         screen, acc = r["rgba8"], np.zeros((H, W, 4), np.float32)
         if row_step == 1:
-            oracle.progressive(screen, acc, 1)
+            oracle.progressive(screen, acc, 1, impl=which)
         return time.perf_counter() - t0, r["stats"]["rays"]
 
     t_probe, _ = frame(1, 8)  # every 8th row: sizes the bounded sample
@@ -153,6 +165,13 @@ def run_reference(args, rank, world):
         t, rays = frame(args.warmup + s + 1, row_step)
         total_t += t; total_rays += rays
     mrays = total_rays / total_t / 1e6
+    port_mrays = None
+    if impl == "reference":  # the restatement beside it, on two frames of the same sample
+        pt, pr = 0.0, 0
+        for s in range(2):
+            t, rays = frame(args.warmup + s + 1, row_step, "restatement")
+            pt += t; pr += rays
+        port_mrays = pr / pt / 1e6
     ref_build = None
     if oracle.ref_available():
         t0 = time.perf_counter()
@@ -164,10 +183,12 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "Mrays/s", "value": mrays, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_t / args.steps * 1e3 * row_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args), "what": "CPU restatement of main.glsl/brdfs.glsl/progressive_rendering.glsl "
-                   "(the reference's GPU half cannot run without Godot+Vulkan); ms_per_step is scaled to a full frame"},
-        "cpu_baseline": {"value": mrays, "unit": "Mrays/s", "cores": threads, "kind": "port", "sample": sample,
-                         "bvh_build_s": build_s, "reference_bvh_build_s": ref_build},
+        "config": {"workload": workload_name(args), "partition": "host CPU, all threads"},
+        "note": ("the reference's own shader text (main.glsl + brdfs.glsl + progressive_rendering.glsl) compiled as C++ and run on the "
+                 "host cores" if kind == "reference" else "C++ restatement of the reference's shaders (the compiled shader text is "
+                 "not on this box)") + "; its GPU half cannot run without Godot + Vulkan; ms_per_step is scaled to a full frame",
+        "cpu_baseline": {"value": mrays, "unit": "Mrays/s", "cores": threads, "kind": kind, "sample": sample,
+                         "restatement_value": port_mrays, "scene_build_s": build_s, "reference_bvh_build_s": ref_build},
         "e2e": {"value": mrays, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -175,14 +196,40 @@ def run_reference(args, rank, world):
 
 
 # ------------------------------------------------------------------------------------------ our arm
-def stage_kinds(n, depth):
-    """Kernel name of each timed K1 stage, from the number of stages the backend reports:
-    1 = single path kernel, 2 = camera-ray classification + path kernel, 2*depth = wavefront."""
-    if n == 1:
-        return ["k_path"]
-    if n == 2:
-        return ["k_primary_cull", "k_path"]
-    return ["k_trace<primary>" if i == 0 else ("k_shade" if i % 2 == 1 else "k_trace<bounce>") for i in range(n)]
+SCHEDULES = {
+    2: ("k_path<all pixels>", "the reference's visiting order on the reference arrays, no culling (trace / DEBUG_STEPS mode)"),
+    3: ("k_primary_cull + k_path<survivors>", "the reference's visiting order on the reference arrays, tight-box culling"),
+    6: ("k_primary_cull + k_path_pool", "closest-hit search over our own four-wide SAH tables + proof that the reference traversal "
+        "returns the same record; paths pooled per warp"),
+    7: ("k_primary_cull + k_path_sorted", "closest-hit search over our own four-wide SAH tables + proof that the reference traversal "
+        "returns the same record; rays sorted by phase in shared memory"),
+}
+
+
+def make_camera(sc, grp, args, local, mode, W=None, H=None, depth=None, variant=None, shard=None, count_work=False, trace=0):
+    from gdpathtracing_b200 import PathTracingCamera
+    cam = PathTracingCamera()
+    cam.fov = sc.fov
+    cam.geometry_group = grp
+    cam.denoising_mode = mode
+    cam.set_window_size(W or args.width, H or args.height)
+    cam.set_global_transform(sc.camera_transform12)
+    cam.set_max_depth(depth or args.depth)
+    cam.set_cuda_device(local)
+    if shard:
+        cam.set_shard(*shard)
+    v = args.variant if variant is None else variant
+    if v >= 0:
+        cam.set_variant(v)
+    for kv in args.tune:
+        k, val = kv.split("=")
+        cam.set_tuning(k, int(val))
+    if count_work:
+        cam.set_count_work(True)
+    if trace:
+        cam.set_trace(trace, 0)
+    cam.init()
+    return cam
 
 
 def run_ours(args, rank, local, world):
@@ -196,26 +243,13 @@ def run_ours(args, rank, local, world):
     sc, grp = build_scene(args)
     W, H, D = args.width, args.height, args.depth
     rows_mode = world > 1 and args.partition == "rows"
+    sample_mode = world > 1 and not rows_mode
 
-    cam = PathTracingCamera()
-    cam.fov = sc.fov
-    cam.geometry_group = grp
-    cam.denoising_mode = PathTracingCamera.PROGRESSIVE_RENDERING
-    cam.set_window_size(W, H)
-    cam.set_global_transform(sc.camera_transform12)
-    cam.set_max_depth(D)
-    cam.set_cuda_device(local)
-    if rows_mode:
-        cam.set_shard(rank, world, args.band)
-    if args.variant >= 0:
-        cam.set_variant(args.variant)
-    for kv in args.tune:
-        k, v = kv.split("=")
-        cam.set_tuning(k, int(v))
-    cam.init()
-    build_s = None  # GeometryGroup3D.build ran inside init(); timed separately below on rank 0
-    # per-kernel split: measured on a few untimed frames after the timed region (the events it records between the K1
-    # kernels cost ~60 us per frame, so they stay out of every timed leg)
+    # N = 1: the reference's own sequence, K1 + K2 per frame.  Row bands: the same on this rank's rows.  Sample index:
+    # K1 per frame; the accumulation happens after the exchange (multigpu.SampleIndexAccumulator), inside the timed region.
+    cam = make_camera(sc, grp, args, local, PathTracingCamera.NONE if sample_mode else PathTracingCamera.PROGRESSIVE_RENDERING,
+                      shard=(rank, world, args.band) if rows_mode else None)
+    backend_stream = torch.cuda.ExternalStream(cam.stream())
 
     def set_index(step):
         # frame_index is incremented by render(); make step s use index s*world + rank + 1 (sample partition)
@@ -232,12 +266,13 @@ def run_ours(args, rank, local, world):
     out_ptr, out_size = cam.device_pointer("output")
     frame_t = multigpu.as_tensor(out_ptr, (H, W, 4), torch.uint8, dev_t)
     # row bands: the presented frame assembles itself in every rank's image (K2 writes its rows to the peers over
-    # NVLink, frames separated by a one-element all-reduce) unless --present gather asks for the NCCL all-gather
+    # NVLink, frames separated by a two-step handshake) unless --present gather asks for the NCCL all-gather
     peer_frame = multigpu.PeerFrame(cam, rank, world) if (rows_mode and args.present == "peer") else None
 
     def present():
         if peer_frame is not None:
-            peer_frame.barrier()
+            peer_frame.barrier()         # frame N is complete in every rank's image
+            peer_frame.frame_consumed()  # ... and nobody overwrites it before everybody is done with it
         else:
             multigpu.gather_row_bands(frame_t, args.band, rank, world)
 
@@ -249,6 +284,12 @@ def run_ours(args, rank, local, world):
         if rows_mode:
             present()
             torch.cuda.synchronize()
+    if sample_mode:  # first use of the exchange + accumulate path
+        warm = multigpu.SampleIndexAccumulator(H, W, rank, world, dev_t, multigpu.cuda_k2(cam))
+        with torch.cuda.stream(backend_stream):
+            warm.add(frame_t.clone().unsqueeze(0))
+            warm.present()
+        del warm
     stage_ms = np.zeros(64)
     n_stage = 0
     launches_per_frame = 0
@@ -258,9 +299,10 @@ def run_ours(args, rank, local, world):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    frames_kept = torch.empty((args.steps, H, W, 4), dtype=torch.uint8, device=dev_t) if sample_mode else None
     barrier()
     wall0 = time.perf_counter()
-    dev_ms, rays_total, k2_ms_total, gather_ms, k1_ms_total = 0.0, 0, 0.0, 0.0, 0.0
+    dev_ms, rays_total, k2_ms_total, gather_ms, k1_ms_total, retraced = 0.0, 0, 0.0, 0.0, 0.0, 0
     for s in range(args.steps):
         if flush is not None:
             flush.fill_(s & 0xFF)
@@ -272,22 +314,35 @@ def run_ours(args, rank, local, world):
         k2_ms_total += st["k2_ms"]
         k1_ms_total += st["k1_ms"]
         rays_total += st["rays"]
-        launches_per_frame = st["kernel_launches"] + 1  # K1 kernels + K2
+        retraced += st["retraced"]
+        launches_per_frame = st["kernel_launches"] + (0 if sample_mode else 1)  # K1 kernels + K2
+        if sample_mode:
+            with torch.cuda.stream(backend_stream):
+                frames_kept[s].copy_(frame_t)  # this rank's frame of the step, kept for the accumulation below (8 MB, device to device)
         if rows_mode:
-            ts = peer_frame._stream if peer_frame is not None else torch.cuda.current_stream()
+            ts = backend_stream if peer_frame is not None else torch.cuda.current_stream()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(ts)
             present()
             e1.record(ts); torch.cuda.synchronize(); cam.synchronize()
             gather_ms += e0.elapsed_time(e1)
-    if world > 1 and not rows_mode:
-        acc_ptr, _ = cam.device_pointer("accum")
-        acc_t = multigpu.as_tensor(acc_ptr, (H, W, 4), torch.float32, dev_t)
+    exchange = None
+    if sample_mode:
+        # the partition's exchange step, inside the timed region: row blocks of every rank's frames to their owners
+        # (NCCL send/recv over NVLink), K2 per frame in frame order on the owner, all-gather of the presented blocks
+        acc = multigpu.SampleIndexAccumulator(H, W, rank, world, dev_t, multigpu.cuda_k2(cam))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        multigpu.reduce_accumulations(acc_t, dst=0)
-        e1.record(); torch.cuda.synchronize()
+        with torch.cuda.stream(backend_stream):
+            e0.record(backend_stream)
+            acc.add(frames_kept)
+            presented = acc.present()
+            e1.record(backend_stream)
+        torch.cuda.synchronize(); cam.synchronize()
         gather_ms += e0.elapsed_time(e1)
+        launches_per_frame += world  # K2 launches of the accumulation, per step
+        exchange = {"bytes_sent_per_rank": int(acc.bytes_exchanged), "frames_accumulated": int(acc.frames_done),
+                    "what": "send/recv of row blocks (NCCL over NVLink) + K2 per frame in frame order + all-gather of the presented blocks"}
+        del presented
     # ---- per-kernel split of K1 (untimed frames, stage events on)
     _lib.check(cuda.gdpt_shader_set_stage_timing(cam.main_shader, 1), cam.device, "set_stage_timing")
     split_frames = min(args.steps, 8)
@@ -321,6 +376,9 @@ def run_ours(args, rank, local, world):
     # (a) the reference's blocking render(): one frame at a time; (b) the pipelined form of the same call
     # (render_begin / render_wait, up to three frames in flight: read-back and the next frame's kernels overlap the tail of a frame).
     # Every step of both does its own H2D camera upload and its own full-frame D2H.
+    if peer_frame is not None:
+        peer_frame.close()  # the end-to-end legs run without the frame handshake: no peer may write this rank's image in them
+        peer_frame = None
     barrier()
     sync_rays = 0
     t0 = time.perf_counter()
@@ -354,88 +412,114 @@ def run_ours(args, rank, local, world):
     barrier()
     e2e_s = time.perf_counter() - t0
     assert touched == 255 * args.steps, "a pipelined frame came back without pixels"
+    schedule = int(cuda.gdpt_shader_get_schedule(cam.main_shader))
 
-    if peer_frame is not None:
-        peer_frame.close()
     # ---- reduce over ranks: slowest rank's time, everybody's rays
     if world > 1:
-        t = torch.tensor([dev_ms, e2e_s, wall_ms, sync_s], dtype=torch.float64, device=dev_t)
+        t = torch.tensor([dev_ms, e2e_s, wall_ms, sync_s, gather_ms], dtype=torch.float64, device=dev_t)
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-        r = torch.tensor([rays_total, e2e_rays, sync_rays], dtype=torch.int64, device=dev_t)
+        r = torch.tensor([rays_total, e2e_rays, sync_rays, retraced], dtype=torch.int64, device=dev_t)
         torch.distributed.all_reduce(r, op=torch.distributed.ReduceOp.SUM)
-        dev_ms, e2e_s, wall_ms, sync_s = [float(x) for x in t.tolist()]
-        rays_total, e2e_rays, sync_rays = [int(x) for x in r.tolist()]
+        dev_ms, e2e_s, wall_ms, sync_s, gather_ms = [float(x) for x in t.tolist()]
+        rays_total, e2e_rays, sync_rays, retraced = [int(x) for x in r.tolist()]
+
+    # ---- work of one representative frame of THIS rank's share: what the timed kernel executes itself (its counting
+    # instantiation, untimed) and what the reference traversal would execute on the same rays (trace mode, untimed)
+    shard = (rank, world, args.band) if rows_mode else None
+    own = own_work(sc, grp, args, local, shard)
+    ref_work = trace_work(sc, grp, args, local, shard)
+    # ---- the reference's visiting order (schedule 3) on the same frames, beside the headline
+    s3 = None
+    if rank == 0 and args.schedule3 and schedule != 3:
+        c3 = make_camera(sc, grp, args, local, PathTracingCamera.PROGRESSIVE_RENDERING, variant=3, shard=shard)
+        t3, r3 = 0.0, 0
+        for s in range(3 + min(args.steps, 8)):
+            c3.set_frame_index(args.warmup + s - 3 if s >= 3 else s)
+            c3.render_device_only()
+            st = c3.stats()
+            if s >= 3:
+                t3 += st["k1_ms"] + st["k2_ms"]; r3 += st["rays"]
+        s3 = {"value": r3 / (t3 * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": t3 / min(args.steps, 8),
+              "kernels": SCHEDULES[3][0], "traversal": SCHEDULES[3][1]}
+        del c3
+    c5 = run_c5(args, rank, local, world, dev_t) if args.c5 else None
     if rank != 0:
         return
 
-    # ---- algorithmic work of one representative frame (instrumented kernels, untimed)
-    work = trace_work(sc, grp, args, local)
-    stage_avg = stage_ms[:n_stage] / min(args.steps, 8)
-    kinds = stage_kinds(n_stage, D)
-    by_kernel = {}
-    for i in range(n_stage):
-        k = by_kernel.setdefault(kinds[i], {"ms": 0.0, "launches": 0, "lane_ops": 0.0})
-        k["ms"] += stage_avg[i]; k["launches"] += 1
-        if n_stage > 2 and i % 2 == 0:
-            k["lane_ops"] += work["lane_ops_per_segment"][i // 2]
-    if n_stage <= 2:
-        # the traversal of every segment runs inside k_path; k_primary_cull (if any) does the TLAS walk of the camera
-        # rays that hit nothing.  The frame's algorithmic work is charged to the pair and timed over both.
-        top = "k_path"
-        # duration: CUDA events around K1 in the timed region (the split above only apportions it)
-        tk = {"ms": k1_ms_total / args.steps, "launches": 1, "lane_ops": float(sum(work["lane_ops_per_segment"]))}
-        top_label = "k_path" if n_stage == 1 else "k_path (+ k_primary_cull, timed together)"
-    else:
-        top = max((k for k in by_kernel if by_kernel[k]["lane_ops"] > 0), key=lambda k: by_kernel[k]["ms"])
-        tk = by_kernel[top]
-        top_label = top
-    peak_lane_ops = 148 * 4 * 32 * peaks["sm_max_mhz"] * 1e6
-    achieved = tk["lane_ops"] / (tk["ms"] * 1e-3) if tk["ms"] > 0 else 0.0
+    stage_avg = stage_ms[:n_stage] / split_frames
+    kinds = stage_kinds(n_stage)
+    k1_avg = k1_ms_total / args.steps
+    # duration of the path kernel: CUDA events around K1 in the timed region, apportioned by the untimed stage split
+    path_share = float(stage_avg[-1] / max(stage_avg.sum(), 1e-9)) if n_stage else 1.0
+    path_ms = k1_avg * path_share
     k2_avg_ms = k2_ms_total / args.steps
-    k2_bytes = 40.0 * W * H
-    roofline = {"kernel": top_label, "bound": "issue", "achieved": achieved / 1e12, "peak": peak_lane_ops / 1e12, "unit": "Tlane-op/s",
-                "frac": achieved / peak_lane_ops, "traffic": None, "launches_per_step": tk["launches"],
-                "algorithmic_bytes": work["algorithmic_bytes"],
-                "avg_launch_ms": tk["ms"] / tk["launches"], "share_of_step": (by_kernel[top]["ms"] / max(stage_avg.sum(), 1e-9)) * tk["ms"] / max(tk["ms"] + k2_avg_ms, 1e-9)
-                if n_stage <= 2 else by_kernel[top]["ms"] / max(stage_avg.sum() + k2_avg_ms, 1e-9),
+    peak_lane_ops = 148 * 4 * 32 * peaks["sm_max_mhz"] * 1e6
+    own_lane_ops = LANE_OPS_BOX * own["box_tests"] + LANE_OPS_TRI * own["tri_tests"] + LANE_OPS_TLAS_LEAF * own["inst_entries"]
+    ref_lane_ops = float(sum(ref_work["lane_ops_per_segment"]))
+    achieved = own_lane_ops / (path_ms * 1e-3) if path_ms > 0 else 0.0
+    step_ms = dev_ms / args.steps
+    roofline = {"kernel": kinds[-1], "bound": "issue", "achieved": achieved / 1e12, "peak": peak_lane_ops / 1e12, "unit": "Tlane-op/s",
+                "frac": achieved / peak_lane_ops, "traffic": None, "launches_per_step": 1,
+                "avg_launch_ms": path_ms, "share_of_step": path_ms / max(step_ms, 1e-9),
+                "own_work_per_launch": own,
+                "reference_work_ratio": ref_lane_ops / own_lane_ops if own_lane_ops > 0 else None,
+                "algorithmic_bytes": own["algorithmic_bytes"],
                 "peak_source": f"148 SM x 4 schedulers x 32 lanes x {peaks['sm_max_mhz']:.0f} MHz ({peaks['source']} sm_max_mhz)",
-                "work_model": "22*box_tests + 55*tri_tests + 45*tlas_leaf_visits lane-ops per ray (SURVEY 8d) of the REFERENCE traversal "
-                              "(no culling), counted by the instrumented kernels on one frame; the timed kernels skip the part of it "
-                              "that tight-box culling proves fruitless"}
-    for rf, kern in ((roofline, "k_path"),):
-        tr = ncu_traffic(kern, args)
-        if tr:
-            rf["traffic"], rf["traffic_unit"], rf["traffic_source"] = tr["bytes"], "bytes of DRAM per launch", tr["source"]
-    roofline_k2 = {"kernel": "k_progressive", "bound": "hbm", "achieved": k2_bytes / (k2_avg_ms * 1e-3) / 1e9 if k2_avg_ms > 0 else 0.0,
-                   "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": (k2_bytes / (k2_avg_ms * 1e-3) / 1e9) / peaks["hbm_gbs"] if k2_avg_ms > 0 else 0.0,
-                   "traffic": None, "avg_launch_ms": k2_avg_ms, "bytes_per_pixel": 40, "peak_source": peaks["source"] + " hbm_gbs"}
-    tr = ncu_traffic("k_progressive", args)
+                "work_model": "lane-ops the TIMED kernel executes itself, counted by its own counting instantiation on one frame of this "
+                              "rank's share: 22 per slab test (4 per four-wide node step) + 55 per triangle test + 45 per instance entry "
+                              "(unit costs of SURVEY 8d); reference_work_ratio = the same formula over the reference traversal of the "
+                              "same rays (trace mode) divided by it"}
+    tr = ncu_traffic(kinds[-1].split("<")[0], args)
     if tr:
-        roofline_k2["traffic"], roofline_k2["traffic_source"] = tr["bytes"], tr["source"]
+        roofline["traffic"], roofline["traffic_unit"], roofline["traffic_source"] = tr["bytes"], "bytes of DRAM per launch", tr["source"]
+    k2_bytes = 36.0 * W * H * (ref_work["local_rows"] / H)
+    roofline_k2 = None
+    if k2_avg_ms > 0:
+        roofline_k2 = {"kernel": "k_progressive", "bound": "hbm", "achieved": k2_bytes / (k2_avg_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
+                       "unit": "GB/s", "frac": (k2_bytes / (k2_avg_ms * 1e-3) / 1e9) / peaks["hbm_gbs"], "traffic": None,
+                       "avg_launch_ms": k2_avg_ms, "bytes_per_pixel": 36, "peak_source": peaks["source"] + " hbm_gbs",
+                       "work_model": "36 B per pixel (SURVEY 8d): 16 R + 16 W accumulation, 4 W screen; the 4 B raw read rides on top"}
+        tr = ncu_traffic("k_progressive", args)
+        if tr:
+            roofline_k2["traffic"], roofline_k2["traffic_source"] = tr["bytes"], tr["source"]
 
     cpu = cpu_baseline(sc, grp, args) if (world == 1 and args.cpu_baseline) else None
     value = rays_total / (dev_ms * 1e-3) / 1e6
+    path_rays = own["proofs"]  # every ray the path kernel answers ends in one verdict
+    if rows_mode:
+        partition = ("row bands; K2 writes its rows into every peer's image over NVLink, frames separated by two one-element "
+                     "all-reduces; equal to the NCCL all-gather of the bands: " + str(present_check)) if args.present == "peer" \
+            else "row bands + NCCL all-gather per step"
+    elif sample_mode:
+        partition = ("sample index: every rank renders its own frames; row blocks exchanged (NCCL send/recv over NVLink) and accumulated "
+                     "in frame order by their owners, presented frame all-gathered -- inside the timed region, bit-identical to one GPU")
+    else:
+        partition = "single GPU"
     line = {
         "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong" if rows_mode else "weak",
+        "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong" if rows_mode else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args), "partition": (("row bands, bands written to every peer's image by K2 over NVLink + "
-                   "one-element all-reduce per step; equal to the NCCL all-gather of the bands: " + str(present_check)
-                   if peer_frame is not None else "row bands + all-gather per step") if rows_mode else
-                   ("sample index, one accumulation sum-reduce at the end" if world > 1 else "single GPU")),
-                   "rays_per_step": rays_total / args.steps / world, "frames_per_step": world if not rows_mode else 1,
+        "config": {"workload": workload_name(args), "partition": partition,
+                   "schedule": schedule, "kernels": SCHEDULES[schedule][0], "traversal": SCHEDULES[schedule][1]
+                   + f"; {retraced / args.steps / world:.1f} of {rays_total / args.steps / world:.0f} rays per frame re-traced in reference order",
+                   "tuning": args.tune, "rays_per_step": rays_total / args.steps / world, "frames_per_step": world if not rows_mode else 1,
+                   "rays_in_path_kernel_per_frame": path_rays,
+                   "mrays_s_over_rays_that_enter_an_instance": path_rays / (path_ms * 1e-3) / 1e6 if path_ms > 0 else None,
+                   "gather_ms": gather_ms, "exchange": exchange,
+                   "reference_visiting_order": s3,
                    "l2": "256 MiB write between steps (outside the per-step events)" if args.l2_flush else "no flush",
-                   "timing": "CUDA events around K1 and K2 on the launching stream, summed over steps, max over ranks",
+                   "timing": "CUDA events around K1 and K2 on the launching stream, summed over steps, max over ranks; gather_ms (events "
+                             "on the same stream) is part of it",
                    "wall_ms_per_step_incl_flush_and_sync": wall_ms / args.steps,
                    "stage_ms_note": "split measured on untimed frames with an event between the K1 kernels",
                    "stage_ms": {f"{i}:{kinds[i]}": round(float(stage_avg[i]), 5) for i in range(n_stage)},
-                   "kernels": {k: {"ms_per_step": v["ms"], "launches": v["launches"]} for k, v in by_kernel.items()},
-                   "work_per_frame": work["totals"]},
+                   "k2_ms": k2_avg_ms,
+                   "reference_work_per_frame": ref_work["totals"]},
         "clocks": clocks,
         "e2e": {"value": e2e_rays / e2e_s / 1e6, "unit": "Mrays/s", "ms_per_step": e2e_s / args.steps * 1e3,
                 "h2d_bytes_per_step": 160 + 12, "d2h_bytes_per_step": W * H * 4,
                 "api": "PathTracingCamera.render_begin()/render_wait() -> gdpt_render_frame_begin/_wait: host camera block in, "
-                       "pinned host RGBA8 frame out, every step; three frames in flight on two streams",
+                       "pinned host RGBA8 frame out, every step; three frames in flight on three streams",
                 "blocking_render": {"value": sync_rays / sync_s / 1e6, "ms_per_step": sync_s / args.steps * 1e3,
                                     "api": "PathTracingCamera.render() -> gdpt_render_frame, one frame at a time"}},
         "gpu_launches": int(launches_per_frame * args.steps * 3),  # device-timed leg + the two end-to-end legs
@@ -443,23 +527,47 @@ def run_ours(args, rank, local, world):
     }
     if cpu:
         line["cpu_baseline"] = cpu
+    if c5:
+        line["extra"] = {"c5": c5}
     print(json.dumps(line), file=JSON_OUT, flush=True)
 
 
-def trace_work(sc, grp, args, local):
-    """Per-segment algorithmic work of one frame from the instrumented (GDPT_TRACE) kernels."""
-    from gdpathtracing_b200 import PathTracingCamera
-    cam = PathTracingCamera()
-    cam.fov = sc.fov
-    cam.geometry_group = grp
-    cam.denoising_mode = PathTracingCamera.NONE
-    cam.set_window_size(args.width, args.height)
+def restart_accumulation(cam, sc):
+    """One frame from a moved camera: the next frame at the scene's pose is frame_count 1 again
+    (progressive_rendering.cpp:53-60 resets the count when the camera transform changes)."""
+    moved = np.array(sc.camera_transform12, np.float32).copy()
+    moved[9] += 1.0
+    cam.set_global_transform(moved)
+    cam.render_device_only()
+    cam.synchronize()
     cam.set_global_transform(sc.camera_transform12)
-    cam.set_max_depth(args.depth)
-    cam.set_cuda_device(local)
-    cam.set_trace(args.depth, 0)
+
+
+def stage_kinds(n):
+    return ["k_path"] if n == 1 else ["k_primary_cull", "k_path"]
+
+
+def own_work(sc, grp, args, local, shard):
+    """What the timed path kernel executes on one frame: its counting instantiation (GDPT_COUNT_WORK), untimed."""
+    from gdpathtracing_b200 import PathTracingCamera
+    cam = make_camera(sc, grp, args, local, PathTracingCamera.NONE, shard=shard, count_work=True)
     cam.set_frame_index(args.warmup)
-    cam.init()
+    cam.render_device_only()
+    st = cam.stats()
+    del cam
+    own = {"node_steps": int(st["own_node_steps"]), "box_tests": int(st["own_box_tests"]), "tri_tests": int(st["own_tri_tests"]),
+           "inst_entries": int(st["own_inst_entries"]), "proofs": int(st["own_proofs"]), "retraced": int(st["retraced"])}
+    # bytes the search asks the memory system for: 128 B per four-wide node, 48 B per triangle, 112 B per instance record,
+    # 324 B per shaded hit (SURVEY 8d: triangle data 80 + instance 176 + material 64 + texel 4)
+    own["algorithmic_bytes"] = 128.0 * own["node_steps"] + 48.0 * own["tri_tests"] + 112.0 * own["inst_entries"] + 324.0 * max(st["rays"] - own["proofs"], 0)
+    return own
+
+
+def trace_work(sc, grp, args, local, shard):
+    """Per-segment algorithmic work of the REFERENCE traversal of one frame, from the instrumented (GDPT_TRACE) kernels."""
+    from gdpathtracing_b200 import PathTracingCamera
+    cam = make_camera(sc, grp, args, local, PathTracingCamera.NONE, shard=shard, trace=args.depth, variant=-1)
+    cam.set_frame_index(args.warmup)
     cam.render_device_only()
     st = cam.stats()
     per_seg = []
@@ -470,41 +578,208 @@ def trace_work(sc, grp, args, local):
                              + LANE_OPS_TRI * t["tri_tests"][live].astype(np.float64).sum()
                              + LANE_OPS_TLAS_LEAF * t["tlas_leaves"][live].astype(np.float64).sum()))
     totals = {k: int(st[k]) for k in ("rays", "primary_hits", "node_pops", "box_tests", "tri_tests", "tlas_leaves", "max_stack")}
+    local_rows = args.height if not shard else int(sum(1 for y in range(args.height) if (y // shard[2]) % shard[1] == shard[0]))
     del cam
-    # SURVEY 8d secondary figure: 144 B per internal pop (= per pair of box tests), 48 B per leaf pop, 48 B per triangle test,
-    # 208 B per TLAS leaf, 324 B per shaded hit -- bytes the reference traversal of these rays asks the memory system for
-    internal = totals["box_tests"] // 2
-    leaves = max(totals["node_pops"] - internal, 0)
-    hits = max(totals["rays"] - args.width * args.height, 0)  # every bounce ray was spawned by one shaded hit (lower bound)
-    alg_bytes = 144.0 * internal + 48.0 * leaves + 48.0 * totals["tri_tests"] + 208.0 * totals["tlas_leaves"] + 324.0 * hits
-    return {"lane_ops_per_segment": per_seg, "totals": totals, "algorithmic_bytes": alg_bytes}
+    return {"lane_ops_per_segment": per_seg, "totals": totals, "local_rows": local_rows}
+
+
+def run_c5(args, rank, local, world, dev_t):
+    """BASELINE config C5: the C4 scene (1 000 instances of a 10 000-triangle BLAS) at 3840x2160, depth 8, accumulated to
+    `--c5-spp` samples per pixel, a presented frame every `--c5-present` samples INSIDE the timed region, in both
+    partitions.  N = 1 is the single-GPU run of the same code; the driver's scaling run gives the ratio."""
+    import torch
+    from gdpathtracing_b200 import PathTracingCamera, multigpu, scenes
+    W, H, D = 3840, 2160, 8
+    spp, every = args.c5_spp, args.c5_present
+    assert spp % world == 0 and every % world == 0 and spp % every == 0
+    sc = scenes.instanced_grid()
+    grp = scenes.populate(sc)
+    out = {"workload": f"C5: C4 scene (10M instanced triangles) {W}x{H}, depth {D}, {spp} spp, presented every {every} spp",
+           "spp": spp, "present_every": every}
+
+    def timed(fn):
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res = fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+        return (time.perf_counter() - t0) * 1e3, res
+
+    def reduce_max(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev_t)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return float(t.item())
+
+    def reduce_sum(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.int64, device=dev_t)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM)
+        return int(t.item())
+
+    first_presented = {}
+    # ---------------- sample index
+    cam = make_camera(sc, grp, args, local, PathTracingCamera.NONE, W=W, H=H, depth=D)
+    stream = torch.cuda.ExternalStream(cam.stream())
+    ptr, _ = cam.device_pointer("output")
+    frame_t = multigpu.as_tensor(ptr, (H, W, 4), torch.uint8, dev_t)
+    batch = every // world
+    kept = torch.empty((batch, H, W, 4), dtype=torch.uint8, device=dev_t)
+    for w in range(3):  # warm-up: kernels, exchange, K2
+        cam.set_frame_index(w)
+        cam.render_device_only()
+    cam.synchronize()
+    warm = multigpu.SampleIndexAccumulator(H, W, rank, world, dev_t, multigpu.cuda_k2(cam))
+    with torch.cuda.stream(stream):
+        warm.add(frame_t.clone().unsqueeze(0)); warm.present()
+    torch.cuda.synchronize()
+    del warm
+
+    def sample_index():
+        acc = multigpu.SampleIndexAccumulator(H, W, rank, world, dev_t, multigpu.cuda_k2(cam))
+        rays, k1_ms, ex_ms = 0, 0.0, 0.0
+        for b in range(spp // every):
+            for j in range(batch):
+                cam.set_frame_index((b * batch + j) * world + rank)  # render() increments: global index (b*batch+j)*world + rank + 1
+                cam.render_device_only()
+                st = cam.stats()
+                rays += st["rays"]; k1_ms += st["k1_ms"]
+                with torch.cuda.stream(stream):
+                    kept[j].copy_(frame_t)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(stream):
+                e0.record(stream)
+                acc.add(kept)
+                shown = acc.present()
+                e1.record(stream)
+            torch.cuda.synchronize()
+            ex_ms += e0.elapsed_time(e1)
+            if b == 0:
+                first_presented["sample_index"] = shown.clone()
+        return rays, k1_ms, ex_ms, acc.bytes_exchanged
+
+    ms, (rays, k1_ms, ex_ms, sent) = timed(sample_index)
+    rays_all = reduce_sum(rays)
+    out["sample_index"] = {"ms_total": ms, "ms_per_spp": ms / spp, "mrays_s": rays_all / (ms * 1e-3) / 1e6,
+                           "k1_ms_slowest_rank": reduce_max(k1_ms), "exchange_accumulate_present_ms_slowest_rank": reduce_max(ex_ms),
+                           "bytes_sent_over_nvlink_per_rank": int(sent), "collective": "NCCL send/recv of row blocks + all-gather of the presented blocks"}
+    del cam, kept
+
+    # ---------------- row bands
+    cam = make_camera(sc, grp, args, local, PathTracingCamera.PROGRESSIVE_RENDERING, W=W, H=H, depth=D, shard=(rank, world, args.band))
+    ptr, _ = cam.device_pointer("output")
+    frame_t = multigpu.as_tensor(ptr, (H, W, 4), torch.uint8, dev_t)
+    peer = multigpu.PeerFrame(cam, rank, world)
+    stream = torch.cuda.ExternalStream(cam.stream())
+    for w in range(3):
+        cam.set_frame_index(w)
+        cam.render_device_only()
+        cam.synchronize()
+        peer.barrier(); peer.frame_consumed()
+    restart_accumulation(cam, sc)
+    peer.barrier(); peer.frame_consumed()
+    torch.cuda.synchronize()
+
+    def rows():
+        rays, k_ms, hs_ms = 0, 0.0, 0.0
+        for f in range(spp):
+            cam.set_frame_index(f)
+            cam.render_device_only()  # frame_count = f + 1 follows the host policy (camera at rest)
+            st = cam.stats()
+            rays += st["rays"]; k_ms += st["k1_ms"] + st["k2_ms"]
+            if (f + 1) % every == 0:  # a presented frame: every rank's image is complete after the handshake
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                peer.barrier()
+                if f + 1 == every:
+                    with torch.cuda.stream(stream):
+                        first_presented["rows"] = frame_t.clone()
+                peer.frame_consumed()
+                e1.record(stream)
+                torch.cuda.synchronize(); cam.synchronize()
+                hs_ms += e0.elapsed_time(e1)
+        return rays, k_ms, hs_ms
+
+    ms, (rays, k_ms, hs_ms) = timed(rows)
+    rays_all = reduce_sum(rays)
+    out["rows"] = {"ms_total": ms, "ms_per_spp": ms / spp, "mrays_s": rays_all / (ms * 1e-3) / 1e6, "band_rows": args.band,
+                   "k1_k2_ms_slowest_rank": reduce_max(k_ms), "handshake_ms_slowest_rank": reduce_max(hs_ms),
+                   "bytes_written_to_peers_per_rank_per_frame": int(W * H * 4 // world * (world - 1)),
+                   "collective": "none on the data path: K2 stores its rows into every peer's image over NVLink (CUDA IPC); two "
+                                 "one-element NCCL all-reduces per presented frame"}
+    peer.close()
+    del cam
+
+    # ---------------- equality with ONE GPU accumulating the same frames sequentially (rank 0, untimed): the first presented frame
+    equal = {}
+    if rank == 0:
+        ref = make_camera(sc, grp, args, local, PathTracingCamera.PROGRESSIVE_RENDERING, W=W, H=H, depth=D)
+        t0 = time.perf_counter()
+        for f in range(every):
+            ref.set_frame_index(f)
+            ref.render_device_only()
+        ref.synchronize()
+        single_ms = (time.perf_counter() - t0) * 1e3 / every
+        rptr, _ = ref.device_pointer("output")
+        want = multigpu.as_tensor(rptr, (H, W, 4), torch.uint8, dev_t)
+        for k, img in first_presented.items():
+            equal[k] = bool(torch.equal(img, want))
+        out["single_gpu_sequential"] = {"ms_per_spp": single_ms, "frames": every}
+        del ref
+    if world > 1:
+        torch.distributed.barrier()
+    out["first_presented_frame_equals_single_gpu"] = equal
+    return out
 
 
 def cpu_baseline(sc, grp, args):
-    """The oracle (kind "port") on the box's host threads, bounded to ~10-30 s; BVH build timed separately."""
+    """The reference on the box's host threads, bounded to ~10-30 s: its own shader text compiled as C++ where that
+    library travelled with the snapshot (kind "reference"), else our restatement (kind "port"); scene build timed apart."""
     from gdpathtracing_b200 import nodes
     from oracle import oracle
     osc = oracle.Scene(grp.buffers(), grp.texture_layers())
     threads = oracle.hardware_threads()
+    impl, kind = reference_impl()
     W, H = args.width, args.height
-    t_total, rays, frames = 0.0, 0, 0
-    while t_total < 10.0 and frames < 16:
-        cam = bytes(nodes.make_camera_block(sc.camera_transform12, sc.fov, W, H, args.warmup + frames + 1))
-        t0 = time.perf_counter()
-        r = oracle.path_trace(osc, W, H, cam, max_depth=args.depth, threads=threads)
-        screen, acc = r["rgba8"], np.zeros((H, W, 4), np.float32)
-        oracle.progressive(screen, acc, 1)
-        t_total += time.perf_counter() - t0
-        rays += r["stats"]["rays"]; frames += 1
-    build_s = {}
-    for th in (1, 0):  # scene build (GeometryGroup3D.build): upstream's single thread, then the multi-threaded top + subtrees
+
+    def run(which, budget_s, most):
+        t_total, rays, frames = 0.0, 0, 0
+        while t_total < budget_s and frames < most:
+            cam = bytes(nodes.make_camera_block(sc.camera_transform12, sc.fov, W, H, args.warmup + frames + 1))
+            t0 = time.perf_counter()
+            r = oracle.path_trace(osc, W, H, cam, max_depth=args.depth, threads=threads, impl=which, counters=False)
+            screen, acc = r["rgba8"], np.zeros((H, W, 4), np.float32)
+            oracle.progressive(screen, acc, 1, impl=which)
+            t_total += time.perf_counter() - t0
+            rays += r["stats"]["rays"]; frames += 1
+        return rays / t_total / 1e6, t_total / frames * 1e3, frames
+
+    mrays, ms_frame, frames = run(impl, 10.0, 16)
+    port = run("restatement", 3.0, 4)[0] if impl == "reference" else None
+    saved = grp.build_threads
+    build = {}
+    for th in (1, 0):  # GeometryGroup3D.build: material conversion + texture resize + BLAS/TLAS build; upstream's single thread, then all
         grp.build_threads = th
         t0 = time.perf_counter()
         grp.build()
-        build_s[th] = time.perf_counter() - t0
-    return {"value": rays / t_total / 1e6, "unit": "Mrays/s", "cores": threads, "kind": "port",
-            "sample": f"{frames} full {W}x{H} frames of the same workload", "ms_per_frame": t_total / frames * 1e3,
-            "bvh_build_s_single_thread": build_s[1], "bvh_build_s_all_threads": build_s[0]}
+        build[th] = time.perf_counter() - t0
+    grp.build_threads = saved
+    ref_bvh = None
+    if oracle.ref_available():  # the reference's own bvh.cpp on the same meshes (BLAS + TLAS only: compare with nothing above)
+        t0 = time.perf_counter()
+        h, _ = oracle.reference_build(sc)
+        oracle.ref().refbvh_free(h)
+        ref_bvh = time.perf_counter() - t0
+    return {"value": mrays, "unit": "Mrays/s", "cores": threads, "kind": kind,
+            "sample": f"{frames} full {W}x{H} frames of the same workload", "ms_per_frame": ms_frame, "restatement_value": port,
+            "scene_build_s": {"what": "GeometryGroup3D.build of our host layer: material conversion, texture resize to the array "
+                                      "resolution, BLAS + TLAS build", "one_thread": build[1], "all_threads": build[0]},
+            "reference_bvh_cpp_build_s": ref_bvh}
 
 
 def main():
@@ -525,6 +800,10 @@ def main():
     ap.add_argument("--variant", type=int, default=-1, help="A/B: kernel schedule (include/gdpt.h GDPT_VARIANT); -1 = backend default")
     ap.add_argument("--tune", action="append", default=[], metavar="NAME=N", help="A/B: scheduling knob (GDPT_TUNE_<NAME>)")
     ap.add_argument("--no-l2-flush", dest="l2_flush", action="store_false")
+    ap.add_argument("--no-c5", dest="c5", action="store_false", help="skip the C5 block (4K instanced, accumulate to --c5-spp)")
+    ap.add_argument("--c5-spp", type=int, default=256)
+    ap.add_argument("--c5-present", type=int, default=64)
+    ap.add_argument("--no-schedule3", dest="schedule3", action="store_false", help="skip the reference-visiting-order comparison value")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false",
                     help="A/B runs of kernel variants only: skip the CPU leg (the official line always carries it)")
     args = ap.parse_args()

@@ -80,6 +80,8 @@ CUDA_API = [
     ("gdpt_device_destroy", None, [c_void_p]),
     ("gdpt_last_error", c_char_p, [c_void_p]),
     ("gdpt_abi_version", c_uint32, []),
+    ("gdpt_shader_get_schedule", c_int, [c_void_p]),
+    ("gdpt_progressive_accumulate", c_int, [c_void_p, c_uint64, c_uint64, c_uint64, c_int, c_int, c_uint32]),
     ("gdpt_shader_create", c_int, [c_void_p, c_char_p, POINTER(c_char_p), c_int, POINTER(c_void_p)]),
     ("gdpt_shader_destroy", None, [c_void_p]),
     ("gdpt_shader_create_storage_buffer_uniform", c_uint64, [c_void_p, c_void_p, c_uint64, c_int, c_int]),

@@ -514,10 +514,9 @@ int enqueue_k2(gdpt_shader *p, int part, int parts, int band, const uint32_t *ra
 {
     gdpt_device *d = p->dev;
     Resource *params = bound(p, 0, 0), *screen = bound(p, 0, 1), *accum = bound(p, 0, 2);
-    if (parts > 1 && (screen->width & 3)) return fail(d, GDPT_ERR_UNSUPPORTED, "sharded accumulation needs a width that is a multiple of 4");
     launch_progressive(raw_in ? raw_in : static_cast<const uint32_t *>(screen->dptr), static_cast<uint32_t *>(screen->dptr),
                        static_cast<float4 *>(accum->dptr),
-                       params_in ? params_in : static_cast<const gdpt_progressive_params *>(params->dptr), screen->width, screen->height,
+                       params_in ? params_in : static_cast<const gdpt_progressive_params *>(params->dptr), 0u, screen->width, screen->height,
                        part, parts, band, p->peers, d->stream);
     GDPT_CUDA(d, cudaGetLastError());
     return GDPT_OK;
@@ -914,6 +913,22 @@ int gdpt_rid_device_pointer(gdpt_device *d, gdpt_rid rid, uint64_t *out_ptr, uin
     return GDPT_OK;
 }
 
+int gdpt_progressive_accumulate(gdpt_device *d, uint64_t raw_rgba8, uint64_t screen_rgba8, uint64_t accum_rgba32f, int width,
+                                int height, uint32_t frame_count)
+{
+    if (!d) return GDPT_ERR_INVALID_ARG;
+    if (!raw_rgba8 || !screen_rgba8 || !accum_rgba32f || width <= 0 || height <= 0 || frame_count == 0u)
+        return fail(d, GDPT_ERR_INVALID_ARG, "gdpt_progressive_accumulate: null image, empty size or frame_count 0");
+    if (accum_rgba32f & 15u) return fail(d, GDPT_ERR_INVALID_ARG, "the accumulation image must be 16-byte aligned");
+    cudaSetDevice(d->ordinal);
+    init_launch_shapes(d->ordinal);
+    const PeerScreens none = {};
+    launch_progressive(reinterpret_cast<const uint32_t *>(raw_rgba8), reinterpret_cast<uint32_t *>(screen_rgba8),
+                       reinterpret_cast<float4 *>(accum_rgba32f), nullptr, frame_count, width, height, 0, 1, 1, none, d->stream);
+    GDPT_CUDA(d, cudaGetLastError());
+    return GDPT_OK;
+}
+
 int gdpt_rid_ipc_export(gdpt_device *d, gdpt_rid rid, void *out_handle)
 {
     if (!d || !out_handle) return GDPT_ERR_INVALID_ARG;
@@ -980,6 +995,8 @@ int gdpt_shader_get_stats(gdpt_shader *s, gdpt_frame_stats *out)
     *out = s->stats;
     return GDPT_OK;
 }
+
+int gdpt_shader_get_schedule(const gdpt_shader *s) { return (s && s->kind == SHADER_MAIN && s->uniforms_ready) ? s->args.schedule : -1; }
 
 int gdpt_shader_set_stage_timing(gdpt_shader *s, int on)
 {

@@ -35,7 +35,7 @@ __device__ __forceinline__ bool pool_can_cross(uint32_t cur, uint32_t pend, uint
     return cur != LINK_NONE && (cur & LINK_TLAS) != 0u && pend == LINK_NONE && ((cur & LINK_LEAF) != 0u || inst != GDPT_NO_INSTANCE);
 }
 
-template <bool REC, int MINB, int kPoolPark, int kPoolSlots, bool WIDE>
+template <bool REC, int MINB, int kPoolPark, int kPoolSlots, bool WIDE, bool COUNT = false>
 __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_pool(const FrameArgs a)
 {
     __shared__ uint32_t s_stack[kSmemStack * kTraceThreads];
@@ -86,6 +86,7 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_pool(const FrameAr
     uint32_t chunk_next = 0, chunk_end = 0;
     bool exhausted = (total == 0u);
     unsigned long long my_rays = 0, my_phits = 0, my_retraced = 0;
+    unsigned long long own_nodes = 0, own_boxes = 0, own_tris = 0, own_insts = 0, own_proofs = 0; // COUNT only
     uint32_t my_overflow = 0;
     const bool prof = a.warp_prof != nullptr;
     const unsigned long long t_start = prof ? global_ns() : 0ull;
@@ -144,6 +145,7 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_pool(const FrameAr
                     uint32_t htri = PF(PF_TRI, sl), hbf = PF(PF_BF, sl), hflags = PF(PF_FLAGS, sl);
                     const uint32_t pixel = PF(PF_PIXEL, sl);
                     const int segment = (int)PF(PF_SEGMENT, sl);
+                    if (COUNT) own_proofs++;
                     if (!fast_verdict_ool(&a.sc, wo, wd, ht, htri, hbf, hflags)) {
                         ExactHit eh; // rare: exact reference-order traversal of this ray
                         exact_retrace(&a.sc, wo, wd, &eh);
@@ -272,6 +274,7 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_pool(const FrameAr
                 if (go) {
                     if (WIDE) fast_step_node4(a.sc, r, st); else fast_step_node(a.sc, r, st);
                     steps++;
+                    if (COUNT) { own_nodes++; own_boxes += WIDE ? 4u : 2u; }
                     if (n_park < (uint32_t)kPoolPark && fast_link_is_leaf(r.cur)) { // park the leaf, keep descending
 #pragma unroll
                         for (int k = 0; k < kPoolPark; k++)
@@ -294,12 +297,13 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_pool(const FrameAr
                 } else { leaf = r.cur; r.cur = fast_pop(r, st); }
                 fast_leaf_tests(a.sc, r, leaf);
                 steps++;
+                if (COUNT) own_tris += ((leaf >> FAST_LEAF_COUNT_SHIFT) & 7u) + 1u;
             }
         } else {
             it_t++;
             if (can_t) { // back to world space (main.glsl:316-327) and/or into the instance the link names
                 if (r.inst != GDPT_NO_INSTANCE) { r.o = r.wo; r.d = r.wd; r.rd = wrd; r.inst = GDPT_NO_INSTANCE; }
-                if (r.cur & LINK_LEAF) fast_enter_instance<WIDE>(a.sc, r, st);
+                if (r.cur & LINK_LEAF) { fast_enter_instance<WIDE>(a.sc, r, st); if (COUNT) own_insts++; }
                 steps++;
             }
         }
@@ -318,6 +322,17 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_pool(const FrameAr
     if (lane == 0) {
         atomicAdd(&cnt->rays, my_rays); atomicAdd(&cnt->primary_hits, my_phits);
         if (my_retraced) atomicAdd(&cnt->retraced, my_retraced);
+    }
+    if (COUNT) { // own work of the search (roofline numerator of bench.py)
+        for (int off = 16; off > 0; off >>= 1) {
+            own_nodes += __shfl_down_sync(kFull, own_nodes, off); own_boxes += __shfl_down_sync(kFull, own_boxes, off);
+            own_tris += __shfl_down_sync(kFull, own_tris, off); own_insts += __shfl_down_sync(kFull, own_insts, off);
+            own_proofs += __shfl_down_sync(kFull, own_proofs, off);
+        }
+        if (lane == 0) {
+            atomicAdd(&cnt->own_node_steps, own_nodes); atomicAdd(&cnt->own_box_tests, own_boxes); atomicAdd(&cnt->own_tri_tests, own_tris);
+            atomicAdd(&cnt->own_inst_entries, own_insts); atomicAdd(&cnt->own_proofs, own_proofs);
+        }
     }
     if (my_overflow) atomicOr(&cnt->overflow, 1u);
 }

@@ -258,17 +258,21 @@ __global__ void __launch_bounds__(kTraceThreads) k_primary_cull(const FrameArgs 
 }
 
 // K2 (progressive_rendering.glsl:28-46): acc = (frame_count > 1 ? acc : 0) + screen;
-// screen = rgba8(ACES(acc / frame_count)).  Four pixels per thread: one 128-bit
-// load of the RGBA8 quad, four 128-bit loads/stores of the RGBA32F accumulator.
+// screen = rgba8(ACES(acc / frame_count)).  HBM-bound: 36 B per pixel (4 R raw + 16 R + 16 W accumulation + 4 W screen;
+// the first frame reads no accumulation).  One pixel per lane: a warp's accumulator load / store is one 512 B
+// instruction over four full lines, its RGBA8 load / store one 128 B line -- no half-used sector -- and every thread
+// has four independent pixels in flight (blockDim apart) before it computes.
 // `peers`: RGBA8 images of the other GPUs of a row-band frame (peer memory over NVLink, CUDA IPC).  Every
-// tone-mapped quad this GPU owns is also stored there, so the presented frame assembles itself in every
+// tone-mapped pixel this GPU owns is also stored there, so the presented frame assembles itself in every
 // GPU's image while the kernel runs -- the exchange step of the row-band partition fused into its producer
 // instead of an all-gather after it.
 // `raw` is the image K1 wrote (the bound screen image itself in the reference's call sequence; a frame-private image
-// when two pipelined frames overlap), `screen` receives the tone-mapped result.
-__global__ void __launch_bounds__(256) k_progressive(const uint32_t *raw, uint32_t *screen, float4 *__restrict__ accum,
-                                                     const gdpt_progressive_params *__restrict__ params, int width,
-                                                     int height, int shard_part, int shard_parts, int shard_band,
+// when two pipelined frames overlap), `screen` receives the tone-mapped result.  frame_count comes from the device
+// Params block (stream-ordered uploads) or, when `params` is null, from the argument.
+constexpr int kProgressiveUnroll = 4;
+__global__ void __launch_bounds__(256) k_progressive(const uint32_t *__restrict__ raw, uint32_t *screen, float4 *accum,
+                                                     const gdpt_progressive_params *__restrict__ params, uint32_t frame_count_arg,
+                                                     int width, int height, int shard_part, int shard_parts, int shard_band,
                                                      const PeerScreens peers)
 {
     // imageLoad of an rgba8 texel = byte / 255.0f (progressive_rendering.glsl:33): every block divides each of the 256
@@ -276,47 +280,41 @@ __global__ void __launch_bounds__(256) k_progressive(const uint32_t *raw, uint32
     __shared__ float s_unorm[256];
     s_unorm[threadIdx.x] = (float)threadIdx.x / 255.0f;
     __syncthreads();
-    const uint32_t frame_count = params->frame_count;
+    const uint32_t frame_count = params ? params->frame_count : frame_count_arg;
     const float fc = (float)frame_count;
-    const size_t n_quads = ((size_t)width * height) >> 2;
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n_quads; q += stride) {
-        const size_t p = q << 2;
-        if (shard_parts > 1) { // width is a multiple of 4 here, so a quad never straddles rows
-            const int y = (int)(p / (size_t)width);
-            if ((y / shard_band) % shard_parts != shard_part) continue;
-        }
-        const uint4 s4 = reinterpret_cast<const uint4 *>(raw)[q];
-        const uint32_t in[4] = { s4.x, s4.y, s4.z, s4.w };
-        uint32_t out[4];
+    const size_t n = (size_t)width * height;
+    // every block takes one contiguous, equally long range of pixels (a multiple of 128, so warps stay line-aligned):
+    // the grid is one wave of resident blocks and they all finish together
+    const size_t per_block = ((n + gridDim.x - 1) / gridDim.x + 127u) & ~(size_t)127u;
+    const size_t begin = (size_t)blockIdx.x * per_block, end = begin + per_block < n ? begin + per_block : n;
+    const size_t tile = (size_t)blockDim.x * kProgressiveUnroll;
+    for (size_t base = begin; base < end; base += tile) {
+        uint32_t in[kProgressiveUnroll];
+        float4 acc[kProgressiveUnroll];
+        bool mine[kProgressiveUnroll];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            f3 rad = mk3(s_unorm[in[k] & 0xffu], s_unorm[(in[k] >> 8) & 0xffu], s_unorm[(in[k] >> 16) & 0xffu]);
-            if (frame_count > 1u) {
-                const float4 acc = accum[p + k];
-                rad = rad + mk3(acc.x, acc.y, acc.z);
+        for (int k = 0; k < kProgressiveUnroll; k++) {
+            const size_t p = base + (size_t)k * blockDim.x + threadIdx.x;
+            mine[k] = p < end;
+            if (mine[k] && shard_parts > 1) mine[k] = ((int)(p / (size_t)width) / shard_band) % shard_parts == shard_part;
+            in[k] = 0u;
+            acc[k] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            if (mine[k]) {
+                in[k] = __ldg(raw + p);
+                if (frame_count > 1u) acc[k] = accum[p];
             }
-            accum[p + k] = make_float4(rad.x, rad.y, rad.z, 1.0f);
-            const f3 avg = (rad / fc) * 1.0f;
-            out[k] = pack_rgba8(mk3(aces_channel(avg.x), aces_channel(avg.y), aces_channel(avg.z)));
         }
-        const uint4 o4 = make_uint4(out[0], out[1], out[2], out[3]);
-        reinterpret_cast<uint4 *>(screen)[q] = o4;
-        for (int k = 0; k < peers.n; k++) reinterpret_cast<uint4 *>(peers.p[k])[q] = o4;
-    }
-    // tail pixels when W*H is not a multiple of 4
-    if (blockIdx.x == 0 && threadIdx.x < (((size_t)width * height) & 3)) {
-        const size_t p = (n_quads << 2) + threadIdx.x;
-        const int y = (int)(p / (size_t)width);
-        if (shard_parts <= 1 || (y / shard_band) % shard_parts == shard_part) {
-            const uint32_t in = raw[p];
-            f3 rad = mk3(s_unorm[in & 0xffu], s_unorm[(in >> 8) & 0xffu], s_unorm[(in >> 16) & 0xffu]);
-            if (frame_count > 1u) { const float4 acc = accum[p]; rad = rad + mk3(acc.x, acc.y, acc.z); }
+#pragma unroll
+        for (int k = 0; k < kProgressiveUnroll; k++) {
+            if (!mine[k]) continue;
+            const size_t p = base + (size_t)k * blockDim.x + threadIdx.x;
+            f3 rad = mk3(s_unorm[in[k] & 0xffu], s_unorm[(in[k] >> 8) & 0xffu], s_unorm[(in[k] >> 16) & 0xffu]);
+            if (frame_count > 1u) rad = rad + mk3(acc[k].x, acc[k].y, acc[k].z);
             accum[p] = make_float4(rad.x, rad.y, rad.z, 1.0f);
             const f3 avg = (rad / fc) * 1.0f;
             const uint32_t o = pack_rgba8(mk3(aces_channel(avg.x), aces_channel(avg.y), aces_channel(avg.z)));
             screen[p] = o;
-            for (int k = 0; k < peers.n; k++) peers.p[k][p] = o;
+            for (int j = 0; j < peers.n; j++) peers.p[j][p] = o;
         }
     }
 }
@@ -346,6 +344,7 @@ struct Shapes {
     int path_list_blocks = 0;    // k_path<false, true, SRC 1, 4, COMPACT>
     int path_list_record_blocks = 0; // k_path<true, true, SRC 1> (hit records of schedule 3)
     int pool_blocks[2][2] = {};  // k_path_pool<REC, .., WIDE>
+    int pool_count_blocks = 0;   // k_path_pool<.., WIDE, COUNT>
     int sorted_blocks = 0;       // k_path_sorted: resident blocks (the same for every REC / COUNT / SORT4)
     int cull_blocks_per_sm = 1;
     int prog_blocks = 0;
@@ -377,6 +376,7 @@ void init_launch_shapes(int device)
     s.pool_blocks[0][1] = grid_of(k_path_pool<false, 4, kPoolParkDefault, kPoolSlotsDefault, true>, kTraceThreads);
     s.pool_blocks[1][0] = grid_of(k_path_pool<true, 4, kPoolParkDefault, kPoolSlotsDefault, false>, kTraceThreads);
     s.pool_blocks[1][1] = grid_of(k_path_pool<true, 4, kPoolParkDefault, kPoolSlotsDefault, true>, kTraceThreads);
+    s.pool_count_blocks = grid_of(k_path_pool<false, 4, kPoolParkDefault, kPoolSlotsDefault, true, true>, kTraceThreads);
     auto sorted_grid = [&](auto kernel, size_t smem) {
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         per_sm = 0;
@@ -438,11 +438,14 @@ void launch_path_list(const FrameArgs &a, bool record, cudaStream_t s)
 }
 
 void launch_progressive(const uint32_t *raw_rgba8, uint32_t *screen_rgba8, float4 *accum, const gdpt_progressive_params *params_dev,
-                        int width, int height, int shard_part, int shard_parts, int shard_band, const PeerScreens &peers, cudaStream_t s)
+                        uint32_t frame_count, int width, int height, int shard_part, int shard_parts, int shard_band,
+                        const PeerScreens &peers, cudaStream_t s)
 {
     Shapes &sh = shapes_for_current_device();
-    k_progressive<<<sh.prog_blocks, 256, 0, s>>>(raw_rgba8, screen_rgba8, accum, params_dev, width, height, shard_part, shard_parts,
-                                                 shard_band, peers);
+    const size_t warps = ((size_t)width * height + 127u) / 128u; // no more blocks than 128-pixel pieces
+    const int blocks = (int)(warps < (size_t)sh.prog_blocks ? (warps > 0 ? warps : 1) : (size_t)sh.prog_blocks);
+    k_progressive<<<blocks, 256, 0, s>>>(raw_rgba8, screen_rgba8, accum, params_dev, frame_count, width, height, shard_part,
+                                         shard_parts, shard_band, peers);
 }
 
 __global__ void __launch_bounds__(128) k_small_copies(const SmallCopies sc)
@@ -471,6 +474,10 @@ void launch_path_pool(const FrameArgs &a, bool record, cudaStream_t s)
     Shapes &sh = shapes_for_current_device();
     const bool wide = a.wide_bvh != 0 && a.sc.fast4_ok != 0; // four-wide tables (fast_bvh.h Collapse)
     const int grid = persistent_grid(sh, a, sh.pool_blocks[record ? 1 : 0][wide ? 1 : 0]);
+    if (a.count_work && wide && !record) { // the instantiation that also counts its own work (bench.py's roofline numerator)
+        k_path_pool<false, 4, kPoolParkDefault, kPoolSlotsDefault, true, true><<<persistent_grid(sh, a, sh.pool_count_blocks), kTraceThreads, 0, s>>>(a);
+        return;
+    }
     if (record) {
         if (wide) k_path_pool<true, 4, kPoolParkDefault, kPoolSlotsDefault, true><<<grid, kTraceThreads, 0, s>>>(a);
         else k_path_pool<true, 4, kPoolParkDefault, kPoolSlotsDefault, false><<<grid, kTraceThreads, 0, s>>>(a);

@@ -96,9 +96,10 @@ void launch_path_sorted(const FrameArgs &a, bool record, cudaStream_t s);
 size_t sorted_spill_words(const FrameArgs &a); // uint32 elements a.sorted_spill must provide on the current device
 size_t path_kernel_warps(const FrameArgs &a); // warps of the path kernel enqueue_k1 would launch for `a`
 // K2: progressive accumulation + ACES (progressive_rendering.glsl:28-46).
+// frame_count is read from params_dev (stream-ordered Params block) or, when that is null, taken from the argument.
 void launch_progressive(const uint32_t *raw_rgba8, uint32_t *screen_rgba8, float4 *accum, const gdpt_progressive_params *params_dev,
-                        int width, int height, int shard_part, int shard_parts, int shard_band, const PeerScreens &peers,
-                        cudaStream_t s);
+                        uint32_t frame_count, int width, int height, int shard_part, int shard_parts, int shard_band,
+                        const PeerScreens &peers, cudaStream_t s);
 // K3: temporal reprojection (temporal_reprojection.glsl:31-71); `history` is the frame buffer the previous dispatch wrote.
 void launch_temporal(uint32_t *screen_rgba8, const float *depth, const float *history, float *next,
                      const gdpt_temporal_params *params_dev, int width, int height, cudaStream_t s);

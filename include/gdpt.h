@@ -223,6 +223,13 @@ GDPT_API int  gdpt_shader_set_shard(gdpt_shader *main_shader, int part, int n_pa
  * torch (the caller must not free it). */
 GDPT_API int  gdpt_rid_device_pointer(gdpt_device *device, gdpt_rid rid,
                                  uint64_t *out_ptr, uint64_t *out_size);
+/* K2 (progressive_rendering.glsl:28-46) on images the caller holds on this device (ours; upstream dispatches it only on
+ * its own bound images): raw_rgba8 is one frame as K1 stored it, accum_rgba32f the accumulation, screen_rgba8 receives
+ * the tone-mapped frame (may alias raw_rgba8), frame_count is Params.frame_count.  Enqueued on the device's stream.
+ * What the sample-index partition needs to stay bit-identical with the sequential accumulation: the per-frame
+ * images of all GPUs are accumulated in frame order, each GPU taking a block of rows (multigpu.SampleIndexAccumulator). */
+GDPT_API int  gdpt_progressive_accumulate(gdpt_device *device, uint64_t raw_rgba8, uint64_t screen_rgba8,
+                                          uint64_t accum_rgba32f, int width, int height, uint32_t frame_count);
 /* Row-band frames without a gather (ours; upstream is single-GPU).  A frame sharded with gdpt_shader_set_shard is
  * rendered by several GPUs, one process each; the presented image is the union of their bands.  Instead of an
  * all-gather after the frame, the accumulate/tone-map kernel of `progressive_shader` stores every pixel it owns into
@@ -261,6 +268,8 @@ typedef struct gdpt_frame_stats {
     uint64_t own_node_steps, own_box_tests, own_tri_tests, own_inst_entries, own_proofs;
 } gdpt_frame_stats;
 GDPT_API int  gdpt_shader_get_stats(gdpt_shader *main_shader, gdpt_frame_stats *out);
+/* Which kernel schedule finish_create_uniforms chose for this main shader (2, 3, 6 or 7: see GDPT_VARIANT above); -1 before. */
+GDPT_API int  gdpt_shader_get_schedule(const gdpt_shader *main_shader);
 
 /* Profiling aid: when on, an event is recorded between the stage kernels of every K1
  * dispatch; get_stage_times returns the number of stages and their device times in launch

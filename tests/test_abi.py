@@ -96,5 +96,8 @@ def test_reference_arm_of_bench_runs_without_a_gpu():
     assert len(lines) == 1, out.stdout
     line = json.loads(lines[0])
     assert line["impl"] == "reference" and line["metric"] == "Mrays/s" and line["value"] > 0
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    from oracle import oracle
+    # the reference's own shader text compiled as C++ where that library exists, our restatement of it otherwise
+    assert line["cpu_baseline"]["kind"] == ("reference" if oracle.ref_shader_available() else "port")
+    assert line["cpu_baseline"]["cores"] >= 1 and set(line["config"]) == {"workload", "partition"}
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0

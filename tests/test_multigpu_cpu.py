@@ -1,8 +1,8 @@
 """N > 1 host logic on CPU: two gloo ranks (127.0.0.1) run the same partition / gather / reduce code the
 NCCL path runs (gdpathtracing_b200/multigpu.py).  The per-rank pixels come from the oracle (test
 infrastructure) because there is no GPU here; what is under test is the partition arithmetic: the row-band
-rule the kernels use, ragged ownership (bit-exact reassembly), and that sample-index accumulation reduces to
-the sequential accumulation within float re-association error (stated in the test)."""
+rule the kernels use, ragged ownership (bit-exact reassembly), and that the sample-index accumulation (row blocks
+swapped between the ranks, K2 in frame order) is bit-identical to the sequential accumulation."""
 import os
 import socket
 import sys
@@ -14,7 +14,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 REPO = os.path.normpath(os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
-W, H, DEPTH, FRAMES = 64, 44, 3, 4  # 44 rows with band 8 over 2 ranks: ragged (24 vs 20 rows)
+W, H, DEPTH, FRAMES = 64, 45, 3, 8  # 45 rows: ragged row bands (band 8 over 2 ranks: 24 vs 21 rows) and row blocks (22 vs 23)
 
 
 def _free_port():
@@ -54,25 +54,33 @@ def _worker(rank, world, port, result_dir):
     whole = multigpu.gather_row_bands(torch.from_numpy(part), band, rank, world).numpy()
     assert np.array_equal(whole, frames[0]), "row-band gather does not reassemble the frame"
 
-    # ---- sample index: rank r accumulates frames r, r+world, ...; one sum-reduce; tone-map on rank 0
-    acc = np.zeros((H, W, 4), np.float32)
-    n_mine = 0
-    for i in range(rank, FRAMES, world):
+    # ---- sample index: rank r renders frames r+1, r+1+world, ...; the ranks swap row blocks of their frames and every
+    # rank accumulates its rows in frame order (SampleIndexAccumulator): the float additions of ONE GPU accumulating
+    # frames 1, 2, 3, ... -- bit-identical accumulation buffer and presented frame, no tolerance
+    def k2(raw, screen, accum, frame_count):
+        s_np, a_np = raw.numpy().copy(), accum.numpy()
+        oracle.progressive(s_np, a_np, frame_count)  # in place on the tensors' memory
+        screen.copy_(torch.from_numpy(s_np))
+
+    acc = multigpu.SampleIndexAccumulator(H, W, rank, world, torch.device("cpu"), k2)
+    mine_frames = torch.from_numpy(np.stack([frames[i] for i in range(rank, FRAMES, world)]))
+    half = mine_frames.shape[0] // 2
+    acc.add(mine_frames[:half])          # two batches: the frame counter carries over
+    first_presented = acc.present().numpy().copy()
+    acc.add(mine_frames[half:])
+    presented = acc.present().numpy()
+    seq = np.zeros((H, W, 4), np.float32)
+    seq_screens = []
+    for i in range(FRAMES):
         screen = frames[i].copy()
-        n_mine += 1
-        oracle.progressive(screen, acc, n_mine)  # acc += rgba8(screen) (frame_count 1 resets)
-    t = torch.from_numpy(acc)
-    multigpu.reduce_accumulations(t, dst=0)
+        oracle.progressive(screen, seq, i + 1)
+        seq_screens.append(screen)
+    b, e = acc.blocks[rank]
+    assert np.array_equal(acc.accum.numpy().view(np.uint32), seq[b:e].view(np.uint32)), "accumulation rows differ from the sequential accumulation"
+    assert np.array_equal(presented, seq_screens[FRAMES - 1]), "presented frame differs from the sequential one"
+    assert np.array_equal(first_presented, seq_screens[half * world - 1])
+    assert acc.frames_done == FRAMES and (world == 1 or acc.bytes_exchanged > 0)
     if rank == 0:
-        seq = np.zeros((H, W, 4), np.float32)
-        for i in range(FRAMES):
-            oracle.progressive(frames[i].copy(), seq, i + 1)
-        got = t.numpy()
-        # Not bit-equal by construction: the addends are fl(k/255), so float addition in a different order rounds
-        # differently (a few ulp).  Stated tolerance: 4 ulp of the sum (2^-21 relative).
-        assert np.allclose(got[..., :3], seq[..., :3], rtol=2.0 ** -21, atol=0.0), \
-            "sum of per-rank accumulations is not the sequential accumulation within 4 ulp"
-        assert not np.array_equal(got[..., :3], np.zeros_like(got[..., :3]))
         open(os.path.join(result_dir, "ok"), "w").write("ok")
     dist.barrier()
     dist.destroy_process_group()

@@ -1,7 +1,10 @@
-run() { name=$1; shift; timeout 600 python bench.py --no-cpu-baseline --steps 20 --warmup 3 "$@" 2>gpurun_out/ab_$name.err | tee gpurun_out/ab_$name.json | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('$name', round(d['value']), d['config']['stage_ms'], round(d['e2e']['value']), round(d['e2e']['blocking_render']['value']))"; }
-run c2_v7 --variant 7
-run c2_v7_noproof2 --variant 7 --tune NOPROOF2=1
-run c2_v7_nibble --variant 7 --tune POOL_ALIVE=1
-run c2_v7_both --variant 7 --tune POOL_ALIVE=1 --tune NOPROOF2=1
-run c2_v6 --variant 6
-run c2_v6_noproof2 --variant 6 --tune NOPROOF2=1
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+timeout 900 python bench.py --c5-spp 32 --c5-present 16 2>gpurun_out/bench_try.err > gpurun_out/bench_try.json; tail -3 gpurun_out/bench_try.err; python -c "
+import json; d=json.load(open('gpurun_out/bench_try.json'))
+print(d['value'], d['ms_per_step'], d['e2e']['value'])
+print(json.dumps(d['roofline'], indent=0)[:1500])
+print(json.dumps(d['roofline_accumulate']))
+print(json.dumps(d['config']['reference_visiting_order']), d['config']['mrays_s_over_rays_that_enter_an_instance'])
+print(json.dumps(d['extra'], indent=0))
+print(json.dumps(d.get('cpu_baseline')))
+"
