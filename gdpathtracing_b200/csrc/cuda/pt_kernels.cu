@@ -269,8 +269,8 @@ __global__ void __launch_bounds__(kTraceThreads) k_primary_cull(const FrameArgs 
 // `raw` is the image K1 wrote (the bound screen image itself in the reference's call sequence; a frame-private image
 // when two pipelined frames overlap), `screen` receives the tone-mapped result.  frame_count comes from the device
 // Params block (stream-ordered uploads) or, when `params` is null, from the argument.
-constexpr int kProgressiveUnroll = 4;
-__global__ void __launch_bounds__(256) k_progressive(const uint32_t *__restrict__ raw, uint32_t *screen, float4 *accum,
+constexpr int kProgressiveUnroll = 2;
+__global__ void __launch_bounds__(256, 8) k_progressive(const uint32_t *__restrict__ raw, uint32_t *screen, float4 *accum,
                                                      const gdpt_progressive_params *__restrict__ params, uint32_t frame_count_arg,
                                                      int width, int height, int shard_part, int shard_parts, int shard_band,
                                                      const PeerScreens peers)
