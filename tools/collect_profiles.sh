@@ -1,5 +1,5 @@
 #!/bin/bash
-# Turn the raw files of tools/gpu_round1_artifacts.sh (gpurun_out/) into the tracked summaries under profiles/.
+# Turn the raw files of tools/gpu_round_artifacts.sh (gpurun_out/) into the tracked summaries under profiles/.
 # usage: tools/collect_profiles.sh r01
 set -e
 tag=${1:-r01}

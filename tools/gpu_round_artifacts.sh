@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q 2>&1 | tail -3 | tee gpurun_out/pytest_gpu.log
 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -2 gpurun_out/bench.err
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 > gpurun_out/bench_under_ncu.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-c5 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_path" -s 2 -c 1 -o gpurun_out/prof_k_path python tools/profile_frame.py --frames 4 > gpurun_out/ncu_k_path.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_primary_cull" -s 2 -c 1 -o gpurun_out/prof_k_primary_cull python tools/profile_frame.py --frames 4 > gpurun_out/ncu_k_primary_cull.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_progressive" -s 2 -c 1 -o gpurun_out/prof_k_progressive python tools/profile_frame.py --frames 4 > gpurun_out/ncu_k_progressive.log 2>&1
