@@ -320,6 +320,8 @@ int finish_main(gdpt_shader *s)
     a.sc.n_blas = (uint32_t)(blas->size / sizeof(gdpt_blas_instance));
     a.sc.n_tlas = (uint32_t)(tlas->size / sizeof(gdpt_tlas_node));
     a.sc.n_materials = (uint32_t)(mat->size / sizeof(gdpt_material));
+    if (a.sc.n_blas > 32768u || a.sc.n_tlas > 65535u)
+        return fail(d, GDPT_ERR_UNSUPPORTED, "%u instances / %u TLAS nodes: the reference's TLAS addresses at most 65 535 nodes (main.glsl:329-330)", a.sc.n_blas, a.sc.n_tlas);
     int rc = build_derived_layout(s, *bvh, *blas, *tlas, *tg);
     if (rc) return rc;
 

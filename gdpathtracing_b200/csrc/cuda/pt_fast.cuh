@@ -193,7 +193,7 @@ GDPT_HD void fast_triangle_test(RayState &r, const q4f a, const q4f b, const q4f
 #else
         memcpy(&r.tri, &a.w, 4);
 #endif
-        r.t = t; r.u = u; r.v = v; r.blas_front = r.inst | front;
+        r.t = t; r.u = u; r.v = v; r.blas_front = r.inst | (r.inst << GDPT_HIT_INST_BITS) | front;
         r.overflow &= ~RAY_TIE;
     } else {
         r.overflow |= RAY_TIE; // t == r.t (or NaN): the reference's answer would depend on its visiting order
@@ -367,7 +367,7 @@ GDPT_HD bool fast_other_pair_within(const SceneView &sc, f3 wo, f3 wd, float bou
 // direction component are sent to the exact traversal: 0 * inf in a slab would void the monotonicity argument.
 GDPT_HD bool fast_proves_reference_hit(const SceneView &sc, const RayState &r)
 {
-    const uint32_t inst = r.blas_front & ~GDPT_FRONT_BIT;
+    const uint32_t inst = hit_blas(r.blas_front); // no tie: also the space of the accepted test
     const q4f c0 = ldq(sc.inst_recs, inst * 7u + 0u);
     const q4f c1 = ldq(sc.inst_recs, inst * 7u + 1u);
     const q4f c2 = ldq(sc.inst_recs, inst * 7u + 2u);

@@ -131,7 +131,7 @@ __device__ __forceinline__ void write_trace_record(const FrameArgs &a, int segme
     const bool hit = r.t < 1e9f;
     rec.hit = hit ? 1u : 0u;
     rec.triangle = hit ? r.tri : 0u;
-    rec.blas = hit ? (r.blas_front & ~GDPT_FRONT_BIT) : 0u;
+    rec.blas = hit ? hit_blas(r.blas_front) : 0u;
     rec.front = hit ? (r.blas_front >> 31) : 0u;
     rec.t = r.t; rec.u = hit ? r.u : 0.0f; rec.v = hit ? r.v : 0.0f;
     rec.node_pops = tc.node_pops; rec.box_tests = tc.box_tests; rec.tri_tests = tc.tri_tests;
@@ -170,7 +170,7 @@ __device__ __forceinline__ void write_hit_record(const FrameArgs &a, int segment
     const bool hit = t < 1e9f;
     rec.hit = hit ? 1u : 0u;
     rec.triangle = hit ? tri : 0u;
-    rec.blas = hit ? (blas_front & ~GDPT_FRONT_BIT) : 0u;
+    rec.blas = hit ? hit_blas(blas_front) : 0u;
     rec.front = hit ? (blas_front >> 31) : 0u;
     rec.t = t; rec.u = hit ? u : 0.0f; rec.v = hit ? v : 0.0f;
     rec.node_pops = rec.box_tests = rec.tri_tests = rec.tlas_leaves = rec.max_stack = 0u;

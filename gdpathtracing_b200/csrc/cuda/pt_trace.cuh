@@ -49,6 +49,15 @@ GDPT_HD q4u ldqu(const void *base, uint32_t quad_index)
 
 #define GDPT_NO_INSTANCE 0xFFFFFFFFu
 #define GDPT_FRONT_BIT 0x80000000u
+// RayState.blas_front = hitInfo.blas | (instance whose local ray the accepted triangle test ran with) << 15 | front << 31.
+// The two instances differ only after an equal-t tie across instances: the later triangle test overwrites
+// triangle / position / out_dir / front (main.glsl:247-255), but hitInfo.blas changes only when t was lowered
+// (main.glsl:322-325), so the reference shades a point of one instance's space with the other instance's transform and
+// materials (main.glsl:194-222).  Instance ids fit 15 bits: a TLAS holds at most 65 535 nodes (leftRight, main.glsl:329-330).
+#define GDPT_HIT_INST_BITS 15u
+#define GDPT_HIT_INST_MASK 0x7FFFu
+GDPT_HD uint32_t hit_blas(uint32_t blas_front) { return blas_front & GDPT_HIT_INST_MASK; }
+GDPT_HD uint32_t hit_space(uint32_t blas_front) { return (blas_front >> GDPT_HIT_INST_BITS) & GDPT_HIT_INST_MASK; }
 #define GDPT_MAX_STACK 128 /* 64 + 64 of the reference (main.glsl:272,307) */
 
 // Optional per-ray parity observables.
@@ -80,7 +89,7 @@ struct RayState {
     f3 o, d, rd;         // ray in the space being traversed (world or instance-local)
     float t, u, v;       // hitInfo.t, barycentrics
     uint32_t tri;        // hitInfo.triangle
-    uint32_t blas_front; // hitInfo.blas | front << 31
+    uint32_t blas_front; // hitInfo.blas | space of the accepted test << 15 | front << 31 (hit_blas / hit_space)
     uint32_t cur;        // link to process next, LINK_NONE when the traversal is over
     uint32_t sp;         // unified stack fill
     uint32_t inst;       // instance being traversed or GDPT_NO_INSTANCE
@@ -127,9 +136,9 @@ GDPT_HD void triangle_test_loaded(RayState &r, uint32_t tri_index, const q4f a, 
     if (t < 0.0f || t > r.t) return;
     // hitInfo.blas is assigned after the BLAS returns iff it lowered t (main.glsl:322-325);
     // since minT == hitInfo.t on entry, that is exactly "a strictly closer triangle was accepted".
-    const uint32_t blas = (t < r.t) ? r.inst : (r.blas_front & ~GDPT_FRONT_BIT);
+    const uint32_t blas = (t < r.t) ? r.inst : hit_blas(r.blas_front);
     const uint32_t front = dot3(cross3(e1, e2), r.d) > 0.0f ? GDPT_FRONT_BIT : 0u;
-    r.t = t; r.u = u; r.v = v; r.tri = tri_index; r.blas_front = blas | front;
+    r.t = t; r.u = u; r.v = v; r.tri = tri_index; r.blas_front = blas | (r.inst << GDPT_HIT_INST_BITS) | front;
 }
 GDPT_HD void triangle_test(const SceneView &sc, RayState &r, uint32_t tri_index)
 {

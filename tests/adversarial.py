@@ -53,6 +53,28 @@ def coincident_instances():
     return sc
 
 
+def decal_on_a_wall():
+    """A quad of a second instance lying exactly in the room's back wall (a decal, an object resting on a floor): equal t
+    across two instances.  The reference then reports the triangle, position and facing of the pair it tested last but the
+    instance -- transform and materials -- of the pair that lowered t first (main.glsl:247-255 against :322-325)."""
+    sc = scenes.SceneDesc("decal_on_a_wall", camera_transform12=scenes.transform12(None, (0.3, 0.2, 8.0)), fov=50.0)
+    sc.materials = [dict(albedo=(0.8, 0.8, 0.8), roughness=0.9), dict(albedo=(0.9, 0.3, 0.2), roughness=0.3, metallic=0.7),
+                    dict(albedo=(0.2, 0.4, 0.9), roughness=0.5)]
+    sc.default_material = 0
+    quad = [scenes._merge([scenes._quad_surface([[-1, -1, 0], [1, -1, 0], [1, 1, 0], [-1, 1, 0]], [0, 0, 1])])]
+    # the room's own back wall (cornell.obj usemtl 2, z = -5) as a mesh of its own, moved by 4 units inside its plane; the
+    # instance's origin moves it back, so both instances test triangles of the same world plane from different spaces
+    wall = [scenes._merge([scenes._quad_surface([[-5, -1, -5], [5, -1, -5], [5, 9, -5], [-5, 9, -5]], [0, 0, 1])])]
+    shifted = scenes.ROOM_TRANSFORM.copy()
+    shifted[10] = np.float32(-2.4)  # origin.y: 0.6 * (-4)
+    sc.meshes = [scenes._cornell_room(), quad, wall]
+    sc.instances = [dict(mesh=1, transform12=scenes.transform12([[1.5, 0, 0], [0, 1.2, 0], [0, 0, 1]], (0.5, 0.0, -3.0)), surface_overrides=[1]),
+                    dict(mesh=0, transform12=scenes.ROOM_TRANSFORM, surface_overrides=[0, 2, 0]),
+                    dict(mesh=1, transform12=scenes.transform12([[0, 0, 1], [0, 1, 0], [-1, 0, 0]], (-3.0, -1.0, 0.0)), surface_overrides=[2]),
+                    dict(mesh=2, transform12=shifted, surface_overrides=[1])]
+    return sc
+
+
 def degenerate_cluster():
     """Triangles the determinant test throws away next to ones it keeps: needles and specks whose |det| < 1e-5, zero-area
     triangles, and walls seen edge-on, in front of an ordinary backdrop."""
@@ -84,6 +106,7 @@ def tlas_root_is_a_leaf():
     """One rotated, scaled instance: the TLAS root is its only node and is never box-tested (main.glsl:309-314)."""
     sc = scenes.triangle_soup(3000, seed=13)
     sc.name = "tlas_root_is_a_leaf"
+    sc.meshes = [[scenes._soup_surface(3000, 13, 10.0, 0.7)]]
     c, s = np.float32(np.cos(0.7)), np.float32(np.sin(0.7))
     sc.instances = [dict(mesh=0, transform12=scenes.transform12([[0.5 * c, -0.5 * s, 0.0], [0.5 * s, 0.5 * c, 0.0], [0.0, 0.0, 0.5]], (0.5, -1.0, 2.0)))]
     return sc
@@ -130,6 +153,7 @@ def planar_camera(sc, W, H, frame_index, zero_axes):
 CASES = [
     ("coplanar_duplicates", coplanar_duplicates, 96, 96, 5, None),
     ("coincident_instances", coincident_instances, 128, 72, 4, None),
+    ("decal_on_a_wall", decal_on_a_wall, 128, 96, 5, None),
     ("degenerate_cluster", degenerate_cluster, 128, 96, 4, None),
     ("tlas_root_is_a_leaf", tlas_root_is_a_leaf, 96, 64, 3, None),
     ("far_tiny_instance", far_tiny_instance, 96, 64, 3, None),

@@ -43,7 +43,8 @@ template <bool CULL> static void run_ray(const SceneView &sc, RayState &r, HostS
         if (g_fast == 2 && sc.fast4_ok) fast_trace_ray4(sc, f, st); // four-wide tables
         else fast_trace_ray(sc, f, st);
         __atomic_add_fetch(&g_fast_rays, 1, __ATOMIC_RELAXED);
-        if (fast_result_is_reference(sc, f)) { r = f; return; }
+        if (fast_result_is_reference(sc, f)) {
+            r = f; return; }
         __atomic_add_fetch(&g_fast_retraced, 1, __ATOMIC_RELAXED);
         if (f.overflow & (RAY_TIE | RAY_FAR)) __atomic_add_fetch(&g_fast_ties, 1, __ATOMIC_RELAXED);
     }
@@ -238,7 +239,7 @@ int devcheck_path_trace(const devcheck_scene *in, const gdpt_render_params *para
                 if (trace && i < trace_segments) {
                     gdpt_trace_record &rec = trace[(size_t)i * W * H + pixel];
                     rec.hit = hit ? 1u : 0u; rec.triangle = hit ? r.tri : 0u;
-                    rec.blas = hit ? (r.blas_front & ~GDPT_FRONT_BIT) : 0u; rec.front = hit ? (r.blas_front >> 31) : 0u;
+                    rec.blas = hit ? hit_blas(r.blas_front) : 0u; rec.front = hit ? (r.blas_front >> 31) : 0u;
                     rec.t = r.t; rec.u = hit ? r.u : 0.0f; rec.v = hit ? r.v : 0.0f;
                     rec.node_pops = tc.node_pops; rec.box_tests = tc.box_tests; rec.tri_tests = tc.tri_tests;
                     rec.tlas_leaves = tc.tlas_leaves; rec.max_stack = tc.max_stack;

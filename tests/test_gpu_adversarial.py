@@ -1,0 +1,80 @@
+"""GPU tier of the adversarial cases (tests/adversarial.py): the kernels that are timed -- the closest-hit search + proof
+with pooled paths (schedule 6) and with phase-sorted rays (7) -- and the reference-order kernel (3) on equal-t ties inside
+and across instances, coincident instances, camera rays with zero direction components, |det| < 1e-5 clusters, a TLAS whose
+root is a leaf and a far, tiny instance.  Through the C-ABI (gdpt_render_frame with the case's own camera block); every hit
+record, the frame, the depth image and the ray count equal the oracle's, and the number of rays the search hands to the
+exact traversal is the number the host-compiled device functions predict (test_adversarial_cpu.py)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import adversarial
+from gdpathtracing_b200 import PathTracingCamera, _lib, scenes
+from oracle import oracle
+from test_device_functions_cpu import fast_counts, run_devcheck
+
+pytestmark = pytest.mark.gpu
+
+FIELDS = ("triangle", "blas", "front", "t", "u", "v")
+
+
+def render_with_block(cam, block, W, H):
+    """One un-denoised frame with an arbitrary camera block: gdpt_render_frame (include/gdpt.h), colour and depth read back."""
+    rgba = np.zeros((H, W, 4), np.uint8)
+    depth = np.zeros((H, W), np.float32)
+    _lib.check(_lib.cuda.gdpt_render_frame(cam.main_shader, None, ctypes.byref(block), PathTracingCamera.NONE, 0,
+                                           rgba.ctypes.data_as(ctypes.c_void_p), depth.ctypes.data_as(ctypes.POINTER(ctypes.c_float))),
+               cam.device, "gdpt_render_frame")
+    return rgba, depth
+
+
+@pytest.mark.parametrize("variant", [7, 6, 3], ids=["sorted_rays", "pooled_paths", "reference_order"])
+@pytest.mark.parametrize("name,make,W,H,depth,zero_axes", adversarial.CASES, ids=adversarial.IDS)
+def test_rendering_kernels_on_adversarial_input(devcheck, name, make, W, H, depth, zero_axes, variant):
+    sc = make()
+    grp = scenes.populate(sc)
+    cam = PathTracingCamera()
+    cam.fov = sc.fov
+    cam.geometry_group = grp
+    cam.denoising_mode = PathTracingCamera.NONE
+    cam.set_window_size(W, H)
+    cam.set_global_transform(sc.camera_transform12)
+    cam.set_max_depth(depth)
+    segs = min(depth, 4)
+    cam.set_record_hits(segs)
+    cam.set_variant(variant)
+    cam.init()
+    osc = oracle.Scene(grp.buffers(), grp.texture_layers())
+    for frame_index in (3, 4):  # the second frame is scheduled by the cost classes of the first
+        block = adversarial.camera_for(sc, W, H, frame_index, zero_axes)
+        frame, dep = render_with_block(cam, block, W, H)
+        st = cam.stats()
+        ref = oracle.path_trace(osc, W, H, bytes(block), max_depth=depth, trace_segments=segs)
+        assert ref["stats"]["primary_hits"] > 0
+        assert st["rays"] == ref["stats"]["rays"] and st["primary_hits"] == ref["stats"]["primary_hits"]
+        for s in range(segs):
+            a, b = cam.read_trace(s), ref["trace"][s]
+            assert np.array_equal(a["hit"], b["hit"]), f"segment {s}: hit flags"
+            live = b["hit"] != 0xFFFFFFFF
+            for f in FIELDS:
+                assert np.array_equal(a[f][live].view(np.uint32), b[f][live].view(np.uint32)), f"frame {frame_index} segment {s} field {f}"
+        assert np.array_equal(frame, ref["rgba8"])
+        assert np.array_equal(dep.view(np.uint32), ref["depth"].view(np.uint32))
+        if variant == 3:
+            assert st["retraced"] == 0
+            continue
+        # what the same search + proof, compiled for the host, sends to the exact traversal on these rays
+        devcheck.devcheck_set_fast(2)
+        try:
+            run_devcheck(devcheck, osc, bytes(block), W, H, depth, 1, 1)
+            predicted = fast_counts(devcheck)
+        finally:
+            devcheck.devcheck_set_fast(0)
+        assert predicted["rays"] == st["rays"]
+        # the camera rays that miss every instance are finished by k_primary_cull and never reach the search
+        assert st["retraced"] <= predicted["retraced"]
+        assert st["retraced"] >= predicted["retraced"] - (W * H - ref["stats"]["primary_hits"]), (st["retraced"], predicted)
+        print(f"{name} frame {frame_index}: {st['retraced']} of {st['rays']} rays re-traced on the GPU, host tier predicts {predicted['retraced']}")
+        if name in ("coplanar_duplicates", "decal_on_a_wall", "rays_in_the_plane_x0", "rays_along_minus_z", "far_tiny_instance"):
+            assert st["retraced"] * 20 > st["rays"], "meant to send more than 5 % of the rays to the exact traversal"
