@@ -14,6 +14,10 @@
 // a full warp per instruction instead of the 10-16 lanes of the quorum scheme -- and camera-ray generation
 // refills free slots up to 32 at a time.  Every number a path produces is the one k_path_fast produces:
 // the per-ray and per-path arithmetic is shared, only the lane that executes it differs.
+#ifndef GDPT_POOL_MINB
+#define GDPT_POOL_MINB 4
+#endif
+constexpr int kPoolMinBlocks = GDPT_POOL_MINB; // resident blocks per SM the register allocation is capped for (launch bounds)
 constexpr int kPoolSlotsDefault = 64; // path slots per warp (template argument kPoolSlots)
 constexpr int kPoolParkDefault = 1; // leaves a lane may park while it keeps descending (template argument kPoolPark)
 enum PoolField {
@@ -35,19 +39,36 @@ __device__ __forceinline__ bool pool_can_cross(uint32_t cur, uint32_t pend, uint
     return cur != LINK_NONE && (cur & LINK_TLAS) != 0u && pend == LINK_NONE && ((cur & LINK_LEAF) != 0u || inst != GDPT_NO_INSTANCE);
 }
 
-template <bool REC, int MINB, int kPoolPark, int kPoolSlots, bool WIDE, bool COUNT = false>
+// Where an accepted triangle's u / v / triangle / instance go: into the ray's path slot (field-major pool), so a lane holds
+// only t while it searches.
+template <int kPoolSlots> struct HitInPool {
+    uint32_t *slot0; // &pool[slot]
+    __device__ __forceinline__ void accept(RayState &, float u, float v, uint32_t tri, uint32_t blas_front) const
+    {
+        slot0[PF_U * kPoolSlots] = __float_as_uint(u); slot0[PF_V * kPoolSlots] = __float_as_uint(v);
+        slot0[PF_TRI * kPoolSlots] = tri; slot0[PF_BF * kPoolSlots] = blas_front;
+    }
+};
+
+// Launch-time form of the scheduling knobs (launch_path_pool): the kernel reads them from the constant bank as they are.
+//   refill_below = lanes without a walking ray before the pool is serviced (1..32)
+//   pool_wait    = ... or this many lane-iterations spent waiting (0xFFFFFFFF = off)
+//   pool_alive   = free slots a warp keeps unused (cap on alive paths), shade_at = finished rays that justify a partial batch
+template <bool REC, int MINB, int kPoolPark, int kPoolSlots, bool WIDE, bool COUNT = false, bool PROF = false>
 __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_pool(const FrameArgs a)
 {
     __shared__ uint32_t s_stack[kSmemStack * kTraceThreads];
     __shared__ uint32_t s_pool[kTraceThreads / 32][PF_COUNT * kPoolSlots];
     __shared__ uint8_t s_lists[kTraceThreads / 32][3 * kPoolSlots];
     __shared__ gdpt_camera s_cam;
+    __shared__ SurvivorLists s_surv;
     uint32_t spill[GDPT_MAX_STACK - kSmemStack];
     SmemStack st;
     st.col = s_stack + threadIdx.x;
     st.spill = spill;
     if (threadIdx.x < sizeof(gdpt_camera) / 4u)
         reinterpret_cast<uint32_t *>(&s_cam)[threadIdx.x] = reinterpret_cast<const uint32_t *>(a.camera)[threadIdx.x];
+    if (threadIdx.x == kTraceThreads - 1) s_surv.load(a);
     static_assert(kPoolSlots >= 32 && kPoolSlots <= 255 && kPoolSlots % 8 == 0, "pool: 32..248 slots");
     const unsigned lane = threadIdx.x & 31u;
     uint32_t *const pool = s_pool[threadIdx.x >> 5];
@@ -62,20 +83,16 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_pool(const FrameAr
 
     const unsigned lanemask_lt = (1u << lane) - 1u;
     FrameCounters *cnt = a.counters;
-    SurvivorLists lists;
-    lists.load(a);
-    const uint32_t total = lists.total;
-    const int swap_at = min(max(a.refill_below, 1), 32);   // lanes without a walking ray before the pool is serviced ...
-    const uint32_t swap_wait = a.pool_wait > 0 ? (uint32_t)a.pool_wait : 0xFFFFFFFFu; // ... or this many lane-iterations spent waiting
+    const SurvivorLists &lists = s_surv;
+#define swap_at a.refill_below
+#define swap_wait ((uint32_t)a.pool_wait)
+#define min_free ((uint32_t)a.pool_alive)
+#define shade_low a.shade_at
     uint32_t waited = 0;
-    const uint32_t min_free = (a.pool_alive >= 32 && a.pool_alive < kPoolSlots) ? (uint32_t)(kPoolSlots - a.pool_alive) : 0u;
-    const int shade_low = min(max(a.shade_at, 1), 32);     // finished rays that justify a partial shading batch
     bool heavy_done = false;
-    const int last_segment = a.max_depth - 1;
 
     RayState r;
     r.cur = LINK_NONE; r.sp = 0; r.overflow = 0; r.t = 1e9f; r.inst = GDPT_NO_INSTANCE;
-    f3 wrd = mk3(0.0f, 0.0f, 0.0f);
     uint32_t park[kPoolPark];  // parked leaves, oldest first (instance-local: flushed before the space changes)
     uint32_t n_park = 0;
 #pragma unroll
@@ -84,11 +101,11 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_pool(const FrameAr
     bool has = false;
     uint32_t ready_count = 0, done_count = 0, free_count = (uint32_t)kPoolSlots; // warp-uniform
     uint32_t chunk_next = 0, chunk_end = 0;
-    bool exhausted = (total == 0u);
-    unsigned long long my_rays = 0, my_phits = 0, my_retraced = 0;
+    bool exhausted = (lists.total == 0u);
+    uint32_t my_rays = 0, my_phits = 0, my_retraced = 0; // per lane and launch: far below 2^32
     unsigned long long own_nodes = 0, own_boxes = 0, own_tris = 0, own_insts = 0, own_proofs = 0; // COUNT only
     uint32_t my_overflow = 0;
-    const bool prof = a.warp_prof != nullptr;
+    const bool prof = PROF && a.warp_prof != nullptr; // the per-warp schedule profile has its own instantiation
     const unsigned long long t_start = prof ? global_ns() : 0ull;
     uint32_t it_i = 0, it_l = 0, it_t = 0, it_f = 0, it_e = 0, n_started = 0;
 
@@ -113,9 +130,8 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_pool(const FrameAr
             // 1. retire: finished searches go to their slots, the slots to the shading queue
             if (n_fin > 0) {
                 const unsigned m = __ballot_sync(kFull, fin);
-                if (fin) {
-                    PF(PF_T, slot) = __float_as_uint(r.t); PF(PF_U, slot) = __float_as_uint(r.u); PF(PF_V, slot) = __float_as_uint(r.v);
-                    PF(PF_TRI, slot) = r.tri; PF(PF_BF, slot) = r.blas_front; PF(PF_FLAGS, slot) = r.overflow;
+                if (fin) { // u / v / triangle / instance are in the slot already (HitInPool)
+                    PF(PF_T, slot) = __float_as_uint(r.t); PF(PF_FLAGS, slot) = r.overflow;
                     PF(PF_STEPS, slot) += steps;
                     done_list[done_count + (uint32_t)__popc(m & lanemask_lt)] = (uint8_t)slot;
                     has = false;
@@ -128,7 +144,7 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_pool(const FrameAr
                                (done_count > 0u && n_out > ready_count && !can_refill && (done_count >= (uint32_t)shade_low || n_walk == 0));
             if (shade) {
                 // 2. S: prove and shade up to 32 finished rays, oldest first
-                it_f++;
+                if (PROF) it_f++;
                 const uint32_t n = min(done_count, 32u);
                 const bool mine = lane < n;
                 const uint32_t sl = mine ? (uint32_t)done_list[lane] : 0u;
@@ -168,7 +184,7 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_pool(const FrameAr
                         shade_and_bounce_ool(&a.sc, wo, wd, ht, hu, hv, htri, hbf, radiance, throughput, &sd, &br);
                         radiance = br.radiance;
                         if (segment == 0) a.out_depth[pixel] = encode_depth(cam, br.first_hit_distance);
-                        alive = br.alive && segment < last_segment;
+                        alive = br.alive && segment < a.max_depth - 1;
                         if (alive) {
                             PF(PF_SEEDX, sl) = sd.x; PF(PF_SEEDY, sl) = sd.y;
                             PF(PF_THR, sl) = __float_as_uint(br.throughput.x); PF(PF_THG, sl) = __float_as_uint(br.throughput.y);
@@ -203,7 +219,7 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_pool(const FrameAr
                 __syncwarp();
             } else if (n_out > ready_count && can_refill) {
                 // 3. R: camera rays into free slots
-                it_e++;
+                if (PROF) it_e++;
                 if (chunk_next == chunk_end) {
                     uint32_t base = 0, len = kChunkPrimary;
                     if (lane == 0) {
@@ -221,9 +237,9 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_pool(const FrameAr
                     base = __shfl_sync(kFull, base, 0);
                     len = __shfl_sync(kFull, len, 0);
                     if (len & 0x80000000u) { heavy_done = true; len &= 0x7FFFFFFFu; }
-                    if (base >= total) { exhausted = true; continue; }
+                    if (base >= lists.total) { exhausted = true; continue; }
                     chunk_next = base;
-                    chunk_end = min(base + len, total);
+                    chunk_end = min(base + len, lists.total);
                 }
                 const uint32_t g = min(min(chunk_end - chunk_next, free_count - min_free), 32u);
                 if (lane < g) {
@@ -240,7 +256,7 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_pool(const FrameAr
                     PF(PF_PIXEL, sl) = p; PF(PF_SEGMENT, sl) = 0u; PF(PF_STEPS, sl) = 0u;
                     ready_list[ready_count + lane] = (uint8_t)sl;
                 }
-                free_count -= g; ready_count += g; chunk_next += g; n_started += g;
+                free_count -= g; ready_count += g; chunk_next += g; if (PROF) n_started += g;
                 __syncwarp();
             }
             // 4. feed: lanes without a ray take ready slots
@@ -252,7 +268,6 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_pool(const FrameAr
                     fast_ray_begin(r, a.sc, mk3(PFF(PF_WOX, slot), PFF(PF_WOY, slot), PFF(PF_WOZ, slot)),
                                    mk3(PFF(PF_WDX, slot), PFF(PF_WDY, slot), PFF(PF_WDZ, slot)));
                     if (WIDE) r.cur = a.sc.fast4_root; // the four-wide tables have their own root link
-                    wrd = r.rd;
                     n_park = 0;
                     steps = 0;
                     has = true;
@@ -266,7 +281,7 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_pool(const FrameAr
         // ---------------- I / L / T: the phase that advances most lanes per instruction ----------------
         const int run = (n_i * 3 >= n_l && n_i * 3 >= n_t * 2) ? 1 : (n_l >= n_t * 2 ? 0 : 2);
         if (run == 1) {
-            it_i++;
+            if (PROF) it_i++;
             bool go = can_i;
             const int need = (n_i + 1) >> 1;
 #pragma unroll 1
@@ -287,7 +302,7 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_pool(const FrameAr
                 if (__popc(__ballot_sync(kFull, go)) < need) break;
             }
         } else if (run == 0) {
-            it_l++;
+            if (PROF) it_l++;
             if (can_l) {
                 uint32_t leaf = park[0];
                 if (n_park) {
@@ -295,14 +310,18 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_pool(const FrameAr
                     for (int k = 0; k + 1 < kPoolPark; k++) park[k] = park[k + 1];
                     n_park--;
                 } else { leaf = r.cur; r.cur = fast_pop(r, st); }
-                fast_leaf_tests(a.sc, r, leaf);
+                HitInPool<kPoolSlots> sink;
+                sink.slot0 = pool + slot;
+                fast_leaf_tests(a.sc, r, leaf, sink);
                 steps++;
                 if (COUNT) own_tris += ((leaf >> FAST_LEAF_COUNT_SHIFT) & 7u) + 1u;
             }
         } else {
-            it_t++;
+            if (PROF) it_t++;
             if (can_t) { // back to world space (main.glsl:316-327) and/or into the instance the link names
-                if (r.inst != GDPT_NO_INSTANCE) { r.o = r.wo; r.d = r.wd; r.rd = wrd; r.inst = GDPT_NO_INSTANCE; }
+                r.wo = mk3(PFF(PF_WOX, slot), PFF(PF_WOY, slot), PFF(PF_WOZ, slot)); // the world ray lives in the slot, not in the lane
+                r.wd = mk3(PFF(PF_WDX, slot), PFF(PF_WDY, slot), PFF(PF_WDZ, slot));
+                if (r.inst != GDPT_NO_INSTANCE) { r.o = r.wo; r.d = r.wd; r.rd = fast_rcp3(r.wd); r.inst = GDPT_NO_INSTANCE; }
                 if (r.cur & LINK_LEAF) { fast_enter_instance<WIDE>(a.sc, r, st); if (COUNT) own_insts++; }
                 steps++;
             }
@@ -310,18 +329,19 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_pool(const FrameAr
     }
 #undef PF
 #undef PFF
+#undef swap_at
+#undef swap_wait
+#undef min_free
+#undef shade_low
     if (prof && lane == 0) {
         unsigned long long *w = a.warp_prof + (size_t)((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 8u;
         w[0] = t_start; w[1] = global_ns(); w[2] = it_i; w[3] = it_l; w[4] = it_t; w[5] = it_f; w[6] = it_e; w[7] = n_started;
     }
-    for (int off = 16; off > 0; off >>= 1) {
-        my_rays += __shfl_down_sync(kFull, my_rays, off);
-        my_phits += __shfl_down_sync(kFull, my_phits, off);
-        my_retraced += __shfl_down_sync(kFull, my_retraced, off);
-    }
+    my_rays = __reduce_add_sync(kFull, my_rays); my_phits = __reduce_add_sync(kFull, my_phits); // per warp: still far below 2^32
+    my_retraced = __reduce_add_sync(kFull, my_retraced);
     if (lane == 0) {
-        atomicAdd(&cnt->rays, my_rays); atomicAdd(&cnt->primary_hits, my_phits);
-        if (my_retraced) atomicAdd(&cnt->retraced, my_retraced);
+        atomicAdd(&cnt->rays, (unsigned long long)my_rays); atomicAdd(&cnt->primary_hits, (unsigned long long)my_phits);
+        if (my_retraced) atomicAdd(&cnt->retraced, (unsigned long long)my_retraced);
     }
     if (COUNT) { // own work of the search (roofline numerator of bench.py)
         for (int off = 16; off > 0; off >>= 1) {

@@ -170,7 +170,15 @@ template <bool SORT = true, class Stack> GDPT_HD void fast_step_node4(const Scen
 
 // intersectTriangle (main.glsl:224-257), same operations as triangle_test_loaded; the running minimum
 // replaces hit.t, and a pair that reaches the minimum exactly is recorded instead of accepted.
-GDPT_HD void fast_triangle_test(RayState &r, const q4f a, const q4f b, const q4f c)
+// Where the accepted pair's u / v / triangle / instance go is the caller's choice (`Sink`): into the RayState, or
+// straight into a path slot in shared memory so that a lane carries only t through the search (k_path_pool).
+struct HitInRay {
+    GDPT_HD void accept(RayState &r, float u, float v, uint32_t tri, uint32_t blas_front) const
+    {
+        r.u = u; r.v = v; r.tri = tri; r.blas_front = blas_front;
+    }
+};
+template <class Sink> GDPT_HD void fast_triangle_test(RayState &r, const q4f a, const q4f b, const q4f c, const Sink &sink)
 {
     const f3 v0 = mk3(a.x, a.y, a.z);
     const f3 e1 = mk3(b.x, b.y, b.z) - v0, e2 = mk3(c.x, c.y, c.z) - v0;
@@ -188,24 +196,21 @@ GDPT_HD void fast_triangle_test(RayState &r, const q4f a, const q4f b, const q4f
     if (t < 0.0f || t > r.t) return;
     if (t < r.t) {
         const uint32_t front = dot3(cross3(e1, e2), r.d) > 0.0f ? GDPT_FRONT_BIT : 0u;
-#if defined(__CUDA_ARCH__)
-        r.tri = __float_as_uint(a.w);
-#else
-        memcpy(&r.tri, &a.w, 4);
-#endif
-        r.t = t; r.u = u; r.v = v; r.blas_front = r.inst | (r.inst << GDPT_HIT_INST_BITS) | front;
+        r.t = t;
+        sink.accept(r, u, v, fast_bits(a.w), r.inst | (r.inst << GDPT_HIT_INST_BITS) | front);
         r.overflow &= ~RAY_TIE;
     } else {
         r.overflow |= RAY_TIE; // t == r.t (or NaN): the reference's answer would depend on its visiting order
     }
 }
+GDPT_HD void fast_triangle_test(RayState &r, const q4f a, const q4f b, const q4f c) { fast_triangle_test(r, a, b, c, HitInRay()); }
 
 // One leaf: 1..8 triangles (fast_bvh.h leaf_max(), 3 by default).  GDPT_FAST_LEAF_UNROLL 4 issues all loads together (more registers, 4 copies of
 // the test in the instruction stream); 1 keeps one copy of the test in a short loop (instruction-cache friendly).
 #ifndef GDPT_FAST_LEAF_UNROLL
 #define GDPT_FAST_LEAF_UNROLL 1
 #endif
-GDPT_HD void fast_leaf_tests(const SceneView &sc, RayState &r, uint32_t leaf_link)
+template <class Sink> GDPT_HD void fast_leaf_tests(const SceneView &sc, RayState &r, uint32_t leaf_link, const Sink &sink)
 {
     const uint32_t first = leaf_link & FAST_LEAF_FIRST_MASK, count = ((leaf_link >> FAST_LEAF_COUNT_SHIFT) & 7u) + 1u;
 #if GDPT_FAST_LEAF_UNROLL == 4
@@ -217,7 +222,7 @@ GDPT_HD void fast_leaf_tests(const SceneView &sc, RayState &r, uint32_t leaf_lin
     }
 #pragma unroll
     for (uint32_t i = 0; i < 4u; i++)
-        if (i < count) fast_triangle_test(r, va[i], vb[i], vc[i]);
+        if (i < count) fast_triangle_test(r, va[i], vb[i], vc[i], sink);
 #elif GDPT_FAST_LEAF_UNROLL == 2
     // two triangles per trip: six loads in flight, one copy of the test in the instruction stream (called twice)
 #pragma unroll 1
@@ -225,8 +230,8 @@ GDPT_HD void fast_leaf_tests(const SceneView &sc, RayState &r, uint32_t leaf_lin
         const uint32_t t0 = first + i, t1 = first + (i + 1u < count ? i + 1u : i);
         const q4f a0 = ldq(sc.fast_tris, t0 * 3u + 0u), b0 = ldq(sc.fast_tris, t0 * 3u + 1u), c0 = ldq(sc.fast_tris, t0 * 3u + 2u);
         const q4f a1 = ldq(sc.fast_tris, t1 * 3u + 0u), b1 = ldq(sc.fast_tris, t1 * 3u + 1u), c1 = ldq(sc.fast_tris, t1 * 3u + 2u);
-        fast_triangle_test(r, a0, b0, c0);
-        if (i + 1u < count) fast_triangle_test(r, a1, b1, c1);
+        fast_triangle_test(r, a0, b0, c0, sink);
+        if (i + 1u < count) fast_triangle_test(r, a1, b1, c1, sink);
     }
 #else
     // software-pipelined by one triangle: the next triangle's vertices are in flight during the current test
@@ -235,11 +240,12 @@ GDPT_HD void fast_leaf_tests(const SceneView &sc, RayState &r, uint32_t leaf_lin
     for (uint32_t i = 0; i < count; i++) {
         const uint32_t tn = first + (i + 1u < count ? i + 1u : i);
         const q4f na = ldq(sc.fast_tris, tn * 3u + 0u), nb = ldq(sc.fast_tris, tn * 3u + 1u), nc = ldq(sc.fast_tris, tn * 3u + 2u);
-        fast_triangle_test(r, a, b, c);
+        fast_triangle_test(r, a, b, c, sink);
         a = na; b = nb; c = nc;
     }
 #endif
 }
+GDPT_HD void fast_leaf_tests(const SceneView &sc, RayState &r, uint32_t leaf_link) { fast_leaf_tests(sc, r, leaf_link, HitInRay()); }
 template <class Stack> GDPT_HD void fast_step_leaf(const SceneView &sc, RayState &r, Stack &st)
 {
     const uint32_t leaf = r.cur;

@@ -372,11 +372,11 @@ void init_launch_shapes(int device)
     s.path_blocks[1][1] = grid_of(k_path<true, true, 0>, kTraceThreads);
     s.path_list_blocks = grid_of(k_path<false, true, 1, 4, true>, kTraceThreads);
     s.path_list_record_blocks = grid_of(k_path<true, true, 1>, kTraceThreads);
-    s.pool_blocks[0][0] = grid_of(k_path_pool<false, 4, kPoolParkDefault, kPoolSlotsDefault, false>, kTraceThreads);
-    s.pool_blocks[0][1] = grid_of(k_path_pool<false, 4, kPoolParkDefault, kPoolSlotsDefault, true>, kTraceThreads);
-    s.pool_blocks[1][0] = grid_of(k_path_pool<true, 4, kPoolParkDefault, kPoolSlotsDefault, false>, kTraceThreads);
-    s.pool_blocks[1][1] = grid_of(k_path_pool<true, 4, kPoolParkDefault, kPoolSlotsDefault, true>, kTraceThreads);
-    s.pool_count_blocks = grid_of(k_path_pool<false, 4, kPoolParkDefault, kPoolSlotsDefault, true, true>, kTraceThreads);
+    s.pool_blocks[0][0] = grid_of(k_path_pool<false, kPoolMinBlocks, kPoolParkDefault, kPoolSlotsDefault, false>, kTraceThreads);
+    s.pool_blocks[0][1] = grid_of(k_path_pool<false, kPoolMinBlocks, kPoolParkDefault, kPoolSlotsDefault, true>, kTraceThreads);
+    s.pool_blocks[1][0] = grid_of(k_path_pool<true, kPoolMinBlocks, kPoolParkDefault, kPoolSlotsDefault, false>, kTraceThreads);
+    s.pool_blocks[1][1] = grid_of(k_path_pool<true, kPoolMinBlocks, kPoolParkDefault, kPoolSlotsDefault, true>, kTraceThreads);
+    s.pool_count_blocks = grid_of(k_path_pool<false, kPoolMinBlocks, kPoolParkDefault, kPoolSlotsDefault, true, true>, kTraceThreads);
     auto sorted_grid = [&](auto kernel, size_t smem) {
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         per_sm = 0;
@@ -469,21 +469,30 @@ void launch_temporal(uint32_t *screen_rgba8, const float *depth, const float *hi
 //   parked leaves 1 | 2 | 3 | 4          0.859 | 0.892 | 0.908 | 0.918      20.3 | 20.9 | 21.4 | 21.8
 //   slots per warp 40 | 64 | 96          0.961 | 0.878 | 0.896              21.5 | 20.5 | 20.9
 //   blocks per SM 4 | 5 | 6 | 8          0.854 | 0.960 | 1.124 | 1.320      19.0 | 18.6 | 21.8 | 24.8   (registers 128 | 96 | 80 | 64)
-void launch_path_pool(const FrameArgs &a, bool record, cudaStream_t s)
+void launch_path_pool(const FrameArgs &a_in, bool record, cudaStream_t s)
 {
     Shapes &sh = shapes_for_current_device();
+    FrameArgs a = a_in; // scheduling knobs in the form the kernel reads them (k_path_pool.cuh)
+    a.refill_below = std::min(std::max(a_in.refill_below, 1), 32);
+    a.pool_wait = a_in.pool_wait > 0 ? a_in.pool_wait : -1; // read as uint32: off
+    a.pool_alive = (a_in.pool_alive >= 32 && a_in.pool_alive < kPoolSlotsDefault) ? kPoolSlotsDefault - a_in.pool_alive : 0; // slots kept free
+    a.shade_at = std::min(std::max(a_in.shade_at, 1), 32);
     const bool wide = a.wide_bvh != 0 && a.sc.fast4_ok != 0; // four-wide tables (fast_bvh.h Collapse)
     const int grid = persistent_grid(sh, a, sh.pool_blocks[record ? 1 : 0][wide ? 1 : 0]);
     if (a.count_work && wide && !record) { // the instantiation that also counts its own work (bench.py's roofline numerator)
-        k_path_pool<false, 4, kPoolParkDefault, kPoolSlotsDefault, true, true><<<persistent_grid(sh, a, sh.pool_count_blocks), kTraceThreads, 0, s>>>(a);
+        k_path_pool<false, kPoolMinBlocks, kPoolParkDefault, kPoolSlotsDefault, true, true><<<persistent_grid(sh, a, sh.pool_count_blocks), kTraceThreads, 0, s>>>(a);
+        return;
+    }
+    if (a.warp_prof && wide && !record) { // per-warp schedule profile (tools/warp_profile.py): same grid as the timed instantiation
+        k_path_pool<false, kPoolMinBlocks, kPoolParkDefault, kPoolSlotsDefault, true, false, true><<<grid, kTraceThreads, 0, s>>>(a);
         return;
     }
     if (record) {
-        if (wide) k_path_pool<true, 4, kPoolParkDefault, kPoolSlotsDefault, true><<<grid, kTraceThreads, 0, s>>>(a);
-        else k_path_pool<true, 4, kPoolParkDefault, kPoolSlotsDefault, false><<<grid, kTraceThreads, 0, s>>>(a);
+        if (wide) k_path_pool<true, kPoolMinBlocks, kPoolParkDefault, kPoolSlotsDefault, true><<<grid, kTraceThreads, 0, s>>>(a);
+        else k_path_pool<true, kPoolMinBlocks, kPoolParkDefault, kPoolSlotsDefault, false><<<grid, kTraceThreads, 0, s>>>(a);
     } else {
-        if (wide) k_path_pool<false, 4, kPoolParkDefault, kPoolSlotsDefault, true><<<grid, kTraceThreads, 0, s>>>(a);
-        else k_path_pool<false, 4, kPoolParkDefault, kPoolSlotsDefault, false><<<grid, kTraceThreads, 0, s>>>(a);
+        if (wide) k_path_pool<false, kPoolMinBlocks, kPoolParkDefault, kPoolSlotsDefault, true><<<grid, kTraceThreads, 0, s>>>(a);
+        else k_path_pool<false, kPoolMinBlocks, kPoolParkDefault, kPoolSlotsDefault, false><<<grid, kTraceThreads, 0, s>>>(a);
     }
 }
 
