@@ -51,13 +51,6 @@ struct FastLayout {
     uint32_t root4 = LINK_NONE;       // TLAS root link in nodes4
     uint32_t need4 = 0;               // stack entries the four-wide search can need
     bool ok4 = false;
-    // one-level form (scenes of a few instances): ONE four-wide tree in world space over every (instance, triangle) pair;
-    // its nodes sit in nodes4, its leaves in tris (FastTri.pad1 = instance).  The search never changes space: the node
-    // steps use the world ray, a triangle test uses the instance-local ray of the pair's instance (pt_fast.cuh).
-    uint32_t flat_root4 = LINK_NONE;
-    uint32_t flat_pairs = 0;
-    float flat_reach = 0.0f;          // largest |world origin coordinate| for which this tree's margins are trusted
-    bool flat_ok = false;
     bool ok = false;
     std::string why_not;
 };
@@ -65,7 +58,6 @@ struct FastLayout {
 namespace fastbvh {
 
 constexpr int kBins = 16;
-constexpr uint32_t kFlatMaxPairs = 1u << 19; // (instance, triangle) pairs up to which the one-level tree is built: tables stay L2-sized
 constexpr uint32_t kLeafMaxDefault = 3; // A/B on the B200 (C2 path kernel ms): 2: 0.799, 3: 0.788, 4: 0.807, 6: 0.825, 8: 0.813
 // triangles per leaf of our trees (1..8, the leaf link holds count-1 in 3 bits); GDPT_FAST_LEAF_MAX overrides for A/B runs
 inline uint32_t leaf_max()
@@ -110,8 +102,6 @@ struct Builder {
     std::vector<Prim> prims;
     FastLayout *out;
     float owner_extent = 0.0f;
-    // one-level tree: Prim.orig numbers (instance, triangle) pairs; the leaves copy the triangle and name the instance
-    const uint32_t *pair_tri = nullptr, *pair_inst = nullptr;
     uint32_t depth_seen = 0;
     // multi-threaded form: ranges of at most `cut_at` primitives become tasks built into private tables, which are
     // placed behind one another in the depth-first order the single-threaded recursion would have produced
@@ -161,11 +151,9 @@ struct Builder {
             for (uint32_t i = b; i < e; i++) {
                 FastTri t;
                 std::memset(&t, 0, sizeof(t));
-                const uint32_t tri = pair_tri ? pair_tri[prims[i].orig] : prims[i].orig;
-                const gdpt_triangle_geometry &g = tris[tri];
+                const gdpt_triangle_geometry &g = tris[prims[i].orig];
                 for (int k = 0; k < 3; k++) { t.v0[k] = g.v[0][k]; t.v1[k] = g.v[1][k]; t.v2[k] = g.v[2][k]; }
-                t.orig = tri;
-                t.pad1 = pair_inst ? pair_inst[prims[i].orig] : 0u;
+                t.orig = prims[i].orig;
                 out->tris.push_back(t);
             }
             return LINK_LEAF | ((n - 1u) << FAST_LEAF_COUNT_SHIFT) | first;
@@ -261,7 +249,6 @@ struct Builder {
             Task &t = tasks[(size_t)k];
             Builder sub;
             sub.tris = tris; sub.out = &t.part; sub.owner_extent = owner_extent;
-            sub.pair_tri = pair_tri; sub.pair_inst = pair_inst;
             sub.prims.assign(prims.begin() + t.b, prims.begin() + t.e);
             TightBox box;
             t.link = sub.build(0, t.e - t.b, t.depth, &box);
@@ -388,95 +375,6 @@ inline bool box_inside(const float *cmin, const float *cmax, const float *pmin, 
 
 } // namespace fastbvh
 
-
-// The one-level tree.  World geometry is derived from inverse_transform -- the matrix the reference makes its local rays
-// with (main.glsl:316-321) -- inverted here in double precision, so a `transform` that is not its exact inverse changes
-// nothing.  A pair's box is the bounds of its three world vertices, inflated like every culling box (tight_inflate:
-// own size / 256 + size of its instance / 512).  What the margins must absorb is what they absorb in the two-level
-// tables (derived_layout.h fast_reach) plus the rounding of the local ray itself (a few ulp of the origin's
-// coordinates); `flat_reach` bounds the world origin so that, for EVERY instance, the local origin stays inside that
-// instance's own reach (|A o + b| <= |A|_inf |o|_inf + |b|_inf) -- the search may cull an instance's triangles without
-// ever computing its local ray.
-inline void build_flat_tree(const gdpt_blas_instance *blas, uint32_t n_blas, const gdpt_triangle_geometry *tris, const DerivedLayout &lay,
-                            const std::vector<std::vector<uint32_t>> &root_tris, const std::vector<uint32_t> &root_owner, FastLayout &out)
-{
-    if (n_blas < 2u) return; // a single instance: the two-level search crosses spaces once per ray
-    uint64_t pairs = 0;
-    for (uint32_t b = 0; b < n_blas; b++) pairs += root_tris[root_owner[blas[b].root]].size();
-    if (pairs == 0 || pairs > fastbvh::kFlatMaxPairs || out.tris.size() + pairs >= (1u << FAST_LEAF_COUNT_SHIFT)) return;
-    std::vector<uint32_t> pair_tri, pair_inst;
-    pair_tri.reserve((size_t)pairs); pair_inst.reserve((size_t)pairs);
-    fastbvh::Builder bld;
-    bld.tris = tris; bld.out = &out; bld.owner_extent = 0.0f; // margins are put on the pairs themselves
-    float reach = lay.world_reach;
-    for (uint32_t b = 0; b < n_blas; b++) {
-        const float *m = blas[b].inverse_transform; // column-major: local = A w + t
-        const double a00 = m[0], a10 = m[1], a20 = m[2], a01 = m[4], a11 = m[5], a21 = m[6], a02 = m[8], a12 = m[9], a22 = m[10];
-        const double det = a00 * (a11 * a22 - a12 * a21) - a01 * (a10 * a22 - a12 * a20) + a02 * (a10 * a21 - a11 * a20);
-        if (!std::isfinite(det) || std::fabs(det) < 1e-30) return;
-        const double i00 = (a11 * a22 - a12 * a21) / det, i01 = (a02 * a21 - a01 * a22) / det, i02 = (a01 * a12 - a02 * a11) / det;
-        const double i10 = (a12 * a20 - a10 * a22) / det, i11 = (a00 * a22 - a02 * a20) / det, i12 = (a02 * a10 - a00 * a12) / det;
-        const double i20 = (a10 * a21 - a11 * a20) / det, i21 = (a01 * a20 - a00 * a21) / det, i22 = (a00 * a11 - a01 * a10) / det;
-        const double tx = m[12], ty = m[13], tz = m[14];
-        const std::vector<uint32_t> &list = root_tris[root_owner[blas[b].root]];
-        const size_t first = bld.prims.size();
-        TightBox inst_box = tight_empty();
-        for (uint32_t t : list) {
-            fastbvh::Prim p;
-            double lo[3] = { DBL_MAX, DBL_MAX, DBL_MAX }, hi[3] = { -DBL_MAX, -DBL_MAX, -DBL_MAX };
-            for (int v = 0; v < 3; v++) {
-                const double x = tris[t].v[v][0] - tx, y = tris[t].v[v][1] - ty, z = tris[t].v[v][2] - tz;
-                const double w[3] = { i00 * x + i01 * y + i02 * z, i10 * x + i11 * y + i12 * z, i20 * x + i21 * y + i22 * z };
-                for (int k = 0; k < 3; k++) { lo[k] = std::min(lo[k], w[k]); hi[k] = std::max(hi[k], w[k]); }
-            }
-            for (int k = 0; k < 3; k++) {
-                p.lo[k] = std::nextafter((float)lo[k], -FLT_MAX); p.hi[k] = std::nextafter((float)hi[k], FLT_MAX);
-                p.c[k] = (float)(0.5 * (lo[k] + hi[k]));
-            }
-            p.orig = (uint32_t)pair_tri.size();
-            pair_tri.push_back(t); pair_inst.push_back(b);
-            tight_grow(inst_box, p.lo); tight_grow(inst_box, p.hi);
-            bld.prims.push_back(p);
-        }
-        const float inst_extent = tight_extent(inst_box);
-        for (size_t i = first; i < bld.prims.size(); i++) { // margin of every pair: relative to itself and to its instance
-            fastbvh::Prim &p = bld.prims[i];
-            TightBox own;
-            for (int k = 0; k < 3; k++) { own.lo[k] = p.lo[k]; own.hi[k] = p.hi[k]; }
-            const TightBox inf = tight_inflate(own, inst_extent);
-            for (int k = 0; k < 3; k++) { p.lo[k] = inf.lo[k]; p.hi[k] = inf.hi[k]; }
-        }
-        // world origins this instance's own reach (InstRec.tight_max[3], local space) allows
-        const double norm = std::max(std::fabs(a00) + std::fabs(a01) + std::fabs(a02),
-                                     std::max(std::fabs(a10) + std::fabs(a11) + std::fabs(a12), std::fabs(a20) + std::fabs(a21) + std::fabs(a22)));
-        const double shift = std::max(std::fabs(tx), std::max(std::fabs(ty), std::fabs(tz)));
-        const double local_reach = lay.inst_recs[b].tight_max[3];
-        const double r = norm > 0.0 ? (local_reach - shift) / norm : 0.0;
-        const float wr = fast_reach(inst_box, inst_extent);
-        reach = std::min(reach, std::min(wr, (float)(r > 0.0 && std::isfinite(r) ? r : 0.0)));
-    }
-    if (!(reach > 0.0f)) return; // some instance cannot be bounded: keep the two-level search, which guards per instance
-    bld.pair_tri = pair_tri.data(); bld.pair_inst = pair_inst.data();
-    const int threads = out.build_threads > 0 ? out.build_threads : (int)std::min(32u, std::max(1u, std::thread::hardware_concurrency()));
-    bld.threads = threads;
-    const uint32_t count = (uint32_t)bld.prims.size();
-    if (threads > 1 && count >= 65536u) bld.cut_at = std::max(4096u, count / (uint32_t)(threads * 8));
-    const uint32_t first_node = (uint32_t)out.nodes.size();
-    const size_t first_tri = out.tris.size(), first_node4 = out.nodes4.size();
-    auto undo = [&] { out.nodes.resize(first_node); out.tris.resize(first_tri); out.nodes4.resize(first_node4); };
-    TightBox box;
-    uint32_t link = bld.build(0, count, 0, &box);
-    link = bld.finish_tasks(link, threads, first_node);
-    if (!fastbvh::Collapse::internal(link)) { undo(); return; } // a single leaf: nothing to search
-    fastbvh::Collapse col;
-    col.o = &out;
-    uint32_t need = 0;
-    const uint32_t root4 = col.run(link, &need);
-    if (need + 2u >= GDPT_FAST_MAX_DEPTH || out.nodes4.size() >= (size_t)LINK_INDEX_MASK) { undo(); return; }
-    if (need + 2u > out.need4) out.need4 = need + 2u;
-    out.flat_root4 = root4; out.flat_pairs = count; out.flat_reach = reach; out.flat_ok = true;
-}
-
 // `lay` is the derived layout of the same arrays (its TLAS records carry the true world boxes).
 inline void build_fast_layout(const gdpt_bvh_node *bvh, uint32_t n_nodes, const gdpt_blas_instance *blas, uint32_t n_blas,
                               const gdpt_tlas_node *tlas, uint32_t n_tlas, const gdpt_triangle_geometry *tris, uint32_t n_tris,
@@ -498,8 +396,6 @@ inline void build_fast_layout(const gdpt_bvh_node *bvh, uint32_t n_nodes, const 
 
     // ---- one tree per distinct BLAS root
     std::vector<uint32_t> root_link(n_nodes, 0xFFFFFFFEu); // 0xFFFFFFFE = not built
-    std::vector<std::vector<uint32_t>> root_tris(n_blas);  // per instance that built a tree: its triangles (one-level tree)
-    std::vector<uint32_t> root_owner(n_nodes, 0xFFFFFFFFu); // BLAS root -> the instance whose root_tris holds its triangles
     std::vector<uint32_t> walk;
     std::vector<uint32_t> depth_of(n_nodes, 0);
     for (uint32_t b = 0; b < n_blas; b++) {
@@ -529,7 +425,6 @@ inline void build_fast_layout(const gdpt_bvh_node *bvh, uint32_t n_nodes, const 
                     }
                     p.orig = t;
                     bld.prims.push_back(p);
-                    root_tris[b].push_back(t);
                 }
                 continue;
             }
@@ -564,7 +459,6 @@ inline void build_fast_layout(const gdpt_bvh_node *bvh, uint32_t n_nodes, const 
             if (bld.depth_seen > out.max_depth) out.max_depth = bld.depth_seen;
         }
         root_link[root] = link;
-        root_owner[root] = b;
         out.inst_root[b] = link;
     }
     // children of a BLAS root are tested against nothing above them, but they must still nest below the root's children:
@@ -628,8 +522,6 @@ inline void build_fast_layout(const gdpt_bvh_node *bvh, uint32_t n_nodes, const 
         out.ok4 = out.need4 < GDPT_FAST_MAX_DEPTH && out.nodes4.size() < (size_t)LINK_INDEX_MASK;
     }
     lap("collapse");
-    if (out.ok4) build_flat_tree(blas, n_blas, tris, lay, root_tris, root_owner, out);
-    lap("one-level");
     out.tlas_base = (uint32_t)out.nodes.size();
     out.nodes.insert(out.nodes.end(), out.tlas.begin(), out.tlas.end());
     out.ok = true;

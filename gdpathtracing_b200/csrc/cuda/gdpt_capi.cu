@@ -218,8 +218,6 @@ int build_derived_layout(gdpt_shader *s, const Resource &bvh_r, const Resource &
                       (uint32_t)(tri_r.size / sizeof(gdpt_triangle_geometry)), lay, fast);
     s->args.sc.fast_ok = fast.ok ? 1u : 0u;
     s->fast_why_not = fast.why_not;
-    s->args.sc.fast_flat_root = (fast.ok && fast.ok4 && fast.flat_ok) ? fast.flat_root4 : LINK_NONE;
-    s->args.sc.fast_flat_reach = fast.flat_reach;
     if (fast.ok) {
         for (size_t b = 0; b < lay.inst_recs.size(); b++) {
             lay.inst_recs[b].fast_root = fast.inst_root[b];
@@ -364,7 +362,6 @@ int finish_main(gdpt_shader *s)
     a.lead_min = tune(s, "LEAD_MIN", 0);
     a.sort4 = tune(s, "SORT4", 1);
     a.all_phases = tune(s, "ALL_PHASES", 1);
-    a.flat_tree = tune(s, "FLAT", 1); // schedule 6: the one-level tree where it was built (a few instances)
     a.count_work = s->count_work ? 1 : 0;
     if (a.schedule == 7) {
         a.burst = tune(s, "BURST", 2);

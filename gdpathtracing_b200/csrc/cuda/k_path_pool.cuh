@@ -54,15 +54,7 @@ template <int kPoolSlots> struct HitInPool {
 //   refill_below = lanes without a walking ray before the pool is serviced (1..32)
 //   pool_wait    = ... or this many lane-iterations spent waiting (0xFFFFFFFF = off)
 //   pool_alive   = free slots a warp keeps unused (cap on alive paths), shade_at = finished rays that justify a partial batch
-// FLAT: the one-level search (pt_fast.cuh fast_leaf_tests_flat) -- world ray in the lane, no space changes, phases I and L only.
-template <int kPoolSlots> struct WorldDirInPool {
-    const uint32_t *slot0; // &pool[slot]
-    __device__ __forceinline__ f3 operator()() const
-    {
-        return mk3(__uint_as_float(slot0[PF_WDX * kPoolSlots]), __uint_as_float(slot0[PF_WDY * kPoolSlots]), __uint_as_float(slot0[PF_WDZ * kPoolSlots]));
-    }
-};
-template <bool REC, int MINB, int kPoolPark, int kPoolSlots, bool WIDE, bool COUNT = false, bool PROF = false, bool FLAT = false>
+template <bool REC, int MINB, int kPoolPark, int kPoolSlots, bool WIDE, bool COUNT = false, bool PROF = false>
 __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_pool(const FrameArgs a)
 {
     __shared__ uint32_t s_stack[kSmemStack * kTraceThreads];
@@ -99,11 +91,8 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_pool(const FrameAr
     uint32_t waited = 0;
     bool heavy_done = false;
 
-    static_assert(!FLAT || WIDE, "the one-level tree exists in four-wide form only");
     RayState r;
     r.cur = LINK_NONE; r.sp = 0; r.overflow = 0; r.t = 1e9f; r.inst = GDPT_NO_INSTANCE;
-    FlatLocalRay loc; // FLAT: local ray of instance r.inst
-    loc.o = mk3(0.0f, 0.0f, 0.0f); loc.d = loc.o;
     uint32_t park[kPoolPark];  // parked leaves, oldest first (instance-local: flushed before the space changes)
     uint32_t n_park = 0;
 #pragma unroll
@@ -122,9 +111,9 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_pool(const FrameAr
 
     for (;;) {
         const uint32_t pend = n_park ? park[0] : LINK_NONE;
-        const bool can_i = has && (FLAT ? (r.cur != LINK_NONE && (r.cur & LINK_LEAF) == 0u) : pool_can_node(r.cur, r.inst));
+        const bool can_i = has && pool_can_node(r.cur, r.inst);
         const bool can_l = has && lane_can_leaf(r.cur, pend);
-        const bool can_t = !FLAT && has && pool_can_cross(r.cur, pend, r.inst);
+        const bool can_t = has && pool_can_cross(r.cur, pend, r.inst);
         const bool fin = has && r.cur == LINK_NONE && pend == LINK_NONE;
         const uint32_t census = __reduce_add_sync(kFull, (can_i ? 1u : 0u) | (can_l ? 1u << 6 : 0u) | (can_t ? 1u << 12 : 0u) |
                                                              (fin ? 1u << 18 : 0u) | (has ? 0u : 1u << 24));
@@ -278,8 +267,7 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_pool(const FrameAr
                     slot = (uint32_t)ready_list[ready_count - 1u - rank];
                     fast_ray_begin(r, a.sc, mk3(PFF(PF_WOX, slot), PFF(PF_WOY, slot), PFF(PF_WOZ, slot)),
                                    mk3(PFF(PF_WDX, slot), PFF(PF_WDY, slot), PFF(PF_WDZ, slot)));
-                    if (FLAT) fast_flat_begin(a.sc, r);
-                    else if (WIDE) r.cur = a.sc.fast4_root; // the four-wide tables have their own root link
+                    if (WIDE) r.cur = a.sc.fast4_root; // the four-wide tables have their own root link
                     n_park = 0;
                     steps = 0;
                     has = true;
@@ -314,7 +302,7 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_pool(const FrameAr
                         n_park++;
                         r.cur = fast_pop(r, st);
                     }
-                    go = FLAT ? (r.cur != LINK_NONE && (r.cur & LINK_LEAF) == 0u) : pool_can_node(r.cur, r.inst);
+                    go = pool_can_node(r.cur, r.inst);
                 }
                 if (__popc(__ballot_sync(kFull, go)) < need) break;
             }
@@ -332,21 +320,14 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_pool(const FrameAr
                 } else { leaf = r.cur; r.cur = fast_pop(r, st); }
                 HitInPool<kPoolSlots> sink;
                 sink.slot0 = pool + slot;
-                if (FLAT) {
-                    WorldDirInPool<kPoolSlots> wd;
-                    wd.slot0 = pool + slot;
-                    const uint32_t switched = fast_leaf_tests_flat(a.sc, r, loc, leaf, sink, wd);
-                    if (COUNT) own_insts += switched;
-                } else {
-                    fast_leaf_tests(a.sc, r, leaf, sink);
-                }
+                fast_leaf_tests(a.sc, r, leaf, sink);
                 steps++;
                 if (COUNT) own_tris += ((leaf >> FAST_LEAF_COUNT_SHIFT) & 7u) + 1u;
             }
         }
         bool now_t = can_t;
-        if (all && !FLAT) now_t = has && pool_can_cross(r.cur, n_park ? park[0] : LINK_NONE, r.inst);
-        if (!FLAT && (all ? __any_sync(kFull, now_t) : (run == 2))) {
+        if (all) now_t = has && pool_can_cross(r.cur, n_park ? park[0] : LINK_NONE, r.inst);
+        if (all ? __any_sync(kFull, now_t) : (run == 2)) {
             if (PROF) it_t++;
             if (now_t) { // back to world space (main.glsl:316-327) and/or into the instance the link names
                 r.wo = mk3(PFF(PF_WOX, slot), PFF(PF_WOY, slot), PFF(PF_WOZ, slot)); // the world ray lives in the slot, not in the lane

@@ -178,35 +178,30 @@ struct HitInRay {
         r.u = u; r.v = v; r.tri = tri; r.blas_front = blas_front;
     }
 };
-// (o, d) = the ray in the space of r.inst: r.o / r.d in the two-level search, the cached local ray in the one-level search
-template <class Sink> GDPT_HD void fast_triangle_test_at(RayState &r, const f3 ro, const f3 rd, const q4f a, const q4f b, const q4f c, const Sink &sink)
+template <class Sink> GDPT_HD void fast_triangle_test(RayState &r, const q4f a, const q4f b, const q4f c, const Sink &sink)
 {
     const f3 v0 = mk3(a.x, a.y, a.z);
     const f3 e1 = mk3(b.x, b.y, b.z) - v0, e2 = mk3(c.x, c.y, c.z) - v0;
-    const f3 pvec = cross3(rd, e2);
+    const f3 pvec = cross3(r.d, e2);
     const float det = dot3(e1, pvec);
     if (fabsf(det) < 1e-5f) return;
     const float inv_det = 1.0f / det;
-    const f3 tvec = ro - v0;
+    const f3 tvec = r.o - v0;
     const float u = dot3(tvec, pvec) * inv_det;
     if (u < 0.0f || u > 1.0f) return;
     const f3 qvec = cross3(tvec, e1);
-    const float v = dot3(rd, qvec) * inv_det;
+    const float v = dot3(r.d, qvec) * inv_det;
     if (v < 0.0f || u + v > 1.0f) return;
     const float t = dot3(e2, qvec) * inv_det;
     if (t < 0.0f || t > r.t) return;
     if (t < r.t) {
-        const uint32_t front = dot3(cross3(e1, e2), rd) > 0.0f ? GDPT_FRONT_BIT : 0u;
+        const uint32_t front = dot3(cross3(e1, e2), r.d) > 0.0f ? GDPT_FRONT_BIT : 0u;
         r.t = t;
         sink.accept(r, u, v, fast_bits(a.w), r.inst | (r.inst << GDPT_HIT_INST_BITS) | front);
         r.overflow &= ~RAY_TIE;
     } else {
         r.overflow |= RAY_TIE; // t == r.t (or NaN): the reference's answer would depend on its visiting order
     }
-}
-template <class Sink> GDPT_HD void fast_triangle_test(RayState &r, const q4f a, const q4f b, const q4f c, const Sink &sink)
-{
-    fast_triangle_test_at(r, r.o, r.d, a, b, c, sink);
 }
 GDPT_HD void fast_triangle_test(RayState &r, const q4f a, const q4f b, const q4f c) { fast_triangle_test(r, a, b, c, HitInRay()); }
 
@@ -327,69 +322,6 @@ template <class Stack> GDPT_HD void fast_trace_ray4(const SceneView &sc, RayStat
         else {
             if (r.inst != GDPT_NO_INSTANCE) { r.o = r.wo; r.d = r.wd; r.rd = fast_rcp3(r.wd); r.inst = GDPT_NO_INSTANCE; }
             if (r.cur & LINK_LEAF) fast_enter_instance<true>(sc, r, st);
-        }
-    }
-}
-
-// ---- one-level search (fast_bvh.h build_flat_tree) -----------------------------------------------------------------
-// One world-space tree over every (instance, triangle) pair: node steps run on the world ray (r.o, r.rd) and never
-// change space.  A triangle test needs the local ray of the pair's instance (main.glsl:316-321, the same expressions as
-// fast_enter_instance); it is computed when the instance differs from the one of the previous test (r.inst) and kept
-// in `loc`.  The numbers a pair produces -- local ray, det / u / v / t / front -- are those of the two-level search, so
-// the minimum, the tie flag and the proof are too.  `wd()` hands in the world direction (a register, or the path slot).
-struct FlatLocalRay { f3 o, d; };
-struct WorldDirInRay {
-    const RayState *r;
-    GDPT_HD f3 operator()() const { return r->wd; }
-};
-// returns the number of local rays it had to compute
-template <class Sink, class WorldDir> GDPT_HD uint32_t fast_leaf_tests_flat(const SceneView &sc, RayState &r, FlatLocalRay &loc, uint32_t leaf_link,
-                                                                           const Sink &sink, const WorldDir &wd)
-{
-    const uint32_t first = leaf_link & FAST_LEAF_FIRST_MASK, count = ((leaf_link >> FAST_LEAF_COUNT_SHIFT) & 7u) + 1u;
-    uint32_t switches = 0u;
-    q4f a = ldq(sc.fast_tris, first * 3u + 0u), b = ldq(sc.fast_tris, first * 3u + 1u), c = ldq(sc.fast_tris, first * 3u + 2u);
-#pragma unroll 1
-    for (uint32_t i = 0; i < count; i++) {
-        const uint32_t tn = first + (i + 1u < count ? i + 1u : i);
-        const q4f na = ldq(sc.fast_tris, tn * 3u + 0u), nb = ldq(sc.fast_tris, tn * 3u + 1u), nc = ldq(sc.fast_tris, tn * 3u + 2u);
-        const uint32_t inst = fast_bits(b.w);
-        if (inst != r.inst) {
-            const q4f c0 = ldq(sc.inst_recs, inst * 7u + 0u), c1 = ldq(sc.inst_recs, inst * 7u + 1u);
-            const q4f c2 = ldq(sc.inst_recs, inst * 7u + 2u), c3 = ldq(sc.inst_recs, inst * 7u + 3u);
-            const q4f tmax4 = ldq(sc.inst_recs, inst * 7u + 6u);
-            fast_local_ray(c0, c1, c2, c3, r.o, wd(), &loc.o, &loc.d);
-            r.inst = inst;
-            if (fast_far_origin(loc.o, tmax4.w)) r.overflow |= RAY_FAR; // implied by fast_flat_reach; kept as the two-level search has it
-            switches++;
-        }
-        fast_triangle_test_at(r, loc.o, loc.d, a, b, c, sink);
-        a = na; b = nb; c = nc;
-    }
-    return switches;
-}
-// Start of a one-level search: world ray in r.o / r.rd (fast_ray_begin), no local ray yet.
-GDPT_HD void fast_flat_begin(const SceneView &sc, RayState &r)
-{
-    r.cur = sc.fast_flat_root;
-    r.inst = GDPT_NO_INSTANCE;
-    if (fast_far_origin(r.o, sc.fast_flat_reach)) r.overflow |= RAY_FAR;
-}
-// Whole one-level search of one ray (host check, cold callers).
-template <class Stack> GDPT_HD void fast_trace_ray_flat(const SceneView &sc, RayState &r, Stack &st)
-{
-    fast_flat_begin(sc, r);
-    FlatLocalRay loc;
-    loc.o = r.o; loc.d = r.d;
-    WorldDirInRay wd;
-    wd.r = &r;
-    while (r.cur != LINK_NONE) {
-        if (r.cur & LINK_LEAF) {
-            const uint32_t leaf = r.cur;
-            r.cur = fast_pop(r, st);
-            fast_leaf_tests_flat(sc, r, loc, leaf, HitInRay(), wd);
-        } else {
-            fast_step_node4(sc, r, st);
         }
     }
 }

@@ -479,14 +479,6 @@ void launch_path_pool(const FrameArgs &a_in, bool record, cudaStream_t s)
     a.shade_at = std::min(std::max(a_in.shade_at, 1), 32);
     const bool wide = a.wide_bvh != 0 && a.sc.fast4_ok != 0; // four-wide tables (fast_bvh.h Collapse)
     const int grid = persistent_grid(sh, a, sh.pool_blocks[record ? 1 : 0][wide ? 1 : 0]);
-    if (wide && a.flat_tree && a.sc.fast_flat_root != LINK_NONE) { // the one-level tree (scenes of a few instances)
-        constexpr int M = kPoolMinBlocks, P = kPoolParkDefault, S = kPoolSlotsDefault;
-        if (record) k_path_pool<true, M, P, S, true, false, false, true><<<grid, kTraceThreads, 0, s>>>(a);
-        else if (a.count_work) k_path_pool<false, M, P, S, true, true, false, true><<<persistent_grid(sh, a, sh.pool_count_blocks), kTraceThreads, 0, s>>>(a);
-        else if (a.warp_prof) k_path_pool<false, M, P, S, true, false, true, true><<<grid, kTraceThreads, 0, s>>>(a);
-        else k_path_pool<false, M, P, S, true, false, false, true><<<grid, kTraceThreads, 0, s>>>(a);
-        return;
-    }
     if (a.count_work && wide && !record) { // the instantiation that also counts its own work (bench.py's roofline numerator)
         k_path_pool<false, kPoolMinBlocks, kPoolParkDefault, kPoolSlotsDefault, true, true><<<persistent_grid(sh, a, sh.pool_count_blocks), kTraceThreads, 0, s>>>(a);
         return;

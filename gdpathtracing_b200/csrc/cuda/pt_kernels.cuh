@@ -54,7 +54,6 @@ struct FrameArgs {
     int sort4;                               // schedules 6/7: children of a four-wide node in full distance order (1) or nearest first (0)
     int count_work;                          // schedule 7: run the instantiation that counts its own work (untimed frames of bench.py)
     int all_phases;                          // schedule 6: every phase that has a lane runs in each iteration (1) or only the majority phase (0)
-    int flat_tree;                           // schedule 6: search the one-level tree when it exists (fast_bvh.h build_flat_tree)
     FrameCounters *counters;
     // scheduling knobs (results do not depend on them)
     int refill_below;  // refill idle lanes when fewer than this many lanes are traversing

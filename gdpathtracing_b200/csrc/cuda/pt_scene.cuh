@@ -90,7 +90,7 @@ static_assert(sizeof(FastNode) == 64, "FastNode is four 128-bit loads");
 // 48 B: the reference's vertices (bit copies) and the triangle's index in the reference arrays.
 struct __attribute__((aligned(16))) FastTri {
     float v0[3]; uint32_t orig;
-    float v1[3]; uint32_t pad1; // one-level tree: the pair's instance
+    float v1[3]; uint32_t pad1;
     float v2[3]; uint32_t pad2;
 };
 static_assert(sizeof(FastTri) == 48, "FastTri is three 128-bit loads");
@@ -136,10 +136,6 @@ struct SceneView {
     // largest |origin coordinate| (world space) for which the search's culling margins are trusted; rays from farther
     // out are answered by the exact traversal (derived_layout.h fast_reach)
     float fast_world_reach;
-    // one-level form (fast_bvh.h build_flat_tree): root of the world-space tree over every (instance, triangle) pair in
-    // fast4 (LINK_NONE = not built: many instances, or one), and the world-origin bound its margins are trusted for
-    uint32_t fast_flat_root;
-    float fast_flat_reach;
 };
 
 } // namespace gdpt

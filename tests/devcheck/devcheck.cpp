@@ -33,17 +33,14 @@ struct HostStack {
 static int g_stepwise = 0;
 static int g_cull = 0;
 static int g_fast = 0;
-static uint64_t g_fast_rays = 0, g_fast_retraced = 0, g_fast_ties = 0, g_fast_flat = 0;
+static uint64_t g_fast_rays = 0, g_fast_retraced = 0, g_fast_ties = 0;
 
 template <bool CULL> static void run_ray(const SceneView &sc, RayState &r, HostStack &st, TraceCounters *tc)
 {
     if (g_fast && sc.fast_ok) {
         // closest-hit search + proof; rays that fail it are re-traced in reference order (what the kernels do)
         RayState f = r;
-        if (g_fast == 3 && sc.fast_flat_root != LINK_NONE) { // the one-level tree over every (instance, triangle) pair
-            fast_trace_ray_flat(sc, f, st);
-            __atomic_add_fetch(&g_fast_flat, 1, __ATOMIC_RELAXED);
-        } else if (g_fast >= 2 && sc.fast4_ok) fast_trace_ray4(sc, f, st); // four-wide tables
+        if (g_fast == 2 && sc.fast4_ok) fast_trace_ray4(sc, f, st); // four-wide tables
         else fast_trace_ray(sc, f, st);
         __atomic_add_fetch(&g_fast_rays, 1, __ATOMIC_RELAXED);
         if (fast_result_is_reference(sc, f)) {
@@ -69,7 +66,6 @@ struct devcheck_scene {
 static void make_view(const devcheck_scene *in, DerivedLayout &lay, FastLayout &fast, SceneView &sc)
 {
     std::memset(&sc, 0, sizeof(sc));
-    sc.fast_flat_root = LINK_NONE;
     sc.tri_geom = (const gdpt_triangle_geometry *)in->tri_geom; sc.tri_data = (const gdpt_triangle_data *)in->tri_data;
     sc.materials = (const gdpt_material *)in->materials; sc.bvh = (const gdpt_bvh_node *)in->bvh;
     sc.blas = (const gdpt_blas_instance *)in->blas; sc.tlas = (const gdpt_tlas_node *)in->tlas;
@@ -84,8 +80,6 @@ static void make_view(const devcheck_scene *in, DerivedLayout &lay, FastLayout &
         sc.fast4 = fast.nodes4.data(); sc.fast4_root = fast.root4; sc.fast4_ok = fast.ok4 ? 1u : 0u;
         sc.fast_nodes = fast.nodes.data(); sc.fast_tlas_base = fast.tlas_base; sc.fast_tris = fast.tris.data();
         sc.tri_leaf = fast.tri_leaf.data(); sc.fast_ok = fast.ok ? 1u : 0u;
-        sc.fast_flat_root = (fast.ok && fast.ok4 && fast.flat_ok) ? fast.flat_root4 : LINK_NONE;
-        sc.fast_flat_reach = fast.flat_reach;
         if (!fast.ok) std::fprintf(stderr, "devcheck: closest-hit tables unavailable: %s\n", fast.why_not.c_str());
     }
     sc.wide_nodes = lay.wide_nodes.data(); sc.leaf_recs = lay.leaf_recs.data();
@@ -148,12 +142,8 @@ int devcheck_fast4_structure(const devcheck_scene *in, uint64_t *out_stats3)
     std::vector<uint32_t> roots_done; // instances of one mesh share a root
     uint64_t nodes_walked = 0, children = 0, deepest = 0;
     struct Item { uint32_t link; float lo[3], hi[3]; bool boxed; uint32_t depth; };
-    const gdpt_blas_instance *blas = (const gdpt_blas_instance *)in->blas;
-    // b == n_blas: the one-level tree (world space; a leaf entry names its instance, its vertices are that instance's local ones)
-    for (uint32_t b = 0; b <= (uint32_t)in->n_blas; b++) {
-        const bool flat = b == (uint32_t)in->n_blas;
-        if (flat && !fast.flat_ok) break;
-        const uint32_t root = flat ? fast.flat_root4 : fast.inst_root4[b];
+    for (uint32_t b = 0; b < (uint32_t)in->n_blas; b++) {
+        const uint32_t root = fast.inst_root4[b];
         if (root == LINK_NONE) continue;
         if (std::find(roots_done.begin(), roots_done.end(), root) != roots_done.end()) continue;
         roots_done.push_back(root);
@@ -172,19 +162,7 @@ int devcheck_fast4_structure(const devcheck_scene *in, uint64_t *out_stats3)
                 for (uint32_t k = f; k < f + n; k++) {
                     seen[k]++;
                     const FastTri &t = fast.tris[k];
-                    float world[3][3];
                     const float *v[3] = { t.v0, t.v1, t.v2 };
-                    if (flat) { // where the instance's transform puts the vertex (independent of the builder's own inverse)
-                        if (t.pad1 >= (uint32_t)in->n_blas) return 18;
-                        const float *m = blas[t.pad1].transform;
-                        for (int c = 0; c < 3; c++) {
-                            const double x = v[c][0], y = v[c][1], z = v[c][2];
-                            world[c][0] = (float)(m[0] * x + m[4] * y + m[8] * z + m[12]);
-                            world[c][1] = (float)(m[1] * x + m[5] * y + m[9] * z + m[13]);
-                            world[c][2] = (float)(m[2] * x + m[6] * y + m[10] * z + m[14]);
-                            v[c] = world[c];
-                        }
-                    }
                     if (it.boxed)
                         for (int c = 0; c < 3; c++)
                             for (int a = 0; a < 3; a++)
@@ -211,21 +189,13 @@ int devcheck_fast4_structure(const devcheck_scene *in, uint64_t *out_stats3)
             if (live < 2) return 15;
         }
     }
-    const size_t expect_seen = fast.flat_ok ? seen.size() : seen.size(); // every copy, of either form, is reached exactly once
-    for (size_t k = 0; k < expect_seen; k++)
+    for (size_t k = 0; k < seen.size(); k++)
         if (seen[k] != 1u) return 16;
-    if (fast.flat_ok) { // the one-level tree holds one copy per (instance, triangle) pair
-        uint64_t pairs = 0;
-        for (size_t k = seen.size() - fast.flat_pairs; k < seen.size(); k++) pairs += seen[k];
-        if (pairs != fast.flat_pairs) return 19;
-    }
     if (deepest * 3u + 2u > GDPT_FAST_MAX_DEPTH + 0u && fast.need4 >= GDPT_FAST_MAX_DEPTH) return 17;
     out_stats3[0] = nodes_walked; out_stats3[1] = children; out_stats3[2] = deepest;
     return 0;
 }
-// 1: two-wide tables, 2: four-wide tables, 3: the one-level tree where it exists (else the four-wide tables)
-void devcheck_set_fast(int on) { g_fast = on; g_fast_rays = g_fast_retraced = g_fast_ties = g_fast_flat = 0; }
-uint64_t devcheck_fast_flat_rays() { return g_fast_flat; }
+void devcheck_set_fast(int on) { g_fast = on; g_fast_rays = g_fast_retraced = g_fast_ties = 0; }
 void devcheck_fast_counts(uint64_t *out3) { out3[0] = g_fast_rays; out3[1] = g_fast_retraced; out3[2] = g_fast_ties; }
 
 

@@ -42,7 +42,7 @@ def test_restatement_equals_reference_shader_text_on_adversarial_input(name, mak
     assert np.array_equal(a["visits"], b["visits"])
 
 
-@pytest.mark.parametrize("tables", [1, 2, 3], ids=["two_wide", "four_wide", "one_level"])
+@pytest.mark.parametrize("tables", [1, 2], ids=["two_wide", "four_wide"])
 @pytest.mark.parametrize("name,make,W,H,depth,zero_axes", adversarial.CASES, ids=adversarial.IDS)
 def test_closest_hit_search_on_adversarial_input(devcheck, name, make, W, H, depth, zero_axes, tables):
     sc, _, osc = build(make)

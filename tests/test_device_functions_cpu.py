@@ -149,8 +149,7 @@ def test_tie_on_equal_t_last_tested_triangle_wins(devcheck):
 def fast_counts(devcheck):
     c = np.zeros(3, np.uint64)
     devcheck.devcheck_fast_counts(ptr(c))
-    devcheck.devcheck_fast_flat_rays.restype = ctypes.c_uint64
-    return dict(rays=int(c[0]), retraced=int(c[1]), ties=int(c[2]), one_level=int(devcheck.devcheck_fast_flat_rays()))
+    return dict(rays=int(c[0]), retraced=int(c[1]), ties=int(c[2]))
 
 
 FAST_CASES = CASES + [
@@ -159,12 +158,12 @@ FAST_CASES = CASES + [
 ]
 
 
-@pytest.mark.parametrize("tables", [1, 2, 3], ids=["two_wide", "four_wide", "one_level"])
+@pytest.mark.parametrize("tables", [1, 2], ids=["two_wide", "four_wide"])
 @pytest.mark.parametrize("name,make,W,H,depth,segs,frame", FAST_CASES, ids=[c[0] for c in FAST_CASES])
 def test_closest_hit_search_with_proof_equals_reference_traversal(devcheck, name, make, W, H, depth, segs, frame, tables):
-    """pt_fast.cuh: an order-free closest-hit search over our own BVH (two-wide, its four-wide collapse, or the one-level
-    world-space tree over every (instance, triangle) pair) plus the proof that the reference reaches that triangle (exact
-    re-trace where the proof fails) returns the reference's hit records, bit for bit."""
+    """pt_fast.cuh: an order-free closest-hit search over our own BVH (two-wide, or its four-wide collapse) plus the proof
+    that the reference reaches that triangle (exact re-trace where the proof fails) returns the reference's hit records,
+    bit for bit."""
     devcheck.devcheck_set_fast(tables)
     try:
         sc = make()
@@ -179,8 +178,6 @@ def test_closest_hit_search_with_proof_equals_reference_traversal(devcheck, name
         devcheck.devcheck_set_fast(0)
     assert rays == ref["stats"]["rays"]
     assert counts["rays"] == rays, "the closest-hit tables were not used"
-    if tables == 3 and len(sc.instances) > 1:
-        assert counts["one_level"] == rays, "the one-level tree was not built for a scene of a few instances"
     for s in range(segs):
         a, b = tr[s], ref["trace"][s]
         assert np.array_equal(a["hit"], b["hit"])
