@@ -201,8 +201,6 @@ SCHEDULES = {
     3: ("k_primary_cull + k_path<survivors>", "the reference's visiting order on the reference arrays, tight-box culling"),
     6: ("k_primary_cull + k_path_pool", "closest-hit search over our own four-wide SAH tables + proof that the reference traversal "
         "returns the same record; paths pooled per warp"),
-    7: ("k_primary_cull + k_path_sorted", "closest-hit search over our own four-wide SAH tables + proof that the reference traversal "
-        "returns the same record; rays sorted by phase in shared memory"),
 }
 
 

@@ -93,7 +93,7 @@ struct gdpt_shader {
         bool pending = false, with_k2 = false;
         // overlapped frames: what K1 of this frame reads and writes (the other frame in flight has its own)
         gdpt_camera *cam_dev = nullptr; gdpt_progressive_params *pp_dev = nullptr;
-        uint32_t *raw_rgba8 = nullptr; float *raw_depth = nullptr; uint32_t *hit_list = nullptr; uint32_t *spill = nullptr;
+        uint32_t *raw_rgba8 = nullptr; float *raw_depth = nullptr; uint32_t *hit_list = nullptr;
         bool finished_once = false;      // k_done has been recorded at least once
         uint32_t launches = 0;
     } slots[GDPT_MAX_FRAMES_IN_FLIGHT];
@@ -337,11 +337,8 @@ int finish_main(gdpt_shader *s)
     if ((rc = dev_alloc(s, &a.counters, 1))) return rc;
     // Which kernels run is decided by the shader's own "#define" list (gdpt_shader_create) and by what the arrays
     // allow -- never by the process environment.
-    // Default: the closest-hit search with pooled paths (6); scenes with many instances keep far more rays in flight per
-    // path step and run faster with the rays sorted by phase (7): C4 at 1080p 15.0 -> 11.8 ms, C2 0.70 -> 0.84 ms.
-    const int by_scene = a.sc.n_blas >= 64u ? 7 : 6;
-    a.schedule = (s->variant == 2 || s->variant == 3 || s->variant == 6 || s->variant == 7) ? s->variant : by_scene;
-    if (a.schedule == 7 && !a.sc.fast4_ok) a.schedule = 6; // the phase-sorted kernel searches the four-wide tables only
+    // Default: the closest-hit search with pooled paths (6).
+    a.schedule = (s->variant == 2 || s->variant == 3 || s->variant == 6) ? s->variant : 6;
     if (a.schedule == 6 && !a.sc.fast_ok) a.schedule = 3; // closest-hit tables unavailable for these arrays (fast_bvh.h)
     // culling (pt_scene.cuh) is the default for rendering; parity traces and the DEBUG_STEPS heat map
     // keep the full reference visit order (their output IS the reference's work)
@@ -363,15 +360,6 @@ int finish_main(gdpt_shader *s)
     a.sort4 = tune(s, "SORT4", 1);
     a.all_phases = tune(s, "ALL_PHASES", 1);
     a.count_work = s->count_work ? 1 : 0;
-    if (a.schedule == 7) {
-        a.burst = tune(s, "BURST", 2);
-        a.shade_at = tune(s, "SHADE_AT", 16);
-        a.refill_below = tune(s, "REFILL_BELOW", 32);
-        // rays of a warp's own phase that keep it on that phase (0 = no phase affinity: best where every phase has work, C4)
-        a.lead_min = tune(s, "AFFINITY", a.sc.n_blas >= 64u ? 0 : 12);
-        a.sorted_spill_depth = s->fast_need4 > (uint32_t)14 ? s->fast_need4 - 14u : 1u; // kSortStack entries live in shared memory
-        if ((rc = dev_alloc(s, &a.sorted_spill, sorted_spill_words(a)))) return rc;
-    }
     if (a.refill_below < 1) a.refill_below = 1;
     if (a.refill_below > 32) a.refill_below = 32;
     if (a.burst < 1) a.burst = 1;
@@ -389,7 +377,7 @@ int finish_main(gdpt_shader *s)
     for (auto &sl : s->slots) {
         sl.dcnt = nullptr; sl.stage_rgba8 = nullptr; sl.stage_depth = nullptr; // (re)allocated with the derived buffers
         sl.cam_dev = nullptr; sl.pp_dev = nullptr; sl.raw_rgba8 = nullptr; sl.raw_depth = nullptr; sl.hit_list = nullptr;
-        sl.spill = nullptr; sl.finished_once = false;
+        sl.finished_once = false;
         if ((rc = ensure_slot(s, sl, false))) return rc;
     }
     if (s->warp_profile) return alloc_warp_profile(s);
@@ -498,8 +486,7 @@ int enqueue_k1(gdpt_shader *s)
     if (a.schedule >= 3) {
         launch_primary_cull(a, d->stream);
         if (timing) GDPT_CUDA(d, cudaEventRecord(s->stage_ev[ev++], d->stream));
-        if (a.schedule == 7) launch_path_sorted(a, rec, d->stream);
-        else if (a.schedule == 6) launch_path_pool(a, rec, d->stream);
+        if (a.schedule == 6) launch_path_pool(a, rec, d->stream);
         else launch_path_list(a, rec, d->stream);
     } else {
         launch_path(a, trace, d->stream);
@@ -1142,7 +1129,6 @@ extern "C" int gdpt_render_frame_begin(gdpt_shader *m, gdpt_shader *p, const gdp
             if ((rc = dev_alloc(m, &sl.raw_rgba8, n))) return rc;
             if ((rc = dev_alloc(m, &sl.raw_depth, n))) return rc;
             if ((rc = dev_alloc(m, &sl.hit_list, (size_t)m->args.queue_cap + (size_t)(kCostClasses - 1) * m->args.heavy_cap))) return rc;
-            if (m->args.schedule == 7 && (rc = dev_alloc(m, &sl.spill, sorted_spill_words(m->args)))) return rc;
         }
         if (!d->extra_streams_made) {
             for (cudaStream_t &x : d->extra_streams) GDPT_CUDA(d, cudaStreamCreateWithFlags(&x, cudaStreamNonBlocking));
@@ -1173,7 +1159,6 @@ extern "C" int gdpt_render_frame_begin(gdpt_shader *m, gdpt_shader *p, const gdp
         const FrameArgs saved = m->args;
         m->args.counters = sl.dcnt; m->args.camera = sl.cam_dev; m->args.out_rgba8 = sl.raw_rgba8; m->args.out_depth = sl.raw_depth;
         m->args.hit_list = sl.hit_list;
-        if (sl.spill) m->args.sorted_spill = sl.spill;
         d->stream = S; // enqueue_k1 / enqueue_k2 launch on the device's current stream
         cudaEventRecord(sl.t0, S);
         rc = enqueue_k1(m);

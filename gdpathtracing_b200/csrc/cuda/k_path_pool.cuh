@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_pool(const FrameAr
                     slot = (uint32_t)ready_list[ready_count - 1u - rank];
                     fast_ray_begin(r, a.sc, mk3(PFF(PF_WOX, slot), PFF(PF_WOY, slot), PFF(PF_WOZ, slot)),
                                    mk3(PFF(PF_WDX, slot), PFF(PF_WDY, slot), PFF(PF_WDZ, slot)));
-                    if (WIDE) r.cur = a.sc.fast4_root; // the four-wide tables have their own root link
+                    r.cur = fast_start_link(r, WIDE ? a.sc.fast4_root : r.cur); // the four-wide tables have their own root link
                     n_park = 0;
                     steps = 0;
                     has = true;
@@ -283,9 +283,11 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_pool(const FrameAr
         // then the crossing), so a ray advances in every iteration -- a frame is one wave of paths whose length is the
         // latency of its longest path, and a lane that waits for its phase to win a vote lengthens exactly that.
         // Otherwise: only the phase that advances most lanes per instruction.
+        // a.all_phases = n > 1: a phase other than the vote's winner runs only with n lanes or more.
         const bool all = a.all_phases != 0;
+        const int few = a.all_phases; // >= 1 when `all`
         const int run = (n_i * 3 >= n_l && n_i * 3 >= n_t * 2) ? 1 : (n_l >= n_t * 2 ? 0 : 2);
-        if (all ? (n_i > 0) : (run == 1)) {
+        if (all ? (n_i >= few || (run == 1 && n_i > 0)) : (run == 1)) {
             if (PROF) it_i++;
             bool go = can_i;
             const int need = (n_i + 1) >> 1;
@@ -309,7 +311,7 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_pool(const FrameAr
         }
         bool now_l = can_l;
         if (all) now_l = has && lane_can_leaf(r.cur, n_park ? park[0] : LINK_NONE);
-        if (all ? __any_sync(kFull, now_l) : (run == 0)) {
+        if (all ? (__popc(__ballot_sync(kFull, now_l)) >= (run == 0 ? 1 : few)) : (run == 0)) {
             if (PROF) it_l++;
             if (now_l) {
                 uint32_t leaf = park[0];
@@ -327,7 +329,7 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_pool(const FrameAr
         }
         bool now_t = can_t;
         if (all) now_t = has && pool_can_cross(r.cur, n_park ? park[0] : LINK_NONE, r.inst);
-        if (all ? __any_sync(kFull, now_t) : (run == 2)) {
+        if (all ? (__popc(__ballot_sync(kFull, now_t)) >= (run == 2 ? 1 : few)) : (run == 2)) {
             if (PROF) it_t++;
             if (now_t) { // back to world space (main.glsl:316-327) and/or into the instance the link names
                 r.wo = mk3(PFF(PF_WOX, slot), PFF(PF_WOY, slot), PFF(PF_WOZ, slot)); // the world ray lives in the slot, not in the lane

@@ -24,7 +24,8 @@ namespace gdpt {
 
 #define RAY_OVERFLOW 1u /* RayState.overflow bit 0: traversal stack exceeded */
 #define RAY_TIE 2u      /* RayState.overflow bit 1: a second pair reached the current minimum t (or t was NaN) */
-#define RAY_FAR 4u      /* RayState.overflow bit 2: the ray starts beyond the reach of the search's culling margins */
+#define RAY_FAR 4u      /* RayState.overflow bit 2: the search is not trusted for this ray (origin beyond the reach of its culling
+                           margins, or a direction component that is zero): the exact traversal answers it, the search is skipped */
 
 // Stack of the search.  The trees' stack need is bounded at upload (fast_bvh.h: max_depth / need4 < GDPT_FAST_MAX_DEPTH
 // < GDPT_MAX_STACK), so no overflow test is needed here -- unlike the reference-order traversal, whose 64+64 entries
@@ -68,12 +69,21 @@ GDPT_HD f3 fast_rcp3(f3 a) { return mk3(fast_rcp(a.x), fast_rcp(a.y), fast_rcp(a
 // true when an origin coordinate is beyond `reach`: the search's culling margins are not trusted there
 GDPT_HD bool fast_far_origin(f3 o, float reach) { return !(max_num(max_num(fabsf(o.x), fabsf(o.y)), fabsf(o.z)) <= reach); }
 
+// A direction component that is zero (or so small that its reciprocal times a coordinate overflows; the hardware
+// reciprocal flushes denormals): the four-wide step computes plane * rd - origin * rd, which is inf - inf = NaN on that
+// axis, and a NaN drops the axis from the test -- nothing is culled along it, and a ray through a million-triangle soup
+// visits thousands of nodes (one such camera ray held a whole C3 frame: 8 000 dependent steps).  The proof refuses these
+// rays anyway (0 * inf voids its monotonicity argument), so they skip the search and go straight to the exact traversal.
+GDPT_HD bool fast_degenerate_dir(f3 d) { return !(fabsf(d.x) >= 1e-30f && fabsf(d.y) >= 1e-30f && fabsf(d.z) >= 1e-30f); }
+
 GDPT_HD void fast_ray_begin(RayState &r, const SceneView &sc, f3 o, f3 d)
 {
     ray_begin(r, sc, o, d);
     r.rd = fast_rcp3(d); // the search's own reciprocal; the proof recomputes the exact one
-    if (fast_far_origin(o, sc.fast_world_reach)) r.overflow |= RAY_FAR;
+    if (fast_far_origin(o, sc.fast_world_reach) || fast_degenerate_dir(d)) r.overflow |= RAY_FAR;
 }
+// Link a search starts from: nothing for a ray the search is not trusted with.
+GDPT_HD uint32_t fast_start_link(const RayState &r, uint32_t root) { return (r.overflow & RAY_FAR) ? LINK_NONE : root; }
 
 // true box of a child: entry distance and whether the subtree can still hold a hit with t <= r.t
 GDPT_HD bool fast_slab(const RayState &r, float nx, float ny, float nz, float xx, float xy, float xz, float *entry)
@@ -289,7 +299,9 @@ template <bool WIDE, class Stack> GDPT_HD void fast_enter_instance(const SceneVi
     fast_local_ray(c0, c1, c2, c3, r.wo, r.wd, &r.o, &r.d);
     r.rd = fast_rcp3(r.d);
     r.inst = idx;
-    if (fast_far_origin(r.o, tmax4.w)) r.overflow |= RAY_FAR; // too far out for this BLAS's margins (derived_layout.h fast_reach)
+    // too far out for this BLAS's margins (derived_layout.h fast_reach), or axis-parallel in this instance's space:
+    // the exact traversal answers the ray, the rest of the search is dropped
+    if (fast_far_origin(r.o, tmax4.w) || fast_degenerate_dir(r.d)) { r.overflow |= RAY_FAR; r.cur = LINK_NONE; r.sp = 0u; return; }
     float entry;
     const bool touches = fast_slab(r, tmin4.x, tmin4.y, tmin4.z, tmax4.x, tmax4.y, tmax4.z, &entry);
     const uint32_t root = WIDE ? fast_bits(tmin4.w) : tail.w; // the BLAS root in the table being searched
@@ -305,6 +317,7 @@ GDPT_HD bool fast_link_is_node(uint32_t l, uint32_t inst)
 // Whole search of one ray (no warp-level scheduling): used by k_primary-style callers and the host check.
 template <class Stack> GDPT_HD void fast_trace_ray(const SceneView &sc, RayState &r, Stack &st)
 {
+    r.cur = fast_start_link(r, r.cur);
     while (r.cur != LINK_NONE) {
         if (fast_link_is_leaf(r.cur)) fast_step_leaf(sc, r, st);
         else if (fast_link_is_node(r.cur, r.inst)) fast_step_node(sc, r, st);
@@ -315,7 +328,7 @@ template <class Stack> GDPT_HD void fast_trace_ray(const SceneView &sc, RayState
 // The same search over the four-wide tables (sc.fast4_ok).
 template <class Stack> GDPT_HD void fast_trace_ray4(const SceneView &sc, RayState &r, Stack &st)
 {
-    r.cur = sc.fast4_root;
+    r.cur = fast_start_link(r, sc.fast4_root);
     while (r.cur != LINK_NONE) {
         if (fast_link_is_leaf(r.cur)) fast_step_leaf(sc, r, st);
         else if (fast_link_is_node(r.cur, r.inst)) fast_step_node4(sc, r, st);
@@ -340,7 +353,7 @@ GDPT_HD bool fast_other_pair_within(const SceneView &sc, f3 wo, f3 wd, float bou
     fast_ray_begin(r, sc, wo, wd);
     r.t = bound;
     const bool wide = sc.fast4_ok != 0u;
-    if (wide) r.cur = sc.fast4_root;
+    r.cur = fast_start_link(r, wide ? sc.fast4_root : r.cur);
     while (r.cur != LINK_NONE) {
         if (fast_link_is_leaf(r.cur)) {
             const uint32_t leaf = r.cur;

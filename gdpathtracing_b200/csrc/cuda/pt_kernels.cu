@@ -189,7 +189,6 @@ __device__ __noinline__ bool fast_verdict_ool(const SceneView *sc, f3 wo, f3 wd,
 __device__ __forceinline__ bool lane_can_leaf(uint32_t cur, uint32_t pend) { return pend != LINK_NONE || fast_link_is_leaf(cur); }
 
 #include "k_path_pool.cuh"
-#include "k_path_sorted.cuh"
 
 // Camera-ray classification (first kernel of the two-kernel schedule): one thread per pixel in
 // 8x4-tile order, so a warp is one tile and runs in lockstep.  The thread generates its camera ray
@@ -345,7 +344,6 @@ struct Shapes {
     int path_list_record_blocks = 0; // k_path<true, true, SRC 1> (hit records of schedule 3)
     int pool_blocks[2][2] = {};  // k_path_pool<REC, .., WIDE>
     int pool_count_blocks = 0;   // k_path_pool<.., WIDE, COUNT>
-    int sorted_blocks = 0;       // k_path_sorted: resident blocks (the same for every REC / COUNT / SORT4)
     int cull_blocks_per_sm = 1;
     int prog_blocks = 0;
 };
@@ -377,16 +375,6 @@ void init_launch_shapes(int device)
     s.pool_blocks[1][0] = grid_of(k_path_pool<true, kPoolMinBlocks, kPoolParkDefault, kPoolSlotsDefault, false>, kTraceThreads);
     s.pool_blocks[1][1] = grid_of(k_path_pool<true, kPoolMinBlocks, kPoolParkDefault, kPoolSlotsDefault, true>, kTraceThreads);
     s.pool_count_blocks = grid_of(k_path_pool<false, kPoolMinBlocks, kPoolParkDefault, kPoolSlotsDefault, true, true>, kTraceThreads);
-    auto sorted_grid = [&](auto kernel, size_t smem) {
-        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        per_sm = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kTraceThreads, smem);
-        return s.sms * (per_sm > 0 ? per_sm : 1);
-    };
-    s.sorted_blocks = sorted_grid(k_path_sorted<false, false, kSortRowsDefault, true>, sorted_smem_bytes<kSortRowsDefault>());
-    sorted_grid(k_path_sorted<false, false, kSortRowsDefault, false>, sorted_smem_bytes<kSortRowsDefault>());
-    sorted_grid(k_path_sorted<true, false, kSortRowsDefault, true>, sorted_smem_bytes<kSortRowsDefault>());
-    sorted_grid(k_path_sorted<false, true, kSortRowsDefault, true>, sorted_smem_bytes<kSortRowsDefault>());
     grid_of(k_primary_cull, kTraceThreads);
     s.cull_blocks_per_sm = per_sm > 0 ? per_sm : 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_progressive, 256, 0); s.prog_blocks = s.sms * (per_sm > 0 ? per_sm : 1);
@@ -496,29 +484,9 @@ void launch_path_pool(const FrameArgs &a_in, bool record, cudaStream_t s)
     }
 }
 
-// k_path_sorted: 32 x 8 rays per block of four warps, full distance order of a node's children by default; nearest-first
-// order and the work-counting instantiation on request (A/B and bench.py's roofline numerator).
-void launch_path_sorted(const FrameArgs &a, bool record, cudaStream_t s)
-{
-    Shapes &sh = shapes_for_current_device();
-    const int grid = persistent_grid(sh, a, sh.sorted_blocks);
-    const size_t smem = sorted_smem_bytes<kSortRowsDefault>();
-    if (record) k_path_sorted<true, false, kSortRowsDefault, true><<<grid, kTraceThreads, smem, s>>>(a);
-    else if (a.count_work) k_path_sorted<false, true, kSortRowsDefault, true><<<grid, kTraceThreads, smem, s>>>(a);
-    else if (!a.sort4) k_path_sorted<false, false, kSortRowsDefault, false><<<grid, kTraceThreads, smem, s>>>(a);
-    else k_path_sorted<false, false, kSortRowsDefault, true><<<grid, kTraceThreads, smem, s>>>(a);
-}
-
-size_t sorted_spill_words(const FrameArgs &a)
-{
-    Shapes &sh = shapes_for_current_device();
-    return (size_t)sh.sorted_blocks * 32u * kSortRowsDefault * a.sorted_spill_depth;
-}
-
 size_t path_kernel_warps(const FrameArgs &a)
 {
     Shapes &sh = shapes_for_current_device();
-    if (a.schedule == 7) return (size_t)sh.sorted_blocks * (kTraceThreads / 32);
     if (a.schedule == 6) return (size_t)sh.pool_blocks[0][(a.wide_bvh != 0 && a.sc.fast4_ok != 0) ? 1 : 0] * (kTraceThreads / 32);
     if (a.schedule == 3) return (size_t)sh.path_list_blocks * (kTraceThreads / 32);
     int most = 0;

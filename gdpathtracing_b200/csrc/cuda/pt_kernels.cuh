@@ -49,10 +49,8 @@ struct FrameArgs {
     int cost_ema;                            // schedule 6: per-pixel cost hint is a running mean over frames (1) or the last frame's (0)
     int pool_alive;                          // schedule 6: cap on the paths a warp keeps alive (32..slots; 0 = all slots)
     int pool_wait;                           // schedule 6: lane-iterations finished rays may wait before a pool service (0 = off)
-    uint32_t *sorted_spill;                  // schedule 7: stack entries beyond the shared-memory part, per block and slot
-    uint32_t sorted_spill_depth;             //   entries per slot (>= 1)
-    int sort4;                               // schedules 6/7: children of a four-wide node in full distance order (1) or nearest first (0)
-    int count_work;                          // schedule 7: run the instantiation that counts its own work (untimed frames of bench.py)
+    int sort4;                               // schedule 6: children of a four-wide node in full distance order (1) or nearest first (0)
+    int count_work;                          // schedule 6: run the instantiation that counts its own work (untimed frames of bench.py)
     int all_phases;                          // schedule 6: every phase that has a lane runs in each iteration (1) or only the majority phase (0)
     FrameCounters *counters;
     // scheduling knobs (results do not depend on them)
@@ -61,7 +59,6 @@ struct FrameArgs {
     int schedule;      // 2: single path kernel over all pixels in reference order (trace mode, DEBUG_STEPS, no culling),
                        // 3: camera-ray classification kernel + reference-order path kernel over the surviving pixels,
                        // 6: classification kernel + closest-hit path kernel with pooled paths (pt_fast.cuh, k_path_pool.cuh)
-                       // 7: classification kernel + closest-hit path kernel with phase-sorted rays (k_path_sorted.cuh)
     int shade_at;      // schedule 2: shade once this many lanes wait with a finished ray
     int cull;          // 1: skip children whose tight box the ray misses (pt_scene.cuh); results identical
     // optional per-warp schedule profile (gdpt_shader_set_warp_profile): 8 x u64 per warp of the path kernel
@@ -92,9 +89,6 @@ void launch_path_list(const FrameArgs &a, bool record, cudaStream_t s);
 // re-trace where it fails), paths kept in per-warp shared-memory pools (k_path_pool): lanes swap rays instead of
 // waiting for a shading quorum, shading and camera-ray generation run on full warps.
 void launch_path_pool(const FrameArgs &a, bool record, cudaStream_t s);
-// ... schedule 7 keeps the rays themselves in shared memory and runs every phase of the search on the rays that are in it.
-void launch_path_sorted(const FrameArgs &a, bool record, cudaStream_t s);
-size_t sorted_spill_words(const FrameArgs &a); // uint32 elements a.sorted_spill must provide on the current device
 size_t path_kernel_warps(const FrameArgs &a); // warps of the path kernel enqueue_k1 would launch for `a`
 // K2: progressive accumulation + ACES (progressive_rendering.glsl:28-46).
 // frame_count is read from params_dev (stream-ordered Params block) or, when that is null, taken from the argument.

@@ -268,7 +268,7 @@ typedef struct gdpt_frame_stats {
     uint64_t own_node_steps, own_box_tests, own_tri_tests, own_inst_entries, own_proofs;
 } gdpt_frame_stats;
 GDPT_API int  gdpt_shader_get_stats(gdpt_shader *main_shader, gdpt_frame_stats *out);
-/* Which kernel schedule finish_create_uniforms chose for this main shader (2, 3, 6 or 7: see GDPT_VARIANT above); -1 before. */
+/* Which kernel schedule finish_create_uniforms chose for this main shader (2, 3 or 6: see GDPT_VARIANT above); -1 before. */
 GDPT_API int  gdpt_shader_get_schedule(const gdpt_shader *main_shader);
 
 /* Profiling aid: when on, an event is recorded between the stage kernels of every K1

@@ -107,7 +107,7 @@ def test_culled_traversal_gives_identical_hits(name, make, W, H, depth, segs):
     del cam
 
 
-@pytest.mark.parametrize("variant", [7, 6, 3], ids=["closest_hit_sorted_rays", "closest_hit_pooled_paths", "reference_order_culled"])
+@pytest.mark.parametrize("variant", [6, 3], ids=["closest_hit_pooled_paths", "reference_order_culled"])
 @pytest.mark.parametrize("name,make,W,H,depth,segs", CASES, ids=[c[0] for c in CASES])
 def test_rendering_kernels_record_the_reference_hits(name, make, W, H, depth, segs, variant):
     """The kernels that are timed (schedule 6: closest-hit search + proof + exact re-trace, pt_fast.cuh, paths pooled in
@@ -140,14 +140,14 @@ def test_rendering_kernels_record_the_reference_hits(name, make, W, H, depth, se
             assert np.array_equal(x, y), f"segment {s} field {f}: {(x != y).sum()} differ"
     assert np.array_equal(frame, ref["rgba8"])
     assert np.array_equal(cam.read_image("depth").view(np.uint32), ref["depth"].view(np.uint32))
-    if variant in (6, 7):
+    if variant == 6:
         assert st["retraced"] * 20 < st["rays"], "the proof should fail for a small minority of rays only"
         print(f"{name}: {st['retraced']} of {st['rays']} rays re-traced in reference order")
     else:
         assert st["retraced"] == 0
 
 
-@pytest.mark.parametrize("variant", [7, 6, 3], ids=["sorted_rays", "pooled_paths", "reference_order"])
+@pytest.mark.parametrize("variant", [6, 3], ids=["pooled_paths", "reference_order"])
 @pytest.mark.parametrize("W,H,depth", [(8, 4, 3), (37, 19, 1), (5, 3, 8), (64, 36, 32)], ids=["one_tile", "ragged_depth1", "sub_tile", "max_depth32"])
 def test_rendering_kernels_on_edge_sizes(W, H, depth, variant):
     """Fewer pixels than one warp's pool, image sizes that are not multiples of the 8x4 tile, a single segment and the

@@ -7,9 +7,9 @@ cp gdpathtracing_b200/libgdpt_cuda.so /tmp/libgdpt_cuda_base.so
 for v in "$@"; do
   if [ "$v" = base ]; then cp /tmp/libgdpt_cuda_base.so gdpathtracing_b200/libgdpt_cuda.so; else cp gdpathtracing_b200/ab/libgdpt_cuda_$v.so gdpathtracing_b200/libgdpt_cuda.so; fi
   touch gdpathtracing_b200/libgdpt_cuda.so gdpathtracing_b200/libgdpt_host.so
-  for cfg in "c2:--scene demo" "c4:--scene instanced --width 1920 --height 1080"; do
+  for cfg in "c2:--scene demo" "c4:--scene instanced --width 1920 --height 1080 --variant 6" "c3:--scene soup --depth 2"; do
     tag=${cfg%%:*}; args=${cfg#*:}
-    python bench.py $args --steps 20 --warmup 5 --no-c5 --no-cpu-baseline --no-schedule3 > gpurun_out/ab_${v}_${tag}.json 2> gpurun_out/ab_${v}_${tag}.err
+    python bench.py $args --steps 20 --warmup 5 --no-c5 --no-cpu-baseline --no-schedule3 $AB_EXTRA > gpurun_out/ab_${v}_${tag}.json 2> gpurun_out/ab_${v}_${tag}.err
     python - <<PY
 import json
 try:

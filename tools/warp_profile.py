@@ -49,7 +49,7 @@ n = _lib.cuda.gdpt_shader_read_warp_profile(cam.main_shader, buf.ctypes.data_as(
 assert n > 0, n
 t = buf[:8 * n].reshape(n, 8).astype(np.int64)
 t = t[t[:, 1] > 0]
-lanes = t[:, 2:7] >> 32          # schedule 7 packs the lanes that held a ray into the high words
+lanes = t[:, 2:7] >> 32          # (unused: no schedule packs lane counts into the high words any more)
 idle_iters = t[:, 7] >> 32
 t[:, 2:8] &= 0xFFFFFFFF
 t0 = t[:, 0].min()
