@@ -359,6 +359,7 @@ int finish_main(gdpt_shader *s)
     a.lead_min = tune(s, "LEAD_MIN", 0);
     a.sort4 = tune(s, "SORT4", 1);
     a.all_phases = tune(s, "ALL_PHASES", 1);
+    a.miss_now = tune(s, "MISS_NOW", 1);
     a.count_work = s->count_work ? 1 : 0;
     if (a.refill_below < 1) a.refill_below = 1;
     if (a.refill_below > 32) a.refill_below = 32;

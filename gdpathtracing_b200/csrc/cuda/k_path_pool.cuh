@@ -129,14 +129,39 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_pool(const FrameAr
             // ---------------- pool service ----------------
             // 1. retire: finished searches go to their slots, the slots to the shading queue
             if (n_fin > 0) {
-                const unsigned m = __ballot_sync(kFull, fin);
-                if (fin) { // u / v / triangle / instance are in the slot already (HitInPool)
+                // a.miss_now: a ray that provably escaped (a miss of the complete search, no flag) is finished by its own lane
+                // right here -- sky colour, pixel, cost hint, slot freed -- so the shading batches hold hits only (the one
+                // ordering of the shading work by the branch it takes that this path offers: hit / sky)
+                const bool escaped = fin && a.miss_now != 0 && !(r.t < 1e9f) && r.overflow == 0u;
+                const unsigned m = __ballot_sync(kFull, fin && !escaped), m_esc = __ballot_sync(kFull, escaped);
+                if (escaped) {
+                    const f3 wd = mk3(PFF(PF_WDX, slot), PFF(PF_WDY, slot), PFF(PF_WDZ, slot));
+                    const f3 radiance = mk3(PFF(PF_RAR, slot), PFF(PF_RAG, slot), PFF(PF_RAB, slot)) +
+                                        mk3(PFF(PF_THR, slot), PFF(PF_THG, slot), PFF(PF_THB, slot)) * sample_sky(wd);
+                    const uint32_t pixel = PF(PF_PIXEL, slot);
+                    const int segment = (int)PF(PF_SEGMENT, slot);
+                    if (segment == 0) a.out_depth[pixel] = encode_depth(cam, cam.z_far);
+                    if (REC) write_hit_record(a, segment, pixel, 1e9f, 0.0f, 0.0f, 0u, 0u);
+                    a.out_rgba8[pixel] = pack_rgba8(radiance);
+                    const uint32_t cost_now = PF(PF_STEPS, slot) + steps;
+                    if (a.cost_ema) {
+                        const uint32_t old = a.cost[pixel];
+                        a.cost[pixel] = old ? (old * 3u + cost_now + 2u) >> 2 : cost_now;
+                    } else {
+                        a.cost[pixel] = cost_now;
+                    }
+                    my_rays++;
+                    if (COUNT) own_proofs++;
+                    free_list[free_count + (uint32_t)__popc(m_esc & lanemask_lt)] = (uint8_t)slot;
+                    has = false;
+                } else if (fin) { // u / v / triangle / instance are in the slot already (HitInPool)
                     PF(PF_T, slot) = __float_as_uint(r.t); PF(PF_FLAGS, slot) = r.overflow;
                     PF(PF_STEPS, slot) += steps;
                     done_list[done_count + (uint32_t)__popc(m & lanemask_lt)] = (uint8_t)slot;
                     has = false;
                 }
                 done_count += (uint32_t)__popc(m);
+                free_count += (uint32_t)__popc(m_esc);
                 __syncwarp();
             }
             const uint32_t n_out = (uint32_t)(n_fin + n_idle); // lanes that hold no walking ray now
