@@ -124,6 +124,9 @@ HOST_API = [
     ("gdpt_group_destroy", None, [c_void_p]),
     ("gdpt_group_add_texture", c_int, [c_void_p, c_void_p, c_int, c_int]),
     ("gdpt_group_add_material", c_int, [c_void_p, POINTER(StandardMaterial)]),
+    ("gdpt_group_add_material_ext", c_int, [c_void_p, POINTER(StandardMaterial), c_int, c_int, c_int]),
+    ("gdpt_group_set_material_ext", None, [c_void_p, c_int]),
+    ("gdpt_group_get_material_ext", c_int, [c_void_p]),
     ("gdpt_group_add_mesh", c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     ("gdpt_group_add_mesh_instance", None, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int]),
     ("gdpt_group_set_default_material", None, [c_void_p, c_int]),

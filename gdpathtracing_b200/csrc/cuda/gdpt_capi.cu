@@ -77,6 +77,7 @@ struct gdpt_shader {
     std::string fast_why_not; // why the closest-hit tables are not in use ("" = in use)
     uint32_t fast_need4 = 0;  // stack entries the four-wide search can need (fast_bvh.h)
     bool count_work = false;  // "#define GDPT_COUNT_WORK": the path kernel also counts its own work (gdpt_frame_stats own_*)
+    bool material_ext = false; // "#define GDPT_MATERIAL_EXT": extension fields of gdpt_material + set 1 binding 6 (gdpt_wire.h)
     // main-shader state built by finish_create_uniforms
     FrameArgs args;
     std::vector<void *> derived; // device allocations owned by this shader
@@ -325,6 +326,32 @@ int finish_main(gdpt_shader *s)
     int rc = build_derived_layout(s, *bvh, *blas, *tlas, *tg);
     if (rc) return rc;
 
+    if (s->material_ext) { // the reference's padding words carry texture slots and flags; optional material tables
+        const gdpt_material *mm = reinterpret_cast<const gdpt_material *>(mat->shadow.data());
+        for (uint32_t i = 0; i < a.sc.n_materials; i++)
+            if (mm[i].ext_roughness_texture > (uint32_t)tex->layers || mm[i].ext_metallic_texture > (uint32_t)tex->layers)
+                return fail(d, GDPT_ERR_BAD_BINDING, "material %u names a texture layer beyond the %d bound ones", i, tex->layers);
+        if (Resource *sm = bound(s, 1, 6)) {
+            const uint32_t *w = reinterpret_cast<const uint32_t *>(sm->shadow.data());
+            const uint64_t words = sm->size / 4u;
+            if (sm->kind != RES_BUFFER || words < (uint64_t)a.sc.n_blas + 1u)
+                return fail(d, GDPT_ERR_BAD_BINDING, "set1 b6 must hold offset[n_instances + 1] followed by the material ids");
+            for (uint32_t i = 0; i <= a.sc.n_blas; i++)
+                if (w[i] < a.sc.n_blas + 1u || w[i] > words || (i > 0 && w[i] < w[i - 1]))
+                    return fail(d, GDPT_ERR_BAD_BINDING, "set1 b6: offset %u out of range", i);
+            for (uint64_t k = a.sc.n_blas + 1u; k < words; k++)
+                if (w[k] >= a.sc.n_materials) return fail(d, GDPT_ERR_BAD_BINDING, "set1 b6: material id %u of %u", w[k], a.sc.n_materials);
+            a.sc.surface_materials = static_cast<const uint32_t *>(sm->dptr);
+        }
+        std::vector<float> lut(256);
+        for (int k = 0; k < 256; k++) { // IEC 61966-2-1 decode of an 8-bit code, rounded once to binary32
+            const double c = k / 255.0;
+            lut[k] = (float)(c <= 0.04045 ? c / 12.92 : std::pow((c + 0.055) / 1.055, 2.4));
+        }
+        if ((rc = dev_upload(s, &a.sc.srgb_lut, lut))) return rc;
+        GDPT_CUDA(d, cudaStreamSynchronize(d->stream)); // `lut` dies with this block
+        a.sc.material_ext = 1u;
+    }
     a.camera = static_cast<const gdpt_camera *>(camera->dptr);
     a.width = rp.width; a.height = rp.height; a.max_depth = s->max_depth;
     a.out_rgba8 = static_cast<uint32_t *>(out->dptr);
@@ -630,6 +657,7 @@ int gdpt_shader_create(gdpt_device *d, const char *shader_path, const char *cons
         else if (name == "GDPT_REFERENCE_ORDER") s->cull = 0;
         else if (name == "GDPT_RECORD_HITS" && has_value) s->record_hits = (int)value;
         else if (name == "GDPT_COUNT_WORK") s->count_work = true;
+        else if (name == "GDPT_MATERIAL_EXT") s->material_ext = true;
         else if (name.rfind("GDPT_TUNE_", 0) == 0 && has_value) s->tuning[name.substr(10)] = (int)value;
     }
     if (s->max_depth < 1 || s->max_depth > kMaxDepth) {

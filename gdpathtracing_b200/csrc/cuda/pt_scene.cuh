@@ -136,6 +136,11 @@ struct SceneView {
     // largest |origin coordinate| (world space) for which the search's culling margins are trusted; rays from farther
     // out are answered by the exact traversal (derived_layout.h fast_reach)
     float fast_world_reach;
+    // "#define GDPT_MATERIAL_EXT" (gdpt_wire.h): roughness / metallic textures, sRGB albedo layers, per-instance material
+    // tables of any length.  material_ext == 0: the reference's shading data, bit for bit
+    uint32_t material_ext;
+    const uint32_t *surface_materials; // set 1 binding 6 or null
+    const float *srgb_lut;             // 256 entries: sRGB byte -> linear
 };
 
 } // namespace gdpt

@@ -148,6 +148,11 @@ void GeometryGroup3D::build()
         g.emission[0] = m.emission[0]; g.emission[1] = m.emission[1]; g.emission[2] = m.emission[2];
         g.emission[3] = m.emission_energy_multiplier;
         g.albedo_texture_index = get_texture_index(m.albedo_texture);
+        if (material_ext_) { // extension words in the reference's padding: layer + 1, 0 = none
+            g.ext_roughness_texture = (uint32_t)(get_texture_index(m.roughness_texture) + 1);
+            g.ext_metallic_texture = (uint32_t)(get_texture_index(m.metallic_texture) + 1);
+            g.ext_flags = m.albedo_srgb ? GDPT_MATERIAL_ALBEDO_SRGB : 0u;
+        }
         materials_.push_back(g);
     }
     // texture array layers (:294-303); a blank layer when the scene has no texture
@@ -174,6 +179,14 @@ void GeometryGroup3D::build()
         blas_instances_.push_back(AccelBuilder::make_instance(roots[r.mesh_slot], r.material_ids.data(),
                                                               (int)r.material_ids.size(), r.transform, bvh_nodes_));
     AccelBuilder::build_tlas(tlas_nodes_, blas_instances_);
+    surface_materials_.clear();
+    if (material_ext_) { // every surface of every instance (BLASInstance.materials stops at three, bvh.h:71)
+        uint32_t at = (uint32_t)node_refs_.size() + 1u;
+        for (const NodeRef &r : node_refs_) { surface_materials_.push_back(at); at += (uint32_t)r.material_ids.size(); }
+        surface_materials_.push_back(at);
+        for (const NodeRef &r : node_refs_)
+            for (int id : r.material_ids) surface_materials_.push_back((uint32_t)id);
+    }
 
     // flatten for the GPU (:356-365)
     triangles_geometry_.resize(triangles_.size());

@@ -24,6 +24,9 @@ struct StandardMaterial {
     float emission[3] = { 0.0f, 0.0f, 0.0f };
     float emission_energy_multiplier = 1.0f;
     int albedo_texture = -1; // texture resource handle, -1 = none
+    // material breadth beyond geometry_group3d.cpp:271-292; converted only when the group's material_ext is on
+    int roughness_texture = -1, metallic_texture = -1; // StandardMaterial3D.roughness_texture / metallic_texture (red channel)
+    bool albedo_srgb = false;                          // the albedo texture holds sRGB-encoded colour
     bool is_standard = true; // false: some other Material subclass -> resolves to index 0 (:128-130)
 };
 
@@ -49,6 +52,12 @@ public:
     // ours (no upstream twin): threads of the BLAS build, 0 = all hardware threads, 1 = upstream's single thread; same bytes
     int get_build_threads() const { return build_threads_; }
     void set_build_threads(int v) { build_threads_ = v < 0 ? 0 : v; }
+
+    // ours: convert roughness / metallic textures and the sRGB flag into the extension words of the material
+    // record, and emit the material table for instances with any number of surfaces (gdpt_wire.h).  Off = upstream's bytes.
+    bool get_material_ext() const { return material_ext_; }
+    void set_material_ext(bool on) { material_ext_ = on; }
+    const std::vector<uint32_t> &get_surface_materials_buffer() const { return surface_materials_; }
 
     void build();
 
@@ -103,6 +112,8 @@ private:
     std::vector<gdpt_triangle_data> triangles_data_;
     std::vector<gdpt_blas_instance> blas_instances_;
     std::vector<gdpt_material> materials_;
+    bool material_ext_ = false;
+    std::vector<uint32_t> surface_materials_; // offset[n_instances + 1], ids (set 1 binding 6 of a GDPT_MATERIAL_EXT shader)
     std::vector<std::vector<uint8_t>> textures_;
     double build_seconds_ = 0.0;
 };

@@ -32,6 +32,22 @@ int gdpt_group_add_material(gdpt_geometry_group *g, const gdpt_standard_material
     return g->impl.add_material(s);
 }
 
+int gdpt_group_add_material_ext(gdpt_geometry_group *g, const gdpt_standard_material *m, int roughness_texture, int metallic_texture,
+                                int albedo_srgb)
+{
+    gdpt::StandardMaterial s;
+    std::memcpy(s.albedo, m->albedo, sizeof(s.albedo));
+    s.metallic = m->metallic; s.roughness = m->roughness;
+    std::memcpy(s.emission, m->emission, sizeof(s.emission));
+    s.emission_energy_multiplier = m->emission_energy_multiplier;
+    s.albedo_texture = m->albedo_texture;
+    s.is_standard = m->is_standard != 0;
+    s.roughness_texture = roughness_texture; s.metallic_texture = metallic_texture; s.albedo_srgb = albedo_srgb != 0;
+    return g->impl.add_material(s);
+}
+void gdpt_group_set_material_ext(gdpt_geometry_group *g, int on) { g->impl.set_material_ext(on != 0); }
+int gdpt_group_get_material_ext(const gdpt_geometry_group *g) { return g->impl.get_material_ext() ? 1 : 0; }
+
 int gdpt_group_add_mesh(gdpt_geometry_group *g, int n_surfaces, const int32_t *vertex_counts, const int32_t *index_counts,
                         const float *positions, const float *normals, const float *uvs, const int32_t *indices)
 {
@@ -71,6 +87,7 @@ uint64_t gdpt_group_buffer_size(const gdpt_geometry_group *g, int which)
     case 3: return i.get_bvh_buffer().size() * sizeof(gdpt_bvh_node);
     case 4: return i.get_blas_buffer().size() * sizeof(gdpt_blas_instance);
     case 5: return i.get_tlas_buffer().size() * sizeof(gdpt_tlas_node);
+    case 6: return i.get_surface_materials_buffer().size() * sizeof(uint32_t);
     }
     return 0;
 }
@@ -85,6 +102,7 @@ const void *gdpt_group_buffer_data(const gdpt_geometry_group *g, int which)
     case 3: return i.get_bvh_buffer().data();
     case 4: return i.get_blas_buffer().data();
     case 5: return i.get_tlas_buffer().data();
+    case 6: return i.get_surface_materials_buffer().data();
     }
     return nullptr;
 }

@@ -151,6 +151,7 @@ bool PathTracingCamera::init()
     if (variant_ >= 0) defines.push_back("#define GDPT_VARIANT " + std::to_string(variant_));
     if (record_hits_ > 0) defines.push_back("#define GDPT_RECORD_HITS " + std::to_string(record_hits_));
     if (count_work_) defines.push_back("#define GDPT_COUNT_WORK");
+    if (geometry_group_ && geometry_group_->get_material_ext()) defines.push_back("#define GDPT_MATERIAL_EXT");
     for (const auto &kv : tuning_) defines.push_back("#define GDPT_TUNE_" + kv.first + " " + std::to_string(kv.second));
     cs_ = new ComputeShader("res://addons/jar_path_tracing/src/shaders/main.glsl", rd_, defines);
 
@@ -179,6 +180,10 @@ bool PathTracingCamera::init()
     bvh_tree_rid_ = cs_->create_storage_buffer_uniform(bv.data(), bv.size() * sizeof(bv[0]), 3, 1);
     blas_rid_ = cs_->create_storage_buffer_uniform(bl.data(), bl.size() * sizeof(bl[0]), 4, 1);
     tlas_rid_ = cs_->create_storage_buffer_uniform(tl.data(), tl.size() * sizeof(tl[0]), 5, 1);
+    if (geometry_group_->get_material_ext()) { // material table for any number of surfaces per instance (gdpt_wire.h)
+        const auto &sm = geometry_group_->get_surface_materials_buffer();
+        cs_->create_storage_buffer_uniform(sm.data(), sm.size() * sizeof(sm[0]), 6, 1);
+    }
 
     std::vector<const void *> layers;
     for (const auto &layer : geometry_group_->get_textures_buffer()) layers.push_back(layer.data());

@@ -45,7 +45,10 @@ class GeometryGroup3D:
         return host.gdpt_group_add_texture(self._h, _ptr(img), img.shape[1], img.shape[0])
 
     def add_material(self, albedo=(1.0, 1.0, 1.0), metallic=0.0, roughness=1.0, emission=(0.0, 0.0, 0.0),
-                     emission_energy_multiplier=1.0, albedo_texture=-1, is_standard=True):
+                     emission_energy_multiplier=1.0, albedo_texture=-1, is_standard=True, roughness_texture=-1,
+                     metallic_texture=-1, albedo_srgb=False):
+        """The StandardMaterial3D fields the reference converts (geometry_group3d.cpp:271-292); roughness_texture,
+        metallic_texture and albedo_srgb are the material-breadth extension, converted only while material_ext is on."""
         m = _lib.StandardMaterial()
         m.albedo[:] = albedo
         m.metallic, m.roughness = metallic, roughness
@@ -53,7 +56,19 @@ class GeometryGroup3D:
         m.emission_energy_multiplier = emission_energy_multiplier
         m.albedo_texture = albedo_texture
         m.is_standard = 1 if is_standard else 0
+        if roughness_texture >= 0 or metallic_texture >= 0 or albedo_srgb:
+            return host.gdpt_group_add_material_ext(self._h, ctypes.byref(m), int(roughness_texture), int(metallic_texture),
+                                                    1 if albedo_srgb else 0)
         return host.gdpt_group_add_material(self._h, ctypes.byref(m))
+
+    @property
+    def material_ext(self):
+        """Ours: roughness / metallic textures, sRGB albedo layers, any number of materials per instance."""
+        return host.gdpt_group_get_material_ext(self._h) == 1
+
+    @material_ext.setter
+    def material_ext(self, on):
+        host.gdpt_group_set_material_ext(self._h, 1 if on else 0)
 
     def add_mesh(self, surfaces):
         """surfaces: list of dicts with positions [n,3], normals [n,3], uvs [n,2], indices [m] (int32)."""
@@ -107,7 +122,10 @@ class GeometryGroup3D:
         return ctypes.string_at(data, size) if size else b""
 
     def buffers(self):
-        return {n: self.buffer(n) for n in BUFFER_NAMES}
+        out = {n: self.buffer(n) for n in BUFFER_NAMES}
+        if self.material_ext:
+            out["surface_materials"] = self.buffer(6)  # set 1 binding 6 of a GDPT_MATERIAL_EXT shader (gdpt_wire.h)
+        return out
 
     def texture_layers(self):
         res = self.texture_array_resolution

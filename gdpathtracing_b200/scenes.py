@@ -28,6 +28,7 @@ class SceneDesc:
     instances: list = field(default_factory=list)
     default_material: int = -1
     texture_array_resolution: int = 512
+    material_ext: bool = False  # SURVEY 8f-4 material breadth (nodes.GeometryGroup3D.material_ext)
     camera_transform12: np.ndarray = field(default_factory=lambda: IDENTITY12.copy())
     fov: float = 90.0
 
@@ -38,12 +39,14 @@ class SceneDesc:
 def populate(scene):
     g = GeometryGroup3D()
     g.texture_array_resolution = scene.texture_array_resolution
+    g.material_ext = scene.material_ext
     tex = [g.add_texture(t) for t in scene.textures]
     mats = []
     for m in scene.materials:
         m = dict(m)
-        if m.get("albedo_texture", -1) >= 0:
-            m["albedo_texture"] = tex[m["albedo_texture"]]
+        for key in ("albedo_texture", "roughness_texture", "metallic_texture"):
+            if m.get(key, -1) >= 0:
+                m[key] = tex[m[key]]
         mats.append(g.add_material(**m))
     if scene.default_material >= 0:
         g.set_default_material(mats[scene.default_material])

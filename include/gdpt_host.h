@@ -36,6 +36,15 @@ GDPT_API void gdpt_group_destroy(gdpt_geometry_group *g);
 /* resources (Ref<Texture2D> / Ref<Material> / Ref<ArrayMesh>); return handles */
 GDPT_API int  gdpt_group_add_texture(gdpt_geometry_group *g, const uint8_t *rgba8, int width, int height);
 GDPT_API int  gdpt_group_add_material(gdpt_geometry_group *g, const gdpt_standard_material *m);
+/* Material breadth beyond geometry_group3d.cpp:271-292, converted only while the group's material_ext
+ * property is on: roughness / metallic texture handles (-1 = none; the red channel scales the scalar) and whether the
+ * albedo texture holds sRGB-encoded colour.  With material_ext on the group also emits buffer 6, the material table for
+ * instances with any number of surfaces (gdpt_wire.h), and PathTracingCamera creates its shader with
+ * "#define GDPT_MATERIAL_EXT".  Off (the default): the reference's bytes and the reference's shading. */
+GDPT_API int  gdpt_group_add_material_ext(gdpt_geometry_group *g, const gdpt_standard_material *m, int roughness_texture,
+                                          int metallic_texture, int albedo_srgb);
+GDPT_API void gdpt_group_set_material_ext(gdpt_geometry_group *g, int on);
+GDPT_API int  gdpt_group_get_material_ext(const gdpt_geometry_group *g);
 /* one ArrayMesh: per-surface vertex/index counts, arrays concatenated surface after surface
  * (Mesh::surface_get_arrays, bvh.cpp:193-199) */
 GDPT_API int  gdpt_group_add_mesh(gdpt_geometry_group *g, int n_surfaces, const int32_t *vertex_counts,

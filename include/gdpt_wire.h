@@ -105,8 +105,19 @@ typedef struct gdpt_material {
     float   metallic;
     float   roughness;
     int32_t albedo_texture_index; /* -1: none */
-    float   _pad[5];
+    /* The reference pads the record with five unused floats (main.glsl:39).  A shader created with
+     * "#define GDPT_MATERIAL_EXT" (material breadth beyond geometry_group3d.cpp:271-292) reads three of
+     * them; without the define they are ignored, as upstream.  Texture fields hold layer + 1, 0 = none. */
+    uint32_t ext_roughness_texture; /* roughness *= red channel of that layer  */
+    uint32_t ext_metallic_texture;  /* metallic  *= red channel of that layer  */
+    uint32_t ext_flags;             /* GDPT_MATERIAL_ALBEDO_SRGB: the albedo layer holds sRGB-encoded colour (upstream samples
+                                     * it as UNORM, path_tracing_camera.cpp:182) */
+    float   _pad[2];
 } gdpt_material;
+#define GDPT_MATERIAL_ALBEDO_SRGB 1u
+/* Optional set 1 binding 6 of a GDPT_MATERIAL_EXT shader: material ids for ANY number of surfaces per instance
+ * (BLASInstance.materials holds three, bvh.h:71).  uint32 words: offset[n_instances + 1] (in words, from the start of
+ * the buffer), then the ids; the material of surface s of instance i is word offset[i] + s. */
 GDPT_STATIC_ASSERT(sizeof(gdpt_material) == 64, "Material is 64 B");
 
 /* progressive_rendering.glsl:12-16, host twin

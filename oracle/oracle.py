@@ -28,7 +28,8 @@ class OrcScene(Structure):
     _fields_ = [("tri_geom", c_void_p), ("n_tris", c_uint64), ("tri_data", c_void_p), ("materials", c_void_p),
                 ("n_materials", c_uint64), ("bvh", c_void_p), ("n_nodes", c_uint64), ("blas", c_void_p),
                 ("n_blas", c_uint64), ("tlas", c_void_p), ("n_tlas", c_uint64), ("textures", c_void_p),
-                ("tex_w", c_int32), ("tex_h", c_int32), ("tex_layers", c_int32), ("_pad", c_int32)]
+                ("tex_w", c_int32), ("tex_h", c_int32), ("tex_layers", c_int32), ("material_ext", c_int32),
+                ("surface_materials", c_void_p)]
 
 
 class OrcStats(Structure):
@@ -135,6 +136,9 @@ class Scene:
         s.tlas = _p(self.np["tlas"]); s.n_tlas = len(self.np["tlas"]) // 32
         s.textures = _p(self.tex)
         s.tex_layers, s.tex_h, s.tex_w = self.tex.shape[0], self.tex.shape[1], self.tex.shape[2]
+        # material-breadth extension (gdpt_wire.h, "#define GDPT_MATERIAL_EXT"): present iff the group emitted its table
+        s.material_ext = 1 if "surface_materials" in self.np else 0
+        s.surface_materials = _p(self.np["surface_materials"]) if s.material_ext else None
         self.c = s
 
 

@@ -125,6 +125,11 @@ struct Scene {
     const gdpt_blas_instance *blas; uint64_t n_blas;
     const gdpt_tlas_node *tlas; uint64_t n_tlas;
     const uint8_t *textures; int32_t tex_w, tex_h, tex_layers;
+    // material-breadth extension (include/gdpt_wire.h, "#define GDPT_MATERIAL_EXT"); NOT part of the reference, hence not
+    // pinned by its shader text: this restatement is the definition the CUDA path is held to.  material_ext == 0 = reference
+    int32_t material_ext = 0;
+    const uint32_t *surface_materials = nullptr;
+    float srgb_lut[256];
 };
 
 struct Ray { V3 d, o, rD; };
@@ -285,6 +290,21 @@ static inline V3 sample_texture(const Scene &sc, float u, float v, int layer)
     const uint8_t *p = sc.textures + (((size_t)layer * sc.tex_h + iy) * sc.tex_w + ix) * 4;
     return mk((float)p[0] / 255.0f, (float)p[1] / 255.0f, (float)p[2] / 255.0f);
 }
+static inline const uint8_t *texel_bytes(const Scene &sc, float u, float v, int layer)
+{
+    int ix = (int)floorf(u * (float)sc.tex_w), iy = (int)floorf(v * (float)sc.tex_h);
+    ix = ix < 0 ? 0 : (ix > sc.tex_w - 1 ? sc.tex_w - 1 : ix);
+    iy = iy < 0 ? 0 : (iy > sc.tex_h - 1 ? sc.tex_h - 1 : iy);
+    if (layer > sc.tex_layers - 1) layer = sc.tex_layers - 1;
+    return sc.textures + (((size_t)layer * sc.tex_h + iy) * sc.tex_w + ix) * 4;
+}
+static void fill_srgb_lut(Scene &sc)
+{
+    for (int k = 0; k < 256; k++) { // IEC 61966-2-1 decode of an 8-bit code, rounded once to binary32
+        const double c = k / 255.0;
+        sc.srgb_lut[k] = (float)(c <= 0.04045 ? c / 12.92 : std::pow((c + 0.055) / 1.055, 2.4));
+    }
+}
 
 // main.glsl:194-222
 static inline Shading get_shading_data(const Scene &sc, const Hit &h)
@@ -292,7 +312,10 @@ static inline Shading get_shading_data(const Scene &sc, const Hit &h)
     Shading s;
     const gdpt_triangle_data &tri = sc.tri_data[h.triangle];
     const gdpt_blas_instance &b = sc.blas[h.blas];
-    const gdpt_material &m = sc.materials[b.materials[tri.material_index]];
+    const uint32_t material_id = (sc.material_ext && sc.surface_materials)
+                                     ? sc.surface_materials[sc.surface_materials[h.blas] + tri.material_index]
+                                     : b.materials[tri.material_index];
+    const gdpt_material &m = sc.materials[material_id];
     s.position = xform(b.transform, h.position, 1.0f);
     s.out_dir = normalize3(xform(b.transform, h.out_dir, 0.0f));
     float u = h.bu, v = h.bv;
@@ -306,11 +329,22 @@ static inline Shading get_shading_data(const Scene &sc, const Hit &h)
     s.lambert_out = dot(s.normal, s.out_dir);
     s.emission = scl(mk(m.emission[0], m.emission[1], m.emission[2]), max_c(0.0f, m.emission[3]));
     V3 albedo = mk(m.albedo[0], m.albedo[1], m.albedo[2]);
-    if (m.albedo_texture_index >= 0) albedo = mulv(albedo, sample_texture(sc, tu, tv, m.albedo_texture_index));
-    float metal = m.metallic;
+    float metal = m.metallic, rough = m.roughness;
+    if (!sc.material_ext) {
+        if (m.albedo_texture_index >= 0) albedo = mulv(albedo, sample_texture(sc, tu, tv, m.albedo_texture_index));
+    } else { // the extension: sRGB albedo layers, roughness / metallic scaled by the red channel of their layers
+        if (m.albedo_texture_index >= 0) {
+            const uint8_t *p = texel_bytes(sc, tu, tv, m.albedo_texture_index);
+            const V3 c = (m.ext_flags & GDPT_MATERIAL_ALBEDO_SRGB) ? mk(sc.srgb_lut[p[0]], sc.srgb_lut[p[1]], sc.srgb_lut[p[2]])
+                                                                   : mk((float)p[0] / 255.0f, (float)p[1] / 255.0f, (float)p[2] / 255.0f);
+            albedo = mulv(albedo, c);
+        }
+        if (m.ext_roughness_texture) rough = rough * ((float)texel_bytes(sc, tu, tv, (int)m.ext_roughness_texture - 1)[0] / 255.0f);
+        if (m.ext_metallic_texture) metal = metal * ((float)texel_bytes(sc, tu, tv, (int)m.ext_metallic_texture - 1)[0] / 255.0f);
+    }
     s.fresnel_0 = mix3(mk(0.02f, 0.02f, 0.02f), albedo, metal);
     s.diffuse_albedo = sub(albedo, scl(albedo, metal));
-    s.roughness = max_c(0.006f, m.roughness);
+    s.roughness = max_c(0.006f, rough);
     return s;
 }
 
@@ -560,7 +594,8 @@ typedef struct orc_scene {
     const void *bvh; uint64_t n_nodes;
     const void *blas; uint64_t n_blas;
     const void *tlas; uint64_t n_tlas;
-    const uint8_t *textures; int32_t tex_w, tex_h, tex_layers, _pad;
+    const uint8_t *textures; int32_t tex_w, tex_h, tex_layers, material_ext;
+    const uint32_t *surface_materials; // extension only (gdpt_wire.h): offset[n_blas + 1], ids
 } orc_scene;
 
 typedef struct orc_stats {
@@ -584,6 +619,8 @@ int orc_path_trace(const orc_scene *scene, const gdpt_render_params *params, con
     job.sc.blas = (const gdpt_blas_instance *)scene->blas; job.sc.n_blas = scene->n_blas;
     job.sc.tlas = (const gdpt_tlas_node *)scene->tlas; job.sc.n_tlas = scene->n_tlas;
     job.sc.textures = scene->textures; job.sc.tex_w = scene->tex_w; job.sc.tex_h = scene->tex_h; job.sc.tex_layers = scene->tex_layers;
+    job.sc.material_ext = scene->material_ext; job.sc.surface_materials = scene->material_ext ? scene->surface_materials : nullptr;
+    fill_srgb_lut(job.sc);
     job.params = params; job.cam = camera;
     job.max_depth = max_depth; job.debug_steps = debug_steps;
     if (y_begin < 0) y_begin = 0;

@@ -60,7 +60,8 @@ struct devcheck_scene {
     const void *bvh; uint64_t n_nodes;
     const void *blas; uint64_t n_blas;
     const void *tlas; uint64_t n_tlas;
-    const uint8_t *textures; int32_t tex_w, tex_h, tex_layers, _pad;
+    const uint8_t *textures; int32_t tex_w, tex_h, tex_layers, material_ext;
+    const uint32_t *surface_materials; // material-breadth extension (gdpt_wire.h), same layout as oracle.OrcScene
 };
 
 static void make_view(const devcheck_scene *in, DerivedLayout &lay, FastLayout &fast, SceneView &sc)
@@ -70,6 +71,17 @@ static void make_view(const devcheck_scene *in, DerivedLayout &lay, FastLayout &
     sc.materials = (const gdpt_material *)in->materials; sc.bvh = (const gdpt_bvh_node *)in->bvh;
     sc.blas = (const gdpt_blas_instance *)in->blas; sc.tlas = (const gdpt_tlas_node *)in->tlas;
     sc.textures = in->textures; sc.tex_w = in->tex_w; sc.tex_h = in->tex_h; sc.tex_layers = in->tex_layers;
+    if (in->material_ext) {
+        static const std::vector<float> lut = [] {
+            std::vector<float> t(256);
+            for (int k = 0; k < 256; k++) {
+                const double c = k / 255.0;
+                t[k] = (float)(c <= 0.04045 ? c / 12.92 : std::pow((c + 0.055) / 1.055, 2.4));
+            }
+            return t;
+        }();
+        sc.material_ext = 1u; sc.surface_materials = in->surface_materials; sc.srgb_lut = lut.data();
+    }
     if (g_fast) {
         build_fast_layout(sc.bvh, (uint32_t)in->n_nodes, sc.blas, (uint32_t)in->n_blas, sc.tlas, (uint32_t)in->n_tlas, sc.tri_geom,
                           (uint32_t)in->n_tris, lay, fast);
