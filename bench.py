@@ -282,12 +282,18 @@ def run_ours(args, rank, local, world):
         if rows_mode:
             present()
             torch.cuda.synchronize()
-    if sample_mode:  # first use of the exchange + accumulate path
-        warm = multigpu.SampleIndexAccumulator(H, W, rank, world, dev_t, multigpu.cuda_k2(cam))
-        with torch.cuda.stream(backend_stream):
-            warm.add(frame_t.clone().unsqueeze(0))
-            warm.present()
-        del warm
+    frames_kept = torch.empty((args.steps, H, W, 4), dtype=torch.uint8, device=dev_t) if sample_mode else None
+    if sample_mode:
+        # warm-up of the exchange + accumulate path at the size the timed region uses: NCCL sets up its peer-to-peer
+        # channels and the allocator its blocks on first use (hundreds of ms, once per process)
+        frames_kept.zero_()
+        for _ in range(2):
+            warm = multigpu.SampleIndexAccumulator(H, W, rank, world, dev_t, multigpu.cuda_k2(cam))
+            with torch.cuda.stream(backend_stream):
+                warm.add(frames_kept)
+                warm.present()
+            torch.cuda.synchronize()
+            del warm
     stage_ms = np.zeros(64)
     n_stage = 0
     launches_per_frame = 0
@@ -297,7 +303,6 @@ def run_ours(args, rank, local, world):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    frames_kept = torch.empty((args.steps, H, W, 4), dtype=torch.uint8, device=dev_t) if sample_mode else None
     barrier()
     wall0 = time.perf_counter()
     dev_ms, rays_total, k2_ms_total, gather_ms, k1_ms_total, retraced = 0.0, 0, 0.0, 0.0, 0.0, 0
@@ -632,11 +637,13 @@ def run_c5(args, rank, local, world, dev_t):
         cam.set_frame_index(w)
         cam.render_device_only()
     cam.synchronize()
-    warm = multigpu.SampleIndexAccumulator(H, W, rank, world, dev_t, multigpu.cuda_k2(cam))
-    with torch.cuda.stream(stream):
-        warm.add(frame_t.clone().unsqueeze(0)); warm.present()
-    torch.cuda.synchronize()
-    del warm
+    kept.zero_()
+    for _ in range(2):  # at the size the timed region uses: NCCL's peer-to-peer channels and the allocator's blocks are set up on first use
+        warm = multigpu.SampleIndexAccumulator(H, W, rank, world, dev_t, multigpu.cuda_k2(cam))
+        with torch.cuda.stream(stream):
+            warm.add(kept); warm.present()
+        torch.cuda.synchronize()
+        del warm
 
     def sample_index():
         acc = multigpu.SampleIndexAccumulator(H, W, rank, world, dev_t, multigpu.cuda_k2(cam))
