@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_pool(const FrameAr
                     if (COUNT) own_proofs++;
                     if (!fast_verdict_ool(&a.sc, wo, wd, ht, htri, hbf, hflags)) {
                         ExactHit eh; // rare: exact reference-order traversal of this ray
-                        exact_retrace(&a.sc, wo, wd, &eh);
+                        exact_retrace(&a.sc, wo, wd, (hflags & RAY_FAR) == 0u, &eh);
                         ht = eh.t; hu = eh.u; hv = eh.v; htri = eh.tri; hbf = eh.blas_front; hflags = eh.overflow & RAY_OVERFLOW;
                         my_retraced++;
                     }

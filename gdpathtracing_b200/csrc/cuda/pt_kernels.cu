@@ -151,14 +151,17 @@ struct LocalStack {
     __device__ __forceinline__ uint32_t load(uint32_t i) const { return slots[i]; }
 };
 struct ExactHit { float t, u, v; uint32_t tri, blas_front, overflow; };
-__device__ __noinline__ void exact_retrace(const SceneView *sc, f3 wo, f3 wd, ExactHit *out)
+// `trust_margins` false (the ray starts beyond the reach the culling margins are sized for, RAY_FAR): the full reference
+// visiting order, no tight-box culling -- exact whatever the distances.
+__device__ __noinline__ void exact_retrace(const SceneView *sc, f3 wo, f3 wd, bool trust_margins, ExactHit *out)
 {
     uint32_t slots[GDPT_MAX_STACK];
     LocalStack st;
     st.slots = slots;
     RayState r;
     ray_begin(r, *sc, wo, wd);
-    trace_ray_compact<false, true>(*sc, r, st, nullptr);
+    if (trust_margins) trace_ray_compact<false, true>(*sc, r, st, nullptr);
+    else trace_ray_compact<false, false>(*sc, r, st, nullptr);
     out->t = r.t; out->u = r.u; out->v = r.v; out->tri = r.tri; out->blas_front = r.blas_front; out->overflow = r.overflow;
 }
 
@@ -225,9 +228,27 @@ __global__ void __launch_bounds__(kTraceThreads) k_primary_cull(const FrameArgs 
             generate_primary_ray(cam, a.width, a.height, px, py, &o, &d);
             pixel = (uint32_t)py * (uint32_t)a.width + (uint32_t)px;
             RayState r;
-            ray_begin(r, a.sc, o, d);
-            while (r.cur != LINK_NONE && (r.cur & LINK_TLAS)) step_tlas<false, true>(a.sc, r, st, nullptr);
-            survivor = r.cur != LINK_NONE;
+            if (a.sc.fast4_ok && a.schedule == 6) {
+                // What the path kernel's search would do at the TLAS level, as an any-hit query: four-wide steps over the
+                // instances' true world boxes, then the touched instance's own box in its space; the first instance whose
+                // box the ray touches makes the pixel a survivor.  Rays the search is not trusted with survive unseen.
+                fast_ray_begin(r, a.sc, o, d);
+                r.cur = fast_start_link(r, a.sc.fast4_root);
+                survivor = (r.overflow & RAY_FAR) != 0u;
+                while (!survivor && r.cur != LINK_NONE) {
+                    if (r.cur & LINK_LEAF) {
+                        fast_enter_instance<true>(a.sc, r, st);
+                        survivor = (r.overflow & RAY_FAR) != 0u || (r.cur != LINK_NONE && (r.cur & LINK_TLAS) == 0u);
+                        r.o = r.wo; r.d = r.wd; r.rd = fast_rcp3(r.wd); r.inst = GDPT_NO_INSTANCE; // missed: back to world space
+                    } else {
+                        fast_step_node4(a.sc, r, st);
+                    }
+                }
+            } else {
+                ray_begin(r, a.sc, o, d);
+                while (r.cur != LINK_NONE && (r.cur & LINK_TLAS)) step_tlas<false, true>(a.sc, r, st, nullptr);
+                survivor = r.cur != LINK_NONE;
+            }
             if (!survivor) {
                 a.out_rgba8[pixel] = pack_rgba8(mk3(0.0f, 0.0f, 0.0f) + mk3(1.0f, 1.0f, 1.0f) * sample_sky(d));
                 a.out_depth[pixel] = encode_depth(cam, cam.z_far);

@@ -23,3 +23,8 @@ for h,u,v in zip(hdr,units,vals):
 done
 python3 tools/ncu_regions.py gpurun_out/prof_k_path.ncu-rep 40 > $out/${tag}_ncu_k_path_regions.txt
 ls -la $out
+for c in c1 c3 c4; do [ -f gpurun_out/bench_$c.json ] && cp gpurun_out/bench_$c.json $out/${tag}_bench_$c.json; done
+[ -f gpurun_out/pytest_gpu_adversarial.log ] && cp gpurun_out/pytest_gpu_adversarial.log $out/${tag}_pytest_gpu_adversarial.log
+[ -f gpurun_out/sanitizer_memcheck.log ] && cp gpurun_out/sanitizer_memcheck.log $out/${tag}_sanitizer_memcheck.log
+[ -f gpurun_out/warp_profile_c4.json ] && cp gpurun_out/warp_profile_c4.json $out/${tag}_warp_profile_c4.json
+true

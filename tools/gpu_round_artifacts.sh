@@ -10,3 +10,7 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_p
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_progressive" -s 2 -c 1 -o gpurun_out/prof_k_progressive python tools/profile_frame.py --frames 4 > gpurun_out/ncu_k_progressive.log 2>&1
 python tools/warp_profile.py --frames 4 > gpurun_out/warp_profile.json 2>&1
 ls -la gpurun_out
+# the other BASELINE configs on one GPU (C1, C3, C4 at 4K) and the adversarial tier's log
+bash tools/gpu_configs.sh > gpurun_out/configs.log 2>&1; tail -4 gpurun_out/configs.log
+python -m pytest tests/test_gpu_adversarial.py -q -s 2>&1 | grep "re-traced\|passed\|failed" > gpurun_out/pytest_gpu_adversarial.log
+timeout 300 compute-sanitizer --tool memcheck python tools/sanitize_small.py > gpurun_out/sanitizer_memcheck.log 2>&1; tail -3 gpurun_out/sanitizer_memcheck.log
