@@ -24,8 +24,11 @@ namespace gdpt {
 
 #define RAY_OVERFLOW 1u /* RayState.overflow bit 0: traversal stack exceeded */
 #define RAY_TIE 2u      /* RayState.overflow bit 1: a second pair reached the current minimum t (or t was NaN) */
-#define RAY_FAR 4u      /* RayState.overflow bit 2: the search is not trusted for this ray (origin beyond the reach of its culling
-                           margins, or a direction component that is zero): the exact traversal answers it, the search is skipped */
+#define RAY_FAR 4u      /* RayState.overflow bit 2: the ray starts beyond the reach of the culling margins: the exact traversal answers
+                           it WITHOUT tight-box culling, the search is skipped */
+#define RAY_AXIAL 8u    /* RayState.overflow bit 3: a direction component is zero: the exact traversal (culling as usual) answers it,
+                           the search is skipped */
+#define RAY_UNSEARCHED (RAY_FAR | RAY_AXIAL)
 
 // Stack of the search.  The trees' stack need is bounded at upload (fast_bvh.h: max_depth / need4 < GDPT_FAST_MAX_DEPTH
 // < GDPT_MAX_STACK), so no overflow test is needed here -- unlike the reference-order traversal, whose 64+64 entries
@@ -80,10 +83,11 @@ GDPT_HD void fast_ray_begin(RayState &r, const SceneView &sc, f3 o, f3 d)
 {
     ray_begin(r, sc, o, d);
     r.rd = fast_rcp3(d); // the search's own reciprocal; the proof recomputes the exact one
-    if (fast_far_origin(o, sc.fast_world_reach) || fast_degenerate_dir(d)) r.overflow |= RAY_FAR;
+    if (fast_far_origin(o, sc.fast_world_reach)) r.overflow |= RAY_FAR;
+    if (fast_degenerate_dir(d)) r.overflow |= RAY_AXIAL;
 }
 // Link a search starts from: nothing for a ray the search is not trusted with.
-GDPT_HD uint32_t fast_start_link(const RayState &r, uint32_t root) { return (r.overflow & RAY_FAR) ? LINK_NONE : root; }
+GDPT_HD uint32_t fast_start_link(const RayState &r, uint32_t root) { return (r.overflow & RAY_UNSEARCHED) ? LINK_NONE : root; }
 
 // true box of a child: entry distance and whether the subtree can still hold a hit with t <= r.t
 GDPT_HD bool fast_slab(const RayState &r, float nx, float ny, float nz, float xx, float xy, float xz, float *entry)
@@ -301,7 +305,8 @@ template <bool WIDE, class Stack> GDPT_HD void fast_enter_instance(const SceneVi
     r.inst = idx;
     // too far out for this BLAS's margins (derived_layout.h fast_reach), or axis-parallel in this instance's space:
     // the exact traversal answers the ray, the rest of the search is dropped
-    if (fast_far_origin(r.o, tmax4.w) || fast_degenerate_dir(r.d)) { r.overflow |= RAY_FAR; r.cur = LINK_NONE; r.sp = 0u; return; }
+    const uint32_t unsearched = (fast_far_origin(r.o, tmax4.w) ? RAY_FAR : 0u) | (fast_degenerate_dir(r.d) ? RAY_AXIAL : 0u);
+    if (unsearched) { r.overflow |= unsearched; r.cur = LINK_NONE; r.sp = 0u; return; }
     float entry;
     const bool touches = fast_slab(r, tmin4.x, tmin4.y, tmin4.z, tmax4.x, tmax4.y, tmax4.z, &entry);
     const uint32_t root = WIDE ? fast_bits(tmin4.w) : tail.w; // the BLAS root in the table being searched
@@ -371,7 +376,7 @@ GDPT_HD bool fast_other_pair_within(const SceneView &sc, f3 wo, f3 wd, float bou
             if (r.cur & LINK_LEAF) { if (wide) fast_enter_instance<true>(sc, r, st); else fast_enter_instance<false>(sc, r, st); }
         }
     }
-    return r.t < bound || (r.overflow & (RAY_TIE | RAY_FAR)) != 0u; // a closer pair, one exactly at the bound, or margins not trusted
+    return r.t < bound || (r.overflow & (RAY_TIE | RAY_UNSEARCHED)) != 0u; // a closer pair, one exactly at the bound, or not searched
 }
 
 // The search ended with a hit at the unique minimum t_w = r.t (no tie).  Does the reference traversal test this pair?
@@ -424,7 +429,7 @@ GDPT_HD bool fast_proves_reference_hit(const SceneView &sc, const RayState &r)
 // Verdict on a finished search: true = the record in `r` is the reference's record.
 GDPT_HD bool fast_result_is_reference(const SceneView &sc, const RayState &r)
 {
-    if (r.overflow & (RAY_TIE | RAY_FAR)) return false;
+    if (r.overflow & (RAY_TIE | RAY_UNSEARCHED)) return false;
     if (!(r.t < 1e9f)) return true;
     return fast_proves_reference_hit(sc, r);
 }

@@ -233,12 +233,22 @@ __global__ void __launch_bounds__(kTraceThreads) k_primary_cull(const FrameArgs 
                 // instances' true world boxes, then the touched instance's own box in its space; the first instance whose
                 // box the ray touches makes the pixel a survivor.  Rays the search is not trusted with survive unseen.
                 fast_ray_begin(r, a.sc, o, d);
-                r.cur = fast_start_link(r, a.sc.fast4_root);
-                survivor = (r.overflow & RAY_FAR) != 0u;
+                const uint32_t unsearched = r.overflow & RAY_UNSEARCHED;
+                if (unsearched) {
+                    // the path kernel will answer this ray with the exact traversal: classify it the same way -- the
+                    // reference's own TLAS walk, with the tight boxes only where their margins are trusted (not RAY_FAR)
+                    ray_begin(r, a.sc, o, d);
+                    if (unsearched & RAY_FAR) { while (r.cur != LINK_NONE && (r.cur & LINK_TLAS)) step_tlas<false, false>(a.sc, r, st, nullptr); }
+                    else { while (r.cur != LINK_NONE && (r.cur & LINK_TLAS)) step_tlas<false, true>(a.sc, r, st, nullptr); }
+                    survivor = r.cur != LINK_NONE;
+                    r.cur = LINK_NONE;
+                } else {
+                    r.cur = a.sc.fast4_root;
+                }
                 while (!survivor && r.cur != LINK_NONE) {
                     if (r.cur & LINK_LEAF) {
                         fast_enter_instance<true>(a.sc, r, st);
-                        survivor = (r.overflow & RAY_FAR) != 0u || (r.cur != LINK_NONE && (r.cur & LINK_TLAS) == 0u);
+                        survivor = (r.overflow & RAY_UNSEARCHED) != 0u || (r.cur != LINK_NONE && (r.cur & LINK_TLAS) == 0u);
                         r.o = r.wo; r.d = r.wd; r.rd = fast_rcp3(r.wd); r.inst = GDPT_NO_INSTANCE; // missed: back to world space
                     } else {
                         fast_step_node4(a.sc, r, st);

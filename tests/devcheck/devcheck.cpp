@@ -39,14 +39,16 @@ template <bool CULL> static void run_ray(const SceneView &sc, RayState &r, HostS
 {
     if (g_fast && sc.fast_ok) {
         // closest-hit search + proof; rays that fail it are re-traced in reference order (what the kernels do)
-        RayState f = r;
+        RayState f = r; // + what fast_ray_begin adds: rays the search is not trusted with go straight to the exact traversal
+        if (fast_far_origin(f.wo, sc.fast_world_reach)) f.overflow |= RAY_FAR;
+        if (fast_degenerate_dir(f.wd)) f.overflow |= RAY_AXIAL;
         if (g_fast == 2 && sc.fast4_ok) fast_trace_ray4(sc, f, st); // four-wide tables
         else fast_trace_ray(sc, f, st);
         __atomic_add_fetch(&g_fast_rays, 1, __ATOMIC_RELAXED);
         if (fast_result_is_reference(sc, f)) {
             r = f; return; }
         __atomic_add_fetch(&g_fast_retraced, 1, __ATOMIC_RELAXED);
-        if (f.overflow & (RAY_TIE | RAY_FAR)) __atomic_add_fetch(&g_fast_ties, 1, __ATOMIC_RELAXED);
+        if (f.overflow & (RAY_TIE | RAY_UNSEARCHED)) __atomic_add_fetch(&g_fast_ties, 1, __ATOMIC_RELAXED);
     }
     if (g_stepwise == 2) trace_ray_compact<true, CULL>(sc, r, st, tc);
     else if (g_stepwise) trace_ray_stepwise<true, CULL>(sc, r, st, tc);
