@@ -22,6 +22,7 @@ struct DerivedLayout {
     std::vector<InstRec> inst_recs;
     uint32_t tlas_root_link = LINK_NONE;
     float world_reach = 0.0f; // SceneView::fast_world_reach
+    std::vector<float> root_extent; // per BVH node index of a BLAS root: the effective extent its culling margins are built on
 };
 
 struct TightBox { float lo[3], hi[3]; };
@@ -46,14 +47,19 @@ inline float tight_extent(const TightBox &b)
     for (int k = 0; k < 3; k++) if (b.hi[k] - b.lo[k] > e) e = b.hi[k] - b.lo[k];
     return e;
 }
-// Safety margin of a culling box: 1/256 of its own size plus 1/512 of the size of the BLAS it
-// belongs to.  The second term is what covers Moller-Trumbore's rounding (absolute error of
-// the order of 1e-6 x distance to the ray origin): it keeps a >10x reserve for rays that start
-// up to ~100 BLAS diameters away.  Non-finite input boxes become "everything" (never cull).
+// Safety margin of a culling box: 1/256 of its own size plus 1/GDPT_MARGIN_DIV of the (effective) size of the BLAS it
+// belongs to.  The second term is what covers Moller-Trumbore's rounding (absolute error of the order of
+// 1e-6 x distance to the ray origin) for rays that start within the reach that goes with it (fast_reach: 7.6 x reserve
+// at the reach itself).  Non-finite input boxes become "everything" (never cull).
+#ifndef GDPT_MARGIN_DIV
+#define GDPT_MARGIN_DIV 4096.0f /* the owner term of the margin is extent / GDPT_MARGIN_DIV; the reach scales with it (fast_reach).
+                                   A/B on the B200 (512 | 2048 | 4096): C2 path kernel 0.638 | 0.609 | 0.604 ms, C4 1080p 11.75 | 11.17 | 11.11,
+                                   C3 7.86 | 5.75 | 5.37 (triangle tests per frame 114 M -> 57 M); same safety factor at every value */
+#endif
 inline TightBox tight_inflate(const TightBox &b, float owner_extent)
 {
     TightBox r;
-    const float m = tight_extent(b) * (1.0f / 256.0f) + owner_extent * (1.0f / 512.0f) + 1e-30f;
+    const float m = tight_extent(b) * (1.0f / 256.0f) + owner_extent * (1.0f / GDPT_MARGIN_DIV) + 1e-30f;
     bool finite = std::isfinite(m);
     for (int k = 0; k < 3; k++) {
         r.lo[k] = b.lo[k] - m; r.hi[k] = b.hi[k] + m;
@@ -69,13 +75,15 @@ inline TightBox tight_inflate(const TightBox &b, float owner_extent)
 //   * Moller-Trumbore accepts hits up to ~1e-6 x (distance to the origin) outside the triangle it tests;
 //   * the search's own slab tests (FFMA + hardware reciprocal) move a plane by a few ulp (~2.4e-7) of the larger
 //     of |origin| and |plane|.
-// With coordinates below 256 x extent both stay under a quarter of the margin.  A box that itself lies farther than
-// half of that from its space's origin gets reach 0: every ray that enters it is answered by the exact traversal.
+// With coordinates below (131072 / GDPT_MARGIN_DIV) x extent both stay under a quarter of the margin (256 extents for a
+// margin of extent / 512, 32 for extent / 4096).  A box that itself lies farther than half of that from its space's origin
+// gets reach 0: every ray that enters it is answered by the exact traversal.  `extent` is the EFFECTIVE extent the margin
+// was built on (derive_layout: at least the box's own, more where the scene needs a longer reach).
 inline float fast_reach(const TightBox &b, float extent)
 {
     float far_corner = 0.0f;
     for (int k = 0; k < 3; k++) { far_corner = std::fmax(far_corner, std::fabs(b.lo[k])); far_corner = std::fmax(far_corner, std::fabs(b.hi[k])); }
-    const float reach = 256.0f * extent;
+    const float reach = (131072.0f / GDPT_MARGIN_DIV) * extent; // 256 extents for the default margin of extent / 512
     return (std::isfinite(reach) && far_corner <= 0.5f * reach) ? reach : 0.0f;
 }
 
@@ -140,16 +148,49 @@ inline std::string derive_layout(const gdpt_bvh_node *bvh, uint32_t n_nodes, con
                 raw[i] = t; state[i] = 2; walk.pop_back();
             }
         }
-        // second walk: stamp the owning BLAS size on every node of this tree
-        const float ext = tight_extent(raw[root]);
+    }
+    // How far out rays may start, by construction of the margins: four scene radii.  A margin of extent / GDPT_MARGIN_DIV
+    // is trusted for origins within (131072 / GDPT_MARGIN_DIV) extents (fast_reach); where that is less than the scene
+    // needs -- a small prop in a large room -- the BLAS (or, at the world level, the instance) gets the margin of a larger
+    // "effective" extent instead, so no ray inside four scene radii is ever sent to the exact traversal for its origin alone.
+    float scene_radius = 0.0f;
+    for (uint32_t b = 0; b < n_blas; b++) {
+        const TightBox &o = raw[blas[b].root];
+        const float *m = blas[b].transform;
+        for (int c = 0; c < 8; c++) {
+            const double x = (c & 1) ? o.hi[0] : o.lo[0], y = (c & 2) ? o.hi[1] : o.lo[1], z = (c & 4) ? o.hi[2] : o.lo[2];
+            for (int k = 0; k < 3; k++) {
+                const float w = std::fabs((float)(m[k] * x + m[4 + k] * y + m[8 + k] * z + m[12 + k]));
+                if (std::isfinite(w) && w > scene_radius) scene_radius = w;
+            }
+        }
+    }
+    const float needed_world = 4.0f * scene_radius;
+    std::vector<float> root_extent(n_nodes, 0.0f); // per BLAS root: the effective extent its margins are built on
+    for (uint32_t b = 0; b < n_blas; b++) {
+        const uint32_t root = blas[b].root;
+        const float *a = blas[b].inverse_transform; // local = A w + t
+        float norm = 0.0f;
+        for (int r = 0; r < 3; r++) norm = std::fmax(norm, std::fabs(a[r]) + std::fabs(a[4 + r]) + std::fabs(a[8 + r]));
+        const float shift = std::fmax(std::fabs(a[12]), std::fmax(std::fabs(a[13]), std::fabs(a[14])));
+        const float needed_local = norm * needed_world + shift;
+        const float eff = std::fmax(tight_extent(raw[root]), std::isfinite(needed_local) ? needed_local * (GDPT_MARGIN_DIV / 131072.0f) : 0.0f);
+        if (eff > root_extent[root]) root_extent[root] = eff;
+    }
+    std::vector<uint8_t> stamped(n_nodes, 0);
+    for (uint32_t b = 0; b < n_blas; b++) { // second walk: stamp the owning BLAS's effective extent on every node of its tree
+        const uint32_t root = blas[b].root;
+        if (stamped[root]) continue;
         walk.assign(1, root);
         while (!walk.empty()) {
             const uint32_t i = walk.back();
             walk.pop_back();
-            owner_extent[i] = ext;
+            owner_extent[i] = root_extent[root];
+            stamped[i] = 1;
             if (bvh[i].tri_count == 0) { walk.push_back(bvh[i].left_child); walk.push_back(bvh[i].right_child); }
         }
     }
+    out.root_extent = root_extent;
 
     out.wide_nodes.assign(n_internal, WideNode());
     out.leaf_recs.assign(n_leaf, LeafRec());
@@ -216,8 +257,9 @@ inline std::string derive_layout(const gdpt_bvh_node *bvh, uint32_t n_nodes, con
                                  (float)(m[2] * x + m[6] * y + m[10] * z + m[14]) };
             tight_grow(w, p);
         }
-        world[b] = tight_inflate(w, tight_extent(w));
-        const float wr = fast_reach(w, tight_extent(w)); // world level: the smallest instance decides
+        const float eff_w = std::fmax(tight_extent(w), needed_world * (GDPT_MARGIN_DIV / 131072.0f)); // see root_extent above
+        world[b] = tight_inflate(w, eff_w);
+        const float wr = fast_reach(w, eff_w); // world level: the smallest instance decides
         out.world_reach = (b == 0 || wr < out.world_reach) ? wr : out.world_reach;
     }
     // tight boxes of TLAS nodes, bottom-up (TLAS nodes are few: plain recursion-free fixpoint by depth)

@@ -445,7 +445,7 @@ inline void build_fast_layout(const gdpt_bvh_node *bvh, uint32_t n_nodes, const 
         uint32_t link = LINK_NONE;
         if (!bld.prims.empty()) {
             const TightBox all = fastbvh::bounds_of(bld.prims, 0, (uint32_t)bld.prims.size());
-            bld.owner_extent = tight_extent(all);
+            bld.owner_extent = root < lay.root_extent.size() && lay.root_extent[root] > 0.0f ? lay.root_extent[root] : tight_extent(all);
             TightBox box;
             const int threads = out.build_threads > 0 ? out.build_threads : (int)std::min(32u, std::max(1u, std::thread::hardware_concurrency()));
             const uint32_t count = (uint32_t)bld.prims.size();

@@ -124,6 +124,19 @@ def far_tiny_instance():
     return sc
 
 
+def small_prop_in_a_large_room():
+    """A 4 cm object on the floor of the 6 m room, seen from across it: 150 of its own diameters away, far beyond what a
+    margin of extent / 4096 covers by itself.  The margins of such a prop are built on a larger effective extent
+    (derived_layout.h root_extent), so its rays stay with the search -- no cliff into the exact traversal."""
+    sc = scenes.SceneDesc("small_prop_in_a_large_room", camera_transform12=scenes.transform12(None, (0.0, -2.0, 2.9)), fov=12.0)
+    sc.materials = [dict(albedo=(0.8, 0.8, 0.8), roughness=0.9), dict(albedo=(0.9, 0.5, 0.2), roughness=0.4, metallic=0.5)]
+    sc.default_material = 0
+    sc.meshes = [scenes._cornell_room(), [scenes._soup_surface(400, 17, 0.015, 0.006)]]
+    sc.instances = [dict(mesh=0, transform12=scenes.ROOM_TRANSFORM),
+                    dict(mesh=1, transform12=scenes.transform12(None, (0.0, -2.97, -2.9)), surface_overrides=[1])]
+    return sc
+
+
 def axis_aligned_boxes():
     """Boxes whose faces lie in coordinate planes through the origin, seen by the degenerate cameras below."""
     sc = scenes.SceneDesc("axis_aligned_boxes", camera_transform12=scenes.transform12(None, (0.0, 0.0, 7.0)), fov=50.0)
@@ -157,6 +170,7 @@ CASES = [
     ("degenerate_cluster", degenerate_cluster, 128, 96, 4, None),
     ("tlas_root_is_a_leaf", tlas_root_is_a_leaf, 96, 64, 3, None),
     ("far_tiny_instance", far_tiny_instance, 96, 64, 3, None),
+    ("small_prop_in_a_large_room", small_prop_in_a_large_room, 96, 64, 4, None),
     ("rays_in_the_plane_x0", axis_aligned_boxes, 64, 96, 4, (0,)),
     ("rays_along_minus_z", axis_aligned_boxes, 48, 32, 4, (0, 1)),
 ]
