@@ -47,7 +47,7 @@ inline float tight_extent(const TightBox &b)
     for (int k = 0; k < 3; k++) if (b.hi[k] - b.lo[k] > e) e = b.hi[k] - b.lo[k];
     return e;
 }
-// Safety margin of a culling box: 1/256 of its own size plus 1/GDPT_MARGIN_DIV of the (effective) size of the BLAS it
+// Safety margin of a culling box: 1/GDPT_MARGIN_OWN_DIV of its own size plus 1/GDPT_MARGIN_DIV of the (effective) size of the BLAS it
 // belongs to.  The second term is what covers Moller-Trumbore's rounding (absolute error of the order of
 // 1e-6 x distance to the ray origin) for rays that start within the reach that goes with it (fast_reach: 7.6 x reserve
 // at the reach itself).  Non-finite input boxes become "everything" (never cull).
@@ -56,10 +56,15 @@ inline float tight_extent(const TightBox &b)
                                    A/B on the B200 (512 | 2048 | 4096): C2 path kernel 0.638 | 0.609 | 0.604 ms, C4 1080p 11.75 | 11.17 | 11.11,
                                    C3 7.86 | 5.75 | 5.37 (triangle tests per frame 114 M -> 57 M); same safety factor at every value */
 #endif
+#ifndef GDPT_MARGIN_OWN_DIV
+#define GDPT_MARGIN_OWN_DIV 2048.0f /* a second, smaller term relative to the box itself (belt and braces: the errors the margin must
+                                       absorb scale with the coordinates, which the owner term covers).  A/B (256 | 2048 | none): C2 path
+                                       kernel 0.610 | 0.600 | 0.592 ms, C4 1080p 11.16 | 10.94 | 10.90, C3 5.37 | 5.23 | 5.23 */
+#endif
 inline TightBox tight_inflate(const TightBox &b, float owner_extent)
 {
     TightBox r;
-    const float m = tight_extent(b) * (1.0f / 256.0f) + owner_extent * (1.0f / GDPT_MARGIN_DIV) + 1e-30f;
+    const float m = tight_extent(b) * (1.0f / GDPT_MARGIN_OWN_DIV) + owner_extent * (1.0f / GDPT_MARGIN_DIV) + 1e-30f;
     bool finite = std::isfinite(m);
     for (int k = 0; k < 3; k++) {
         r.lo[k] = b.lo[k] - m; r.hi[k] = b.hi[k] + m;

@@ -58,16 +58,15 @@ struct FastLayout {
 namespace fastbvh {
 
 constexpr int kBins = 16;
-constexpr uint32_t kLeafMaxDefault = 3; // A/B on the B200 (C2 path kernel ms): 2: 0.799, 3: 0.788, 4: 0.807, 6: 0.825, 8: 0.813
-// triangles per leaf of our trees (1..8, the leaf link holds count-1 in 3 bits); GDPT_FAST_LEAF_MAX overrides for A/B runs
+constexpr uint32_t kLeafMaxDefault = 2; // A/B on the B200, C2 path kernel ms | C3 ms: round 1 (majority-phase loop) 2: 0.799, 3: 0.788, 4: 0.807, 6: 0.825, 8: 0.813; round 2 (every phase per iteration, margins / 4096) 2: 0.596 | 4.78, 3: 0.611 | 5.22, 4: 0.643 | 5.51
+// triangles per leaf of our trees (1..8, the leaf link holds count-1 in 3 bits); -DGDPT_FAST_LEAF_MAX=n for A/B builds
+#ifndef GDPT_FAST_LEAF_MAX
+#define GDPT_FAST_LEAF_MAX kLeafMaxDefault
+#endif
 inline uint32_t leaf_max()
 {
-    static const uint32_t v = [] {
-        const char *e = std::getenv("GDPT_FAST_LEAF_MAX");
-        const int n = e ? std::atoi(e) : (int)kLeafMaxDefault;
-        return (uint32_t)(n < 1 ? 1 : (n > 8 ? 8 : n));
-    }();
-    return v;
+    static_assert((uint32_t)(GDPT_FAST_LEAF_MAX) >= 1u && (uint32_t)(GDPT_FAST_LEAF_MAX) <= 8u, "1..8 triangles per leaf");
+    return (uint32_t)(GDPT_FAST_LEAF_MAX);
 }
 
 struct Prim { float lo[3], hi[3], c[3]; uint32_t orig; };
@@ -380,7 +379,11 @@ inline void build_fast_layout(const gdpt_bvh_node *bvh, uint32_t n_nodes, const 
                               const gdpt_tlas_node *tlas, uint32_t n_tlas, const gdpt_triangle_geometry *tris, uint32_t n_tris,
                               const DerivedLayout &lay, FastLayout &out)
 {
-    const bool timing = std::getenv("GDPT_BUILD_TIMING") != nullptr;
+#ifdef GDPT_BUILD_TIMING
+    const bool timing = true; // diagnostic builds only: the process environment is never consulted
+#else
+    const bool timing = false;
+#endif
     auto t_lap = std::chrono::steady_clock::now();
     auto lap = [&](const char *what) {
         const auto now = std::chrono::steady_clock::now();

@@ -326,7 +326,11 @@ void AccelBuilder::subdivide(std::vector<gdpt_bvh_node> &nodes, std::vector<gdpt
                              int last) const
 {
     const int count = last - first;
-    const bool timing = std::getenv("GDPT_BUILD_TIMING") != nullptr;
+#ifdef GDPT_BUILD_TIMING
+    const bool timing = true; // diagnostic builds only: the process environment is never consulted
+#else
+    const bool timing = false;
+#endif
     auto now = [] { return std::chrono::steady_clock::now(); };
     auto lap = [&](const char *what, std::chrono::steady_clock::time_point &t) {
         if (timing) std::fprintf(stderr, "[accel_build] %-12s %.3f s\n", what, std::chrono::duration<double>(now() - t).count());
