@@ -375,14 +375,15 @@ int finish_main(gdpt_shader *s)
     if (a.schedule >= 3 && (!a.cull || observes_work)) a.schedule = 2;
     init_launch_shapes(d->ordinal);
     // scheduling knobs ("#define GDPT_TUNE_<NAME> n"; results do not depend on them)
-    a.refill_below = tune(s, "REFILL_BELOW", a.schedule == 6 ? 12 : 24); // schedule 6: lanes without a walking ray before a pool service
+    // schedule 6: lanes without a walking ray before a pool service (8 | 12: C2 0.609 | 0.594 ms, C4 1080p 10.30 | 10.66)
+    a.refill_below = tune(s, "REFILL_BELOW", a.schedule == 6 ? (a.sc.n_blas >= 64u ? 8 : 12) : 24);
     a.burst = tune(s, "BURST", a.schedule == 3 ? 4 : (a.schedule == 6 ? 8 : 16));
     a.shade_at = tune(s, "SHADE_AT", a.schedule == 6 ? 24 : 8);          // schedule 6: finished rays that justify a partial batch
     a.blocks_per_sm = tune(s, "BLOCKS_PER_SM", 0);
     a.wide_bvh = tune(s, "WIDE_BVH", 1);
     a.cost_ema = tune(s, "COST_EMA", 1);
     a.pool_alive = tune(s, "POOL_ALIVE", 0);
-    a.pool_wait = tune(s, "POOL_WAIT", 32);
+    a.pool_wait = tune(s, "POOL_WAIT", 16); // A/B with every phase per iteration (16 | 32): C2 0.598 | 0.594 ms, C4 1080p 10.26 | 10.66
     a.lead_min = tune(s, "LEAD_MIN", 0);
     a.sort4 = tune(s, "SORT4", 1);
     a.all_phases = tune(s, "ALL_PHASES", 1);
