@@ -388,6 +388,10 @@ int finish_main(gdpt_shader *s)
     a.sort4 = tune(s, "SORT4", 1);
     a.all_phases = tune(s, "ALL_PHASES", 1);
     a.miss_now = tune(s, "MISS_NOW", 1);
+    // A frame of a few instances is one wave of paths and bound by their latency: 128 registers, no spills, four blocks per
+    // SM.  Frames with far more traversal per path are throughput-bound and take the fifth block at 96 registers
+    // (A/B 4 | 5 blocks: C2 path kernel 0.606 | 0.638 ms, C4 1080p 10.22 | 9.76, C3 4.64 | 4.41).
+    a.pool_dense = tune(s, "DENSE", (a.sc.n_blas >= 64u || a.sc.n_tris >= 262144u) ? 1 : 0);
     a.count_work = s->count_work ? 1 : 0;
     if (a.refill_below < 1) a.refill_below = 1;
     if (a.refill_below > 32) a.refill_below = 32;

@@ -18,6 +18,7 @@
 #define GDPT_POOL_MINB 4
 #endif
 constexpr int kPoolMinBlocks = GDPT_POOL_MINB; // resident blocks per SM the register allocation is capped for (launch bounds)
+constexpr int kPoolDenseMinBlocks = 5; // the second build of the timed instantiation, for throughput-bound scenes (FrameArgs::pool_dense)
 constexpr int kPoolSlotsDefault = 64; // path slots per warp (template argument kPoolSlots)
 constexpr int kPoolParkDefault = 1; // leaves a lane may park while it keeps descending (template argument kPoolPark)
 enum PoolField {

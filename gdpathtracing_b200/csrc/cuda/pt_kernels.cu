@@ -375,6 +375,7 @@ struct Shapes {
     int path_list_record_blocks = 0; // k_path<true, true, SRC 1> (hit records of schedule 3)
     int pool_blocks[2][2] = {};  // k_path_pool<REC, .., WIDE>
     int pool_count_blocks = 0;   // k_path_pool<.., WIDE, COUNT>
+    int pool_dense_blocks = 0;   // k_path_pool<false, kPoolDenseMinBlocks, .., WIDE>: 96 registers, five blocks per SM
     int cull_blocks_per_sm = 1;
     int prog_blocks = 0;
 };
@@ -406,6 +407,7 @@ void init_launch_shapes(int device)
     s.pool_blocks[1][0] = grid_of(k_path_pool<true, kPoolMinBlocks, kPoolParkDefault, kPoolSlotsDefault, false>, kTraceThreads);
     s.pool_blocks[1][1] = grid_of(k_path_pool<true, kPoolMinBlocks, kPoolParkDefault, kPoolSlotsDefault, true>, kTraceThreads);
     s.pool_count_blocks = grid_of(k_path_pool<false, kPoolMinBlocks, kPoolParkDefault, kPoolSlotsDefault, true, true>, kTraceThreads);
+    s.pool_dense_blocks = grid_of(k_path_pool<false, kPoolDenseMinBlocks, kPoolParkDefault, kPoolSlotsDefault, true>, kTraceThreads);
     grid_of(k_primary_cull, kTraceThreads);
     s.cull_blocks_per_sm = per_sm > 0 ? per_sm : 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_progressive, 256, 0); s.prog_blocks = s.sms * (per_sm > 0 ? per_sm : 1);
@@ -504,6 +506,11 @@ void launch_path_pool(const FrameArgs &a_in, bool record, cudaStream_t s)
     }
     if (a.warp_prof && wide && !record) { // per-warp schedule profile (tools/warp_profile.py): same grid as the timed instantiation
         k_path_pool<false, kPoolMinBlocks, kPoolParkDefault, kPoolSlotsDefault, true, false, true><<<grid, kTraceThreads, 0, s>>>(a);
+        return;
+    }
+    if (a.pool_dense && wide && !record) { // throughput-bound scenes: five blocks per SM at 96 registers (a few spilled words)
+        k_path_pool<false, kPoolDenseMinBlocks, kPoolParkDefault, kPoolSlotsDefault, true>
+            <<<persistent_grid(sh, a, sh.pool_dense_blocks), kTraceThreads, 0, s>>>(a);
         return;
     }
     if (record) {

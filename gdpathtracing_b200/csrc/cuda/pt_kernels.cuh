@@ -51,6 +51,7 @@ struct FrameArgs {
     int pool_wait;                           // schedule 6: lane-iterations finished rays may wait before a pool service (0 = off)
     int sort4;                               // schedule 6: children of a four-wide node in full distance order (1) or nearest first (0)
     int count_work;                          // schedule 6: run the instantiation that counts its own work (untimed frames of bench.py)
+    int pool_dense;                          // schedule 6: the 96-register build, five blocks per SM (many instances / large meshes)
     int miss_now;                            // schedule 6: escaped rays are finished at retire time, shading batches hold hits only
     int all_phases;                          // schedule 6: every phase that has a lane runs in each iteration (1) or only the majority phase (0)
     FrameCounters *counters;
