@@ -196,6 +196,9 @@ def run_reference(args, rank, world):
 
 
 # ------------------------------------------------------------------------------------------ our arm
+IN_FLIGHT = 4  # GDPT_MAX_FRAMES_IN_FLIGHT (include/gdpt.h): frames the end-to-end leg keeps in flight
+
+
 SCHEDULES = {
     2: ("k_path<all pixels>", "the reference's visiting order on the reference arrays, no culling (trace / DEBUG_STEPS mode)"),
     3: ("k_primary_cull + k_path<survivors>", "the reference's visiting order on the reference arrays, tight-box culling"),
@@ -377,7 +380,7 @@ def run_ours(args, rank, local, world):
 
     # ---- end-to-end leg: host camera block in, RGBA8 frame back in (pinned) host memory, every step.
     # (a) the reference's blocking render(): one frame at a time; (b) the pipelined form of the same call
-    # (render_begin / render_wait, up to three frames in flight: read-back and the next frame's kernels overlap the tail of a frame).
+    # (render_begin / render_wait, up to four frames in flight: read-back and the next frames' kernels overlap the tail of a frame).
     # Every step of both does its own H2D camera upload and its own full-frame D2H.
     if peer_frame is not None:
         peer_frame.close()  # the end-to-end legs run without the frame handshake: no peer may write this rank's image in them
@@ -393,10 +396,10 @@ def run_ours(args, rank, local, world):
     sync_s = time.perf_counter() - t0
 
     for rep in range(2):  # untimed: first use of the pipelined path (every frame slot allocates its buffers and stream once)
-        for s in range(3):
-            set_index(3 * rep + s)
+        for s in range(IN_FLIGHT):
+            set_index(IN_FLIGHT * rep + s)
             cam.render_begin()
-        for s in range(3):
+        for s in range(IN_FLIGHT):
             cam.render_wait()
     barrier()
     e2e_rays, in_flight, touched = 0, 0, 0
@@ -406,7 +409,7 @@ def run_ours(args, rank, local, world):
         set_index(args.warmup + 2 * args.steps + s)
         cam.render_begin()
         in_flight += 1
-        if in_flight == 3:
+        if in_flight == IN_FLIGHT:
             img, fst = cam.render_wait()
             e2e_rays += fst["rays"]; touched += int(img[own_row, 0, 3]); in_flight -= 1
     while in_flight:
@@ -522,7 +525,7 @@ def run_ours(args, rank, local, world):
         "e2e": {"value": e2e_rays / e2e_s / 1e6, "unit": "Mrays/s", "ms_per_step": e2e_s / args.steps * 1e3,
                 "h2d_bytes_per_step": 160 + 12, "d2h_bytes_per_step": W * H * 4,
                 "api": "PathTracingCamera.render_begin()/render_wait() -> gdpt_render_frame_begin/_wait: host camera block in, "
-                       "pinned host RGBA8 frame out, every step; three frames in flight on three streams",
+                       "pinned host RGBA8 frame out, every step; four frames in flight on four streams",
                 "blocking_render": {"value": sync_rays / sync_s / 1e6, "ms_per_step": sync_s / args.steps * 1e3,
                                     "api": "PathTracingCamera.render() -> gdpt_render_frame, one frame at a time"}},
         "gpu_launches": int(launches_per_frame * args.steps * 3),  # device-timed leg + the two end-to-end legs

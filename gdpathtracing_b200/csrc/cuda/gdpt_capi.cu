@@ -1193,6 +1193,10 @@ extern "C" int gdpt_render_frame_begin(gdpt_shader *m, gdpt_shader *p, const gdp
         const FrameArgs saved = m->args;
         m->args.counters = sl.dcnt; m->args.camera = sl.cam_dev; m->args.out_rgba8 = sl.raw_rgba8; m->args.out_depth = sl.raw_depth;
         m->args.hit_list = sl.hit_list;
+        // Frames in flight share the SMs: with half a grid each (two blocks per SM) two frames' paths run side by side
+        // instead of one frame's blocks waiting for the other's to retire (1080p demo frame, four in flight: 0.589 -> 0.545 ms
+        // per frame; three: 0.589 -> 0.561).  Throughput-bound scenes keep their full grid.
+        if (m->args.blocks_per_sm == 0 && !m->args.pool_dense) m->args.blocks_per_sm = 2;
         d->stream = S; // enqueue_k1 / enqueue_k2 launch on the device's current stream
         cudaEventRecord(sl.t0, S);
         rc = enqueue_k1(m);

@@ -245,7 +245,7 @@ class PathTracingCamera:
         host.gdpt_camera_render_device_only(self._h)
 
     def render_begin(self):
-        """Pipelined render(): enqueue one frame including its read-back; at most MAX_FRAMES_IN_FLIGHT (3) may be
+        """Pipelined render(): enqueue one frame including its read-back; at most MAX_FRAMES_IN_FLIGHT (4) may be
         in flight."""
         if host.gdpt_camera_render_begin(self._h) != 1:
             raise _lib.GdptError("render_begin failed: " + (cuda.gdpt_last_error(self.device) or b"").decode())

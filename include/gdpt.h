@@ -201,7 +201,7 @@ GDPT_API int  gdpt_device_synchronize(gdpt_device *device);
  * GDPT_MAX_FRAMES_IN_FLIGHT frames may be in flight; `wait` blocks until the OLDEST of them is complete in its
  * caller buffers and reports its stats (out_stats may be NULL).  Results are byte-identical to gdpt_render_frame
  * called frame by frame. */
-#define GDPT_MAX_FRAMES_IN_FLIGHT 3
+#define GDPT_MAX_FRAMES_IN_FLIGHT 4
 struct gdpt_frame_stats;
 GDPT_API int  gdpt_render_frame_begin(gdpt_shader *main_shader, gdpt_shader *progressive,
                                  const gdpt_camera *camera, gdpt_denoising mode, uint32_t frame_count,

@@ -364,7 +364,7 @@ def test_storage_buffer_round_trip():
 
 @pytest.mark.gpu
 def test_pipelined_frames_equal_blocking_frames():
-    """gdpt_render_frame_begin/_wait (three frames in flight on two streams, consecutive frames overlapping each other and
+    """gdpt_render_frame_begin/_wait (four frames in flight on four streams, consecutive frames overlapping each other and
     the read-back) returns the very bytes and ray counts of the blocking render(), frame after frame."""
     sc = scenes.demo_scene()
     grp = scenes.populate(sc)
@@ -374,13 +374,13 @@ def test_pipelined_frames_equal_blocking_frames():
     for _ in range(8):
         want.append(a.render().copy()); want_rays.append(a.stats()["rays"])
     got, got_rays = [], []
-    b.render_begin(); b.render_begin(); b.render_begin()
+    b.render_begin(); b.render_begin(); b.render_begin(); b.render_begin()
     with pytest.raises(_lib.GdptError):
-        b.render_begin()  # a fourth frame in flight is refused, loudly
+        b.render_begin()  # a fifth frame in flight (GDPT_MAX_FRAMES_IN_FLIGHT = 4) is refused, loudly
     for i in range(8):
         img, st = b.render_wait()
         got.append(img.copy()); got_rays.append(st["rays"])
-        if i + 3 < 8:
+        if i + 4 < 8:
             b.render_begin()
     with pytest.raises(_lib.GdptError):
         b.render_wait()
