@@ -16,7 +16,7 @@ import numpy as np
 from .nodes import IDENTITY12, GeometryGroup3D
 
 _REPO = os.path.normpath(os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
-DEMO_FIXTURE = os.path.join(_REPO, "tests", "golden", "demo_scene.npz")
+DEMO_FIXTURE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "assets", "demo_scene.npz")  # workload input (the demo scene's meshes and textures), not a golden output
 
 
 @dataclass

@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Generate tests/golden/demo_scene.npz from the reference's demo ASSETS (data, not source).
+"""Generate gdpathtracing_b200/assets/demo_scene.npz from the reference's demo ASSETS (data, not source).
 
 Run in the authoring container only (needs /root/reference).  The GPU box has no reference
 checkout, so the benchmark scene of BASELINE config C2 ("project demo scene: Gobot character +
@@ -27,7 +27,7 @@ import numpy as np
 from PIL import Image
 
 REF = "/root/reference/project"
-OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "demo_scene.npz")
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "gdpathtracing_b200", "assets", "demo_scene.npz")
 
 
 def load_obj(path):
