@@ -285,15 +285,15 @@ def run_ours(args, rank, local, world):
         if rows_mode:
             present()
             torch.cuda.synchronize()
-    frames_kept = torch.empty((args.steps, H, W, 4), dtype=torch.uint8, device=dev_t) if sample_mode else None
+    # sample index: every rank keeps its frames in device memory the other ranks can read over NVLink (CUDA IPC); the owner
+    # of a row block accumulates straight from the source rank's copy (multigpu.PeerFrameStore: the exchange is K2's loads)
+    store = multigpu.PeerFrameStore(cam, args.steps, H, W, rank, world, dev_t) if sample_mode else None
+    frames_kept = store.frames if sample_mode else None
     if sample_mode:
-        # warm-up of the exchange + accumulate path at the size the timed region uses: NCCL sets up its peer-to-peer
-        # channels and the allocator its blocks on first use (hundreds of ms, once per process)
-        frames_kept.zero_()
-        for _ in range(2):
-            warm = multigpu.SampleIndexAccumulator(H, W, rank, world, dev_t, multigpu.cuda_k2(cam))
+        for _ in range(2):  # warm-up of the path at the size the timed region uses (peer mappings, NCCL channels, allocator blocks)
+            warm = multigpu.SampleIndexAccumulator(H, W, rank, world, dev_t, multigpu.cuda_k2_at(cam))
             with torch.cuda.stream(backend_stream):
-                warm.add(frames_kept)
+                warm.add_from_store(store)
                 warm.present()
             torch.cuda.synchronize()
             del warm
@@ -334,21 +334,25 @@ def run_ours(args, rank, local, world):
             gather_ms += e0.elapsed_time(e1)
     exchange = None
     if sample_mode:
-        # the partition's exchange step, inside the timed region: row blocks of every rank's frames to their owners
-        # (NCCL send/recv over NVLink), K2 per frame in frame order on the owner, all-gather of the presented blocks
-        acc = multigpu.SampleIndexAccumulator(H, W, rank, world, dev_t, multigpu.cuda_k2(cam))
+        # the partition's exchange step, inside the timed region: every owner runs K2 over its row block of every rank's
+        # frames, in frame order, reading the block from the source rank's memory over NVLink; two one-element all-reduces
+        # fence the reads; all-gather of the presented blocks
+        acc = multigpu.SampleIndexAccumulator(H, W, rank, world, dev_t, multigpu.cuda_k2_at(cam))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with torch.cuda.stream(backend_stream):
             e0.record(backend_stream)
-            acc.add(frames_kept)
+            acc.add_from_store(store)
             presented = acc.present()
             e1.record(backend_stream)
         torch.cuda.synchronize(); cam.synchronize()
         gather_ms += e0.elapsed_time(e1)
         launches_per_frame += world  # K2 launches of the accumulation, per step
-        exchange = {"bytes_sent_per_rank": int(acc.bytes_exchanged), "frames_accumulated": int(acc.frames_done),
-                    "what": "send/recv of row blocks (NCCL over NVLink) + K2 per frame in frame order + all-gather of the presented blocks"}
+        exchange = {"bytes_read_from_peers_per_rank": int(acc.bytes_exchanged), "frames_accumulated": int(acc.frames_done),
+                    "what": "K2 per frame in frame order on the owner of each row block, reading the block from the source rank's "
+                            "memory over NVLink (CUDA IPC) + two one-element all-reduces + all-gather of the presented blocks"}
         del presented
+        frames_kept = None
+        store.close()
     # ---- per-kernel split of K1 (untimed frames, stage events on)
     _lib.check(cuda.gdpt_shader_set_stage_timing(cam.main_shader, 1), cam.device, "set_stage_timing")
     split_frames = min(args.steps, 8)
@@ -635,21 +639,21 @@ def run_c5(args, rank, local, world, dev_t):
     ptr, _ = cam.device_pointer("output")
     frame_t = multigpu.as_tensor(ptr, (H, W, 4), torch.uint8, dev_t)
     batch = every // world
-    kept = torch.empty((batch, H, W, 4), dtype=torch.uint8, device=dev_t)
+    store = multigpu.PeerFrameStore(cam, batch, H, W, rank, world, dev_t)  # this rank's frames of a batch, readable by every rank
+    kept = store.frames
     for w in range(3):  # warm-up: kernels, exchange, K2
         cam.set_frame_index(w)
         cam.render_device_only()
     cam.synchronize()
-    kept.zero_()
-    for _ in range(2):  # at the size the timed region uses: NCCL's peer-to-peer channels and the allocator's blocks are set up on first use
-        warm = multigpu.SampleIndexAccumulator(H, W, rank, world, dev_t, multigpu.cuda_k2(cam))
+    for _ in range(2):  # at the size the timed region uses: peer mappings, NCCL channels and the allocator's blocks are set up on first use
+        warm = multigpu.SampleIndexAccumulator(H, W, rank, world, dev_t, multigpu.cuda_k2_at(cam))
         with torch.cuda.stream(stream):
-            warm.add(kept); warm.present()
+            warm.add_from_store(store); warm.present()
         torch.cuda.synchronize()
         del warm
 
     def sample_index():
-        acc = multigpu.SampleIndexAccumulator(H, W, rank, world, dev_t, multigpu.cuda_k2(cam))
+        acc = multigpu.SampleIndexAccumulator(H, W, rank, world, dev_t, multigpu.cuda_k2_at(cam))
         rays, k1_ms, ex_ms = 0, 0.0, 0.0
         for b in range(spp // every):
             for j in range(batch):
@@ -662,7 +666,7 @@ def run_c5(args, rank, local, world, dev_t):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             with torch.cuda.stream(stream):
                 e0.record(stream)
-                acc.add(kept)
+                acc.add_from_store(store)
                 shown = acc.present()
                 e1.record(stream)
             torch.cuda.synchronize()
@@ -675,8 +679,12 @@ def run_c5(args, rank, local, world, dev_t):
     rays_all = reduce_sum(rays)
     out["sample_index"] = {"ms_total": ms, "ms_per_spp": ms / spp, "mrays_s": rays_all / (ms * 1e-3) / 1e6,
                            "k1_ms_slowest_rank": reduce_max(k1_ms), "exchange_accumulate_present_ms_slowest_rank": reduce_max(ex_ms),
-                           "bytes_sent_over_nvlink_per_rank": int(sent), "collective": "NCCL send/recv of row blocks + all-gather of the presented blocks"}
-    del cam, kept
+                           "bytes_read_over_nvlink_per_rank": int(sent),
+                           "collective": "none on the data path: K2 reads each frame's row block from the source rank's memory over NVLink "
+                                         "(CUDA IPC); two one-element NCCL all-reduces per batch + all-gather of the presented blocks"}
+    del kept
+    store.close()
+    del cam
 
     # ---------------- row bands
     cam = make_camera(sc, grp, args, local, PathTracingCamera.PROGRESSIVE_RENDERING, W=W, H=H, depth=D, shard=(rank, world, args.band))

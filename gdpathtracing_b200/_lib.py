@@ -106,6 +106,8 @@ CUDA_API = [
     ("gdpt_host_alloc", c_void_p, [c_uint64]),
     ("gdpt_host_free", None, [c_void_p]),
     ("gdpt_device_stream", c_uint64, [c_void_p]),
+    ("gdpt_device_create_buffer", c_uint64, [c_void_p, c_uint64]),
+    ("gdpt_device_free_buffer", c_int, [c_void_p, c_uint64]),
     ("gdpt_rid_ipc_export", c_int, [c_void_p, c_uint64, c_void_p]),
     ("gdpt_device_ipc_open", c_int, [c_void_p, c_void_p, POINTER(c_uint64)]),
     ("gdpt_device_ipc_close", c_int, [c_void_p, c_uint64]),

@@ -953,6 +953,35 @@ int gdpt_progressive_accumulate(gdpt_device *d, uint64_t raw_rgba8, uint64_t scr
     return GDPT_OK;
 }
 
+gdpt_rid gdpt_device_create_buffer(gdpt_device *d, uint64_t size)
+{
+    if (!d || size == 0) { if (d) fail(d, GDPT_ERR_INVALID_ARG, "gdpt_device_create_buffer: empty size"); return 0; }
+    cudaSetDevice(d->ordinal);
+    Resource r;
+    r.kind = RES_BUFFER; r.size = size; // device memory only: no host copy is kept
+    if (cudaMalloc(&r.dptr, size) != cudaSuccess) { fail(d, GDPT_ERR_CUDA, "cudaMalloc(%llu) failed: %s", (unsigned long long)size, cudaGetErrorString(cudaGetLastError())); return 0; }
+    if (cudaMemsetAsync(r.dptr, 0, size, d->stream) != cudaSuccess || cudaStreamSynchronize(d->stream) != cudaSuccess) {
+        fail(d, GDPT_ERR_CUDA, "clearing the buffer failed: %s", cudaGetErrorString(cudaGetLastError()));
+        cudaFree(r.dptr);
+        return 0;
+    }
+    const gdpt_rid rid = d->next_rid++;
+    d->resources[rid] = std::move(r);
+    return rid;
+}
+
+int gdpt_device_free_buffer(gdpt_device *d, gdpt_rid rid)
+{
+    if (!d) return GDPT_ERR_INVALID_ARG;
+    Resource *r = find(d, rid);
+    if (!r || r->kind != RES_BUFFER) return fail(d, GDPT_ERR_INVALID_ARG, "gdpt_device_free_buffer: unknown buffer RID");
+    cudaSetDevice(d->ordinal);
+    GDPT_CUDA(d, cudaDeviceSynchronize());
+    cudaFree(r->dptr);
+    d->resources.erase(rid);
+    return GDPT_OK;
+}
+
 int gdpt_rid_ipc_export(gdpt_device *d, gdpt_rid rid, void *out_handle)
 {
     if (!d || !out_handle) return GDPT_ERR_INVALID_ARG;

@@ -166,6 +166,21 @@ class SampleIndexAccumulator:
                 self.k2(mine[s][j], self.screen, self.accum, self.frames_done)
         return self.frames_done
 
+    def add_from_store(self, store, n=None):
+        """The same accumulation with the exchange fused into K2: every rank's frames sit in a PeerFrameStore, and this rank
+        runs K2 over its row block of frame j of rank s by READING that block from rank s's memory over NVLink.  `k2` must
+        accept a device address (cuda_k2_at).  Frame order and arithmetic are those of add()."""
+        n = store.n if n is None else int(n)
+        b, e = self.blocks[self.rank]
+        store.barrier()  # every rank's frames are complete
+        for j in range(n):
+            for s in range(self.world):
+                self.frames_done += 1
+                self.k2(store.block_address(s, j, b), e - b, self.W, self.screen, self.accum, self.frames_done)
+        store.barrier()  # every rank has read what it needs: the stores may be overwritten
+        self.bytes_exchanged += n * (self.world - 1) * (e - b) * self.W * 4  # read from peers
+        return self.frames_done
+
     def present(self):
         """The tone-mapped frame after the frames added so far, assembled on every rank."""
         if self.world == 1:
@@ -181,6 +196,61 @@ class SampleIndexAccumulator:
         return out
 
 
+class PeerFrameStore:
+    """The frames a rank keeps for the sample-index accumulation, in device memory every other rank can READ over NVLink
+    (CUDA IPC peer memory): the owner of a row block runs K2 straight from the source rank's copy of the frame, so the
+    exchange step is the accumulate kernel's own loads -- no send / recv, no staging copies.  One process per GPU; handles
+    travel through torch.distributed.  `frames` is this rank's (n, H, W, 4) uint8 tensor over the store."""
+
+    def __init__(self, cam, n, height, width, rank, world, device):
+        from ._lib import check, cuda
+        self.cam, self.n, self.H, self.W, self.rank, self.world = cam, int(n), int(height), int(width), rank, world
+        size = self.n * self.H * self.W * 4
+        self.rid = cuda.gdpt_device_create_buffer(cam.device, size)
+        if not self.rid:
+            raise RuntimeError("gdpt_device_create_buffer failed: " + (cuda.gdpt_last_error(cam.device) or b"").decode())
+        import ctypes
+        p, s = ctypes.c_uint64(), ctypes.c_uint64()
+        check(cuda.gdpt_rid_device_pointer(cam.device, self.rid, ctypes.byref(p), ctypes.byref(s)), cam.device, "rid_device_pointer")
+        self.frames = as_tensor(p.value, (self.n, self.H, self.W, 4), torch.uint8, device)
+        self.base = [0] * world
+        self.base[rank] = p.value
+        self.opened = []
+        if world > 1:
+            buf = ctypes.create_string_buffer(64)
+            check(cuda.gdpt_rid_ipc_export(cam.device, self.rid, buf), cam.device, "rid_ipc_export")
+            handles = [None] * world
+            dist.all_gather_object(handles, buf.raw)
+            for q, h in enumerate(handles):
+                if q != rank:
+                    self.base[q] = cam.open_peer_image(h)
+                    self.opened.append(self.base[q])
+        self._token = torch.zeros(1, dtype=torch.int32, device=device)
+        self._stream = torch.cuda.ExternalStream(cam.stream())
+
+    def block_address(self, source_rank, frame, first_row):
+        return self.base[source_rank] + ((frame * self.H + first_row) * self.W) * 4
+
+    def barrier(self):
+        """Device-side: everything every rank enqueued on its backend stream so far has completed once this has
+        (a one-element NCCL all-reduce on that stream).  Called once after the frames were written (they may now be read)
+        and once after they were read (they may now be overwritten)."""
+        if self.world > 1:
+            with torch.cuda.stream(self._stream):
+                dist.all_reduce(self._token)
+
+    def close(self):
+        from ._lib import cuda
+        self.cam.synchronize()
+        if self.world > 1:
+            dist.barrier()
+        for p in self.opened:
+            self.cam.close_peer_image(p)
+        self.opened = []
+        self.frames = None
+        cuda.gdpt_device_free_buffer(self.cam.device, self.rid)
+
+
 def cuda_k2(cam):
     """K2 of the CUDA backend on torch tensors of `cam`'s device (SampleIndexAccumulator's k2 on the GPU)."""
     from ._lib import check, cuda
@@ -190,6 +260,16 @@ def cuda_k2(cam):
         h, w = int(raw.shape[0]), int(raw.shape[1])
         check(cuda.gdpt_progressive_accumulate(cam.device, raw.data_ptr(), screen.data_ptr(), accum.data_ptr(), w, h, int(frame_count)),
               cam.device, "progressive_accumulate")
+    return k2
+
+
+def cuda_k2_at(cam):
+    """K2 of the CUDA backend with the raw frame given as a device address (possibly a peer's, PeerFrameStore)."""
+    from ._lib import check, cuda
+
+    def k2(raw_address, rows, width, screen, accum, frame_count):
+        check(cuda.gdpt_progressive_accumulate(cam.device, int(raw_address), screen.data_ptr(), accum.data_ptr(), int(width), int(rows),
+                                               int(frame_count)), cam.device, "progressive_accumulate")
     return k2
 
 

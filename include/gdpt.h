@@ -239,6 +239,11 @@ GDPT_API int  gdpt_progressive_accumulate(gdpt_device *device, uint64_t raw_rgba
  * peers' handles, hand the addresses to the progressive shader.  n = 0 clears.  Pointers of images on the same
  * device are accepted too (single-process tests). */
 #define GDPT_IPC_HANDLE_BYTES 64
+/* A plain device buffer owned by the device object (zero-filled, no host copy): frames a process keeps for the other
+ * per-GPU processes to read over NVLink (gdpt_rid_ipc_export + gdpt_rid_device_pointer; multigpu.PeerFrameStore).
+ * Returns 0 on failure.  Freed by gdpt_device_free_buffer or with the device. */
+GDPT_API gdpt_rid gdpt_device_create_buffer(gdpt_device *device, uint64_t size);
+GDPT_API int  gdpt_device_free_buffer(gdpt_device *device, gdpt_rid rid);
 GDPT_API int  gdpt_rid_ipc_export(gdpt_device *device, gdpt_rid rid, void *out_handle);
 GDPT_API int  gdpt_device_ipc_open(gdpt_device *device, const void *handle, uint64_t *out_ptr);
 GDPT_API int  gdpt_device_ipc_close(gdpt_device *device, uint64_t ptr);
