@@ -6,9 +6,11 @@ only on (x, y, frame_index) (main.glsl:409), the scene is replicated.  Two parti
   sample-index  rank r renders whole frames with frame_index = step * world + r + 1 (K1 only).  The
                 accumulation of the reference is a chain of float additions in FRAME order
                 (progressive_rendering.glsl:33-38), so summing per-rank accumulations would differ from it by
-                rounding.  Instead every rank takes a block of rows: the ranks swap the row blocks of their
-                frames (all-to-all over NVLink) and each rank runs K2 over its rows in frame order --
-                bit-identical to one GPU accumulating the same frames (SampleIndexAccumulator).
+                rounding.  Instead every rank takes a block of rows and runs K2 over its rows of EVERY rank's
+                frames in frame order -- bit-identical to one GPU accumulating the same frames
+                (SampleIndexAccumulator).  On GPUs the exchange is K2's own loads: the frames sit in device memory
+                the other ranks map through CUDA IPC (PeerFrameStore, add_from_store); add() is the same with NCCL
+                send/recv of the row blocks (the form the gloo CPU tests run).
   row bands     every rank renders the rows y with (y // band) % world == rank of the SAME frame
                 (bit-identical to the single-GPU frame); a presented image needs one all-gather
                 of the RGBA8 bands.
