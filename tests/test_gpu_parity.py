@@ -436,3 +436,41 @@ def test_frames_in_flight_through_the_c_abi_with_depth_read_back(mode):
         b.synchronize()
         for rgba, dep in slots:
             cuda.gdpt_host_free(rgba); cuda.gdpt_host_free(dep)
+
+
+def test_sample_index_accumulation_from_a_frame_store_equals_progressive_rendering():
+    """multigpu.PeerFrameStore + SampleIndexAccumulator.add_from_store (one rank: the store is this GPU's own memory; across
+    ranks the same addresses are CUDA IPC mappings, checked by bench.py's first_presented_frame_equals_single_gpu): K2 run
+    from the kept frames, in frame order, equals the PROGRESSIVE_RENDERING camera frame for frame and the oracle's K2."""
+    import torch
+    from gdpathtracing_b200 import multigpu
+    sc = scenes.cornell32()
+    grp = scenes.populate(sc)
+    W, H, n = 192, 128, 5
+    ref_cam = make_camera(sc, grp, W, H, 4, mode=PathTracingCamera.PROGRESSIVE_RENDERING)
+    want = [ref_cam.render().copy() for _ in range(n)]
+    cam = make_camera(sc, grp, W, H, 4, mode=PathTracingCamera.NONE)
+    dev = torch.device("cuda", 0)
+    store = multigpu.PeerFrameStore(cam, n, H, W, 0, 1, dev)
+    stream = torch.cuda.ExternalStream(cam.stream())
+    ptr, _ = cam.device_pointer("output")
+    frame_t = multigpu.as_tensor(ptr, (H, W, 4), torch.uint8, dev)
+    for f in range(n):
+        cam.set_frame_index(f)
+        cam.render_device_only()
+        with torch.cuda.stream(stream):
+            store.frames[f].copy_(frame_t)
+    acc = multigpu.SampleIndexAccumulator(H, W, 0, 1, dev, multigpu.cuda_k2_at(cam))
+    with torch.cuda.stream(stream):
+        assert acc.add_from_store(store, 3) == 3
+        third = acc.present().clone()
+    torch.cuda.synchronize()
+    assert np.array_equal(third.cpu().numpy(), want[2])
+    acc2 = multigpu.SampleIndexAccumulator(H, W, 0, 1, dev, multigpu.cuda_k2_at(cam))
+    with torch.cuda.stream(stream):
+        acc2.add_from_store(store)
+        last = acc2.present().clone()
+    torch.cuda.synchronize()
+    assert np.array_equal(last.cpu().numpy(), want[-1])
+    assert np.array_equal(acc2.accum.cpu().numpy().view(np.uint32), ref_cam.read_image("accum").view(np.uint32))
+    store.close()
