@@ -290,8 +290,7 @@ __global__ void __launch_bounds__(kTraceThreads) k_primary_cull(const FrameArgs 
 // K2 (progressive_rendering.glsl:28-46): acc = (frame_count > 1 ? acc : 0) + screen;
 // screen = rgba8(ACES(acc / frame_count)).  HBM-bound: 36 B per pixel (4 R raw + 16 R + 16 W accumulation + 4 W screen;
 // the first frame reads no accumulation).  One pixel per lane: a warp's accumulator load / store is one 512 B
-// instruction over four full lines, its RGBA8 load / store one 128 B line -- no half-used sector -- and every thread
-// has four independent pixels in flight (blockDim apart) before it computes.
+// instruction over four full lines, its RGBA8 load / store one 128 B line -- no half-used sector.
 // `peers`: RGBA8 images of the other GPUs of a row-band frame (peer memory over NVLink, CUDA IPC).  Every
 // tone-mapped pixel this GPU owns is also stored there, so the presented frame assembles itself in every
 // GPU's image while the kernel runs -- the exchange step of the row-band partition fused into its producer
@@ -299,8 +298,29 @@ __global__ void __launch_bounds__(kTraceThreads) k_primary_cull(const FrameArgs 
 // `raw` is the image K1 wrote (the bound screen image itself in the reference's call sequence; a frame-private image
 // when two pipelined frames overlap), `screen` receives the tone-mapped result.  frame_count comes from the device
 // Params block (stream-ordered uploads) or, when `params` is null, from the argument.
-constexpr int kProgressiveUnroll = 2;
-__global__ void __launch_bounds__(256, 8) k_progressive(const uint32_t *__restrict__ raw, uint32_t *screen, float4 *accum,
+//
+// The six quotients of a pixel (acc / frame_count and the ACES fraction, three channels each) are IEEE divisions in the
+// reference's arithmetic.  K2 runs the reciprocal + FMA sequence of the compiler's own division fast path itself
+// (pt_shade.cuh, `quotient_in_window`) behind ONE test per pixel: the three sums are +0 or inside [2^-40, 2^40] and
+// frame_count >= 1.  Then x = sum / frame_count is +0 or inside [2^-72, 2^40], the ACES denominator inside [0.14, 2^82],
+// its numerator +0 or at least 2^-78, and every product, residual and reciprocal of the six sequences is +0 or a normal
+// number, so each returns the correctly rounded quotient (+0 for a +0 numerator: 0 * r = +0, residual +0).  The
+// reciprocal of frame_count is shared by the three channels.  Any other pixel (a negative, tiny, huge or non-finite
+// value somebody stored in the accumulation buffer) takes the plain `/` path, out of line.
+// (tests/test_gpu_k2.py: crafted sums on both sides of the window's edges against the oracle's divisions.)
+#ifndef GDPT_K2_UNROLL
+#define GDPT_K2_UNROLL 1
+#endif
+#ifndef GDPT_K2_MINB
+#define GDPT_K2_MINB 8
+#endif
+constexpr int kProgressiveUnroll = GDPT_K2_UNROLL;
+__device__ __noinline__ uint32_t progressive_tone_map_generic(f3 rad, float fc)
+{
+    const f3 avg = (rad / fc) * 1.0f;
+    return pack_rgba8(mk3(aces_channel(avg.x), aces_channel(avg.y), aces_channel(avg.z)));
+}
+__global__ void __launch_bounds__(256, GDPT_K2_MINB) k_progressive(const uint32_t *__restrict__ raw, uint32_t *screen, float4 *accum,
                                                      const gdpt_progressive_params *__restrict__ params, uint32_t frame_count_arg,
                                                      int width, int height, int shard_part, int shard_parts, int shard_band,
                                                      const PeerScreens peers)
@@ -312,6 +332,7 @@ __global__ void __launch_bounds__(256, 8) k_progressive(const uint32_t *__restri
     __syncthreads();
     const uint32_t frame_count = params ? params->frame_count : frame_count_arg;
     const float fc = (float)frame_count;
+    const float r_fc = refined_rcp(fc); // (unused garbage when frame_count is 0: those pixels take the generic path)
     const size_t n = (size_t)width * height;
     // every block takes one contiguous, equally long range of pixels (a multiple of 128, so warps stay line-aligned):
     // the grid is one wave of resident blocks and they all finish together
@@ -341,10 +362,21 @@ __global__ void __launch_bounds__(256, 8) k_progressive(const uint32_t *__restri
             f3 rad = mk3(s_unorm[in[k] & 0xffu], s_unorm[(in[k] >> 8) & 0xffu], s_unorm[(in[k] >> 16) & 0xffu]);
             if (frame_count > 1u) rad = rad + mk3(acc[k].x, acc[k].y, acc[k].z);
             accum[p] = make_float4(rad.x, rad.y, rad.z, 1.0f);
-            const f3 avg = (rad / fc) * 1.0f;
-            const uint32_t o = pack_rgba8(mk3(aces_channel(avg.x), aces_channel(avg.y), aces_channel(avg.z)));
+            const bool window = frame_count != 0u && in_quotient_window(rad);
+            uint32_t o;
+            if (window) {
+                o = pack_rgba8(mk3(aces_channel_in_window(quotient_in_window(rad.x, fc, r_fc)),
+                                   aces_channel_in_window(quotient_in_window(rad.y, fc, r_fc)),
+                                   aces_channel_in_window(quotient_in_window(rad.z, fc, r_fc))));
+            } else {
+                o = progressive_tone_map_generic(rad, fc);
+            }
             screen[p] = o;
-            for (int j = 0; j < peers.n; j++) peers.p[j][p] = o;
+            if (peers.n > 0) {
+#pragma unroll
+                for (int j = 0; j < kMaxPeerScreens; j++) // (constant indices: the pointer table stays in the parameter bank)
+                    if (j < peers.n) peers.p[j][p] = o;
+            }
         }
     }
 }
@@ -357,13 +389,15 @@ __global__ void __launch_bounds__(256) k_temporal(uint32_t *__restrict__ screen,
                                                   const gdpt_temporal_params *__restrict__ params)
 {
     __shared__ gdpt_temporal_params p;
+    __shared__ float s_unorm[256]; // imageLoad of an rgba8 texel = byte / 255.0f (temporal_reprojection.glsl:36), as in k_progressive
     if (threadIdx.x < sizeof(gdpt_temporal_params) / 4u)
         reinterpret_cast<uint32_t *>(&p)[threadIdx.x] = reinterpret_cast<const uint32_t *>(params)[threadIdx.x];
+    s_unorm[threadIdx.x] = (float)threadIdx.x / 255.0f;
     __syncthreads();
     const int tiles_x = (p.width + 31) >> 5, tiles_y = (p.height + 7) >> 3;
     for (int tile = blockIdx.x; tile < tiles_x * tiles_y; tile += gridDim.x) {
         const int x = (tile % tiles_x) * 32 + (int)(threadIdx.x & 31u), y = (tile / tiles_x) * 8 + (int)(threadIdx.x >> 5);
-        if (x < p.width && y < p.height) temporal_pixel(p, x, y, screen, depth, history, next);
+        if (x < p.width && y < p.height) temporal_pixel(p, x, y, screen, depth, history, next, s_unorm);
     }
 }
 

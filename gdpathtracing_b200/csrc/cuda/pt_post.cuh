@@ -25,13 +25,15 @@ GDPT_HD int float_to_int_trunc(float v)
 //   depth    r32f of the CURRENT frame, read at `pos` and at the reprojected position (:37, :61)
 //   history  the rgba32f frame buffer the previous dispatch wrote (frameBuffer1 when frameCount is even, :46, :62)
 //   next     the other frame buffer, written at `pos` (:66)
+// `unorm` (device only, may be null): table of the 256 quotients k / 255.0f, the same IEEE divisions done once per block
 GDPT_HD void temporal_pixel(const gdpt_temporal_params &p, int x, int y, uint32_t *screen, const float *depth,
-                            const float *history, float *next)
+                            const float *history, float *next, const float *unorm = nullptr)
 {
     const int width = p.width, height = p.height;
     const size_t at = (size_t)y * (size_t)width + (size_t)x;
     const uint32_t in = screen[at];
-    const f3 current = mk3((float)(in & 0xffu) / 255.0f, (float)((in >> 8) & 0xffu) / 255.0f, (float)((in >> 16) & 0xffu) / 255.0f);
+    const f3 current = unorm ? mk3(unorm[in & 0xffu], unorm[(in >> 8) & 0xffu], unorm[(in >> 16) & 0xffu])
+                             : mk3((float)(in & 0xffu) / 255.0f, (float)((in >> 8) & 0xffu) / 255.0f, (float)((in >> 16) & 0xffu) / 255.0f);
     const float d = depth[at];
     const float fw = (float)(uint32_t)width, fh = (float)(uint32_t)height;
     const float nx = ((float)x + 0.5f) / fw * 2.0f - 1.0f;
@@ -64,7 +66,7 @@ GDPT_HD void temporal_pixel(const gdpt_temporal_params &p, int x, int y, uint32_
 #else
     next[at * 4 + 0] = blended.x; next[at * 4 + 1] = blended.y; next[at * 4 + 2] = blended.z; next[at * 4 + 3] = 1.0f;
 #endif
-    screen[at] = pack_rgba8(mk3(aces_channel(blended.x), aces_channel(blended.y), aces_channel(blended.z)));
+    screen[at] = tone_map_rgba8(blended);
 }
 
 } // namespace gdpt
