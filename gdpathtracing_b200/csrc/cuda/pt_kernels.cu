@@ -46,11 +46,19 @@ struct SmemStack {
     }
 };
 
-__device__ __forceinline__ bool work_to_pixel(const FrameArgs &a, uint32_t w, int *px, int *py)
+// tiles_x_magic = ceil(2^32 / tiles_x): tile / tiles_x = umulhi(tile, magic) while tile * tiles_x < 2^32 (the error of the
+// magic number is below tiles_x / 2^32 per unit of tile); 0 = use the division
+__device__ __forceinline__ uint32_t tiles_x_magic(const FrameArgs &a)
+{
+    const uint32_t tiles_x = ((uint32_t)a.width + 7u) >> 3;
+    const unsigned long long tiles = (unsigned long long)(a.n_work >> 5);
+    return (tiles_x > 1u && tiles * tiles_x < 0xFFFFFFFFull) ? 0xFFFFFFFFu / tiles_x + 1u : 0u;
+}
+__device__ __forceinline__ bool work_to_pixel(const FrameArgs &a, uint32_t w, int *px, int *py, uint32_t magic = 0u)
 {
     const uint32_t tile = w >> 5, lane = w & 31u;
     const uint32_t tiles_x = ((uint32_t)a.width + 7u) >> 3;
-    const uint32_t tx = tile % tiles_x, ty = tile / tiles_x;
+    const uint32_t ty = magic ? __umulhi(tile, magic) : tile / tiles_x, tx = tile - ty * tiles_x;
     const int lx = (int)(tx * 8u + (lane & 7u)), ly = (int)(ty * 4u + (lane >> 3));
     if (lx >= a.width || ly >= a.local_rows) return false;
     int y = ly;
@@ -217,10 +225,12 @@ __global__ void __launch_bounds__(kTraceThreads) k_primary_cull(const FrameArgs 
     FrameCounters *cnt = a.counters;
     unsigned long long my_done = 0;
     const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t magic = tiles_x_magic(a);
+    const float far_depth = encode_depth(cam, cam.z_far); // what every finished pixel stores (main.glsl:430-431)
     for (uint32_t w0 = blockIdx.x * blockDim.x; w0 < a.n_work; w0 += stride) { // warp-uniform trip count
         const uint32_t w = w0 + threadIdx.x;
         int px, py;
-        const bool valid = w < a.n_work && work_to_pixel(a, w, &px, &py);
+        const bool valid = w < a.n_work && work_to_pixel(a, w, &px, &py, magic);
         bool survivor = false;
         uint32_t pixel = 0;
         if (valid) {
@@ -261,7 +271,7 @@ __global__ void __launch_bounds__(kTraceThreads) k_primary_cull(const FrameArgs 
             }
             if (!survivor) {
                 a.out_rgba8[pixel] = pack_rgba8(mk3(0.0f, 0.0f, 0.0f) + mk3(1.0f, 1.0f, 1.0f) * sample_sky(d));
-                a.out_depth[pixel] = encode_depth(cam, cam.z_far);
+                a.out_depth[pixel] = far_depth;
                 if (a.trace) write_hit_record(a, 0, pixel, 1e9f, 0.0f, 0.0f, 0u, 0u); // GDPT_RECORD_HITS: a miss
                 my_done++;
             }
