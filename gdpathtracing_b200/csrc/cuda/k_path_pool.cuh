@@ -19,7 +19,10 @@
 #endif
 constexpr int kPoolMinBlocks = GDPT_POOL_MINB; // resident blocks per SM the register allocation is capped for (launch bounds)
 constexpr int kPoolDenseMinBlocks = 5; // the second build of the timed instantiation, for throughput-bound scenes (FrameArgs::pool_dense)
-constexpr int kPoolSlotsDefault = 64; // path slots per warp (template argument kPoolSlots)
+#ifndef GDPT_POOL_SLOTS
+#define GDPT_POOL_SLOTS 80
+#endif
+constexpr int kPoolSlotsDefault = GDPT_POOL_SLOTS; // path slots per warp (template argument kPoolSlots)
 constexpr int kPoolParkDefault = 1; // leaves a lane may park while it keeps descending (template argument kPoolPark)
 enum PoolField {
     PF_WOX, PF_WOY, PF_WOZ, PF_WDX, PF_WDY, PF_WDZ,   // ray.o, ray.d (world)

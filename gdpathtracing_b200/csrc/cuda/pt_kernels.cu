@@ -533,6 +533,7 @@ void launch_temporal(uint32_t *screen_rgba8, const float *depth, const float *hi
 // Compile-time shape of k_path_pool, chosen by A/B on the B200 (C2 demo frame / C4 instanced at 1080p, ms):
 //   parked leaves 1 | 2 | 3 | 4          0.859 | 0.892 | 0.908 | 0.918      20.3 | 20.9 | 21.4 | 21.8
 //   slots per warp 40 | 64 | 96          0.961 | 0.878 | 0.896              21.5 | 20.5 | 20.9
+//   (with every phase per iteration, 64 | 80 | 96: C2 0.595 | 0.591 | 0.590, end to end 4 580 | 4 790 | 4 757 Mrays/s; C4 9.94 | 9.75 | 9.88 -> 80)
 //   blocks per SM 4 | 5 | 6 | 8          0.854 | 0.960 | 1.124 | 1.320      19.0 | 18.6 | 21.8 | 24.8   (registers 128 | 96 | 80 | 64)
 void launch_path_pool(const FrameArgs &a_in, bool record, cudaStream_t s)
 {
