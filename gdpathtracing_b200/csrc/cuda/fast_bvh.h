@@ -63,10 +63,19 @@ constexpr uint32_t kLeafMaxDefault = 2; // A/B on the B200, C2 path kernel ms | 
 #ifndef GDPT_FAST_LEAF_MAX
 #define GDPT_FAST_LEAF_MAX kLeafMaxDefault
 #endif
-inline uint32_t leaf_max()
+// A mesh of kLeafOneFrom triangles and more gets one triangle per leaf: its rays spend their time in deep, small boxes, and
+// a second triangle per leaf is a second Moller-Trumbore for rays that mostly miss both (C3, 1 M-triangle soup: path kernel
+// 4.78 -> 4.25 ms with 1-triangle leaves; C2's meshes, 1 k-50 k triangles: 0.596 -> 0.669, so they keep 2).
+constexpr uint32_t kLeafOneFrom = 262144u;
+inline uint32_t leaf_max(uint32_t mesh_triangles)
 {
     static_assert((uint32_t)(GDPT_FAST_LEAF_MAX) >= 1u && (uint32_t)(GDPT_FAST_LEAF_MAX) <= 8u, "1..8 triangles per leaf");
+#ifdef GDPT_FAST_LEAF_NO_RULE
+    (void)mesh_triangles;
     return (uint32_t)(GDPT_FAST_LEAF_MAX);
+#else
+    return mesh_triangles >= kLeafOneFrom ? 1u : (uint32_t)(GDPT_FAST_LEAF_MAX);
+#endif
 }
 
 struct Prim { float lo[3], hi[3], c[3]; uint32_t orig; };
@@ -101,6 +110,7 @@ struct Builder {
     std::vector<Prim> prims;
     FastLayout *out;
     float owner_extent = 0.0f;
+    uint32_t leaf_cap = 1;  // triangles per leaf (leaf_max of the mesh)
     uint32_t depth_seen = 0;
     // multi-threaded form: ranges of at most `cut_at` primitives become tasks built into private tables, which are
     // placed behind one another in the depth-first order the single-threaded recursion would have produced
@@ -145,7 +155,7 @@ struct Builder {
             tasks.back().b = b; tasks.back().e = e; tasks.back().depth = depth;
             return kTaskMark | (uint32_t)(tasks.size() - 1);
         }
-        if (n <= leaf_max()) {
+        if (n <= leaf_cap) {
             const uint32_t first = (uint32_t)out->tris.size();
             for (uint32_t i = b; i < e; i++) {
                 FastTri t;
@@ -247,7 +257,7 @@ struct Builder {
         parallel_parts(threads, (int)tasks.size(), [&](int k) {
             Task &t = tasks[(size_t)k];
             Builder sub;
-            sub.tris = tris; sub.out = &t.part; sub.owner_extent = owner_extent;
+            sub.tris = tris; sub.out = &t.part; sub.owner_extent = owner_extent; sub.leaf_cap = leaf_cap;
             sub.prims.assign(prims.begin() + t.b, prims.begin() + t.e);
             TightBox box;
             t.link = sub.build(0, t.e - t.b, t.depth, &box);
@@ -453,6 +463,7 @@ inline void build_fast_layout(const gdpt_bvh_node *bvh, uint32_t n_nodes, const 
             const int threads = out.build_threads > 0 ? out.build_threads : (int)std::min(32u, std::max(1u, std::thread::hardware_concurrency()));
             const uint32_t count = (uint32_t)bld.prims.size();
             bld.threads = threads;
+            bld.leaf_cap = fastbvh::leaf_max(count);
             if (threads > 1 && count >= 65536u) bld.cut_at = std::max(4096u, count / (uint32_t)(threads * 8));
             const uint32_t first_node = (uint32_t)out.nodes.size();
             link = bld.build(0, count, 0, &box);

@@ -219,7 +219,7 @@ template <class Sink> GDPT_HD void fast_triangle_test(RayState &r, const q4f a, 
 }
 GDPT_HD void fast_triangle_test(RayState &r, const q4f a, const q4f b, const q4f c) { fast_triangle_test(r, a, b, c, HitInRay()); }
 
-// One leaf: 1..8 triangles (fast_bvh.h leaf_max(), 3 by default).  GDPT_FAST_LEAF_UNROLL 4 issues all loads together (more registers, 4 copies of
+// One leaf: 1..8 triangles (fast_bvh.h leaf_max(): 2, or 1 for very large meshes).  GDPT_FAST_LEAF_UNROLL 4 issues all loads together (more registers, 4 copies of
 // the test in the instruction stream); 1 keeps one copy of the test in a short loop (instruction-cache friendly).
 #ifndef GDPT_FAST_LEAF_UNROLL
 #define GDPT_FAST_LEAF_UNROLL 1
