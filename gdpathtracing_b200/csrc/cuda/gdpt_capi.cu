@@ -386,7 +386,6 @@ int finish_main(gdpt_shader *s)
     a.pool_wait = tune(s, "POOL_WAIT", 16); // A/B with every phase per iteration (16 | 32): C2 0.598 | 0.594 ms, C4 1080p 10.26 | 10.66
     a.lead_min = tune(s, "LEAD_MIN", 0);
     a.sort4 = tune(s, "SORT4", 1);
-    a.all_phases = tune(s, "ALL_PHASES", 1);
     a.miss_now = tune(s, "MISS_NOW", 1);
     // A frame of a few instances is one wave of paths and bound by their latency: 128 registers, no spills, four blocks per
     // SM.  Frames with far more traversal per path are throughput-bound and take the fifth block at 96 registers

@@ -116,13 +116,9 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_pool(const FrameAr
     for (;;) {
         const uint32_t pend = n_park ? park[0] : LINK_NONE;
         const bool can_i = has && pool_can_node(r.cur, r.inst);
-        const bool can_l = has && lane_can_leaf(r.cur, pend);
-        const bool can_t = has && pool_can_cross(r.cur, pend, r.inst);
         const bool fin = has && r.cur == LINK_NONE && pend == LINK_NONE;
-        const uint32_t census = __reduce_add_sync(kFull, (can_i ? 1u : 0u) | (can_l ? 1u << 6 : 0u) | (can_t ? 1u << 12 : 0u) |
-                                                             (fin ? 1u << 18 : 0u) | (has ? 0u : 1u << 24));
-        const int n_i = (int)(census & 63u), n_l = (int)((census >> 6) & 63u), n_t = (int)((census >> 12) & 63u),
-                  n_fin = (int)((census >> 18) & 63u), n_idle = (int)(census >> 24);
+        const uint32_t census = __reduce_add_sync(kFull, (can_i ? 1u : 0u) | (fin ? 1u << 8 : 0u) | (has ? 0u : 1u << 16));
+        const int n_i = (int)(census & 63u), n_fin = (int)((census >> 8) & 63u), n_idle = (int)(census >> 16);
         const int n_walk = 32 - n_idle - n_fin;
         const bool can_refill = !exhausted && free_count > min_free; // alive paths (slots in use) stay below the cap
 
@@ -308,15 +304,11 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_pool(const FrameAr
             continue;
         }
         // ---------------- I / L / T ----------------
-        // a.all_phases: every phase that has a lane runs, in the order a ray meets them (nodes, then the leaf it reached,
-        // then the crossing), so a ray advances in every iteration -- a frame is one wave of paths whose length is the
-        // latency of its longest path, and a lane that waits for its phase to win a vote lengthens exactly that.
-        // Otherwise: only the phase that advances most lanes per instruction.
-        // a.all_phases = n > 1: a phase other than the vote's winner runs only with n lanes or more.
-        const bool all = a.all_phases != 0;
-        const int few = a.all_phases; // >= 1 when `all`
-        const int run = (n_i * 3 >= n_l && n_i * 3 >= n_t * 2) ? 1 : (n_l >= n_t * 2 ? 0 : 2);
-        if (all ? (n_i >= few || (run == 1 && n_i > 0)) : (run == 1)) {
+        // Every phase that has a lane runs, in the order a ray meets them (nodes, then the leaf it reached, then the
+        // crossing), so a ray advances in every iteration -- a frame is one wave of paths whose length is the latency of its
+        // longest path, and a lane that waits for its phase to win a vote lengthens exactly that.  (The majority-phase loop
+        // this replaced, and thresholds of 2 / 4 / 8 lanes for the other phases, were slower on every config: DESIGN.md 4.)
+        if (n_i > 0) {
             if (PROF) it_i++;
             bool go = can_i;
             const int need = (n_i + 1) >> 1;
@@ -338,9 +330,8 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_pool(const FrameAr
                 if (__popc(__ballot_sync(kFull, go)) < need) break;
             }
         }
-        bool now_l = can_l;
-        if (all) now_l = has && lane_can_leaf(r.cur, n_park ? park[0] : LINK_NONE);
-        if (all ? (__popc(__ballot_sync(kFull, now_l)) >= (run == 0 ? 1 : few)) : (run == 0)) {
+        const bool now_l = has && lane_can_leaf(r.cur, n_park ? park[0] : LINK_NONE);
+        if (__ballot_sync(kFull, now_l)) {
             if (PROF) it_l++;
             if (now_l) {
                 uint32_t leaf = park[0];
@@ -356,9 +347,8 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_pool(const FrameAr
                 if (COUNT) own_tris += ((leaf >> FAST_LEAF_COUNT_SHIFT) & 7u) + 1u;
             }
         }
-        bool now_t = can_t;
-        if (all) now_t = has && pool_can_cross(r.cur, n_park ? park[0] : LINK_NONE, r.inst);
-        if (all ? (__popc(__ballot_sync(kFull, now_t)) >= (run == 2 ? 1 : few)) : (run == 2)) {
+        const bool now_t = has && pool_can_cross(r.cur, n_park ? park[0] : LINK_NONE, r.inst);
+        if (__ballot_sync(kFull, now_t)) {
             if (PROF) it_t++;
             if (now_t) { // back to world space (main.glsl:316-327) and/or into the instance the link names
                 r.wo = mk3(PFF(PF_WOX, slot), PFF(PF_WOY, slot), PFF(PF_WOZ, slot)); // the world ray lives in the slot, not in the lane

@@ -53,7 +53,6 @@ struct FrameArgs {
     int count_work;                          // schedule 6: run the instantiation that counts its own work (untimed frames of bench.py)
     int pool_dense;                          // schedule 6: the 96-register build, five blocks per SM (many instances / large meshes)
     int miss_now;                            // schedule 6: escaped rays are finished at retire time, shading batches hold hits only
-    int all_phases;                          // schedule 6: every phase that has a lane runs in each iteration (1) or only the majority phase (0)
     FrameCounters *counters;
     // scheduling knobs (results do not depend on them)
     int refill_below;  // refill idle lanes when fewer than this many lanes are traversing
