@@ -23,7 +23,6 @@ constexpr int kPoolDenseMinBlocks = 5; // the second build of the timed instanti
 #define GDPT_POOL_SLOTS 80
 #endif
 constexpr int kPoolSlotsDefault = GDPT_POOL_SLOTS; // path slots per warp (template argument kPoolSlots)
-constexpr int kPoolParkDefault = 1; // leaves a lane may park while it keeps descending (template argument kPoolPark)
 enum PoolField {
     PF_WOX, PF_WOY, PF_WOZ, PF_WDX, PF_WDY, PF_WDZ,   // ray.o, ray.d (world)
     PF_T, PF_U, PF_V, PF_TRI, PF_BF, PF_FLAGS,        // finished search
@@ -38,9 +37,9 @@ __device__ __forceinline__ bool pool_can_node(uint32_t cur, uint32_t inst)
 {
     return cur != LINK_NONE && (cur & LINK_LEAF) == 0u && ((cur & LINK_TLAS) == 0u || inst == GDPT_NO_INSTANCE);
 }
-__device__ __forceinline__ bool pool_can_cross(uint32_t cur, uint32_t pend, uint32_t inst)
+__device__ __forceinline__ bool pool_can_cross(uint32_t cur, uint32_t inst)
 {
-    return cur != LINK_NONE && (cur & LINK_TLAS) != 0u && pend == LINK_NONE && ((cur & LINK_LEAF) != 0u || inst != GDPT_NO_INSTANCE);
+    return cur != LINK_NONE && (cur & LINK_TLAS) != 0u && ((cur & LINK_LEAF) != 0u || inst != GDPT_NO_INSTANCE);
 }
 
 // Where an accepted triangle's u / v / triangle / instance go: into the ray's path slot (field-major pool), so a lane holds
@@ -58,7 +57,7 @@ template <int kPoolSlots> struct HitInPool {
 //   refill_below = lanes without a walking ray before the pool is serviced (1..32)
 //   pool_wait    = ... or this many lane-iterations spent waiting (0xFFFFFFFF = off)
 //   pool_alive   = free slots a warp keeps unused (cap on alive paths), shade_at = finished rays that justify a partial batch
-template <bool REC, int MINB, int kPoolPark, int kPoolSlots, bool WIDE, bool COUNT = false, bool PROF = false>
+template <bool REC, int MINB, int kPoolSlots, bool WIDE, bool COUNT = false, bool PROF = false>
 __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_pool(const FrameArgs a)
 {
     __shared__ uint32_t s_stack[kSmemStack * kTraceThreads];
@@ -82,6 +81,7 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_pool(const FrameAr
     for (unsigned i = lane; i < (unsigned)kPoolSlots; i += 32u) free_list[i] = (uint8_t)(kPoolSlots - 1 - i);
     __syncthreads();
     const gdpt_camera &cam = s_cam;
+    const float far_depth = encode_depth(cam, cam.z_far); // what a primary ray that escapes stores (main.glsl:430-431)
 #define PF(f, sl) pool[(f) * kPoolSlots + (sl)]
 #define PFF(f, sl) __uint_as_float(pool[(f) * kPoolSlots + (sl)])
 
@@ -97,10 +97,6 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_pool(const FrameAr
 
     RayState r;
     r.cur = LINK_NONE; r.sp = 0; r.overflow = 0; r.t = 1e9f; r.inst = GDPT_NO_INSTANCE;
-    uint32_t park[kPoolPark];  // parked leaves, oldest first (instance-local: flushed before the space changes)
-    uint32_t n_park = 0;
-#pragma unroll
-    for (int k = 0; k < kPoolPark; k++) park[k] = LINK_NONE;
     uint32_t slot = 0, steps = 0;
     bool has = false;
     uint32_t ready_count = 0, done_count = 0, free_count = (uint32_t)kPoolSlots; // warp-uniform
@@ -114,9 +110,8 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_pool(const FrameAr
     uint32_t it_i = 0, it_l = 0, it_t = 0, it_f = 0, it_e = 0, n_started = 0;
 
     for (;;) {
-        const uint32_t pend = n_park ? park[0] : LINK_NONE;
         const bool can_i = has && pool_can_node(r.cur, r.inst);
-        const bool fin = has && r.cur == LINK_NONE && pend == LINK_NONE;
+        const bool fin = has && r.cur == LINK_NONE;
         const uint32_t census = __reduce_add_sync(kFull, (can_i ? 1u : 0u) | (fin ? 1u << 8 : 0u) | (has ? 0u : 1u << 16));
         const int n_i = (int)(census & 63u), n_fin = (int)((census >> 8) & 63u), n_idle = (int)(census >> 16);
         const int n_walk = 32 - n_idle - n_fin;
@@ -140,7 +135,7 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_pool(const FrameAr
                                         mk3(PFF(PF_THR, slot), PFF(PF_THG, slot), PFF(PF_THB, slot)) * sample_sky(wd);
                     const uint32_t pixel = PF(PF_PIXEL, slot);
                     const int segment = (int)PF(PF_SEGMENT, slot);
-                    if (segment == 0) a.out_depth[pixel] = encode_depth(cam, cam.z_far);
+                    if (segment == 0) a.out_depth[pixel] = far_depth;
                     if (REC) write_hit_record(a, segment, pixel, 1e9f, 0.0f, 0.0f, 0u, 0u);
                     a.out_rgba8[pixel] = pack_rgba8(radiance);
                     const uint32_t cost_now = PF(PF_STEPS, slot) + steps;
@@ -202,7 +197,7 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_pool(const FrameAr
                     const f3 throughput = mk3(PFF(PF_THR, sl), PFF(PF_THG, sl), PFF(PF_THB, sl));
                     if (!hit) {
                         radiance = radiance + throughput * sample_sky(wd);
-                        if (segment == 0) a.out_depth[pixel] = encode_depth(cam, cam.z_far);
+                        if (segment == 0) a.out_depth[pixel] = far_depth;
                     } else {
                         BounceResult br;
                         u2 sd; sd.x = PF(PF_SEEDX, sl); sd.y = PF(PF_SEEDY, sl);
@@ -293,7 +288,6 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_pool(const FrameAr
                     fast_ray_begin(r, a.sc, mk3(PFF(PF_WOX, slot), PFF(PF_WOY, slot), PFF(PF_WOZ, slot)),
                                    mk3(PFF(PF_WDX, slot), PFF(PF_WDY, slot), PFF(PF_WDZ, slot)));
                     r.cur = fast_start_link(r, WIDE ? a.sc.fast4_root : r.cur); // the four-wide tables have their own root link
-                    n_park = 0;
                     steps = 0;
                     has = true;
                 }
@@ -318,28 +312,17 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_pool(const FrameAr
                     if (WIDE) fast_step_node4(a.sc, r, st); else fast_step_node(a.sc, r, st);
                     steps++;
                     if (COUNT) { own_nodes++; own_boxes += WIDE ? 4u : 2u; }
-                    if (n_park < (uint32_t)kPoolPark && fast_link_is_leaf(r.cur)) { // park the leaf, keep descending
-#pragma unroll
-                        for (int k = 0; k < kPoolPark; k++)
-                            if (n_park == (uint32_t)k) park[k] = r.cur;
-                        n_park++;
-                        r.cur = fast_pop(r, st);
-                    }
                     go = pool_can_node(r.cur, r.inst);
                 }
                 if (__popc(__ballot_sync(kFull, go)) < need) break;
             }
         }
-        const bool now_l = has && lane_can_leaf(r.cur, n_park ? park[0] : LINK_NONE);
+        const bool now_l = has && fast_link_is_leaf(r.cur);
         if (__ballot_sync(kFull, now_l)) {
             if (PROF) it_l++;
             if (now_l) {
-                uint32_t leaf = park[0];
-                if (n_park) {
-#pragma unroll
-                    for (int k = 0; k + 1 < kPoolPark; k++) park[k] = park[k + 1];
-                    n_park--;
-                } else { leaf = r.cur; r.cur = fast_pop(r, st); }
+                const uint32_t leaf = r.cur;
+                r.cur = fast_pop(r, st);
                 HitInPool<kPoolSlots> sink;
                 sink.slot0 = pool + slot;
                 fast_leaf_tests(a.sc, r, leaf, sink);
@@ -347,7 +330,7 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_path_pool(const FrameAr
                 if (COUNT) own_tris += ((leaf >> FAST_LEAF_COUNT_SHIFT) & 7u) + 1u;
             }
         }
-        const bool now_t = has && pool_can_cross(r.cur, n_park ? park[0] : LINK_NONE, r.inst);
+        const bool now_t = has && pool_can_cross(r.cur, r.inst);
         if (__ballot_sync(kFull, now_t)) {
             if (PROF) it_t++;
             if (now_t) { // back to world space (main.glsl:316-327) and/or into the instance the link names

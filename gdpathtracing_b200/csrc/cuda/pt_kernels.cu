@@ -197,8 +197,6 @@ __device__ __noinline__ bool fast_verdict_ool(const SceneView *sc, f3 wo, f3 wd,
     return fast_result_is_reference(*sc, r);
 }
 
-__device__ __forceinline__ bool lane_can_leaf(uint32_t cur, uint32_t pend) { return pend != LINK_NONE || fast_link_is_leaf(cur); }
-
 #include "k_path_pool.cuh"
 
 // Camera-ray classification (first kernel of the two-kernel schedule): one thread per pixel in
@@ -446,12 +444,12 @@ void init_launch_shapes(int device)
     s.path_blocks[1][1] = grid_of(k_path<true, true, 0>, kTraceThreads);
     s.path_list_blocks = grid_of(k_path<false, true, 1, 4, true>, kTraceThreads);
     s.path_list_record_blocks = grid_of(k_path<true, true, 1>, kTraceThreads);
-    s.pool_blocks[0][0] = grid_of(k_path_pool<false, kPoolMinBlocks, kPoolParkDefault, kPoolSlotsDefault, false>, kTraceThreads);
-    s.pool_blocks[0][1] = grid_of(k_path_pool<false, kPoolMinBlocks, kPoolParkDefault, kPoolSlotsDefault, true>, kTraceThreads);
-    s.pool_blocks[1][0] = grid_of(k_path_pool<true, kPoolMinBlocks, kPoolParkDefault, kPoolSlotsDefault, false>, kTraceThreads);
-    s.pool_blocks[1][1] = grid_of(k_path_pool<true, kPoolMinBlocks, kPoolParkDefault, kPoolSlotsDefault, true>, kTraceThreads);
-    s.pool_count_blocks = grid_of(k_path_pool<false, kPoolMinBlocks, kPoolParkDefault, kPoolSlotsDefault, true, true>, kTraceThreads);
-    s.pool_dense_blocks = grid_of(k_path_pool<false, kPoolDenseMinBlocks, kPoolParkDefault, kPoolSlotsDefault, true>, kTraceThreads);
+    s.pool_blocks[0][0] = grid_of(k_path_pool<false, kPoolMinBlocks, kPoolSlotsDefault, false>, kTraceThreads);
+    s.pool_blocks[0][1] = grid_of(k_path_pool<false, kPoolMinBlocks, kPoolSlotsDefault, true>, kTraceThreads);
+    s.pool_blocks[1][0] = grid_of(k_path_pool<true, kPoolMinBlocks, kPoolSlotsDefault, false>, kTraceThreads);
+    s.pool_blocks[1][1] = grid_of(k_path_pool<true, kPoolMinBlocks, kPoolSlotsDefault, true>, kTraceThreads);
+    s.pool_count_blocks = grid_of(k_path_pool<false, kPoolMinBlocks, kPoolSlotsDefault, true, true>, kTraceThreads);
+    s.pool_dense_blocks = grid_of(k_path_pool<false, kPoolDenseMinBlocks, kPoolSlotsDefault, true>, kTraceThreads);
     grid_of(k_primary_cull, kTraceThreads);
     s.cull_blocks_per_sm = per_sm > 0 ? per_sm : 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_progressive, 256, 0); s.prog_blocks = s.sms * (per_sm > 0 ? per_sm : 1);
@@ -532,6 +530,8 @@ void launch_temporal(uint32_t *screen_rgba8, const float *depth, const float *hi
 
 // Compile-time shape of k_path_pool, chosen by A/B on the B200 (C2 demo frame / C4 instanced at 1080p, ms):
 //   parked leaves 1 | 2 | 3 | 4          0.859 | 0.892 | 0.908 | 0.918      20.3 | 20.9 | 21.4 | 21.8
+//   (a lane that reached a leaf kept descending with the leaf parked; under the all-phases loop the code this takes costs more
+//   than the descent it saves -- 1 | 0 parked leaves: C2 0.559 | 0.514, C4 9.58 | 9.13 -- and it is gone)
 //   slots per warp 40 | 64 | 96          0.961 | 0.878 | 0.896              21.5 | 20.5 | 20.9
 //   (with every phase per iteration, 64 | 80 | 96: C2 0.595 | 0.591 | 0.590, end to end 4 580 | 4 790 | 4 757 Mrays/s; C4 9.94 | 9.75 | 9.88 -> 80)
 //   blocks per SM 4 | 5 | 6 | 8          0.854 | 0.960 | 1.124 | 1.320      19.0 | 18.6 | 21.8 | 24.8   (registers 128 | 96 | 80 | 64)
@@ -546,24 +546,24 @@ void launch_path_pool(const FrameArgs &a_in, bool record, cudaStream_t s)
     const bool wide = a.wide_bvh != 0 && a.sc.fast4_ok != 0; // four-wide tables (fast_bvh.h Collapse)
     const int grid = persistent_grid(sh, a, sh.pool_blocks[record ? 1 : 0][wide ? 1 : 0]);
     if (a.count_work && wide && !record) { // the instantiation that also counts its own work (bench.py's roofline numerator)
-        k_path_pool<false, kPoolMinBlocks, kPoolParkDefault, kPoolSlotsDefault, true, true><<<persistent_grid(sh, a, sh.pool_count_blocks), kTraceThreads, 0, s>>>(a);
+        k_path_pool<false, kPoolMinBlocks, kPoolSlotsDefault, true, true><<<persistent_grid(sh, a, sh.pool_count_blocks), kTraceThreads, 0, s>>>(a);
         return;
     }
     if (a.warp_prof && wide && !record) { // per-warp schedule profile (tools/warp_profile.py): same grid as the timed instantiation
-        k_path_pool<false, kPoolMinBlocks, kPoolParkDefault, kPoolSlotsDefault, true, false, true><<<grid, kTraceThreads, 0, s>>>(a);
+        k_path_pool<false, kPoolMinBlocks, kPoolSlotsDefault, true, false, true><<<grid, kTraceThreads, 0, s>>>(a);
         return;
     }
     if (a.pool_dense && wide && !record) { // throughput-bound scenes: five blocks per SM at 96 registers (a few spilled words)
-        k_path_pool<false, kPoolDenseMinBlocks, kPoolParkDefault, kPoolSlotsDefault, true>
+        k_path_pool<false, kPoolDenseMinBlocks, kPoolSlotsDefault, true>
             <<<persistent_grid(sh, a, sh.pool_dense_blocks), kTraceThreads, 0, s>>>(a);
         return;
     }
     if (record) {
-        if (wide) k_path_pool<true, kPoolMinBlocks, kPoolParkDefault, kPoolSlotsDefault, true><<<grid, kTraceThreads, 0, s>>>(a);
-        else k_path_pool<true, kPoolMinBlocks, kPoolParkDefault, kPoolSlotsDefault, false><<<grid, kTraceThreads, 0, s>>>(a);
+        if (wide) k_path_pool<true, kPoolMinBlocks, kPoolSlotsDefault, true><<<grid, kTraceThreads, 0, s>>>(a);
+        else k_path_pool<true, kPoolMinBlocks, kPoolSlotsDefault, false><<<grid, kTraceThreads, 0, s>>>(a);
     } else {
-        if (wide) k_path_pool<false, kPoolMinBlocks, kPoolParkDefault, kPoolSlotsDefault, true><<<grid, kTraceThreads, 0, s>>>(a);
-        else k_path_pool<false, kPoolMinBlocks, kPoolParkDefault, kPoolSlotsDefault, false><<<grid, kTraceThreads, 0, s>>>(a);
+        if (wide) k_path_pool<false, kPoolMinBlocks, kPoolSlotsDefault, true><<<grid, kTraceThreads, 0, s>>>(a);
+        else k_path_pool<false, kPoolMinBlocks, kPoolSlotsDefault, false><<<grid, kTraceThreads, 0, s>>>(a);
     }
 }
 
