@@ -3,6 +3,7 @@
 #include "geometry_group3d.h"
 
 #include <chrono>
+#include <thread>
 #include <cmath>
 #include <cstring>
 
@@ -74,12 +75,28 @@ int GeometryGroup3D::get_texture_index(int handle)
 // (geometry_group3d.cpp:295-299).  Godot's own resampler lives in the engine,
 // which is not part of the reference tree, so this is NOT pinned to it: pixel
 // centres are mapped with the usual (i+0.5)*scale-0.5 rule, edges clamp.
-std::vector<uint8_t> GeometryGroup3D::resize_bilinear(const TextureRes &src, int res)
+// Rows are independent: `threads` workers take equal bands of rows (0 = all hardware threads); the bytes do not depend on it.
+std::vector<uint8_t> GeometryGroup3D::resize_bilinear(const TextureRes &src, int res, int threads)
 {
     std::vector<uint8_t> out((size_t)res * res * 4);
     if (src.w == res && src.h == res) { out = src.rgba; return out; }
+    if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    threads = std::min(threads, std::max(1, res / 64));
+    if (threads > 1) {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < threads; t++)
+            pool.emplace_back([&, t] { resize_rows(src, res, (int)((long long)res * t / threads), (int)((long long)res * (t + 1) / threads), out.data()); });
+        for (std::thread &th : pool) th.join();
+    } else {
+        resize_rows(src, res, 0, res, out.data());
+    }
+    return out;
+}
+
+void GeometryGroup3D::resize_rows(const TextureRes &src, int res, int y_begin, int y_end, uint8_t *out)
+{
     const float sx = (float)src.w / (float)res, sy = (float)src.h / (float)res;
-    for (int y = 0; y < res; y++) {
+    for (int y = y_begin; y < y_end; y++) {
         float fy = ((float)y + 0.5f) * sy - 0.5f;
         if (fy < 0) fy = 0;
         int y0 = (int)fy, y1 = y0 + 1 < src.h ? y0 + 1 : src.h - 1;
@@ -98,7 +115,6 @@ std::vector<uint8_t> GeometryGroup3D::resize_bilinear(const TextureRes &src, int
             }
         }
     }
-    return out;
 }
 
 void GeometryGroup3D::build()
@@ -156,7 +172,7 @@ void GeometryGroup3D::build()
         materials_.push_back(g);
     }
     // texture array layers (:294-303); a blank layer when the scene has no texture
-    for (int handle : texture_refs_) textures_.push_back(resize_bilinear(texture_pool_[handle], texture_array_resolution_));
+    for (int handle : texture_refs_) textures_.push_back(resize_bilinear(texture_pool_[handle], texture_array_resolution_, build_threads_));
     if (textures_.empty())
         textures_.emplace_back((size_t)texture_array_resolution_ * texture_array_resolution_ * 4, (uint8_t)0);
 

@@ -89,7 +89,8 @@ private:
 
     unsigned get_material_index(int material_handle);
     int get_texture_index(int texture_handle);
-    static std::vector<uint8_t> resize_bilinear(const TextureRes &src, int res);
+    static std::vector<uint8_t> resize_bilinear(const TextureRes &src, int res, int threads = 1);
+    static void resize_rows(const TextureRes &src, int res, int y_begin, int y_end, uint8_t *out);
 
     std::vector<TextureRes> texture_pool_;
     std::vector<StandardMaterial> material_pool_;

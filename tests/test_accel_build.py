@@ -146,3 +146,21 @@ def test_multithreaded_build_matches_reference_on_degenerate_input():
     ref = reference_buffers(sc)
     for key in got:
         assert np.array_equal(got[key], ref[key]), f"{key}: differs from reference bvh.cpp"
+
+
+def test_texture_layers_do_not_depend_on_the_thread_count():
+    """The bilinear resize to the texture-array resolution (geometry_group3d.cpp:294-303) runs in bands of rows on the build
+    threads; every pixel is computed from the source alone, so the layers are the single-thread bytes."""
+    from gdpathtracing_b200 import scenes
+    sc = scenes.demo_scene()
+    layers = {}
+    for threads in (1, 3, 8, 0):
+        grp = scenes.populate(sc)
+        grp.build_threads = threads
+        grp.build()
+        layers[threads] = [l.copy() for l in grp.texture_layers()]
+    assert len(layers[1]) >= 1 and layers[1][0].shape[0] >= 64
+    for threads in (3, 8, 0):
+        assert len(layers[threads]) == len(layers[1])
+        for a, b in zip(layers[threads], layers[1]):
+            assert np.array_equal(a, b), f"{threads} threads"
